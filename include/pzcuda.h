@@ -150,8 +150,8 @@ enum pz_stream_event { PZ_S_NEED_MORE = 0, PZ_S_CHUNK = 1, PZ_S_DONE = 2, PZ_S_E
 pz_stream *pz_stream_new(void);
 /* Supply the strict chunk that answers a NeedMore (Monad.hs:185-197). The bytes are copied. */
 int pz_stream_feed(pz_stream *s, const uint8_t *data, size_t len);
-/* Next decoder state.  For PZ_S_CHUNK, *chunk/*len describe bytes owned by the stream and
- * valid until the next call.  For PZ_S_ERROR, *res (if non-NULL) receives the verdict.   */
+/* Next decoder state.  For PZ_S_CHUNK, `chunk` and `len` describe bytes owned by the stream and
+ * valid until the next call.  For PZ_S_ERROR, `res` (if non-NULL) receives the verdict.   */
 int pz_stream_next(pz_stream *s, const uint8_t **chunk, size_t *len, pz_result *res);
 void pz_stream_free(pz_stream *s);
 

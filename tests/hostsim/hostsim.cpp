@@ -1,0 +1,31 @@
+/*
+ * hostsim.cpp -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Compiles pure_zlib_b200/csrc/pz_device.cuh with a host compiler (PZ_HOSTSIM: a warp is
+ * one lane) so the decoder LOGIC -- bit accounting, LUT construction, verdict order, the
+ * window model -- can be fuzzed against the oracle on a machine without a GPU.  It proves
+ * nothing about the CUDA build's warp-level code; the `-m gpu` tests do that.  Never linked
+ * into libpzcuda.so.
+ */
+#define PZ_HOSTSIM 1
+#include "../../pure_zlib_b200/csrc/pz_device.cuh"
+
+#include <stdlib.h>
+
+extern "C" int hs_inflate(const uint8_t *in, uint64_t in_len, uint8_t *out, uint64_t out_cap, pz_result *res, int count_only) {
+  /* the device reads whole 16-byte pieces around the stream: give it a padded, aligned copy
+   * with a deliberately odd misalignment so the (mis != 0) paths run */
+  size_t mis = 5;
+  uint8_t *buf = (uint8_t *)aligned_alloc(16, ((in_len + mis + 15) & ~(size_t)15) + 1024 + 16);
+  memset(buf, 0xA5, ((in_len + mis + 15) & ~(size_t)15) + 1024 + 16);
+  memcpy(buf + mis, in, in_len);
+  PzWarpSmem *sm = (PzWarpSmem *)aligned_alloc(16, sizeof(PzWarpSmem));
+  memset(sm, 0xCD, sizeof(PzWarpSmem));
+  if (count_only) pz_inflate_stream<true>(buf + mis, in_len, out, out_cap, sm, res);
+  else pz_inflate_stream<false>(buf + mis, in_len, out, out_cap, sm, res);
+  free(sm);
+  free(buf);
+  return 0;
+}
+
+extern "C" int hs_smem_bytes(void) { return (int)sizeof(PzWarpSmem); }

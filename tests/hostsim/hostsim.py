@@ -1,0 +1,32 @@
+"""ctypes binding of the host-compiled decoder logic -- TEST INFRASTRUCTURE ONLY."""
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libpzhostsim.so")
+
+
+class PzResult(C.Structure):
+    _fields_ = [("status", C.c_int32), ("detail", C.c_int32), ("out_len", C.c_uint64),
+                ("adler_computed", C.c_uint32), ("adler_stored", C.c_uint32), ("err_bitpos", C.c_uint64),
+                ("payload", C.c_int64 * 2)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        subprocess.check_call(["make", "-C", _HERE, "-s", "libpzhostsim.so"])
+        _lib = C.CDLL(_SO)
+        _lib.hs_inflate.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(PzResult), C.c_int]
+    return _lib
+
+
+def inflate(data: bytes, out_cap: int, count_only: bool = False):
+    out = C.create_string_buffer(max(out_cap, 1))
+    res = PzResult()
+    lib().hs_inflate(bytes(data), len(data), out, out_cap, C.byref(res), int(count_only))
+    return res, out.raw[: min(res.out_len, out_cap)]

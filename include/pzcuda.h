@@ -140,6 +140,13 @@ int pz_batch_results(pz_batch *b, pz_result *res, void *stream);
 int pz_batch_launches(const pz_batch *b);
 void pz_batch_destroy(pz_batch *b);
 
+/* ---- pinned host memory ------------------------------------------------------------ *
+ * Page-locked buffers for callers that want pz_inflate_batch_contig's host<->device copies
+ * to overlap with decoding (the reference's strict ByteStrings are pinned ForeignPtrs;
+ * this is the CUDA notion of the same thing).                                            */
+void *pz_pinned_alloc(size_t bytes);
+void pz_pinned_free(void *p);
+
 /* ---- incremental decoder ----------------------------------------------------------- *
  * Replaces `decompressIncremental` / `ZlibDecoder` (Zlib.hs:29-30, Monad.hs:163-197,
  * 338-358).  The event sequence is the reference's: after each fed chunk the decoder

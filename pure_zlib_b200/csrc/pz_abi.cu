@@ -1,0 +1,578 @@
+/*
+ * pz_abi.cu -- the C ABI of libpzcuda.so (include/pzcuda.h) and the host driver.
+ *
+ * The driver replaces the reference's decoder monad as a *driver* (Monad.hs:163-197: the
+ * NeedMore/Chunk coroutine) with: pinned staging, slices of the batch pipelined over several
+ * CUDA streams (H2D, kernels, D2H overlap), and a resident-batch object whose run() is
+ * kernel launches only.  There is no CPU decode path: without a device every call fails
+ * with PZ_E_CUDA.
+ */
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "pz_internal.h"
+#include "pzcuda.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail_cuda(cudaError_t e, const char *what) {
+  char buf[512];
+  snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+  g_last_error = buf;
+  return PZ_E_CUDA;
+}
+#define PZ_CUDA(call)                                 \
+  do {                                                \
+    cudaError_t e__ = (call);                         \
+    if (e__ != cudaSuccess) return fail_cuda(e__, #call); \
+  } while (0)
+
+std::once_flag g_once;
+int g_init_rc = PZ_E_STATE;
+int g_device = -1;
+
+void do_init(const pz_config *cfg) {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_init_rc = fail_cuda(e != cudaSuccess ? e : cudaErrorNoDevice, "cudaGetDeviceCount");
+    return;
+  }
+  if (cfg && cfg->device >= 0) {
+    e = cudaSetDevice(cfg->device);
+    if (e != cudaSuccess) { g_init_rc = fail_cuda(e, "cudaSetDevice"); return; }
+  }
+  cudaGetDevice(&g_device);
+  e = pz_kernels_configure();
+  if (e != cudaSuccess) { g_init_rc = fail_cuda(e, "pz_kernels_configure"); return; }
+  g_init_rc = PZ_E_OK;
+}
+
+int ensure_init() {
+  std::call_once(g_once, do_init, (const pz_config *)nullptr);
+  if (g_init_rc != PZ_E_OK && g_last_error.empty()) g_last_error = "libpzcuda: initialisation failed (no usable CUDA device)";
+  return g_init_rc;
+}
+
+inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
+
+bool is_device_ptr(const void *p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+/* Grow-only device / pinned buffers kept per host thread, so repeated calls do not pay
+ * cudaMalloc.  Freed at thread exit. */
+struct Buf {
+  void *p = nullptr;
+  size_t cap = 0;
+  bool pinned = false;
+  int reserve(size_t n) {
+    if (n <= cap) return PZ_E_OK;
+    release();
+    size_t want = align_up(n + 256, 1 << 20);
+    cudaError_t e = pinned ? cudaHostAlloc(&p, want, cudaHostAllocDefault) : cudaMalloc(&p, want);
+    if (e != cudaSuccess) { p = nullptr; cap = 0; fail_cuda(e, pinned ? "cudaHostAlloc" : "cudaMalloc"); return PZ_E_NOMEM; }
+    cap = want;
+    return PZ_E_OK;
+  }
+  void release() {
+    if (p) { if (pinned) cudaFreeHost(p); else cudaFree(p); }
+    p = nullptr; cap = 0;
+  }
+};
+
+constexpr int kStreams = 4;
+constexpr size_t PZ_EXCESS_CHUNK = 32768; /* excessChunkSize (OutputWindow.hs:42-43) */
+
+struct Workspace {
+  Buf d_in, d_out, d_in_off, d_out_off, d_seg_off, d_res, d_parts;
+  Buf h_in, h_out; /* pinned staging for the pointer-array entry point */
+  cudaStream_t streams[kStreams] = {};
+  bool have_streams = false;
+  Workspace() { h_in.pinned = true; h_out.pinned = true; }
+  int ensure_streams() {
+    if (have_streams) return PZ_E_OK;
+    for (int i = 0; i < kStreams; i++) PZ_CUDA(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking));
+    have_streams = true;
+    return PZ_E_OK;
+  }
+  ~Workspace() {
+    /* the CUDA context may already be gone at process exit; errors are ignored */
+    d_in.release(); d_out.release(); d_in_off.release(); d_out_off.release(); d_seg_off.release();
+    d_res.release(); d_parts.release(); h_in.release(); h_out.release();
+    if (have_streams) for (int i = 0; i < kStreams; i++) cudaStreamDestroy(streams[i]);
+  }
+};
+thread_local Workspace g_ws;
+
+/* seg_off[i] = first checksum segment of stream i; capacities bound the decoded length */
+uint64_t build_seg_off(const uint64_t *out_off, size_t n, std::vector<uint64_t> &seg_off) {
+  seg_off.resize(n + 1);
+  uint64_t acc = 0;
+  for (size_t i = 0; i < n; i++) {
+    seg_off[i] = acc;
+    acc += (out_off[i + 1] - out_off[i] + PZ_ADLER_SEG - 1) / PZ_ADLER_SEG;
+  }
+  seg_off[n] = acc;
+  return acc;
+}
+
+bool offsets_ok(const uint64_t *off, size_t n) {
+  for (size_t i = 0; i < n; i++) if (off[i + 1] < off[i]) return false;
+  return true;
+}
+
+}  // namespace
+
+struct pz_batch {
+  size_t n = 0;
+  uint32_t flags = 0;
+  uint64_t *d_in_off = nullptr, *d_out_off = nullptr, *d_seg_off = nullptr;
+  pz_result *d_res = nullptr;
+  uint2 *d_parts = nullptr;
+  uint64_t total_segs = 0;
+  int launches = 0;
+};
+
+extern "C" {
+
+int pz_abi_version(void) { return PZ_ABI_VERSION; }
+
+const char *pz_last_error(void) { return g_last_error.c_str(); }
+
+int pz_init(const pz_config *cfg) {
+  std::call_once(g_once, do_init, cfg);
+  return g_init_rc;
+}
+
+void pz_shutdown(void) {
+  g_ws.~Workspace();
+  new (&g_ws) Workspace();
+}
+
+/* ---- resident batches ---------------------------------------------------------------- */
+pz_batch *pz_batch_create(const uint64_t *in_off, const uint64_t *out_off, size_t n, uint32_t flags) {
+  if (ensure_init() != PZ_E_OK) return nullptr;
+  if (!in_off || n > 0xfffffff0ull || !offsets_ok(in_off, n)) { g_last_error = "pz_batch_create: bad arguments"; return nullptr; }
+  const bool count_only = (flags & PZ_F_COUNT_ONLY) != 0;
+  if (!count_only && (!out_off || !offsets_ok(out_off, n))) { g_last_error = "pz_batch_create: bad output offsets"; return nullptr; }
+  pz_batch *b = new (std::nothrow) pz_batch();
+  if (!b) return nullptr;
+  b->n = n; b->flags = flags;
+  const size_t ob = (n + 1) * sizeof(uint64_t);
+  cudaError_t e = cudaMalloc(&b->d_in_off, ob);
+  if (e == cudaSuccess) e = cudaMalloc(&b->d_res, std::max<size_t>(n, 1) * sizeof(pz_result));
+  if (e == cudaSuccess) e = cudaMemcpy(b->d_in_off, in_off, ob, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && !count_only) {
+    e = cudaMalloc(&b->d_out_off, ob);
+    if (e == cudaSuccess) e = cudaMemcpy(b->d_out_off, out_off, ob, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && !(flags & PZ_F_NO_ADLER)) {
+      std::vector<uint64_t> seg;
+      b->total_segs = build_seg_off(out_off, n, seg);
+      e = cudaMalloc(&b->d_seg_off, ob);
+      if (e == cudaSuccess) e = cudaMemcpy(b->d_seg_off, seg.data(), ob, cudaMemcpyHostToDevice);
+      if (e == cudaSuccess) e = cudaMalloc(&b->d_parts, std::max<uint64_t>(b->total_segs, 1) * sizeof(uint2));
+    }
+  }
+  if (e != cudaSuccess) { fail_cuda(e, "pz_batch_create"); pz_batch_destroy(b); return nullptr; }
+  b->launches = 1 + ((count_only || (flags & PZ_F_NO_ADLER)) ? 0 : (b->total_segs ? 2 : 1));
+  return b;
+}
+
+int pz_batch_run(pz_batch *b, const uint8_t *d_in, uint8_t *d_out, void *stream) {
+  if (!b) return PZ_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool count_only = (b->flags & PZ_F_COUNT_ONLY) != 0;
+  if (!count_only && !d_out) return PZ_E_ARG;
+  PZ_CUDA(pz_launch_inflate(d_in, b->d_in_off, count_only ? nullptr : d_out, b->d_out_off, 0, (uint32_t)b->n, b->d_res, st));
+  if (!count_only && !(b->flags & PZ_F_NO_ADLER))
+    PZ_CUDA(pz_launch_adler(d_out, b->d_out_off, b->d_seg_off, (uint32_t)b->n, 0, (uint32_t)b->n, 0, b->total_segs, b->d_res, b->d_parts, st));
+  return PZ_E_OK;
+}
+
+int pz_batch_results(pz_batch *b, pz_result *res, void *stream) {
+  if (!b || !res) return PZ_E_ARG;
+  PZ_CUDA(cudaMemcpyAsync(res, b->d_res, b->n * sizeof(pz_result), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  PZ_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return PZ_E_OK;
+}
+
+int pz_batch_launches(const pz_batch *b) { return b ? b->launches : 0; }
+
+void pz_batch_destroy(pz_batch *b) {
+  if (!b) return;
+  cudaFree(b->d_in_off); cudaFree(b->d_out_off); cudaFree(b->d_seg_off); cudaFree(b->d_res); cudaFree(b->d_parts);
+  delete b;
+}
+
+/* ---- pinned host memory for callers that want truly asynchronous staging -------------- */
+void *pz_pinned_alloc(size_t bytes) {
+  if (ensure_init() != PZ_E_OK) return nullptr;
+  void *p = nullptr;
+  cudaError_t e = cudaHostAlloc(&p, std::max<size_t>(bytes, 1), cudaHostAllocDefault);
+  if (e != cudaSuccess) { fail_cuda(e, "cudaHostAlloc"); return nullptr; }
+  return p;
+}
+void pz_pinned_free(void *p) { if (p) cudaFreeHost(p); }
+
+/* ---- one-shot batch over contiguous blobs --------------------------------------------- */
+int pz_inflate_batch_contig(const uint8_t *in_blob, const uint64_t *in_off, uint8_t *out_blob, const uint64_t *out_off,
+                            size_t n, pz_result *res, void *stream, uint32_t flags) {
+  int rc = ensure_init();
+  if (rc != PZ_E_OK) return rc;
+  if (n == 0) return PZ_E_OK;
+  const bool count_only = (flags & PZ_F_COUNT_ONLY) != 0;
+  if (!in_blob || !in_off || !res || n > 0xfffffff0ull || !offsets_ok(in_off, n)) return PZ_E_ARG;
+  if (!count_only && (!out_blob || !out_off || !offsets_ok(out_off, n))) return PZ_E_ARG;
+  const bool adler = !count_only && !(flags & PZ_F_NO_ADLER);
+
+  const bool in_dev = is_device_ptr(in_blob);
+  const bool out_dev = count_only ? true : is_device_ptr(out_blob);
+  if (in_dev != out_dev && !count_only) { g_last_error = "pz_inflate_batch_contig: in_blob and out_blob must both be host or both be device"; return PZ_E_ARG; }
+
+  Workspace &ws = g_ws;
+  const size_t ob = (n + 1) * sizeof(uint64_t);
+  std::vector<uint64_t> seg;
+  uint64_t total_segs = 0;
+  if ((rc = ws.d_in_off.reserve(ob)) != PZ_E_OK) return rc;
+  if ((rc = ws.d_res.reserve(n * sizeof(pz_result))) != PZ_E_OK) return rc;
+  if (!count_only && (rc = ws.d_out_off.reserve(ob)) != PZ_E_OK) return rc;
+  if (adler) {
+    total_segs = build_seg_off(out_off, n, seg);
+    if ((rc = ws.d_seg_off.reserve(ob)) != PZ_E_OK) return rc;
+    if ((rc = ws.d_parts.reserve(std::max<uint64_t>(total_segs, 1) * sizeof(uint2))) != PZ_E_OK) return rc;
+  }
+  uint64_t *d_in_off = (uint64_t *)ws.d_in_off.p, *d_out_off = (uint64_t *)ws.d_out_off.p, *d_seg_off = (uint64_t *)ws.d_seg_off.p;
+  pz_result *d_res = (pz_result *)ws.d_res.p;
+  uint2 *d_parts = (uint2 *)ws.d_parts.p;
+
+  if (in_dev) {
+    /* device-resident blobs: descriptor upload + launches on the caller's stream */
+    cudaStream_t st = (cudaStream_t)stream;
+    PZ_CUDA(cudaMemcpyAsync(d_in_off, in_off, ob, cudaMemcpyHostToDevice, st));
+    if (!count_only) PZ_CUDA(cudaMemcpyAsync(d_out_off, out_off, ob, cudaMemcpyHostToDevice, st));
+    if (adler) PZ_CUDA(cudaMemcpyAsync(d_seg_off, seg.data(), ob, cudaMemcpyHostToDevice, st));
+    PZ_CUDA(pz_launch_inflate(in_blob, d_in_off, count_only ? nullptr : out_blob, d_out_off, 0, (uint32_t)n, d_res, st));
+    if (adler) PZ_CUDA(pz_launch_adler(out_blob, d_out_off, d_seg_off, (uint32_t)n, 0, (uint32_t)n, 0, total_segs, d_res, d_parts, st));
+    PZ_CUDA(cudaMemcpyAsync(res, d_res, n * sizeof(pz_result), cudaMemcpyDeviceToHost, st));
+    PZ_CUDA(cudaStreamSynchronize(st));
+    return PZ_E_OK;
+  }
+
+  /* host blobs: slices of the batch pipelined over kStreams CUDA streams */
+  if ((rc = ws.ensure_streams()) != PZ_E_OK) return rc;
+  const uint64_t in_base = in_off[0] & ~(uint64_t)15, in_end = in_off[n];
+  const uint64_t out_base = count_only ? 0 : (out_off[0] & ~(uint64_t)15), out_end = count_only ? 0 : out_off[n];
+  if ((rc = ws.d_in.reserve(in_end - in_base + 64)) != PZ_E_OK) return rc;
+  if (!count_only && (rc = ws.d_out.reserve(out_end - out_base + 64)) != PZ_E_OK) return rc;
+  /* device copies keep the host blobs' offsets modulo 16, so the offset tables are shared */
+  const uint8_t *d_in = (const uint8_t *)ws.d_in.p - in_base;
+  uint8_t *d_out = count_only ? nullptr : (uint8_t *)ws.d_out.p - out_base;
+
+  cudaStream_t s0 = ws.streams[0];
+  PZ_CUDA(cudaMemcpyAsync(d_in_off, in_off, ob, cudaMemcpyHostToDevice, s0));
+  if (!count_only) PZ_CUDA(cudaMemcpyAsync(d_out_off, out_off, ob, cudaMemcpyHostToDevice, s0));
+  if (adler) PZ_CUDA(cudaMemcpyAsync(d_seg_off, seg.data(), ob, cudaMemcpyHostToDevice, s0));
+  cudaEvent_t tables_ready;
+  PZ_CUDA(cudaEventCreateWithFlags(&tables_ready, cudaEventDisableTiming));
+  PZ_CUDA(cudaEventRecord(tables_ready, s0));
+
+  const uint64_t total_bytes = (in_end - in_off[0]) + (count_only ? 0 : out_end - out_off[0]);
+  const uint64_t slice_bytes = std::max<uint64_t>(total_bytes / 16, 8ull << 20);
+  size_t first = 0;
+  int k = 0;
+  rc = PZ_E_OK;
+  while (first < n && rc == PZ_E_OK) {
+    size_t last = first;
+    uint64_t acc = 0;
+    while (last < n && (acc < slice_bytes || last == first)) {
+      acc += (in_off[last + 1] - in_off[last]) + (count_only ? 0 : out_off[last + 1] - out_off[last]);
+      last++;
+    }
+    cudaStream_t st = ws.streams[k % kStreams];
+    k++;
+    auto step = [&]() -> int {
+      PZ_CUDA(cudaStreamWaitEvent(st, tables_ready, 0));
+      const uint64_t i0 = in_off[first], i1 = in_off[last];
+      if (i1 > i0) PZ_CUDA(cudaMemcpyAsync((void *)(d_in + i0), in_blob + i0, i1 - i0, cudaMemcpyHostToDevice, st));
+      PZ_CUDA(pz_launch_inflate(d_in, d_in_off, d_out, d_out_off, (uint32_t)first, (uint32_t)(last - first), d_res, st));
+      if (adler)
+        PZ_CUDA(pz_launch_adler(d_out, d_out_off, d_seg_off, (uint32_t)n, (uint32_t)first, (uint32_t)(last - first), seg[first],
+                                seg[last] - seg[first], d_res, d_parts, st));
+      if (!count_only) {
+        const uint64_t o0 = out_off[first], o1 = out_off[last];
+        if (o1 > o0) PZ_CUDA(cudaMemcpyAsync(out_blob + o0, d_out + o0, o1 - o0, cudaMemcpyDeviceToHost, st));
+      }
+      PZ_CUDA(cudaMemcpyAsync(res + first, d_res + first, (last - first) * sizeof(pz_result), cudaMemcpyDeviceToHost, st));
+      return PZ_E_OK;
+    };
+    rc = step();
+    first = last;
+  }
+  for (int i = 0; i < kStreams; i++) {
+    cudaError_t e = cudaStreamSynchronize(ws.streams[i]);
+    if (e != cudaSuccess && rc == PZ_E_OK) rc = fail_cuda(e, "cudaStreamSynchronize");
+  }
+  cudaEventDestroy(tables_ready);
+  return rc;
+}
+
+/* ---- pointer-array entry point: what the Haskell shim binds --------------------------- */
+static int inflate_ptrs(const uint8_t *const *in, const size_t *in_len, uint8_t *const *out, const size_t *out_cap, size_t n,
+                        pz_result *res, uint32_t flags) {
+  int rc = ensure_init();
+  if (rc != PZ_E_OK) return rc;
+  if (n == 0) return PZ_E_OK;
+  const bool count_only = (flags & PZ_F_COUNT_ONLY) != 0;
+  if (!in || !in_len || !res || (!count_only && (!out || !out_cap))) return PZ_E_ARG;
+  std::vector<uint64_t> in_off(n + 1), out_off(n + 1);
+  uint64_t ia = 0, oa = 0;
+  for (size_t i = 0; i < n; i++) {
+    in_off[i] = ia; out_off[i] = oa;
+    ia += in_len[i];
+    if (!count_only) oa += out_cap[i];
+  }
+  in_off[n] = ia; out_off[n] = oa;
+  /* streams are packed back to back; the kernel copes with any alignment */
+  Workspace &ws = g_ws;
+  if ((rc = ws.h_in.reserve(ia + 64)) != PZ_E_OK) return rc;
+  if (!count_only && (rc = ws.h_out.reserve(oa + 64)) != PZ_E_OK) return rc;
+  uint8_t *h_in = (uint8_t *)ws.h_in.p, *h_out = (uint8_t *)ws.h_out.p;
+  for (size_t i = 0; i < n; i++)
+    if (in_len[i]) memcpy(h_in + in_off[i], in[i], in_len[i]);
+  rc = pz_inflate_batch_contig(h_in, in_off.data(), h_out, out_off.data(), n, res, nullptr, flags);
+  if (rc != PZ_E_OK) return rc;
+  if (!count_only)
+    for (size_t i = 0; i < n; i++) {
+      size_t k = (size_t)std::min<uint64_t>(res[i].out_len, out_cap[i]);
+      if (k) memcpy(out[i], h_out + out_off[i], k);
+    }
+  return PZ_E_OK;
+}
+
+int pz_inflate_batch(const uint8_t *const *in, const size_t *in_len, uint8_t *const *out, const size_t *out_cap, size_t n,
+                     pz_result *res, uint32_t flags) {
+  return inflate_ptrs(in, in_len, out, out_cap, n, res, flags & ~PZ_F_COUNT_ONLY);
+}
+
+int pz_inflate_sizes(const uint8_t *const *in, const size_t *in_len, size_t n, pz_result *res) {
+  return inflate_ptrs(in, in_len, nullptr, nullptr, n, res, PZ_F_COUNT_ONLY);
+}
+
+/* ---- incremental decoder (decompressIncremental, Zlib.hs:29-30) ----------------------- */
+}  // extern "C"
+
+struct pz_stream {
+  std::vector<uint8_t> in;   /* every chunk fed so far, concatenated */
+  std::vector<uint8_t> out;  /* decoded bytes */
+  uint64_t published = 0;    /* bytes already handed out as chunks */
+  uint64_t publish_to = 0;   /* bytes the reference has published at the current state */
+  bool dirty = false;        /* input arrived since the last decode */
+  bool started = false;
+  bool terminal = false;     /* verdict reached */
+  bool final_pending = false;/* the final (possibly empty) chunk has not been delivered */
+  bool done_delivered = false;
+  pz_result verdict{};
+  size_t cap_hint = 1 << 16;
+};
+
+extern "C" {
+
+pz_stream *pz_stream_new(void) {
+  if (ensure_init() != PZ_E_OK) return nullptr;
+  return new (std::nothrow) pz_stream();
+}
+
+void pz_stream_free(pz_stream *s) { delete s; }
+
+int pz_stream_feed(pz_stream *s, const uint8_t *data, size_t len) {
+  if (!s || (len && !data)) return PZ_E_ARG;
+  if (s->terminal) return PZ_E_STATE; /* the decoder never asked for this chunk */
+  s->in.insert(s->in.end(), data, data + len);
+  s->dirty = true;
+  return PZ_E_OK;
+}
+
+/* Runs the batch engine over everything fed so far.  A "ran out of data" verdict on the
+ * prefix is exactly the reference's NeedMore state; any other verdict is final because it
+ * only depends on bytes already seen. */
+static int stream_decode(pz_stream *s) {
+  for (;;) {
+    s->out.resize(s->cap_hint);
+    const uint8_t *inp = s->in.data();
+    size_t in_len = s->in.size();
+    uint8_t *outp = s->out.data();
+    size_t cap = s->out.size();
+    static const uint8_t empty = 0;
+    if (!inp) inp = &empty;
+    pz_result r;
+    int rc = pz_inflate_batch(&inp, &in_len, &outp, &cap, 1, &r, 0);
+    if (rc != PZ_E_OK) return rc;
+    if (r.status == PZ_OUTPUT_FULL) { s->cap_hint *= 4; continue; }
+    s->verdict = r;
+    return PZ_E_OK;
+  }
+}
+
+int pz_stream_next(pz_stream *s, const uint8_t **chunk, size_t *len, pz_result *res) {
+  if (!s) return PZ_E_ARG;
+  if (chunk) *chunk = nullptr;
+  if (len) *len = 0;
+  if (s->done_delivered) {
+    if (s->verdict.status == PZ_OK) return PZ_S_DONE;
+    if (res) *res = s->verdict;
+    return PZ_S_ERROR;
+  }
+  if (s->dirty && !s->terminal) {
+    int rc = stream_decode(s);
+    if (rc != PZ_E_OK) return rc;
+    s->dirty = false;
+    const pz_result &r = s->verdict;
+    const bool need_more = r.status == PZ_ERR_DECOMPRESSION && r.detail == PZ_D_RAN_OUT;
+    uint64_t base = (r.status == PZ_REF_BOTTOM && r.detail == PZ_D_BOT_DIST_TOO_FAR) ? r.out_len - (uint64_t)r.payload[1]
+                                                                                    : (uint64_t)r.payload[1];
+    s->publish_to = base;
+    if (!need_more) {
+      s->terminal = true;
+      s->final_pending = (r.status == PZ_OK); /* finalize publishes what is left (Monad.hs:349-353) */
+    }
+  }
+  if (s->published < s->publish_to) { /* emitExcess hands out exactly 32 KiB at a time */
+    if (chunk) *chunk = s->out.data() + s->published;
+    if (len) *len = PZ_EXCESS_CHUNK;
+    s->published += PZ_EXCESS_CHUNK;
+    return PZ_S_CHUNK;
+  }
+  if (!s->terminal) return PZ_S_NEED_MORE;
+  if (s->final_pending) {
+    s->final_pending = false;
+    if (chunk) *chunk = s->out.data() + s->published;
+    if (len) *len = (size_t)(s->verdict.out_len - s->published);
+    s->published = s->verdict.out_len;
+    return PZ_S_CHUNK;
+  }
+  s->done_delivered = true;
+  if (s->verdict.status == PZ_OK) return PZ_S_DONE;
+  if (res) *res = s->verdict;
+  return PZ_S_ERROR;
+}
+
+/* ---- auxiliaries ----------------------------------------------------------------------- */
+size_t pz_strerror(const pz_result *r, char *buf, size_t cap) {
+  char tmp[256];
+  tmp[0] = 0;
+  if (!r) return 0;
+  const long long p0 = (long long)r->payload[0];
+  switch (r->status) {
+    case PZ_OK: break;
+    case PZ_ERR_HUFFMAN_TREE: {
+      const char *m = "?";
+      char t2[96];
+      switch (r->detail) {
+        case PZ_D_TWO_VALUES: m = "Two values point to the same place!"; break;
+        case PZ_D_VALUE_HIT: m = "HuffmanValue hit while inserting a value!"; break;
+        case PZ_D_LEAF_IS_NODE: snprintf(t2, sizeof t2, "Tried to add where the leaf is a node: %lld", p0); m = t2; break;
+        case PZ_D_ADVANCE_EMPTY_TREE: m = "Tried to advance empty tree!"; break;
+        case PZ_D_ADVANCED_TO_EMPTY: m = "Advanced to empty tree!"; break;
+      }
+      snprintf(tmp, sizeof tmp, "Huffman tree manipulation error: %s", m);
+      break;
+    }
+    case PZ_ERR_FORMAT:
+      if (r->detail == PZ_D_LEN_NLEN) snprintf(tmp, sizeof tmp, "Block format error: Len/nlen mismatch in uncompressed block.");
+      else snprintf(tmp, sizeof tmp, "Block format error: Unacceptable BTYPE: %lld", p0);
+      break;
+    case PZ_ERR_DECOMPRESSION:
+      snprintf(tmp, sizeof tmp, "Decompression error: %s",
+               r->detail == PZ_D_RAN_OUT ? "Ran out of data mid-decompression 2." : "Finished with data remaining.");
+      break;
+    case PZ_ERR_HEADER:
+      if (r->detail == PZ_D_HDR_CHECKSUM) snprintf(tmp, sizeof tmp, "Header error: Header checksum failed");
+      else if (r->detail == PZ_D_HDR_METHOD) snprintf(tmp, sizeof tmp, "Header error: Bad compression method: %lld", p0);
+      else snprintf(tmp, sizeof tmp, "Header error: Window size too big: %lld", p0);
+      break;
+    case PZ_ERR_CHECKSUM:
+      snprintf(tmp, sizeof tmp, "Checksum error: checksum mismatch: %x != %x", r->adler_stored, r->adler_computed);
+      break;
+    case PZ_REF_BOTTOM:
+      snprintf(tmp, sizeof tmp, "_|_ %s",
+               r->detail == PZ_D_BOT_LENGTH_SYM ? "lengthArray index" : r->detail == PZ_D_BOT_DIST_SYM ? "distanceArray index"
+               : r->detail == PZ_D_BOT_DIST_TOO_FAR ? "negative slice" : "window overflow");
+      break;
+    case PZ_OUTPUT_FULL: snprintf(tmp, sizeof tmp, "output buffer full"); break;
+    default: snprintf(tmp, sizeof tmp, "status %d", r->status);
+  }
+  size_t n = strlen(tmp);
+  if (buf && cap) {
+    size_t k = std::min(n, cap - 1);
+    memcpy(buf, tmp, k);
+    buf[k] = 0;
+  }
+  return n;
+}
+
+int pz_compute_code_values(const int32_t *sym, const int32_t *len, int n, int32_t *out_triples) {
+  int rc = ensure_init();
+  if (rc != PZ_E_OK) return rc;
+  if (n < 0 || (n && (!sym || !len || !out_triples))) return PZ_E_ARG;
+  uint8_t lens[288] = {0};
+  for (int i = 0; i < n; i++) {
+    if (sym[i] < 0 || sym[i] >= 288 || len[i] < 0 || len[i] > 15) return PZ_E_ARG;
+    lens[sym[i]] = (uint8_t)len[i];
+  }
+  uint8_t *d_lens = nullptr;
+  uint16_t *d_codes = nullptr, codes[288];
+  PZ_CUDA(cudaMalloc(&d_lens, 288));
+  PZ_CUDA(cudaMalloc(&d_codes, 288 * sizeof(uint16_t)));
+  PZ_CUDA(cudaMemcpy(d_lens, lens, 288, cudaMemcpyHostToDevice));
+  PZ_CUDA(pz_launch_code_values(d_lens, 288, d_codes, nullptr));
+  PZ_CUDA(cudaMemcpy(codes, d_codes, sizeof codes, cudaMemcpyDeviceToHost));
+  cudaFree(d_lens);
+  cudaFree(d_codes);
+  int m = 0;
+  for (int s = 0; s < 288; s++)
+    if (lens[s]) { out_triples[3 * m] = s; out_triples[3 * m + 1] = lens[s]; out_triples[3 * m + 2] = codes[s]; m++; }
+  return m;
+}
+
+uint32_t pz_adler32(uint32_t init, const uint8_t *data, size_t len) {
+  if (ensure_init() != PZ_E_OK) return 0;
+  /* checksum of `data` from the initial state on the device, then zlib's combine identity
+   * to continue from `init` (two modular adds and one multiply; no bytes touched here) */
+  Workspace &ws = g_ws;
+  uint64_t off[2] = {0, len};
+  std::vector<uint64_t> seg;
+  uint64_t total = build_seg_off(off, 1, seg);
+  if (ws.d_out.reserve(len + 64) != PZ_E_OK || ws.d_out_off.reserve(16) != PZ_E_OK || ws.d_seg_off.reserve(16) != PZ_E_OK ||
+      ws.d_res.reserve(sizeof(pz_result)) != PZ_E_OK || ws.d_parts.reserve(std::max<uint64_t>(total, 1) * sizeof(uint2)) != PZ_E_OK)
+    return 0;
+  pz_result r;
+  memset(&r, 0, sizeof r);
+  r.status = PZ_OK; r.out_len = len;
+  if (len && cudaMemcpy(ws.d_out.p, data, len, cudaMemcpyHostToDevice) != cudaSuccess) return 0;
+  if (cudaMemcpy(ws.d_out_off.p, off, 16, cudaMemcpyHostToDevice) != cudaSuccess) return 0;
+  if (cudaMemcpy(ws.d_seg_off.p, seg.data(), 16, cudaMemcpyHostToDevice) != cudaSuccess) return 0;
+  if (cudaMemcpy(ws.d_res.p, &r, sizeof r, cudaMemcpyHostToDevice) != cudaSuccess) return 0;
+  if (pz_launch_adler((const uint8_t *)ws.d_out.p, (const uint64_t *)ws.d_out_off.p, (const uint64_t *)ws.d_seg_off.p, 1, 0, 1, 0, total,
+                      (pz_result *)ws.d_res.p, (uint2 *)ws.d_parts.p, nullptr) != cudaSuccess)
+    return 0;
+  if (cudaMemcpy(&r, ws.d_res.p, sizeof r, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+  const uint32_t M = 65521u;
+  uint32_t a1 = init & 0xffffu, b1 = init >> 16, a2 = r.adler_computed & 0xffffu, b2 = r.adler_computed >> 16;
+  uint32_t a = (a1 + a2 + M - 1u) % M;
+  uint32_t b = (uint32_t)((b1 + b2 + (uint64_t)(len % M) * ((a1 + M - 1u) % M)) % M);
+  return (b << 16) | a;
+}
+
+}  // extern "C"

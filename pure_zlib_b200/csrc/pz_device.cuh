@@ -223,10 +223,10 @@ PZ_DEV uint32_t pz_make_entry(uint32_t sym, uint32_t nbits) {
   return PZ_ENTRY(nbits + PZ_DIST_EXTRA[sym], nbits, PZ_T_BASE, PZ_DIST_BASE[sym]);
 }
 
-/* createHuffmanTree's verdict when the lengths over-subscribe the code space: replay the
- * reference's insertion order (descending symbol, HuffmanTree.hs:29-34) on the canonical
- * codes (Deflate.hs:261-288) and report the first collision.  `codes` is n uint16 scratch. */
-PZ_DEV int pz_tree_error(const uint8_t *lens, int n, const PzTree *t, const uint16_t *perm, uint16_t *codes, int64_t *val) {
+/* computeCodeValues (Deflate.hs:261-288) from the sorted symbol list: codes[s] for every
+ * symbol with a non-zero length.  `mask` keeps only the low `len` bits, which is all the
+ * trie insertion ever inspects (testBit, HuffmanTree.hs:52,64). */
+PZ_DEV void pz_canon_codes(const uint8_t *lens, const PzTree *t, const uint16_t *perm, uint16_t *codes, bool mask) {
   uint32_t nc[16], start[16];
   uint32_t code = 0, acc = 0;
   nc[0] = 0; start[0] = 0;
@@ -244,9 +244,16 @@ PZ_DEV int pz_tree_error(const uint8_t *lens, int n, const PzTree *t, const uint
     uint32_t cv = 0;
 #pragma unroll
     for (int k = 1; k <= 15; k++) if (k == l) cv = nc[k] + ((uint32_t)p - start[k]);
-    codes[s] = (uint16_t)(cv & ((1u << l) - 1u)); /* testBit only ever looks at the low l bits */
+    codes[s] = (uint16_t)(mask ? (cv & ((1u << l) - 1u)) : cv);
   }
   pz_syncwarp();
+}
+
+/* createHuffmanTree's verdict when the lengths over-subscribe the code space: replay the
+ * reference's insertion order (descending symbol, HuffmanTree.hs:29-34) on the canonical
+ * codes and report the first collision.  `codes` is n uint16 scratch. */
+PZ_DEV int pz_tree_error(const uint8_t *lens, int n, const PzTree *t, const uint16_t *perm, uint16_t *codes, int64_t *val) {
+  pz_canon_codes(lens, t, perm, codes, true);
   for (int i = n - 1; i >= 0; i--) {
     int li = lens[i];
     if (!li) continue;
@@ -630,6 +637,8 @@ PZ_DEV void pz_inflate_stream(const uint8_t *in, uint64_t in_len, uint8_t *out, 
     res->adler_stored = adler_stored;
     res->err_bitpos = pz_cur_bit(c) - mis * 8u;
     res->payload[0] = c.p0;
-    res->payload[1] = c.p1;
+    /* payload[1]: bytes the reference has already published as 32 KiB chunks (the shim's
+     * incremental driver needs it); DIST_TOO_FAR keeps the retained-byte count instead */
+    res->payload[1] = (c.status == PZ_REF_BOTTOM && c.detail == PZ_D_BOT_DIST_TOO_FAR) ? c.p1 : (int64_t)c.base;
   }
 }

@@ -1,0 +1,22 @@
+/* pz_internal.h -- launch wrappers shared by pz_kernels.cu and pz_abi.cu (not installed). */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pzcuda.h"
+
+#define PZ_WARPS_PER_CTA 4
+#define PZ_ADLER_SEG 16384u /* bytes per checksum segment (one warp each) */
+
+/* Stream s = first + k decodes in_blob[in_off[s], in_off[s+1]) into out_blob[out_off[s], out_off[s+1]).
+ * d_out == nullptr selects the sizing pass. */
+cudaError_t pz_launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uint8_t *d_out, const uint64_t *d_out_off,
+                              uint32_t first, uint32_t count, pz_result *d_res, cudaStream_t st);
+/* Adler-32 of each decoded stream (segments [seg_off[first], seg_off[first+count])), then the
+ * trailer comparison that completes the verdict (Deflate.hs:52-63). */
+cudaError_t pz_launch_adler(const uint8_t *d_out, const uint64_t *d_out_off, const uint64_t *d_seg_off, uint32_t n_total,
+                            uint32_t first, uint32_t count, uint64_t seg_first, uint64_t seg_count, pz_result *d_res,
+                            uint2 *d_parts, cudaStream_t st);
+/* canonical codes of lens[0..n) (n <= 288) into codes[0..n) */
+cudaError_t pz_launch_code_values(const uint8_t *d_lens, int n, uint16_t *d_codes, cudaStream_t st);
+cudaError_t pz_kernels_configure(void);

@@ -1,0 +1,166 @@
+/*
+ * pz_kernels.cu -- the sm_100a kernels of libpzcuda.so.
+ *
+ *   pz_inflate_warp_kernel   K1: one warp per zlib stream (pz_device.cuh)
+ *   pz_adler_partial_kernel  K3a: one warp per 16 KiB segment of decoded output, dp4a sums
+ *   pz_adler_finish_kernel   K3b: per stream, combines the segments (adler32-combine
+ *                            identity) and compares with the stored trailer
+ *   pz_code_values_kernel    canonical-code KAT hook (test/Test.hs:107-120)
+ */
+#include "pz_device.cuh"
+#include "pz_internal.h"
+
+template <bool COUNT_ONLY>
+__global__ void __launch_bounds__(PZ_WARPS_PER_CTA * 32, 7)
+pz_inflate_warp_kernel(const uint8_t *__restrict__ in_blob, const uint64_t *__restrict__ in_off, uint8_t *out_blob,
+                       const uint64_t *__restrict__ out_off, uint32_t first, uint32_t count, pz_result *res) {
+  extern __shared__ __align__(16) unsigned char pz_smem_raw[];
+  const uint32_t w = threadIdx.x >> 5;
+  PzWarpSmem *sm = reinterpret_cast<PzWarpSmem *>(pz_smem_raw) + w;
+  const uint32_t k = blockIdx.x * PZ_WARPS_PER_CTA + w;
+  if (k >= count) return;
+  const uint32_t s = first + k;
+  const uint64_t i0 = in_off[s], i1 = in_off[s + 1];
+  if (COUNT_ONLY) {
+    pz_inflate_stream<true>(in_blob + i0, i1 - i0, nullptr, ~0ull, sm, res + s);
+  } else {
+    const uint64_t o0 = out_off[s], o1 = out_off[s + 1];
+    pz_inflate_stream<false>(in_blob + i0, i1 - i0, out_blob + o0, o1 - o0, sm, res + s);
+  }
+}
+
+/* ---- Adler-32 (Adler32.hs:17-57) as a segmented reduction ------------------------------
+ * For a segment of L bytes d_0..d_{L-1}:  S1 = sum d_i,  S2 = sum (L - i) d_i.  Appending it
+ * to a running (a, b):  b' = b + L*a + S2,  a' = a + S1  (mod 65521). */
+#define PZ_ADLER_MOD 65521u
+
+__global__ void __launch_bounds__(256)
+pz_adler_partial_kernel(const uint8_t *__restrict__ out_blob, const uint64_t *__restrict__ out_off,
+                        const uint64_t *__restrict__ seg_off, uint32_t n_total, uint64_t seg_first, uint64_t seg_count,
+                        const pz_result *__restrict__ res, uint2 *__restrict__ parts) {
+  const uint64_t gw = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (gw >= seg_count) return;
+  const uint64_t g = seg_first + gw;
+  const uint32_t lane = threadIdx.x & 31u;
+  /* the stream owning segment g: the last i with seg_off[i] <= g */
+  uint32_t lo = 0, hi = n_total;
+  while (hi - lo > 1) {
+    uint32_t mid = lo + (hi - lo) / 2;
+    if (seg_off[mid] <= g) lo = mid; else hi = mid;
+  }
+  const uint32_t i = lo;
+  if (res[i].status != PZ_OK) return;
+  const uint64_t len = res[i].out_len;
+  const uint64_t start = (g - seg_off[i]) * (uint64_t)PZ_ADLER_SEG;
+  if (start >= len) return;
+  const uint32_t L = (uint32_t)(len - start < PZ_ADLER_SEG ? len - start : PZ_ADLER_SEG);
+  const uint8_t *p0 = out_blob + out_off[i] + start;
+  const uint32_t head = (uint32_t)((uintptr_t)p0 & 15u);
+  const uint4 *v = reinterpret_cast<const uint4 *>(p0 - head);
+  const uint32_t nvec = (head + L + 15u) >> 4;
+  uint32_t s1 = 0;
+  uint64_t s2 = 0;
+  for (uint32_t t = lane; t < nvec; t += 32u) {
+    uint4 w = v[t];
+    const int32_t q = (int32_t)(t * 16u) - (int32_t)head; /* index of this vector's first byte */
+    if (q < 0 || q + 16 > (int32_t)L) {                   /* boundary vector: drop foreign bytes */
+      uint32_t x[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int b = 0; b < 16; b++) {
+        int32_t idx = q + b;
+        if (idx < 0 || idx >= (int32_t)L) x[b >> 2] &= ~(0xffu << (8 * (b & 3)));
+      }
+      w = make_uint4(x[0], x[1], x[2], x[3]);
+    }
+    uint32_t sum = __dp4a(w.x, 0x01010101u, 0u);
+    sum = __dp4a(w.y, 0x01010101u, sum);
+    sum = __dp4a(w.z, 0x01010101u, sum);
+    sum = __dp4a(w.w, 0x01010101u, sum);
+    uint32_t ks = __dp4a(w.x, 0x03020100u, 0u);
+    ks = __dp4a(w.y, 0x07060504u, ks);
+    ks = __dp4a(w.z, 0x0b0a0908u, ks);
+    ks = __dp4a(w.w, 0x0f0e0d0cu, ks);
+    s1 += sum;
+    s2 += (uint64_t)((int32_t)L - q) * sum - ks; /* sum_k (L - (q+k)) d_k */
+  }
+  s1 = __reduce_add_sync(0xffffffffu, s1);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s2 += __shfl_down_sync(0xffffffffu, s2, o);
+  if (lane == 0) parts[g] = make_uint2(s1 % PZ_ADLER_MOD, (uint32_t)(s2 % PZ_ADLER_MOD));
+}
+
+__global__ void __launch_bounds__(128)
+pz_adler_finish_kernel(const uint64_t *__restrict__ seg_off, uint32_t first, uint32_t count, pz_result *res,
+                       const uint2 *__restrict__ parts) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  const uint32_t i = first + k;
+  if (res[i].status != PZ_OK) return;
+  const uint64_t len = res[i].out_len;
+  const uint64_t nseg = (len + PZ_ADLER_SEG - 1) / PZ_ADLER_SEG;
+  const uint2 *p = parts + seg_off[i];
+  uint32_t a = 1, b = 0; /* initialAdlerState (Adler32.hs:19-20) */
+  for (uint64_t j = 0; j < nseg; j++) {
+    const uint64_t rest = len - j * PZ_ADLER_SEG;
+    const uint32_t L = (uint32_t)(rest < PZ_ADLER_SEG ? rest : PZ_ADLER_SEG);
+    const uint2 s = p[j];
+    b = (uint32_t)(((uint64_t)b + (uint64_t)L * a + s.y) % PZ_ADLER_MOD);
+    a = (a + s.x) % PZ_ADLER_MOD;
+  }
+  const uint32_t adler = (b << 16) | a; /* finalizeAdler (Adler32.hs:53-57) */
+  res[i].adler_computed = adler;
+  if (adler != res[i].adler_stored) { /* checkChecksum (Deflate.hs:56-63) */
+    res[i].status = PZ_ERR_CHECKSUM;
+    res[i].detail = PZ_D_ADLER_MISMATCH;
+  }
+}
+
+__global__ void pz_code_values_kernel(const uint8_t *lens, int n, uint16_t *codes) {
+  __shared__ PzWarpSmem sm;
+  for (int i = threadIdx.x; i < n; i += 32) sm.lens[i] = lens[i];
+  __syncwarp();
+  int64_t val;
+  (void)pz_build<PZ_LIT_BITS, 1>(sm.lens, n, &sm.lit, sm.lit_perm, sm.lit_lut, sm.scratch, &val);
+  uint16_t *c16 = reinterpret_cast<uint16_t *>(sm.dist_lut);
+  pz_canon_codes(sm.lens, &sm.lit, sm.lit_perm, c16, false);
+  for (int i = threadIdx.x; i < n; i += 32) codes[i] = sm.lens[i] ? c16[i] : 0;
+}
+
+/* ---- launch wrappers ------------------------------------------------------------------ */
+cudaError_t pz_kernels_configure(void) {
+  cudaError_t e;
+  e = cudaFuncSetAttribute(pz_inflate_warp_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(pz_inflate_warp_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  return e;
+}
+
+cudaError_t pz_launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uint8_t *d_out, const uint64_t *d_out_off,
+                              uint32_t first, uint32_t count, pz_result *d_res, cudaStream_t st) {
+  if (count == 0) return cudaSuccess;
+  const unsigned grid = (count + PZ_WARPS_PER_CTA - 1) / PZ_WARPS_PER_CTA;
+  const size_t smem = sizeof(PzWarpSmem) * PZ_WARPS_PER_CTA;
+  if (d_out == nullptr)
+    pz_inflate_warp_kernel<true><<<grid, PZ_WARPS_PER_CTA * 32, smem, st>>>(d_in, d_in_off, nullptr, d_out_off, first, count, d_res);
+  else
+    pz_inflate_warp_kernel<false><<<grid, PZ_WARPS_PER_CTA * 32, smem, st>>>(d_in, d_in_off, d_out, d_out_off, first, count, d_res);
+  return cudaGetLastError();
+}
+
+cudaError_t pz_launch_adler(const uint8_t *d_out, const uint64_t *d_out_off, const uint64_t *d_seg_off, uint32_t n_total,
+                            uint32_t first, uint32_t count, uint64_t seg_first, uint64_t seg_count, pz_result *d_res,
+                            uint2 *d_parts, cudaStream_t st) {
+  if (count == 0) return cudaSuccess;
+  if (seg_count) {
+    const uint64_t warps_per_cta = 8;
+    const unsigned grid = (unsigned)((seg_count + warps_per_cta - 1) / warps_per_cta);
+    pz_adler_partial_kernel<<<grid, 256, 0, st>>>(d_out, d_out_off, d_seg_off, n_total, seg_first, seg_count, d_res, d_parts);
+  }
+  pz_adler_finish_kernel<<<(count + 127) / 128, 128, 0, st>>>(d_seg_off, first, count, d_res, d_parts);
+  return cudaGetLastError();
+}
+
+cudaError_t pz_launch_code_values(const uint8_t *d_lens, int n, uint16_t *d_codes, cudaStream_t st) {
+  pz_code_values_kernel<<<1, 32, 0, st>>>(d_lens, n, d_codes);
+  return cudaGetLastError();
+}

@@ -1,0 +1,260 @@
+"""Host-side mirror of `Codec.Compression.Zlib` (reference: src/Codec/Compression/Zlib.hs:3-8).
+
+Same names, argument meaning and error behaviour as the reference module, so the parity
+tests read like test/Test.hs:
+
+    decompress            :: L.ByteString -> Either DecompressionError L.ByteString   (Zlib.hs:32)
+    decompressIncremental :: ST s (ZlibDecoder s)                                     (Zlib.hs:29)
+    data ZlibDecoder = NeedMore (ByteString -> ..) | Chunk ByteString (..) | Done | DecompError e
+    data DecompressionError = HuffmanTreeError | FormatError | DecompressionError | HeaderError
+                            | ChecksumError                                            (Monad.hs:87-93)
+
+A lazy ByteString is `bytes` (one chunk) or a list of `bytes` (its strict chunks).  Where the
+reference dies with an impure exception `ReferenceBottom` is raised.
+`decompress_batch` is the one extension: many independent streams in one kernel launch.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, List, Sequence, Union
+
+from . import _lib
+from ._lib import PzResult
+
+LazyByteString = Union[bytes, bytearray, memoryview, Sequence[bytes]]
+
+
+# ---- DecompressionError (Monad.hs:87-104) ---------------------------------------------------
+class DecompressionError(Exception):
+    """The reference's error type; subclasses are its five constructors.  Equality compares
+    constructor and string, like the derived `Eq`."""
+    prefix = ""
+
+    def __init__(self, msg: str):
+        super().__init__(msg)
+        self.msg = msg
+
+    def __str__(self):  # `show`
+        return self.prefix + self.msg
+
+    def __eq__(self, other):
+        return type(self) is type(other) and self.msg == other.msg
+
+    def __hash__(self):
+        return hash((type(self).__name__, self.msg))
+
+    def __repr__(self):
+        return f"{type(self).__name__}({self.msg!r})"
+
+
+class HuffmanTreeError(DecompressionError):
+    prefix = "Huffman tree manipulation error: "
+
+
+class FormatError(DecompressionError):
+    prefix = "Block format error: "
+
+
+class DecompressionError_(DecompressionError):
+    """The constructor that shares the type's name (`DecompressionError String`)."""
+    prefix = "Decompression error: "
+
+
+class HeaderError(DecompressionError):
+    prefix = "Header error: "
+
+
+class ChecksumError(DecompressionError):
+    prefix = "Checksum error: "
+
+
+class ReferenceBottom(Exception):
+    """pure-zlib would have thrown an impure exception here (array / vector bounds error)."""
+
+
+_CTORS = {_lib.PZ_ERR_HUFFMAN_TREE: HuffmanTreeError, _lib.PZ_ERR_FORMAT: FormatError,
+          _lib.PZ_ERR_DECOMPRESSION: DecompressionError_, _lib.PZ_ERR_HEADER: HeaderError,
+          _lib.PZ_ERR_CHECKSUM: ChecksumError}
+
+
+def _error_of(res: PzResult) -> DecompressionError:
+    text = _lib.strerror(res)
+    cls = _CTORS[res.status]
+    assert text.startswith(cls.prefix), text
+    return cls(text[len(cls.prefix):])
+
+
+# ---- Either ------------------------------------------------------------------------------------
+class Left:
+    def __init__(self, value):
+        self.value = value
+
+    def __eq__(self, other):
+        return isinstance(other, Left) and self.value == other.value
+
+    def __repr__(self):
+        return f"Left({self.value!r})"
+
+
+class Right:
+    def __init__(self, value):
+        self.value = value
+
+    def __eq__(self, other):
+        return isinstance(other, Right) and self.value == other.value
+
+    def __repr__(self):
+        return f"Right(<{len(self.value)} bytes>)"
+
+
+# ---- ZlibDecoder (Monad.hs:163-167) -------------------------------------------------------------
+class NeedMore:
+    """`NeedMore f`: call `.feed(chunk)` to obtain the next state."""
+
+    def __init__(self, feed):
+        self.feed = feed
+
+
+class Chunk:
+    """`Chunk bytes m`: `.data` is the output, `.next()` the next state."""
+
+    def __init__(self, data: bytes, nxt):
+        self.data = data
+        self.next = nxt
+
+
+class Done:
+    pass
+
+
+class DecompError:
+    def __init__(self, error: DecompressionError):
+        self.error = error
+
+
+class _Decoder:
+    def __init__(self):
+        L = _lib.load()
+        self._L = L
+        self._s = L.pz_stream_new()
+        if not self._s:
+            msg = L.pz_last_error()
+            raise _lib.PzCudaError("pz_stream_new failed: " + (msg.decode() if msg else ""))
+
+    def __del__(self):
+        if getattr(self, "_s", None):
+            self._L.pz_stream_free(self._s)
+            self._s = None
+
+    def state(self):
+        ptr = C.c_void_p()
+        n = C.c_size_t()
+        res = PzResult()
+        ev = _lib.check(self._L.pz_stream_next(self._s, C.byref(ptr), C.byref(n), C.byref(res)), "pz_stream_next")
+        if ev == _lib.PZ_S_NEED_MORE:
+            return NeedMore(self._feed)
+        if ev == _lib.PZ_S_CHUNK:
+            return Chunk(C.string_at(ptr.value, n.value) if n.value else b"", self.state)
+        if ev == _lib.PZ_S_DONE:
+            return Done()
+        if res.status == _lib.PZ_REF_BOTTOM:
+            raise ReferenceBottom(_lib.strerror(res))
+        return DecompError(_error_of(res))
+
+    def _feed(self, chunk: bytes):
+        chunk = bytes(chunk)
+        _lib.check(self._L.pz_stream_feed(self._s, chunk, len(chunk)), "pz_stream_feed")
+        return self.state()
+
+
+def decompress_incremental():
+    """`decompressIncremental` (Zlib.hs:29-30): the initial decoder state (always NeedMore)."""
+    return _Decoder().state()
+
+
+def _chunks_of(lazy: LazyByteString) -> List[bytes]:
+    if isinstance(lazy, (bytes, bytearray, memoryview)):
+        b = bytes(lazy)
+        return [b] if b else []          # L.toChunks never yields an empty chunk
+    return [bytes(c) for c in lazy if len(c)]
+
+
+def decompress(ifile: LazyByteString):
+    """`decompress` (Zlib.hs:32-51)."""
+    chunks = _chunks_of(ifile)
+    if len(chunks) <= 1:
+        return decompress_batch([chunks[0] if chunks else b""])[0]
+    # the driver loop `run` (Zlib.hs:37-51) over the incremental decoder
+    state = decompress_incremental()
+    acc = []
+    rest = list(chunks)
+    while True:
+        if isinstance(state, NeedMore):
+            if not rest:
+                return Left(DecompressionError_("Ran out of data mid-decompression 2."))
+            state = state.feed(rest.pop(0))
+        elif isinstance(state, Chunk):
+            acc.append(state.data)
+            state = state.next()
+        elif isinstance(state, Done):
+            if rest:
+                return Left(DecompressionError_("Finished with data remaining."))
+            return Right(b"".join(acc))
+        else:
+            return Left(state.error)
+
+
+def _ptr_arrays(streams: Sequence[bytes]):
+    n = len(streams)
+    keep = [C.create_string_buffer(s, max(len(s), 1)) for s in streams]
+    ptrs = (C.c_void_p * n)(*[C.addressof(k) for k in keep])
+    lens = (C.c_size_t * n)(*[len(s) for s in streams])
+    return keep, ptrs, lens
+
+
+def inflate_batch_raw(streams: Sequence[bytes], flags: int = 0):
+    """Batch decode through the ABI; returns ([PzResult], [bytes]) without interpreting
+    verdicts.  Sizing pass first (the zlib format does not carry the decoded length)."""
+    L = _lib.load()
+    n = len(streams)
+    if n == 0:
+        return [], []
+    keep, ptrs, lens = _ptr_arrays(streams)
+    sizes = (PzResult * n)()
+    _lib.check(L.pz_inflate_sizes(ptrs, lens, n, sizes), "pz_inflate_sizes")
+    caps = (C.c_size_t * n)(*[int(sizes[i].out_len) for i in range(n)])
+    outs = [C.create_string_buffer(max(int(caps[i]), 1)) for i in range(n)]
+    optrs = (C.c_void_p * n)(*[C.addressof(o) for o in outs])
+    res = (PzResult * n)()
+    _lib.check(L.pz_inflate_batch(ptrs, lens, optrs, caps, n, res, flags), "pz_inflate_batch")
+    return [res[i] for i in range(n)], [outs[i].raw[: int(res[i].out_len)] for i in range(n)]
+
+
+def decompress_batch(streams: Iterable[bytes]):
+    """Extension (not in the reference): `map decompress` over independent single-chunk
+    streams, one kernel launch for the whole list."""
+    streams = [bytes(s) for s in streams]
+    res, outs = inflate_batch_raw(streams)
+    out = []
+    for r, data in zip(res, outs):
+        if r.status == _lib.PZ_OK:
+            out.append(Right(data))
+        elif r.status == _lib.PZ_REF_BOTTOM:
+            out.append(ReferenceBottom(_lib.strerror(r)))
+        else:
+            out.append(Left(_error_of(r)))
+    if len(out) == 1 and isinstance(out[0], ReferenceBottom):
+        raise out[0]
+    return out
+
+
+def compute_code_values(pairs: Sequence[tuple]):
+    """`computeCodeValues` (Deflate.hs:261-288) on the device table builder; the KAT hook of
+    test/Test.hs:107-120."""
+    L = _lib.load()
+    n = len(pairs)
+    sym = (C.c_int32 * max(n, 1))(*[p[0] for p in pairs])
+    ln = (C.c_int32 * max(n, 1))(*[p[1] for p in pairs])
+    out = (C.c_int32 * (3 * max(n, 1)))()
+    m = _lib.check(L.pz_compute_code_values(sym, ln, n, out), "pz_compute_code_values")
+    return [(out[3 * i], out[3 * i + 1], out[3 * i + 2]) for i in range(m)]

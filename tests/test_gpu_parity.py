@@ -1,0 +1,241 @@
+"""GPU suite: the CUDA path, called through the C ABI, against the oracle (bit-exact bytes
+and verdicts).  Mirrors test/Test.hs (2 KATs + 9 goldens) and widens to the behaviours the
+reference's own tests do not reach."""
+import ctypes as C
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+import fuzzlib
+import streams
+from conftest import GOLDEN_NAMES
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pz():
+    import pure_zlib_b200 as pz
+    return pz
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    from oracle import oracle
+    return oracle
+
+
+def verdict_of(pz, data):
+    try:
+        return pz.decompress(data)
+    except pz.ReferenceBottom as e:
+        return ("bottom", str(e))
+
+
+def expect_of(pz, o):
+    if o.status == 0:
+        return pz.Right(o.data)
+    if o.status == 6:
+        return ("bottom", o.message)
+    return ("left", o.message)
+
+
+def same(pz, got, o):
+    if o.status == 0:
+        return got == pz.Right(o.data)
+    if o.status == 6:
+        return got == ("bottom", o.message)
+    return isinstance(got, pz.Left) and str(got.value) == o.message
+
+
+# ---- test/Test.hs -----------------------------------------------------------------------
+def test_kat_rfc1951_code_generation(pz):
+    lens = [(ord(c), l) for c, l in zip("ABCDEFGH", [3, 3, 3, 3, 3, 2, 4, 4])]
+    want = [(ord("A"), 3, 2), (ord("B"), 3, 3), (ord("C"), 3, 4), (ord("D"), 3, 5), (ord("E"), 3, 6),
+            (ord("F"), 2, 0), (ord("G"), 4, 14), (ord("H"), 4, 15)]
+    assert pz.compute_code_values(lens) == want
+
+
+def test_kat_fixed_huffman(pz):
+    lens = [(x, 8) for x in range(144)] + [(x, 9) for x in range(144, 256)] + \
+           [(x, 7) for x in range(256, 280)] + [(x, 8) for x in range(280, 288)]
+    want = [(x, 8, c) for x, c in zip(range(144), range(48, 192))] + \
+           [(x, 9, c) for x, c in zip(range(144, 256), range(400, 512))] + \
+           [(x, 7, c) for x, c in zip(range(256, 280), range(0, 24))] + \
+           [(x, 8, c) for x, c in zip(range(280, 288), range(192, 200))]
+    assert pz.compute_code_values(lens) == want
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_golden(pz, name, golden_dir):
+    z = open(os.path.join(golden_dir, name + ".z"), "rb").read()
+    gold = open(os.path.join(golden_dir, name + ".gold"), "rb").read()
+    assert pz.decompress(z) == pz.Right(gold)
+
+
+# ---- beyond the reference's tests --------------------------------------------------------
+@pytest.mark.parametrize("vec", streams.appendix_b_vectors(), ids=lambda v: v[0])
+def test_appendix_b(pz, oracle, vec):
+    name, data, want = vec
+    o = oracle.decompress(data)
+    got = verdict_of(pz, data)
+    assert same(pz, got, o), (name, got, o.message)
+    if want[0] == "left":
+        assert str(got.value) == want[1]
+
+
+def test_batch_matches_oracle_mixed_verdicts(pz, oracle):
+    """One launch holding valid, malformed and truncated streams: each verdict is the
+    oracle's, and a bad stream does not disturb its neighbours."""
+    cases = []
+    for seed in range(6):
+        cases += list(fuzzlib.fuzz_cases(seed, 500))
+    cases += fuzzlib.base_corpus(9, 60)
+    res, outs = pz.zlib.inflate_batch_raw(cases)
+    from pure_zlib_b200 import _lib
+    bad = []
+    for i, (data, r, out) in enumerate(zip(cases, res, outs)):
+        o = oracle.decompress(data)
+        ok = r.status == o.status and r.detail == o.detail and r.out_len == o.out_len and out == o.data
+        if o.status in (1, 2, 4, 6):
+            ok = ok and r.payload[0] == o.payload[0]
+        if o.status in (0, 5):
+            ok = ok and r.adler_computed == o.adler_computed and r.adler_stored == o.adler_stored
+        if o.status != 0:
+            ok = ok and _lib.strerror(r) == o.message
+        if not ok:
+            bad.append((i, data.hex()[:80], o.message, (r.status, r.detail, r.out_len), (o.status, o.detail, o.out_len)))
+    assert not bad, bad[:5]
+
+
+def test_valid_streams_levels_and_strategies(pz):
+    rng = np.random.default_rng(5)
+    cases, plain = [], []
+    for it in range(64):
+        n = int(rng.integers(0, 300_000))
+        data = streams.small_text(n, it) if it % 2 == 0 else (rng.integers(0, 7, n, dtype=np.uint8) * 31).tobytes()
+        level = [1, 6, 9][it % 3]
+        strategy = [zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE][it % 4]
+        co = zlib.compressobj(level, zlib.DEFLATED, 15, 8, strategy)
+        cases.append(co.compress(data) + co.flush())
+        plain.append(data)
+    got = pz.decompress_batch(cases)
+    for g, d in zip(got, plain):
+        assert g == pz.Right(d)
+
+
+def test_empty_and_ragged_batch(pz):
+    a = zlib.compress(b"")
+    b = zlib.compress(b"x" * 100_000)
+    got = pz.decompress_batch([a, b, b"", a, b[:-3]])
+    assert got[0] == pz.Right(b"") and got[3] == pz.Right(b"")
+    assert got[1] == pz.Right(b"x" * 100_000)
+    assert str(got[2].value) == "Decompression error: Ran out of data mid-decompression 2."
+    assert str(got[4].value) == "Decompression error: Ran out of data mid-decompression 2."
+    assert pz.decompress_batch([]) == []
+
+
+def test_large_expansion_and_output_full(pz):
+    from pure_zlib_b200 import _lib
+    L = _lib.load()
+    data = bytes(3_000_000)
+    z = zlib.compress(data, 9)
+    assert pz.decompress(z) == pz.Right(data)
+    # capacity one byte short -> PZ_OUTPUT_FULL, never a wrong verdict
+    inb = C.create_string_buffer(z, len(z))
+    out = C.create_string_buffer(len(data))
+    ptr = (C.c_void_p * 1)(C.addressof(inb))
+    ln = (C.c_size_t * 1)(len(z))
+    optr = (C.c_void_p * 1)(C.addressof(out))
+    cap = (C.c_size_t * 1)(len(data) - 1)
+    res = (_lib.PzResult * 1)()
+    _lib.check(L.pz_inflate_batch(ptr, ln, optr, cap, 1, res, 0), "pz_inflate_batch")
+    assert res[0].status == _lib.PZ_OUTPUT_FULL
+
+
+def test_adler32_entry_point(pz):
+    from pure_zlib_b200 import _lib
+    L = _lib.load()
+    rng = np.random.default_rng(2)
+    for n in (0, 1, 15, 16, 17, 5551, 5552, 16384, 16385, 1_000_003):
+        d = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        assert L.pz_adler32(1, d, n) == zlib.adler32(d)
+    d = b"\xff" * 70000
+    assert L.pz_adler32(1, d, len(d)) == zlib.adler32(d)
+    assert L.pz_adler32(zlib.adler32(b"abc"), b"defgh", 5) == zlib.adler32(b"abcdefgh")
+
+
+def test_incremental_event_sequence(pz, oracle):
+    """decompressIncremental: the NeedMore / Chunk / Done sequence is the reference's."""
+    data = streams.small_text(200_000, 77)
+    z = zlib.compress(data, 6)
+    for cuts in ([len(z)], [1, 2, len(z) - 3], [5000, 9000, 20000], [len(z) - 4], [len(z) - 1]):
+        pieces, prev = [], 0
+        for c in cuts:
+            pieces.append(z[prev:c])
+            prev = c
+        if prev < len(z):
+            pieces.append(z[prev:])
+        o = oracle.decompress(pieces, want_events=True)
+        events = []
+        st = pz.decompress_incremental()
+        rest = list(pieces)
+        acc = b""
+        while True:
+            if isinstance(st, pz.NeedMore):
+                events.append((0, 0))
+                if not rest:
+                    break
+                st = st.feed(rest.pop(0))
+            elif isinstance(st, pz.Chunk):
+                events.append((1, len(st.data)))
+                acc += st.data
+                st = st.next()
+            elif isinstance(st, pz.Done):
+                events.append((2, 0))
+                break
+            else:
+                events.append((3, 0))
+                break
+        assert events == o.events, (cuts, events[:8], o.events[:8])
+        assert acc == data
+
+
+def test_multichunk_decompress(pz):
+    data = streams.small_text(50_000, 3)
+    z = zlib.compress(data, 6)
+    assert pz.decompress([z[:100], z[100:]]) == pz.Right(data)
+    got = pz.decompress([z, b"tail"])
+    assert str(got.value) == "Decompression error: Finished with data remaining."
+    got = pz.decompress([z[:100], z[100:200]])
+    assert str(got.value) == "Decompression error: Ran out of data mid-decompression 2."
+
+
+def test_contig_device_pointers_and_resident_batch(pz):
+    """The launch-only path bench.py times: device-resident blobs, pz_batch_*."""
+    import torch
+    from pure_zlib_b200 import _lib, corpus
+    L = _lib.load()
+    c = corpus.text256k(48, workers=4)
+    d_in = torch.from_numpy(c.in_blob).cuda()
+    d_out = torch.zeros(int(c.out_off[-1]) + 64, dtype=torch.uint8, device="cuda")
+    in_off = np.ascontiguousarray(c.in_off.copy())
+    # true stream ends (not padded) are what the decoder may read
+    ends = c.in_off[:-1] + c.in_len
+    res = (_lib.PzResult * c.n)()
+    b = L.pz_batch_create(in_off.ctypes.data_as(C.POINTER(C.c_uint64)), c.out_off.ctypes.data_as(C.POINTER(C.c_uint64)), c.n, 0)
+    assert b
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(L.pz_batch_run(b, d_in.data_ptr(), d_out.data_ptr(), st), "pz_batch_run")
+    _lib.check(L.pz_batch_results(b, res, st), "pz_batch_results")
+    assert L.pz_batch_launches(b) == 3
+    L.pz_batch_destroy(b)
+    out = d_out.cpu().numpy()
+    for i in range(c.n):
+        assert res[i].status == 0, (i, res[i].status, res[i].detail)
+        assert res[i].out_len == 262144 and res[i].adler_computed == c.adler[i]
+        o = int(c.out_off[i])
+        assert out[o:o + 262144].tobytes() == corpus.decoded(c, i)
+    assert ends is not None

@@ -292,7 +292,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic", "config": config,
-            "roofline": {"bound": "hbm", "kernel": "pz_inflate_warp_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "pz_inflate_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": load_traffic(a.config), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": ms_k1,
                          "note": "issue/latency-bound integer path: frac of HBM is expected to be small (SURVEY 7, hard part 1)"},

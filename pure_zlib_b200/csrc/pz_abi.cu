@@ -98,9 +98,10 @@ constexpr size_t PZ_EXCESS_CHUNK = 32768; /* excessChunkSize (OutputWindow.hs:42
 struct Workspace {
   Buf d_in, d_out, d_in_off, d_out_off, d_seg_off, d_res, d_parts;
   Buf h_in, h_out; /* pinned staging for the pointer-array entry point */
+  Buf h_res;       /* pinned landing zone for the verdicts: a D2H copy into pageable memory would block the host */
   cudaStream_t streams[kStreams] = {};
   bool have_streams = false;
-  Workspace() { h_in.pinned = true; h_out.pinned = true; }
+  Workspace() { h_in.pinned = true; h_out.pinned = true; h_res.pinned = true; }
   int ensure_streams() {
     if (have_streams) return PZ_E_OK;
     for (int i = 0; i < kStreams; i++) PZ_CUDA(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking));
@@ -110,7 +111,7 @@ struct Workspace {
   ~Workspace() {
     /* the CUDA context may already be gone at process exit; errors are ignored */
     d_in.release(); d_out.release(); d_in_off.release(); d_out_off.release(); d_seg_off.release();
-    d_res.release(); d_parts.release(); h_in.release(); h_out.release();
+    d_res.release(); d_parts.release(); h_in.release(); h_out.release(); h_res.release();
     if (have_streams) for (int i = 0; i < kStreams; i++) cudaStreamDestroy(streams[i]);
   }
 };
@@ -130,6 +131,12 @@ uint64_t build_seg_off(const uint64_t *out_off, size_t n, std::vector<uint64_t> 
 
 bool offsets_ok(const uint64_t *off, size_t n) {
   for (size_t i = 0; i < n; i++) if (off[i + 1] < off[i]) return false;
+  return true;
+}
+
+/* the kernels keep bit positions in 32 bits: one compressed stream must stay below 512 MiB */
+bool in_sizes_ok(const uint64_t *off, size_t n) {
+  for (size_t i = 0; i < n; i++) if (off[i + 1] - off[i] > PZ_MAX_STREAM_BYTES) return false;
   return true;
 }
 
@@ -164,7 +171,7 @@ void pz_shutdown(void) {
 /* ---- resident batches ---------------------------------------------------------------- */
 pz_batch *pz_batch_create(const uint64_t *in_off, const uint64_t *out_off, size_t n, uint32_t flags) {
   if (ensure_init() != PZ_E_OK) return nullptr;
-  if (!in_off || n > 0xfffffff0ull || !offsets_ok(in_off, n)) { g_last_error = "pz_batch_create: bad arguments"; return nullptr; }
+  if (!in_off || n > 0xfffffff0ull || !offsets_ok(in_off, n) || !in_sizes_ok(in_off, n)) { g_last_error = "pz_batch_create: bad arguments (offsets must ascend; one stream is at most 512 MiB - 16)"; return nullptr; }
   const bool count_only = (flags & PZ_F_COUNT_ONLY) != 0;
   if (!count_only && (!out_off || !offsets_ok(out_off, n))) { g_last_error = "pz_batch_create: bad output offsets"; return nullptr; }
   pz_batch *b = new (std::nothrow) pz_batch();
@@ -233,7 +240,7 @@ int pz_inflate_batch_contig(const uint8_t *in_blob, const uint64_t *in_off, uint
   if (rc != PZ_E_OK) return rc;
   if (n == 0) return PZ_E_OK;
   const bool count_only = (flags & PZ_F_COUNT_ONLY) != 0;
-  if (!in_blob || !in_off || !res || n > 0xfffffff0ull || !offsets_ok(in_off, n)) return PZ_E_ARG;
+  if (!in_blob || !in_off || !res || n > 0xfffffff0ull || !offsets_ok(in_off, n) || !in_sizes_ok(in_off, n)) return PZ_E_ARG;
   if (!count_only && (!out_blob || !out_off || !offsets_ok(out_off, n))) return PZ_E_ARG;
   const bool adler = !count_only && !(flags & PZ_F_NO_ADLER);
 
@@ -288,8 +295,14 @@ int pz_inflate_batch_contig(const uint8_t *in_blob, const uint64_t *in_off, uint
   PZ_CUDA(cudaEventCreateWithFlags(&tables_ready, cudaEventDisableTiming));
   PZ_CUDA(cudaEventRecord(tables_ready, s0));
 
+  /* A stream's decode is one serial chain, so a slice of the batch takes about as long on the
+   * device as the whole batch: slicing only pays for overlapping the PCIe copies of one slice
+   * with the decode of the next.  A few big slices, one CUDA stream each. */
   const uint64_t total_bytes = (in_end - in_off[0]) + (count_only ? 0 : out_end - out_off[0]);
-  const uint64_t slice_bytes = std::max<uint64_t>(total_bytes / 16, 8ull << 20);
+  const int n_slices = (n >= 64 && total_bytes >= (64ull << 20)) ? kStreams : 1;
+  const uint64_t slice_bytes = total_bytes / n_slices + 1;
+  if ((rc = ws.h_res.reserve(n * sizeof(pz_result))) != PZ_E_OK) { cudaEventDestroy(tables_ready); return rc; }
+  pz_result *h_res = (pz_result *)ws.h_res.p;
   size_t first = 0;
   int k = 0;
   rc = PZ_E_OK;
@@ -300,6 +313,7 @@ int pz_inflate_batch_contig(const uint8_t *in_blob, const uint64_t *in_off, uint
       acc += (in_off[last + 1] - in_off[last]) + (count_only ? 0 : out_off[last + 1] - out_off[last]);
       last++;
     }
+    if (k == n_slices - 1) last = n;
     cudaStream_t st = ws.streams[k % kStreams];
     k++;
     auto step = [&]() -> int {
@@ -314,7 +328,7 @@ int pz_inflate_batch_contig(const uint8_t *in_blob, const uint64_t *in_off, uint
         const uint64_t o0 = out_off[first], o1 = out_off[last];
         if (o1 > o0) PZ_CUDA(cudaMemcpyAsync(out_blob + o0, d_out + o0, o1 - o0, cudaMemcpyDeviceToHost, st));
       }
-      PZ_CUDA(cudaMemcpyAsync(res + first, d_res + first, (last - first) * sizeof(pz_result), cudaMemcpyDeviceToHost, st));
+      PZ_CUDA(cudaMemcpyAsync(h_res + first, d_res + first, (last - first) * sizeof(pz_result), cudaMemcpyDeviceToHost, st));
       return PZ_E_OK;
     };
     rc = step();
@@ -325,6 +339,7 @@ int pz_inflate_batch_contig(const uint8_t *in_blob, const uint64_t *in_off, uint
     if (e != cudaSuccess && rc == PZ_E_OK) rc = fail_cuda(e, "cudaStreamSynchronize");
   }
   cudaEventDestroy(tables_ready);
+  if (rc == PZ_E_OK) memcpy(res, h_res, n * sizeof(pz_result));
   return rc;
 }
 

@@ -1,60 +1,77 @@
 /*
- * pz_device.cuh -- the device-side inflate engine (warp-per-stream).
+ * pz_device.cuh -- the device-side inflate engine.
  *
- * One warp decodes one zlib stream: all 32 lanes keep the same 64-bit bit buffer
- * (warp-uniform control flow, broadcast shared-memory lookups), lane 0 stores literals and
- * LZ77 matches are copied cooperatively (lane i moves byte i), straight into the stream's
- * slice of the HBM output blob -- the output itself is the history window.
+ * Execution model: a warp is split into 32/PZ_G "groups" of PZ_G lanes; each group decodes one
+ * zlib stream, so a warp advances 32/PZ_G independent streams in lockstep and every issued
+ * instruction does useful work for all of them (the decode chain of one stream is serial, so
+ * the win is in sharing issue slots, not lanes).  All PZ_G lanes of a group hold the same
+ * decoder state; lane 0 stores literals and LZ77 matches are copied by the whole group
+ * (lane i moves bytes i, i+PZ_G, ...), straight into the stream's slice of the HBM output
+ * blob -- the output itself is the history window.
+ *
+ * Each group runs a small state machine (IDLE -> HDR -> SYMS <-> FAST -> ... -> IDLE) so that
+ * the groups of a warp meet in ONE hot loop (pz_fast_loop) no matter where their streams are;
+ * everything that is rare or needs the reference's exact verdict order (block headers, table
+ * construction, codes longer than the first-level LUT, the last bytes of the input or of the
+ * output buffer) runs in the "slow" part, one group at a time.
  *
  * What it replaces in the reference (file:line relative to the pure-zlib checkout):
- *   bit reader            Monad.hs:199-263   -> PzCtx bit buffer over a cp.async-staged smem ring
+ *   bit reader            Monad.hs:199-263   -> bit position over a cp.async-staged smem ring,
+ *                                               32-bit windows assembled with a funnel shift
  *   tree build + walk     HuffmanTree.hs:25-83, Deflate.hs:255-288 -> canonical counts + flat LUT
- *   block parser          Deflate.hs:65-156  -> pz_inflate_stream()
- *   symbol loop           Deflate.hs:106-120 -> fast LUT loop + exact bit-serial "careful" path
+ *   block parser          Deflate.hs:65-156  -> pz_slow_step()
+ *   symbol loop           Deflate.hs:106-120 -> pz_fast_loop() + exact bit-serial "careful" path
  *   output window         OutputWindow.hs:29-114 -> direct stores; the window is only *modelled*
  *                                              (fill/base counters) to reproduce its verdicts
  *   zlib framing          Zlib.hs:53-69, Deflate.hs:52-63
  *
- * The file also compiles with a host C++ compiler when PZ_HOSTSIM is defined: a "warp" is
- * then a single lane.  That build exists only for tests/hostsim (CPU-side differential
- * fuzzing of this logic against the oracle); the product library never contains it.
+ * The file also compiles with a host C++ compiler when PZ_HOSTSIM is defined: a group is then
+ * a single lane and a "warp" a single group.  That build exists only for tests/hostsim
+ * (CPU-side differential fuzzing of this logic against the oracle); the product library never
+ * contains it.
  */
 #pragma once
 #include <stdint.h>
 
 #include "pzcuda.h"
 
+#ifndef PZ_GROUP
+#define PZ_GROUP 8 /* lanes per stream on the device: 32, 16, 8 or 4 */
+#endif
+
 #ifdef PZ_HOSTSIM
 #include <string.h>
 #define PZ_DEV static inline
-#define PZ_WARP 1
+#define PZ_G 1
 PZ_DEV int pz_lane() { return 0; }
 PZ_DEV void pz_syncwarp() {}
 PZ_DEV unsigned pz_ballot(int p) { return p ? 1u : 0u; }
 PZ_DEV unsigned pz_match_any(unsigned) { return 1u; }
 PZ_DEV unsigned pz_lanemask_lt() { return 0u; }
 PZ_DEV int pz_shfl(int v, int) { return v; }
+PZ_DEV bool pz_warp_any(bool p) { return p; }
 PZ_DEV void pz_smem_inc(uint32_t *p) { ++*p; }
 PZ_DEV int pz_popc(unsigned x) { return __builtin_popcount(x); }
 PZ_DEV int pz_ffs(unsigned x) { return __builtin_ffs((int)x); }
+PZ_DEV uint32_t pz_funnel_r(uint32_t lo, uint32_t hi, uint32_t s) { return (uint32_t)(((((uint64_t)hi) << 32) | lo) >> (s & 31u)); }
 PZ_DEV void pz_copy16_async(void *smem_dst, const void *gsrc) { memcpy(smem_dst, gsrc, 16); }
 PZ_DEV void pz_async_wait_all() {}
 #else
 #define PZ_DEV __device__ __forceinline__
-#define PZ_WARP 32
-PZ_DEV int pz_lane() { return (int)(threadIdx.x & 31u); }
-PZ_DEV void pz_syncwarp() { __syncwarp(); }
-PZ_DEV unsigned pz_ballot(int p) { return __ballot_sync(0xffffffffu, p); }
-PZ_DEV unsigned pz_match_any(unsigned v) { return __match_any_sync(0xffffffffu, v); }
-PZ_DEV unsigned pz_lanemask_lt() {
-  unsigned m;
-  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
-  return m;
-}
-PZ_DEV int pz_shfl(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+#define PZ_G PZ_GROUP
+PZ_DEV unsigned pz_gshift() { return (threadIdx.x & 31u) & ~(unsigned)(PZ_G - 1); }
+PZ_DEV unsigned pz_gmask() { return PZ_G == 32 ? 0xffffffffu : (((1u << (PZ_G & 31)) - 1u) << pz_gshift()); }
+PZ_DEV int pz_lane() { return (int)(threadIdx.x & (unsigned)(PZ_G - 1)); }
+PZ_DEV void pz_syncwarp() { __syncwarp(pz_gmask()); }
+PZ_DEV unsigned pz_ballot(int p) { return __ballot_sync(pz_gmask(), p) >> pz_gshift(); }
+PZ_DEV unsigned pz_match_any(unsigned v) { return __match_any_sync(pz_gmask(), v) >> pz_gshift(); }
+PZ_DEV unsigned pz_lanemask_lt() { return (1u << pz_lane()) - 1u; }
+PZ_DEV int pz_shfl(int v, int src) { return __shfl_sync(pz_gmask(), v, src, PZ_G); }
+PZ_DEV bool pz_warp_any(bool p) { return __any_sync(0xffffffffu, p) != 0; } /* all groups of the warp */
 PZ_DEV void pz_smem_inc(uint32_t *p) { atomicAdd(p, 1u); }
 PZ_DEV int pz_popc(unsigned x) { return __popc(x); }
 PZ_DEV int pz_ffs(unsigned x) { return __ffs((int)x); }
+PZ_DEV uint32_t pz_funnel_r(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_r(lo, hi, s); }
 PZ_DEV void pz_copy16_async(void *smem_dst, const void *gsrc) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
@@ -68,19 +85,24 @@ PZ_DEV void pz_async_wait_all() {
 #define PZ_LIT_BITS 10  /* first-level bits of the literal/length LUT */
 #define PZ_DIST_BITS 8  /* first-level bits of the distance LUT        */
 #define PZ_PRE_BITS 7   /* the code-length code never exceeds 7 bits    */
-#define PZ_RING_WORDS 256u /* staged input: two 512-byte halves          */
-#define PZ_HALF_WORDS 128u
+#define PZ_RING_WORDS 256u /* staged input: four 256-byte quarters       */
+#define PZ_QUARTER_WORDS 64u
+#define PZ_QUARTER_SHIFT 11 /* log2(bits per quarter) */
 #define PZ_MAX_LENS 464 /* 288 + 32 + 137 overshoot (Deflate.hs:124-156), padded */
 #define PZ_WINDOW 131072u /* OutputWindow.hs:29-30 */
 #define PZ_EXCESS 32768u  /* OutputWindow.hs:42-43 */
+#define PZ_STEP_BITS 48u  /* most bits one literal/length + distance pair can consume: 15+5+15+13 */
+#define PZ_MAX_IN_BYTES 0x1ffffff0ull /* bit positions are 32-bit: streams below 512 MiB */
 
-/* LUT entry: total bits [0,5) | code bits [8,12) | type [12,14) | value [16,32) */
+/* LUT entry: total bits [0,5) | code bits [8,12) | type [12,14) | value [16,31) | literal flag 31.
+ * total == 0 marks an entry the hot loop must not act on (long code, dead prefix, end of
+ * block, or a symbol the reference cannot index): the careful path decides. */
 #define PZ_T_LIT 0u
 #define PZ_T_BASE 1u /* length / distance base + extra bits */
-#define PZ_T_EOB 2u
-#define PZ_T_SLOW 3u /* long code, dead prefix or a symbol the reference cannot index */
+#define PZ_T_SLOW 3u
 #define PZ_ENTRY(total, nbits, type, value) ((uint32_t)(total) | ((uint32_t)(nbits) << 8) | ((uint32_t)(type) << 12) | ((uint32_t)(value) << 16))
 #define PZ_SLOW_ENTRY PZ_ENTRY(0, 0, PZ_T_SLOW, 0)
+#define PZ_LIT_FLAG 0x80000000u
 
 /* Canonical description of one prefix code: enough for the bit-serial walker to reproduce
  * the reference trie's accept / "Advanced to empty tree!" behaviour (HuffmanTree.hs:73-83). */
@@ -91,10 +113,11 @@ struct PzTree {
   uint16_t pad;
 };
 
-struct __attribute__((aligned(16))) PzWarpSmem {
+/* Shared memory of one stream (one group). */
+struct __attribute__((aligned(16))) PzStreamSmem {
   uint32_t lit_lut[1 << PZ_LIT_BITS];
   uint32_t dist_lut[1 << PZ_DIST_BITS]; /* the precode LUT aliases its first 128 entries */
-  uint32_t ring[PZ_RING_WORDS];
+  uint32_t ring[PZ_RING_WORDS + 4];     /* + a copy of words 0..3 so that ring[i+1] never wraps */
   uint32_t scratch[32]; /* [0,16) per-length counters, [16,32) per-length offsets */
   uint16_t lit_perm[288];
   uint16_t dist_perm[176];
@@ -118,22 +141,41 @@ static __constant__ uint8_t PZ_DIST_EXTRA[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4
 static __constant__ uint8_t PZ_CL_ORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 #endif
 
-/* ---- per-stream decoder state (registers; identical in every lane) -------------------- */
+/* ---- the batch a kernel launch works on ------------------------------------------------ */
+struct PzJob {
+  const uint8_t *in_blob;
+  const uint64_t *in_off;
+  uint8_t *out_blob; /* nullptr = sizing pass */
+  const uint64_t *out_off;
+  pz_result *res;
+  uint32_t first, count; /* streams [first, first+count) */
+};
+
+/* ---- per-stream decoder state (registers; identical in every lane of the group) -------- */
+enum PzMode { PZ_M_IDLE = 0, PZ_M_HDR = 1, PZ_M_SYMS = 2, PZ_M_FAST = 3, PZ_M_DEAD = 4 };
+
 struct PzCtx {
   const uint8_t *in_al; /* input, rounded down to 16 bytes                                */
-  uint64_t in_al_bytes; /* bytes readable from in_al (multiple of 16)                      */
-  uint64_t end_bit;     /* first bit past the stream, counted from in_al                   */
-  uint32_t *ring;
-  uint64_t bitbuf;
-  uint32_t cnt;      /* valid bits in bitbuf                                               */
-  uint32_t word_idx; /* next 32-bit word (from in_al) to append to bitbuf                  */
-  int32_t safe_word; /* word_idx <= safe_word: >= 48 input bits remain, no checks needed   */
+  uint32_t in_al_bytes; /* bytes readable from in_al (multiple of 16)                      */
+  uint32_t start_bit;   /* first bit of the stream, counted from in_al                     */
+  uint32_t end_bit;     /* first bit past the stream, counted from in_al                   */
+  uint32_t safe_end;    /* bp <= safe_end: a whole symbol pair (PZ_STEP_BITS) is available */
+  uint32_t bp;          /* bit position of the reader, counted from in_al; bp <= end_bit   */
+  uint32_t q;           /* ring quarter holding bp; quarters q and q+1 are resident        */
   uint8_t *out;
   uint32_t pos;  /* bytes decoded                                                          */
   uint32_t base; /* bytes the reference would already have published (multiple of 32 KiB)  */
   uint32_t cap;
   int32_t status, detail;
   int64_t p0, p1;
+  /* state machine */
+  uint32_t mode;
+  uint32_t bfinal;
+  uint32_t adler_stored;
+  bool fixed_ready;
+  bool need_careful; /* the hot loop met something only the careful path may decide */
+  uint32_t next;     /* next stream index of this group */
+  pz_result *res;
 };
 
 PZ_DEV void pz_fail(PzCtx &c, int status, int detail, int64_t p0 = 0, int64_t p1 = 0) {
@@ -141,62 +183,71 @@ PZ_DEV void pz_fail(PzCtx &c, int status, int detail, int64_t p0 = 0, int64_t p1
 }
 
 /* ---- staged input ---------------------------------------------------------------------
- * Block k = bytes [512k, 512k+512) of in_al, staged into ring half (k & 1) with cp.async
- * (16 bytes per lane).  Invariant: the block holding word_idx and its successor are loaded
- * or in flight. */
-PZ_DEV void pz_ring_issue(PzCtx &c, uint32_t k) {
-  uint32_t *dst = c.ring + (k & 1u) * PZ_HALF_WORDS;
-  for (uint32_t p = (uint32_t)pz_lane(); p < 32u; p += PZ_WARP) {
-    uint64_t bo = (uint64_t)k * 512u + p * 16u;
-    if (bo < c.in_al_bytes) pz_copy16_async(dst + p * 4u, c.in_al + bo);
-    /* past the stream: never consumed (the careful path counts bits), left as is */
+ * Quarter k = bytes [256k, 256k+256) of in_al, staged into ring slot (k & 3) with cp.async
+ * (16 bytes per request).  Invariant: quarters q and q+1 are resident, q+2 is in flight. */
+PZ_DEV void pz_ring_issue(PzCtx &c, PzStreamSmem *sm, uint32_t k) {
+  uint32_t *dst = sm->ring + (k & 3u) * PZ_QUARTER_WORDS;
+  for (uint32_t p = (uint32_t)pz_lane(); p < 16u; p += PZ_G) {
+    uint32_t bo = k * 256u + p * 16u;
+    if (bo < c.in_al_bytes) {
+      pz_copy16_async(dst + p * 4u, c.in_al + bo);
+      if (((k & 3u) | p) == 0u) pz_copy16_async(sm->ring + PZ_RING_WORDS, c.in_al + bo);
+    }
+    /* past the stream: never consumed (every reader counts bits first), left as is */
   }
 }
-PZ_DEV void pz_ring_cross(PzCtx &c) {
+PZ_DEV void pz_cross(PzCtx &c, PzStreamSmem *sm) {
+  while (c.q != (c.bp >> PZ_QUARTER_SHIFT)) {
+    c.q++;
+    pz_async_wait_all(); /* quarter q+1 was requested one crossing ago */
+    pz_syncwarp();
+    pz_ring_issue(c, sm, c.q + 2u);
+  }
+}
+PZ_DEV void pz_seek(PzCtx &c, PzStreamSmem *sm, uint32_t bit) {
+  uint32_t k = bit >> PZ_QUARTER_SHIFT;
+  pz_async_wait_all(); /* nothing may still be landing in the slots reused below */
+  pz_syncwarp();
+  pz_ring_issue(c, sm, k);
+  pz_ring_issue(c, sm, k + 1u);
   pz_async_wait_all();
   pz_syncwarp();
-  pz_ring_issue(c, c.word_idx / PZ_HALF_WORDS + 1u);
+  pz_ring_issue(c, sm, k + 2u);
+  c.q = k; c.bp = bit;
 }
-PZ_DEV void pz_refill(PzCtx &c) { /* appends 32 bits; requires cnt <= 32 */
-  uint32_t w = c.ring[c.word_idx & (PZ_RING_WORDS - 1u)];
-  c.bitbuf |= (uint64_t)w << c.cnt;
-  c.cnt += 32u;
-  c.word_idx++;
-  if ((c.word_idx & (PZ_HALF_WORDS - 1u)) == 0u) pz_ring_cross(c);
+/* The 32 stream bits starting at bit position bp (bits past end_bit are garbage). */
+PZ_DEV uint32_t pz_peek(const uint32_t *ring, uint32_t bp) {
+  uint32_t t = (bp >> 5) & (PZ_RING_WORDS - 1u);
+  return pz_funnel_r(ring[t], ring[t + 1u], bp);
 }
-PZ_DEV void pz_consume(PzCtx &c, uint32_t n) { c.bitbuf >>= n; c.cnt -= n; }
-PZ_DEV uint64_t pz_cur_bit(const PzCtx &c) { return (uint64_t)c.word_idx * 32u - c.cnt; }
-PZ_DEV int64_t pz_avail(const PzCtx &c) { return (int64_t)(c.end_bit - pz_cur_bit(c)); }
-PZ_DEV void pz_seek(PzCtx &c, uint64_t bit) {
-  uint32_t word = (uint32_t)(bit >> 5);
-  uint32_t k = word / PZ_HALF_WORDS;
-  pz_syncwarp();
-  pz_ring_issue(c, k);
-  pz_ring_issue(c, k + 1u);
-  pz_async_wait_all();
-  pz_syncwarp();
-  c.word_idx = word; c.bitbuf = 0; c.cnt = 0;
-  pz_refill(c);
-  pz_consume(c, (uint32_t)(bit & 31u));
+PZ_DEV void pz_advance(PzCtx &c, PzStreamSmem *sm, uint32_t n) {
+  c.bp += n;
+  if ((c.bp >> PZ_QUARTER_SHIFT) != c.q) pz_cross(c, sm);
 }
+PZ_DEV uint32_t pz_avail(const PzCtx &c) { return c.end_bit - c.bp; }
 /* nextBits n (Monad.hs:199-230), n <= 16: running past the input is the truncation verdict
  * (Zlib.hs:38-39). */
-PZ_DEV bool pz_take(PzCtx &c, uint32_t n, uint32_t &v) {
-  if (pz_avail(c) < (int64_t)n) { pz_fail(c, PZ_ERR_DECOMPRESSION, PZ_D_RAN_OUT); return false; }
-  if (c.cnt < n) pz_refill(c);
-  v = (uint32_t)c.bitbuf & ((1u << n) - 1u);
-  pz_consume(c, n);
+PZ_DEV bool pz_take(PzCtx &c, PzStreamSmem *sm, uint32_t n, uint32_t &v) {
+  if (pz_avail(c) < n) { pz_fail(c, PZ_ERR_DECOMPRESSION, PZ_D_RAN_OUT); return false; }
+  v = pz_peek(sm->ring, c.bp) & ((1u << n) - 1u);
+  pz_advance(c, sm, n);
   return true;
+}
+/* advanceToByte (Monad.hs:303-307): the dropped bits belong to a byte that was already
+ * fetched, so this is never a truncation. */
+PZ_DEV void pz_align_byte(PzCtx &c, PzStreamSmem *sm) {
+  uint32_t drop = (8u - (c.bp & 7u)) & 7u;
+  if (drop) pz_advance(c, sm, drop);
 }
 
 /* ---- exact bit-serial walk (nextCode / advanceTree, Monad.hs:295-302, HuffmanTree.hs:73-83)
  * Consumes one bit per step and stops exactly where the reference's trie walk stops:
  * truncation if the input ends first, "Advanced to empty tree!" on an unused prefix. */
-PZ_DEV int pz_walk(PzCtx &c, const PzTree *t, const uint16_t *perm) {
+PZ_DEV int pz_walk(PzCtx &c, PzStreamSmem *sm, const PzTree *t, const uint16_t *perm) {
   uint32_t code = 0, first = 0, index = 0;
   for (int len = 1; len <= 15; len++) {
     uint32_t bit;
-    if (!pz_take(c, 1, bit)) return -1;
+    if (!pz_take(c, sm, 1, bit)) return -1;
     if (t->nsyms == 0) { pz_fail(c, PZ_ERR_HUFFMAN_TREE, PZ_D_ADVANCE_EMPTY_TREE); return -1; }
     code |= bit;
     uint32_t count = t->cnt[len];
@@ -214,9 +265,9 @@ template <int KIND> /* 0 = code-length code, 1 = literal/length, 2 = distance */
 PZ_DEV uint32_t pz_make_entry(uint32_t sym, uint32_t nbits) {
   if (KIND == 0) return PZ_ENTRY(nbits, nbits, PZ_T_LIT, sym);
   if (KIND == 1) {
-    if (sym < 256u) return PZ_ENTRY(nbits, nbits, PZ_T_LIT, sym);
-    if (sym == 256u) return PZ_ENTRY(nbits, nbits, PZ_T_EOB, 0);
-    if (sym > 285u) return PZ_SLOW_ENTRY; /* lengthArray ! 286/287 is a bounds error */
+    if (sym < 256u) return PZ_ENTRY(nbits, nbits, PZ_T_LIT, sym) | PZ_LIT_FLAG;
+    if (sym == 256u) return PZ_SLOW_ENTRY; /* end of block: the careful path ends it */
+    if (sym > 285u) return PZ_SLOW_ENTRY;  /* lengthArray ! 286/287 is a bounds error */
     return PZ_ENTRY(nbits + PZ_LEN_EXTRA[sym - 257u], nbits, PZ_T_BASE, PZ_LEN_BASE[sym - 257u]);
   }
   if (sym > 29u) return PZ_SLOW_ENTRY; /* distanceArray ! >=30 is a bounds error */
@@ -238,7 +289,7 @@ PZ_DEV void pz_canon_codes(const uint8_t *lens, const PzTree *t, const uint16_t 
     acc += t->cnt[l];
   }
   pz_syncwarp();
-  for (int p = pz_lane(); p < (int)t->nsyms; p += PZ_WARP) {
+  for (int p = pz_lane(); p < (int)t->nsyms; p += PZ_G) {
     int s = perm[p];
     int l = lens[s];
     uint32_t cv = 0;
@@ -258,7 +309,7 @@ PZ_DEV int pz_tree_error(const uint8_t *lens, int n, const PzTree *t, const uint
     int li = lens[i];
     if (!li) continue;
     uint32_t ci = codes[i];
-    for (int jb = i + 1; jb < n; jb += PZ_WARP) {
+    for (int jb = i + 1; jb < n; jb += PZ_G) {
       int j = jb + pz_lane();
       int k = 0;
       if (j < n) {
@@ -279,15 +330,15 @@ PZ_DEV int pz_tree_error(const uint8_t *lens, int n, const PzTree *t, const uint
 
 /* computeHuffmanTree (Deflate.hs:255-259) for symbols 0..n-1 with lengths lens[]: canonical
  * counts, symbols sorted by (length, symbol), and the 2^BITS-entry LUT, all built
- * cooperatively.  Returns 0, or the HuffmanTreeError detail with *val. */
+ * cooperatively by the group.  Returns 0, or the HuffmanTreeError detail with *val. */
 template <int BITS, int KIND>
 PZ_DEV int pz_build(const uint8_t *lens, int n, PzTree *t, uint16_t *perm, uint32_t *lut, uint32_t *scratch, int64_t *val) {
   uint32_t *cnt32 = scratch, *offs = scratch + 16;
   const int lane = pz_lane();
   pz_syncwarp();
-  for (int i = lane; i < 16; i += PZ_WARP) cnt32[i] = 0;
+  for (int i = lane; i < 16; i += PZ_G) cnt32[i] = 0;
   pz_syncwarp();
-  for (int i = lane; i < n; i += PZ_WARP) {
+  for (int i = lane; i < n; i += PZ_G) {
     int l = lens[i];
     if (l) pz_smem_inc(&cnt32[l]);
   }
@@ -318,7 +369,7 @@ PZ_DEV int pz_build(const uint8_t *lens, int n, PzTree *t, uint16_t *perm, uint3
   if (lane == 0) t->nsyms = (uint16_t)acc;
   pz_syncwarp();
   /* stable counting sort by length: perm[] */
-  for (int b = 0; b < n; b += PZ_WARP) {
+  for (int b = 0; b < n; b += PZ_G) {
     int i = b + lane;
     uint32_t l = i < n ? lens[i] : 0u;
     unsigned m = pz_match_any(l);
@@ -330,7 +381,7 @@ PZ_DEV int pz_build(const uint8_t *lens, int n, PzTree *t, uint16_t *perm, uint3
   }
   if (over) return pz_tree_error(lens, n, t, perm, (uint16_t *)lut, val);
   /* LUT, entry-major: each lane walks the canonical code along the bits of its index */
-  for (uint32_t e = (uint32_t)lane; e < (1u << BITS); e += PZ_WARP) {
+  for (uint32_t e = (uint32_t)lane; e < (1u << BITS); e += PZ_G) {
     uint32_t code = 0, first = 0, index = 0, entry = PZ_SLOW_ENTRY;
     for (int len = 1; len <= BITS; len++) {
       code |= (e >> (len - 1)) & 1u;
@@ -353,6 +404,44 @@ PZ_DEV void pz_move_window(PzCtx &c) {
   if (c.pos - c.base >= 2u * PZ_EXCESS) c.base += PZ_EXCESS;
 }
 
+/* The LZ77 copy (OutputWindow.hs:82-101: copyChunked = byte-serial replicate semantics) of
+ * len bytes from dist back, all lanes of the group. */
+PZ_DEV void pz_copy_match(uint8_t *out, uint32_t pos, uint32_t len, uint32_t dist) {
+  const uint32_t lane = (uint32_t)pz_lane();
+  uint8_t *dst = out + pos;
+  const uint8_t *src = dst - dist;
+  pz_syncwarp(); /* earlier stores by other lanes are ordered before the loads below */
+  if (dist >= len) {
+    /* disjoint: up to 4*PZ_G bytes are loaded before any is stored (one memory round trip) */
+    const int32_t rem = (int32_t)len - (int32_t)lane;
+    uint8_t v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+    if (rem > 0) v0 = src[lane];
+    if (rem > PZ_G) v1 = src[lane + PZ_G];
+    if (rem > 2 * PZ_G) v2 = src[lane + 2 * PZ_G];
+    if (rem > 3 * PZ_G) v3 = src[lane + 3 * PZ_G];
+    if (rem > 0) dst[lane] = v0;
+    if (rem > PZ_G) dst[lane + PZ_G] = v1;
+    if (rem > 2 * PZ_G) dst[lane + 2 * PZ_G] = v2;
+    if (rem > 3 * PZ_G) dst[lane + 3 * PZ_G] = v3;
+    if (len > 4u * PZ_G)
+      for (uint32_t i = lane + 4u * PZ_G; i < len; i += PZ_G) dst[i] = src[i];
+  } else if (dist >= PZ_G) {
+    for (uint32_t i0 = 0; i0 < len; i0 += PZ_G) { /* each chunk may read the previous one */
+      uint32_t i = i0 + lane;
+      if (i < len) dst[i] = src[i];
+      pz_syncwarp();
+    }
+  } else { /* dist < PZ_G and dist < len: replicate the dist-byte pattern */
+    uint32_t m = lane % dist;
+    const uint32_t step = PZ_G % dist;
+    for (uint32_t i = lane; i < len; i += PZ_G) {
+      dst[i] = src[m];
+      m += step;
+      if (m >= dist) m -= dist;
+    }
+  }
+}
+
 /* emitPastChunk (Monad.hs:324-333, OutputWindow.hs:82-101).  Returns false with the
  * verdict set when the reference would fault or the caller's buffer is full. */
 template <bool COUNT_ONLY>
@@ -360,30 +449,8 @@ PZ_DEV bool pz_match(PzCtx &c, uint32_t len, uint32_t dist) {
   uint32_t fill = c.pos - c.base;
   if (dist > fill) { pz_fail(c, PZ_REF_BOTTOM, PZ_D_BOT_DIST_TOO_FAR, dist, fill); return false; }
   if (fill + len > PZ_WINDOW) { pz_fail(c, PZ_REF_BOTTOM, PZ_D_BOT_WINDOW_OVERFLOW); return false; }
-  if (c.pos + len > c.cap) { pz_fail(c, PZ_OUTPUT_FULL, 0); return false; }
-  if (!COUNT_ONLY) {
-    uint8_t *dst = c.out + c.pos;
-    const uint8_t *src = dst - dist;
-    const uint32_t lane = (uint32_t)pz_lane();
-    pz_syncwarp(); /* earlier stores by other lanes are ordered before the loads below */
-    if (dist >= len) {
-      for (uint32_t i = lane; i < len; i += PZ_WARP) dst[i] = src[i];
-    } else if (dist >= PZ_WARP) {
-      for (uint32_t i0 = 0; i0 < len; i0 += PZ_WARP) { /* each chunk may read the previous one */
-        uint32_t i = i0 + lane;
-        if (i < len) dst[i] = src[i];
-        pz_syncwarp();
-      }
-    } else { /* dist < 32 and dist < len: replicate the dist-byte pattern (copyChunked) */
-      uint32_t m = lane % dist;
-      const uint32_t step = PZ_WARP % dist;
-      for (uint32_t i = lane; i < len; i += PZ_WARP) {
-        dst[i] = src[m];
-        m += step;
-        if (m >= dist) m -= dist;
-      }
-    }
-  }
+  if (len > c.cap - c.pos) { pz_fail(c, PZ_OUTPUT_FULL, 0); return false; }
+  if (!COUNT_ONLY) pz_copy_match(c.out, c.pos, len, dist);
   c.pos += len;
   pz_move_window(c);
   return true;
@@ -399,94 +466,149 @@ PZ_DEV bool pz_literal_checked(PzCtx &c, uint32_t b) {
   return true;
 }
 
-/* ---- the careful symbol: exact verdict order, used near the end of the input and whenever
- * the LUT cannot answer (Deflate.hs:106-120).  Returns 1 = continue, 0 = end of block,
- * -1 = verdict set. */
+/* ---- the careful symbol: exact verdict order, used near the end of the input or of the
+ * output and whenever the LUT cannot answer (Deflate.hs:106-120).  Returns 1 = continue,
+ * 0 = end of block, -1 = verdict set. */
 template <bool COUNT_ONLY>
-PZ_DEV int pz_dist_careful(PzCtx &c, PzWarpSmem *sm, uint32_t len) {
-  int ds = pz_walk(c, &sm->dist, sm->dist_perm);
-  if (ds < 0) return -1;
-  if (ds > 29) { pz_fail(c, PZ_REF_BOTTOM, PZ_D_BOT_DIST_SYM, ds); return -1; }
-  uint32_t ex;
-  if (!pz_take(c, PZ_DIST_EXTRA[ds], ex)) return -1;
-  return pz_match<COUNT_ONLY>(c, len, PZ_DIST_BASE[ds] + ex) ? 1 : -1;
-}
-template <bool COUNT_ONLY>
-PZ_DEV int pz_symbol_careful(PzCtx &c, PzWarpSmem *sm) {
-  int sym = pz_walk(c, &sm->lit, sm->lit_perm);
+PZ_DEV int pz_symbol_careful(PzCtx &c, PzStreamSmem *sm) {
+  int sym = pz_walk(c, sm, &sm->lit, sm->lit_perm);
   if (sym < 0) return -1;
   if (sym < 256) return pz_literal_checked<COUNT_ONLY>(c, (uint32_t)sym) ? 1 : -1;
   if (sym == 256) return 0;
   if (sym > 285) { pz_fail(c, PZ_REF_BOTTOM, PZ_D_BOT_LENGTH_SYM, sym); return -1; }
   uint32_t ex;
-  if (!pz_take(c, PZ_LEN_EXTRA[sym - 257], ex)) return -1;
-  return pz_dist_careful<COUNT_ONLY>(c, sm, PZ_LEN_BASE[sym - 257] + ex);
+  if (!pz_take(c, sm, PZ_LEN_EXTRA[sym - 257], ex)) return -1;
+  const uint32_t len = PZ_LEN_BASE[sym - 257] + ex;
+  int ds = pz_walk(c, sm, &sm->dist, sm->dist_perm);
+  if (ds < 0) return -1;
+  if (ds > 29) { pz_fail(c, PZ_REF_BOTTOM, PZ_D_BOT_DIST_SYM, ds); return -1; }
+  if (!pz_take(c, sm, PZ_DIST_EXTRA[ds], ex)) return -1;
+  return pz_match<COUNT_ONLY>(c, len, PZ_DIST_BASE[ds] + ex) ? 1 : -1;
 }
 
-/* runInflate (Deflate.hs:106-120) */
+/* ---- the hot loop (runInflate, Deflate.hs:106-120) ---------------------------------------
+ * Every group in FAST mode decodes one symbol (a literal, or a length/distance pair with its
+ * copy) per iteration.  The body is straight-line predicated code: the groups of a warp take
+ * different "branches" (literal / match) in the same iteration, and a lone warp per scheduler
+ * cannot afford branch latencies.  The bytes of a match are loaded in the iteration that
+ * decodes it and stored one iteration later, so the L2 round trip of the copy overlaps the
+ * decode of the next symbol; the stores precede the next iteration's loads in program order,
+ * so no hazard analysis is needed.
+ *
+ * The loop ends as soon as ANY group of the warp meets something it must not decide here
+ * (long code, end of block, end of input or output in sight, a verdict, an overlapping or very
+ * long copy): that group has consumed nothing and sets need_careful.  Groups that are not in
+ * FAST mode (no streams left) idle along. */
+#ifdef PZ_HOSTSIM
+PZ_DEV void pz_st8_if(bool p, uint8_t *a, uint32_t v) { if (p) *a = (uint8_t)v; }
+PZ_DEV uint32_t pz_ld8_if(bool p, const uint8_t *a, uint32_t old) { return p ? *a : old; }
+PZ_DEV void pz_syncwarp_all() {}
+#else
+PZ_DEV void pz_st8_if(bool p, uint8_t *a, uint32_t v) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %0, 0;\n\t@q st.global.u8 [%1], %2;\n\t}" ::"r"((int)p), "l"(a), "r"(v) : "memory");
+}
+PZ_DEV uint32_t pz_ld8_if(bool p, const uint8_t *a, uint32_t old) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t@q ld.global.u8 %0, [%2];\n\t}" : "+r"(old) : "r"((int)p), "l"(a) : "memory");
+  return old;
+}
+PZ_DEV void pz_syncwarp_all() { __syncwarp(); }
+#endif
+
 template <bool COUNT_ONLY>
-PZ_DEV bool pz_run_inflate(PzCtx &c, PzWarpSmem *sm) {
-  for (;;) {
-    uint32_t lim = c.base + PZ_WINDOW;
-    if (c.cap < lim) lim = c.cap;
-    bool fast = (int32_t)c.word_idx <= c.safe_word && c.pos + 258u <= lim;
-    if (fast) {
-      if (c.cnt <= 32u) pz_refill(c);
-      uint32_t e = sm->lit_lut[(uint32_t)c.bitbuf & ((1u << PZ_LIT_BITS) - 1u)];
-      uint32_t type = (e >> 12) & 3u;
-      if (type != PZ_T_SLOW) {
-        uint32_t saved = (uint32_t)c.bitbuf;
-        pz_consume(c, e & 31u);
-        if (type == PZ_T_LIT) {
-          if (!COUNT_ONLY && pz_lane() == 0) c.out[c.pos] = (uint8_t)(e >> 16);
-          c.pos++;
-          continue;
-        }
-        if (type == PZ_T_EOB) return true;
-        uint32_t nb = (e >> 8) & 15u;
-        uint32_t len = (e >> 16) + ((saved & ((1u << (e & 31u)) - 1u)) >> nb);
-        if (c.cnt <= 32u) pz_refill(c);
-        uint32_t d = sm->dist_lut[(uint32_t)c.bitbuf & ((1u << PZ_DIST_BITS) - 1u)];
-        if (((d >> 12) & 3u) == PZ_T_SLOW) {
-          if (pz_dist_careful<COUNT_ONLY>(c, sm, len) < 0) return false;
-          continue;
-        }
-        saved = (uint32_t)c.bitbuf;
-        pz_consume(c, d & 31u);
-        uint32_t dist = (d >> 16) + ((saved & ((1u << (d & 31u)) - 1u)) >> ((d >> 8) & 15u));
-        if (!pz_match<COUNT_ONLY>(c, len, dist)) return false;
-        continue;
-      }
+PZ_DEV void pz_fast_loop(PzCtx &c, PzStreamSmem *sm) {
+  const bool live = c.mode == PZ_M_FAST;
+  const uint32_t *ring = sm->ring;
+  const uint32_t *lit = sm->lit_lut;
+  const uint32_t *dl = sm->dist_lut;
+  const int32_t lane = pz_lane();
+  uint32_t bp = c.bp, pos = c.pos, base = c.base;
+  const uint32_t safe_end = c.safe_end;
+  /* first position this run may not write at: a stale `base` only makes it conservative */
+  uint32_t lim = base + PZ_WINDOW;
+  if (c.cap < lim) lim = c.cap;
+  uint8_t *const out = c.out;
+  /* the match whose bytes are in flight: this lane owns bytes lane, lane+G, lane+2G, lane+3G */
+  uint8_t *pdst = out;
+  int32_t prem = 0;
+  uint32_t pv0 = 0, pv1 = 0, pv2 = 0, pv3 = 0;
+  bool stop;
+  do {
+    const uint32_t win = pz_peek(ring, bp);
+    const uint32_t e = lit[win & ((1u << PZ_LIT_BITS) - 1u)];
+    const uint32_t tb = e & 31u;
+    const bool is_lit = (int32_t)e < 0;
+    /* the distance code itself is still inside `win` (tb <= 15, index 8 bits); its extra
+     * bits may not be, so they come from a second window */
+    const uint32_t d = dl[(win >> tb) & ((1u << PZ_DIST_BITS) - 1u)];
+    const uint32_t bp2 = bp + tb;
+    const uint32_t win2 = pz_peek(ring, bp2);
+    const uint32_t tb2 = d & 31u;
+    const uint32_t len = (e >> 16) + ((win & ~(0xffffffffu << tb)) >> ((e >> 8) & 15u));
+    const uint32_t dist = (d >> 16) + ((win2 & ~(0xffffffffu << tb2)) >> ((d >> 8) & 15u));
+    const uint32_t room = lim - pos;
+    const bool pre_ok = live && bp <= safe_end && room != 0u;
+    const bool m_ok = !is_lit && tb != 0u && tb2 != 0u && dist <= pos - base && len <= room && dist >= len && len <= 4u * PZ_G;
+    const bool do_lit = pre_ok && is_lit;
+    const bool do_m = pre_ok && m_ok;
+    stop = live && !(do_lit || do_m);
+    uint8_t *const nd = out + pos + lane;
+    if (!COUNT_ONLY) {
+      pz_st8_if(do_lit && lane == 0, nd, e >> 16);
+      /* the previous iteration's match lands now ... */
+      pz_st8_if(prem > 0, pdst, pv0);
+      pz_st8_if(prem > PZ_G, pdst + PZ_G, pv1);
+      pz_st8_if(prem > 2 * PZ_G, pdst + 2 * PZ_G, pv2);
+      pz_st8_if(prem > 3 * PZ_G, pdst + 3 * PZ_G, pv3);
+      pz_syncwarp_all(); /* ... and is visible to the other lanes before this one's loads */
+      const uint8_t *const ns = nd - dist;
+      prem = do_m ? (int32_t)len - lane : 0;
+      pdst = nd;
+      pv0 = pz_ld8_if(prem > 0, ns, pv0);
+      pv1 = pz_ld8_if(prem > PZ_G, ns + PZ_G, pv1);
+      pv2 = pz_ld8_if(prem > 2 * PZ_G, ns + 2 * PZ_G, pv2);
+      pv3 = pz_ld8_if(prem > 3 * PZ_G, ns + 3 * PZ_G, pv3);
     }
-    int r = pz_symbol_careful<COUNT_ONLY>(c, sm);
-    if (r < 0) return false;
-    if (r == 0) return true;
+    bp += do_lit ? tb : (do_m ? tb + tb2 : 0u);
+    pos += do_lit ? 1u : (do_m ? len : 0u);
+    if (do_m && pos - base >= 2u * PZ_EXCESS) base += PZ_EXCESS; /* moveWindow after every match */
+    if (live && (bp >> PZ_QUARTER_SHIFT) != c.q) { c.bp = bp; pz_cross(c, sm); }
+  } while (!pz_warp_any(stop));
+  if (!COUNT_ONLY) {
+    pz_st8_if(prem > 0, pdst, pv0);
+    pz_st8_if(prem > PZ_G, pdst + PZ_G, pv1);
+    pz_st8_if(prem > 2 * PZ_G, pdst + 2 * PZ_G, pv2);
+    pz_st8_if(prem > 3 * PZ_G, pdst + 3 * PZ_G, pv3);
+    pz_syncwarp_all();
+  }
+  if (live) {
+    c.bp = bp; c.pos = pos; c.base = base;
+    c.mode = PZ_M_SYMS;
+    c.need_careful = stop;
   }
 }
 
-/* One symbol of the code-length code plus its repeat count (getCodeLengths, Deflate.hs:124-156). */
-PZ_DEV int pz_pre_symbol(PzCtx &c, PzWarpSmem *sm, uint32_t *pre_lut) {
-  if (pz_avail(c) >= PZ_PRE_BITS) { /* all peeked bits are real; the repeat field uses pz_take */
-    if (c.cnt < (uint32_t)PZ_PRE_BITS) pz_refill(c);
-    uint32_t e = pre_lut[(uint32_t)c.bitbuf & ((1u << PZ_PRE_BITS) - 1u)];
-    if (((e >> 12) & 3u) != PZ_T_SLOW) { pz_consume(c, e & 31u); return (int)(e >> 16); }
+/* One symbol of the code-length code (getCodeLengths, Deflate.hs:124-156). */
+PZ_DEV int pz_pre_symbol(PzCtx &c, PzStreamSmem *sm, const uint32_t *pre_lut) {
+  if (pz_avail(c) >= (uint32_t)PZ_PRE_BITS) { /* all peeked bits are real */
+    uint32_t e = pre_lut[pz_peek(sm->ring, c.bp) & ((1u << PZ_PRE_BITS) - 1u)];
+    if ((e & 31u) != 0u) { pz_advance(c, sm, e & 31u); return (int)((e >> 16) & 0xffu); }
   }
-  return pz_walk(c, &sm->pre, sm->pre_perm);
+  return pz_walk(c, sm, &sm->pre, sm->pre_perm);
 }
 
 /* inflateBlock's dynamic arm (Deflate.hs:83-101): returns false with the verdict set. */
-PZ_DEV bool pz_dynamic_header(PzCtx &c, PzWarpSmem *sm) {
+PZ_DEV bool pz_dynamic_header(PzCtx &c, PzStreamSmem *sm) {
   uint32_t hlit, hdist, hclen, v;
-  if (!pz_take(c, 5, hlit)) return false;
-  if (!pz_take(c, 5, hdist)) return false;
-  if (!pz_take(c, 4, hclen)) return false;
+  if (!pz_take(c, sm, 5, hlit)) return false;
+  if (!pz_take(c, sm, 5, hdist)) return false;
+  if (!pz_take(c, sm, 4, hclen)) return false;
   hlit += 257u; hdist += 1u; hclen += 4u;
   const int lane = pz_lane();
   pz_syncwarp();
-  for (int i = lane; i < 19; i += PZ_WARP) sm->lens[i] = 0;
+  for (int i = lane; i < 19; i += PZ_G) sm->lens[i] = 0;
   pz_syncwarp();
   for (uint32_t i = 0; i < hclen; i++) {
-    if (!pz_take(c, 3, v)) return false;
+    if (!pz_take(c, sm, 3, v)) return false;
     if (lane == 0) sm->lens[PZ_CL_ORDER[i]] = (uint8_t)v;
   }
   int64_t val = 0;
@@ -504,10 +626,10 @@ PZ_DEV bool pz_dynamic_header(PzCtx &c, PzWarpSmem *sm) {
       n++; prev = (uint32_t)code;
     } else {
       uint32_t num, fill;
-      if (code == 16) { if (!pz_take(c, 2, num)) return false; num += 3u; fill = prev; }
-      else if (code == 17) { if (!pz_take(c, 3, num)) return false; num += 3u; fill = 0; prev = 0; }
-      else { if (!pz_take(c, 7, num)) return false; num += 11u; fill = 0; prev = 0; }
-      for (uint32_t i = (uint32_t)lane; i < num; i += PZ_WARP) sm->lens[n + i] = (uint8_t)fill;
+      if (code == 16) { if (!pz_take(c, sm, 2, num)) return false; num += 3u; fill = prev; }
+      else if (code == 17) { if (!pz_take(c, sm, 3, num)) return false; num += 3u; fill = 0; prev = 0; }
+      else { if (!pz_take(c, sm, 7, num)) return false; num += 11u; fill = 0; prev = 0; }
+      for (uint32_t i = (uint32_t)lane; i < num; i += PZ_G) sm->lens[n + i] = (uint8_t)fill;
       n += num;
     }
   }
@@ -520,9 +642,9 @@ PZ_DEV bool pz_dynamic_header(PzCtx &c, PzWarpSmem *sm) {
 }
 
 /* buildFixedLitTree / buildFixedDistanceTree (Deflate.hs:241-251) */
-PZ_DEV void pz_fixed_tables(PzWarpSmem *sm) {
+PZ_DEV void pz_fixed_tables(PzStreamSmem *sm) {
   pz_syncwarp();
-  for (int i = pz_lane(); i < 288 + 32; i += PZ_WARP)
+  for (int i = pz_lane(); i < 288 + 32; i += PZ_G)
     sm->lens[i] = (uint8_t)(i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : i < 288 ? 8 : 5);
   pz_syncwarp();
   int64_t val;
@@ -532,113 +654,154 @@ PZ_DEV void pz_fixed_tables(PzWarpSmem *sm) {
 
 /* The stored arm (Deflate.hs:70-78, Monad.hs:265-293 for a single-chunk input). */
 template <bool COUNT_ONLY>
-PZ_DEV bool pz_stored_block(PzCtx &c) {
+PZ_DEV bool pz_stored_block(PzCtx &c, PzStreamSmem *sm) {
   uint32_t len, nlen;
-  uint64_t cur = pz_cur_bit(c);
-  uint32_t drop = (uint32_t)((8u - (cur & 7u)) & 7u); /* advanceToByte */
-  if (drop) {
-    /* the dropped bits belong to a byte that was already fetched: never a truncation */
-    if (c.cnt < drop) pz_refill(c);
-    pz_consume(c, drop);
-  }
-  if (pz_avail(c) < 32) { pz_fail(c, PZ_ERR_DECOMPRESSION, PZ_D_RAN_OUT); return false; }
-  if (!pz_take(c, 16, len)) return false;
-  if (!pz_take(c, 16, nlen)) return false;
+  pz_align_byte(c, sm);
+  if (pz_avail(c) < 32u) { pz_fail(c, PZ_ERR_DECOMPRESSION, PZ_D_RAN_OUT); return false; }
+  if (!pz_take(c, sm, 16, len)) return false;
+  if (!pz_take(c, sm, 16, nlen)) return false;
   if (len != ((~nlen) & 0xffffu)) { pz_fail(c, PZ_ERR_FORMAT, PZ_D_LEN_NLEN); return false; }
-  uint64_t boff = pz_cur_bit(c) >> 3;
-  uint64_t remaining = (c.end_bit >> 3) - boff;
+  uint32_t boff = c.bp >> 3;
+  uint32_t remaining = (c.end_bit >> 3) - boff;
   /* getBlock takes the data only when strictly more than len bytes are left in the chunk */
-  if ((uint64_t)len >= remaining) { pz_fail(c, PZ_ERR_DECOMPRESSION, PZ_D_RAN_OUT); return false; }
+  if (len >= remaining) { pz_fail(c, PZ_ERR_DECOMPRESSION, PZ_D_RAN_OUT); return false; }
   uint32_t fill = c.pos - c.base;
   if (fill + len > PZ_WINDOW) { pz_fail(c, PZ_REF_BOTTOM, PZ_D_BOT_WINDOW_OVERFLOW); return false; }
-  if (c.pos + len > c.cap) { pz_fail(c, PZ_OUTPUT_FULL, 0); return false; }
+  if (len > c.cap - c.pos) { pz_fail(c, PZ_OUTPUT_FULL, 0); return false; }
   if (!COUNT_ONLY) {
     const uint8_t *src = c.in_al + boff;
     uint8_t *dst = c.out + c.pos;
-    for (uint32_t i = (uint32_t)pz_lane(); i < len; i += PZ_WARP) dst[i] = src[i];
+    for (uint32_t i = (uint32_t)pz_lane(); i < len; i += PZ_G) dst[i] = src[i];
   }
   c.pos += len;
-  pz_seek(c, (boff + len) * 8u);
+  pz_seek(c, sm, (boff + len) * 8u);
   return true;
 }
 
-/* `decompress` for one single-chunk stream: inflateWithHeaders (Zlib.hs:53-69), inflate
- * (Deflate.hs:39-63).  The Adler-32 comparison itself is done by the checksum kernels; this
- * function leaves the stored trailer in *adler_stored. */
-template <bool COUNT_ONLY>
-PZ_DEV void pz_inflate_stream(const uint8_t *in, uint64_t in_len, uint8_t *out, uint64_t out_cap, PzWarpSmem *sm, pz_result *res) {
-  PzCtx c;
-  uint64_t mis = (uint64_t)((uintptr_t)in & 15u);
-  c.in_al = in - mis;
-  c.in_al_bytes = (mis + in_len + 15u) & ~(uint64_t)15u;
-  c.end_bit = (mis + in_len) * 8u;
-  c.ring = sm->ring;
-  c.out = out;
-  c.pos = 0; c.base = 0;
-  c.cap = out_cap > 0xfffdff00ull ? 0xfffdff00u : (uint32_t)out_cap; /* base + 128 KiB stays in 32 bits */
-  c.status = PZ_OK; c.detail = 0; c.p0 = 0; c.p1 = 0;
-  c.safe_word = c.end_bit >= 48u ? (int32_t)((c.end_bit - 48u) >> 5) : -1;
-  uint32_t adler_stored = 0;
-  pz_seek(c, mis * 8u);
-
-  do {
-    /* zlib header (Zlib.hs:53-69) */
-    uint32_t cmf, flg;
-    if (!pz_take(c, 8, cmf)) break;
-    if (!pz_take(c, 8, flg)) break;
-    if (((cmf << 8) | flg) % 31u != 0u) { pz_fail(c, PZ_ERR_HEADER, PZ_D_HDR_CHECKSUM); break; }
-    if ((cmf & 15u) != 8u) { pz_fail(c, PZ_ERR_HEADER, PZ_D_HDR_METHOD, cmf & 15u); break; }
-    if ((cmf >> 4) > 7u) { pz_fail(c, PZ_ERR_HEADER, PZ_D_HDR_WINDOW, cmf >> 4); break; }
-    if (flg & 0x20u) { /* FDICT: the four DICTID bytes are skipped (Zlib.hs:68) */
-      uint32_t skip;
-      if (!pz_take(c, 16, skip)) break;
-      if (!pz_take(c, 16, skip)) break;
-    }
-    bool fixed_ready = false;
-    for (;;) { /* inflate's go loop (Deflate.hs:45-50) */
-      uint32_t bfinal, btype;
-      if (!pz_take(c, 1, bfinal)) break;
-      if (!pz_take(c, 2, btype)) break;
-      if (btype == 0u) {
-        if (!pz_stored_block<COUNT_ONLY>(c)) break;
-      } else if (btype == 1u) {
-        if (!fixed_ready) { pz_fixed_tables(sm); fixed_ready = true; }
-        if (!pz_run_inflate<COUNT_ONLY>(c, sm)) break;
-      } else if (btype == 2u) {
-        fixed_ready = false;
-        if (!pz_dynamic_header(c, sm)) break;
-        if (!pz_run_inflate<COUNT_ONLY>(c, sm)) break;
-      } else {
-        pz_fail(c, PZ_ERR_FORMAT, PZ_D_BAD_BTYPE, 3);
-        break;
-      }
-      pz_move_window(c);
-      if (bfinal) {
-        /* checkChecksum (Deflate.hs:52-63): align, then four bytes, most significant first */
-        uint64_t cur = pz_cur_bit(c);
-        uint32_t drop = (uint32_t)((8u - (cur & 7u)) & 7u);
-        if (drop) { if (c.cnt < drop) pz_refill(c); pz_consume(c, drop); }
-        uint32_t hi, lo;
-        if (pz_avail(c) < 32) { pz_fail(c, PZ_ERR_DECOMPRESSION, PZ_D_RAN_OUT); break; }
-        if (!pz_take(c, 16, hi)) break;
-        if (!pz_take(c, 16, lo)) break;
-        adler_stored = ((hi & 0xffu) << 24) | ((hi >> 8) << 16) | ((lo & 0xffu) << 8) | (lo >> 8);
-        break;
-      }
-    }
-  } while (0);
-
+/* ---- the state machine ------------------------------------------------------------------ */
+/* Publishes the verdict of the current stream and frees the group for its next one. */
+PZ_DEV void pz_finish(PzCtx &c) {
   pz_syncwarp();
   if (pz_lane() == 0) {
+    pz_result *res = c.res;
     res->status = c.status;
     res->detail = c.detail;
     res->out_len = c.pos;
     res->adler_computed = 0;
-    res->adler_stored = adler_stored;
-    res->err_bitpos = pz_cur_bit(c) - mis * 8u;
+    res->adler_stored = c.adler_stored;
+    res->err_bitpos = c.bp - c.start_bit;
     res->payload[0] = c.p0;
     /* payload[1]: bytes the reference has already published as 32 KiB chunks (the shim's
      * incremental driver needs it); DIST_TOO_FAR keeps the retained-byte count instead */
     res->payload[1] = (c.status == PZ_REF_BOTTOM && c.detail == PZ_D_BOT_DIST_TOO_FAR) ? c.p1 : (int64_t)c.base;
   }
+  c.mode = PZ_M_IDLE;
+}
+
+/* `decompress` for one single-chunk stream starts here: inflateWithHeaders (Zlib.hs:53-69). */
+PZ_DEV void pz_begin(PzCtx &c, PzStreamSmem *sm, const uint8_t *in, uint64_t in_len, uint8_t *out, uint64_t out_cap, pz_result *res) {
+  uint32_t mis = (uint32_t)((uintptr_t)in & 15u);
+  c.in_al = in - mis;
+  c.res = res;
+  c.out = out;
+  c.pos = 0; c.base = 0;
+  c.cap = out_cap > 0xfffdff00ull ? 0xfffdff00u : (uint32_t)out_cap; /* base + 128 KiB stays in 32 bits */
+  c.status = PZ_OK; c.detail = 0; c.p0 = 0; c.p1 = 0;
+  c.adler_stored = 0; c.bfinal = 0; c.fixed_ready = false; c.need_careful = false;
+  c.start_bit = mis * 8u;
+  if (in_len > PZ_MAX_IN_BYTES) { /* the C ABI refuses such streams before launching */
+    c.in_al_bytes = 0; c.end_bit = c.start_bit; c.safe_end = 0; c.bp = c.start_bit; c.q = 0;
+    pz_fail(c, PZ_OUTPUT_FULL, 0);
+    pz_finish(c);
+    return;
+  }
+  c.in_al_bytes = (mis + (uint32_t)in_len + 15u) & ~15u;
+  c.end_bit = (mis + (uint32_t)in_len) * 8u;
+  c.safe_end = c.end_bit >= PZ_STEP_BITS ? c.end_bit - PZ_STEP_BITS : 0u; /* bp >= 16 once the header is read */
+  pz_seek(c, sm, c.start_bit);
+  uint32_t cmf, flg;
+  bool ok = pz_take(c, sm, 8, cmf) && pz_take(c, sm, 8, flg);
+  if (ok) {
+    if (((cmf << 8) | flg) % 31u != 0u) { pz_fail(c, PZ_ERR_HEADER, PZ_D_HDR_CHECKSUM); ok = false; }
+    else if ((cmf & 15u) != 8u) { pz_fail(c, PZ_ERR_HEADER, PZ_D_HDR_METHOD, cmf & 15u); ok = false; }
+    else if ((cmf >> 4) > 7u) { pz_fail(c, PZ_ERR_HEADER, PZ_D_HDR_WINDOW, cmf >> 4); ok = false; }
+    else if (flg & 0x20u) { /* FDICT: the four DICTID bytes are skipped (Zlib.hs:68) */
+      uint32_t skip;
+      ok = pz_take(c, sm, 16, skip) && pz_take(c, sm, 16, skip);
+    }
+  }
+  if (!ok) { pz_finish(c); return; }
+  c.mode = PZ_M_HDR;
+}
+
+/* End of a block (Deflate.hs:45-50): moveWindow, then either the next block or the trailer
+ * (checkChecksum, Deflate.hs:52-63: align, four bytes, most significant first). */
+PZ_DEV void pz_block_end(PzCtx &c, PzStreamSmem *sm) {
+  pz_move_window(c);
+  if (!c.bfinal) { c.mode = PZ_M_HDR; return; }
+  pz_align_byte(c, sm);
+  uint32_t hi, lo;
+  if (pz_avail(c) < 32u) pz_fail(c, PZ_ERR_DECOMPRESSION, PZ_D_RAN_OUT);
+  else if (pz_take(c, sm, 16, hi) && pz_take(c, sm, 16, lo))
+    c.adler_stored = ((hi & 0xffu) << 24) | ((hi >> 8) << 16) | ((lo & 0xffu) << 8) | (lo >> 8);
+  pz_finish(c);
+}
+
+/* One transition of a group that is not in the hot loop. */
+template <bool COUNT_ONLY>
+PZ_DEV void pz_slow_step(PzCtx &c, PzStreamSmem *sm, const PzJob &job, uint32_t stride) {
+  if (c.mode == PZ_M_IDLE) {
+    if (c.next >= job.first + job.count) { c.mode = PZ_M_DEAD; return; }
+    const uint32_t s = c.next;
+    c.next += stride;
+    const uint64_t i0 = job.in_off[s], i1 = job.in_off[s + 1];
+    if (COUNT_ONLY) {
+      pz_begin(c, sm, job.in_blob + i0, i1 - i0, nullptr, ~0ull, job.res + s);
+    } else {
+      const uint64_t o0 = job.out_off[s], o1 = job.out_off[s + 1];
+      pz_begin(c, sm, job.in_blob + i0, i1 - i0, job.out_blob + o0, o1 - o0, job.res + s);
+    }
+  } else if (c.mode == PZ_M_HDR) { /* inflateBlock (Deflate.hs:65-104) */
+    uint32_t btype;
+    if (!pz_take(c, sm, 1, c.bfinal) || !pz_take(c, sm, 2, btype)) { pz_finish(c); return; }
+    if (btype == 0u) {
+      if (!pz_stored_block<COUNT_ONLY>(c, sm)) { pz_finish(c); return; }
+      pz_block_end(c, sm);
+    } else if (btype == 1u) {
+      if (!c.fixed_ready) { pz_fixed_tables(sm); c.fixed_ready = true; }
+      c.mode = PZ_M_SYMS;
+    } else if (btype == 2u) {
+      c.fixed_ready = false;
+      if (!pz_dynamic_header(c, sm)) { pz_finish(c); return; }
+      c.mode = PZ_M_SYMS;
+    } else {
+      pz_fail(c, PZ_ERR_FORMAT, PZ_D_BAD_BTYPE, 3);
+      pz_finish(c);
+    }
+  } else { /* PZ_M_SYMS */
+    if (!c.need_careful) {
+      uint32_t lim = c.base + PZ_WINDOW;
+      if (c.cap < lim) lim = c.cap;
+      if (c.bp <= c.safe_end && c.pos < lim) { c.mode = PZ_M_FAST; return; }
+    }
+    c.need_careful = false;
+    int r = pz_symbol_careful<COUNT_ONLY>(c, sm);
+    if (r < 0) pz_finish(c);
+    else if (r == 0) pz_block_end(c, sm);
+  }
+}
+
+/* All the streams of one group: streams first_stream, first_stream + stride, ... of the job. */
+template <bool COUNT_ONLY>
+PZ_DEV void pz_inflate_group(const PzJob &job, uint32_t first_stream, uint32_t stride, PzStreamSmem *sm) {
+  PzCtx c;
+  c.mode = PZ_M_IDLE;
+  c.next = first_stream;
+  c.in_al = nullptr; c.in_al_bytes = 0; c.bp = 0; c.q = 0; c.res = nullptr;
+  for (;;) {
+    while (c.mode != PZ_M_FAST && c.mode != PZ_M_DEAD) pz_slow_step<COUNT_ONLY>(c, sm, job, stride);
+    if (!pz_warp_any(c.mode == PZ_M_FAST)) break; /* every group of the warp is out of streams */
+    pz_fast_loop<COUNT_ONLY>(c, sm);
+  }
+  pz_async_wait_all();
 }

@@ -5,7 +5,12 @@
 
 #include "pzcuda.h"
 
-#define PZ_WARPS_PER_CTA 4
+#ifndef PZ_GROUP
+#define PZ_GROUP 8 /* lanes per stream (pz_device.cuh) */
+#endif
+#define PZ_WARPS_PER_CTA 1
+#define PZ_GROUPS_PER_CTA (PZ_WARPS_PER_CTA * 32 / PZ_GROUP)
+#define PZ_MAX_STREAM_BYTES 0x1ffffff0ull /* == PZ_MAX_IN_BYTES in pz_device.cuh */
 #define PZ_ADLER_SEG 16384u /* bytes per checksum segment (one warp each) */
 
 /* Stream s = first + k decodes in_blob[in_off[s], in_off[s+1]) into out_blob[out_off[s], out_off[s+1]).

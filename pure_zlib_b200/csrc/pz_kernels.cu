@@ -1,7 +1,8 @@
 /*
  * pz_kernels.cu -- the sm_100a kernels of libpzcuda.so.
  *
- *   pz_inflate_warp_kernel   K1: one warp per zlib stream (pz_device.cuh)
+ *   pz_inflate_kernel        K1: persistent CTAs, PZ_G lanes per zlib stream, 32/PZ_G streams
+ *                            advancing in lockstep per warp (pz_device.cuh)
  *   pz_adler_partial_kernel  K3a: one warp per 16 KiB segment of decoded output, dp4a sums
  *   pz_adler_finish_kernel   K3b: per stream, combines the segments (adler32-combine
  *                            identity) and compares with the stored trailer
@@ -11,22 +12,15 @@
 #include "pz_internal.h"
 
 template <bool COUNT_ONLY>
-__global__ void __launch_bounds__(PZ_WARPS_PER_CTA * 32, 7)
-pz_inflate_warp_kernel(const uint8_t *__restrict__ in_blob, const uint64_t *__restrict__ in_off, uint8_t *out_blob,
-                       const uint64_t *__restrict__ out_off, uint32_t first, uint32_t count, pz_result *res) {
+__global__ void __launch_bounds__(PZ_WARPS_PER_CTA * 32)
+pz_inflate_kernel(const PzJob job) {
   extern __shared__ __align__(16) unsigned char pz_smem_raw[];
-  const uint32_t w = threadIdx.x >> 5;
-  PzWarpSmem *sm = reinterpret_cast<PzWarpSmem *>(pz_smem_raw) + w;
-  const uint32_t k = blockIdx.x * PZ_WARPS_PER_CTA + w;
-  if (k >= count) return;
-  const uint32_t s = first + k;
-  const uint64_t i0 = in_off[s], i1 = in_off[s + 1];
-  if (COUNT_ONLY) {
-    pz_inflate_stream<true>(in_blob + i0, i1 - i0, nullptr, ~0ull, sm, res + s);
-  } else {
-    const uint64_t o0 = out_off[s], o1 = out_off[s + 1];
-    pz_inflate_stream<false>(in_blob + i0, i1 - i0, out_blob + o0, o1 - o0, sm, res + s);
-  }
+  const uint32_t g = threadIdx.x / PZ_G; /* group within the CTA */
+  PzStreamSmem *sm = reinterpret_cast<PzStreamSmem *>(pz_smem_raw) + g;
+  /* persistent groups: group gid takes streams gid, gid + stride, ... */
+  const uint32_t gid = blockIdx.x * PZ_GROUPS_PER_CTA + g;
+  const uint32_t stride = gridDim.x * PZ_GROUPS_PER_CTA;
+  pz_inflate_group<COUNT_ONLY>(job, job.first + gid, stride, sm);
 }
 
 /* ---- Adler-32 (Adler32.hs:17-57) as a segmented reduction ------------------------------
@@ -116,34 +110,58 @@ pz_adler_finish_kernel(const uint64_t *__restrict__ seg_off, uint32_t first, uin
 }
 
 __global__ void pz_code_values_kernel(const uint8_t *lens, int n, uint16_t *codes) {
-  __shared__ PzWarpSmem sm;
-  for (int i = threadIdx.x; i < n; i += 32) sm.lens[i] = lens[i];
-  __syncwarp();
+  __shared__ PzStreamSmem sm; /* launched with one group (PZ_G threads) */
+  for (int i = threadIdx.x; i < n; i += PZ_G) sm.lens[i] = lens[i];
+  pz_syncwarp();
   int64_t val;
   (void)pz_build<PZ_LIT_BITS, 1>(sm.lens, n, &sm.lit, sm.lit_perm, sm.lit_lut, sm.scratch, &val);
   uint16_t *c16 = reinterpret_cast<uint16_t *>(sm.dist_lut);
   pz_canon_codes(sm.lens, &sm.lit, sm.lit_perm, c16, false);
-  for (int i = threadIdx.x; i < n; i += 32) codes[i] = sm.lens[i] ? c16[i] : 0;
+  for (int i = threadIdx.x; i < n; i += PZ_G) codes[i] = sm.lens[i] ? c16[i] : 0;
 }
 
 /* ---- launch wrappers ------------------------------------------------------------------ */
+static int g_inflate_ctas_per_sm[2] = {0, 0};
+static int g_sm_count = 0;
+
 cudaError_t pz_kernels_configure(void) {
   cudaError_t e;
-  e = cudaFuncSetAttribute(pz_inflate_warp_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  const size_t smem = sizeof(PzStreamSmem) * PZ_GROUPS_PER_CTA;
+  int dev = 0;
+  if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+  if ((e = cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(pz_inflate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(pz_inflate_warp_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  return e;
+  e = cudaFuncSetAttribute(pz_inflate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(pz_inflate_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(pz_inflate_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_inflate_ctas_per_sm[0], pz_inflate_kernel<false>, PZ_WARPS_PER_CTA * 32, smem);
+  if (e != cudaSuccess) return e;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_inflate_ctas_per_sm[1], pz_inflate_kernel<true>, PZ_WARPS_PER_CTA * 32, smem);
+  if (e != cudaSuccess) return e;
+  if (g_inflate_ctas_per_sm[0] < 1 || g_inflate_ctas_per_sm[1] < 1) return cudaErrorLaunchOutOfResources;
+  return cudaSuccess;
 }
 
+/* One resident wave of persistent CTAs: 148 SMs x CTAs/SM on B200, fewer for small batches. */
 cudaError_t pz_launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uint8_t *d_out, const uint64_t *d_out_off,
                               uint32_t first, uint32_t count, pz_result *d_res, cudaStream_t st) {
   if (count == 0) return cudaSuccess;
-  const unsigned grid = (count + PZ_WARPS_PER_CTA - 1) / PZ_WARPS_PER_CTA;
-  const size_t smem = sizeof(PzWarpSmem) * PZ_WARPS_PER_CTA;
-  if (d_out == nullptr)
-    pz_inflate_warp_kernel<true><<<grid, PZ_WARPS_PER_CTA * 32, smem, st>>>(d_in, d_in_off, nullptr, d_out_off, first, count, d_res);
+  const bool count_only = d_out == nullptr;
+  const unsigned want = (count + PZ_GROUPS_PER_CTA - 1) / PZ_GROUPS_PER_CTA;
+  const unsigned wave = (unsigned)(g_sm_count * g_inflate_ctas_per_sm[count_only ? 1 : 0]);
+  const unsigned grid = want < wave ? want : wave;
+  const size_t smem = sizeof(PzStreamSmem) * PZ_GROUPS_PER_CTA;
+  PzJob job;
+  job.in_blob = d_in; job.in_off = d_in_off; job.out_blob = d_out; job.out_off = d_out_off; job.res = d_res;
+  job.first = first; job.count = count;
+  if (count_only)
+    pz_inflate_kernel<true><<<grid, PZ_WARPS_PER_CTA * 32, smem, st>>>(job);
   else
-    pz_inflate_warp_kernel<false><<<grid, PZ_WARPS_PER_CTA * 32, smem, st>>>(d_in, d_in_off, d_out, d_out_off, first, count, d_res);
+    pz_inflate_kernel<false><<<grid, PZ_WARPS_PER_CTA * 32, smem, st>>>(job);
   return cudaGetLastError();
 }
 
@@ -161,6 +179,6 @@ cudaError_t pz_launch_adler(const uint8_t *d_out, const uint64_t *d_out_off, con
 }
 
 cudaError_t pz_launch_code_values(const uint8_t *d_lens, int n, uint16_t *d_codes, cudaStream_t st) {
-  pz_code_values_kernel<<<1, 32, 0, st>>>(d_lens, n, d_codes);
+  pz_code_values_kernel<<<1, PZ_G, 0, st>>>(d_lens, n, d_codes);
   return cudaGetLastError();
 }

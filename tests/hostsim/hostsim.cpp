@@ -19,13 +19,18 @@ extern "C" int hs_inflate(const uint8_t *in, uint64_t in_len, uint8_t *out, uint
   uint8_t *buf = (uint8_t *)aligned_alloc(16, ((in_len + mis + 15) & ~(size_t)15) + 1024 + 16);
   memset(buf, 0xA5, ((in_len + mis + 15) & ~(size_t)15) + 1024 + 16);
   memcpy(buf + mis, in, in_len);
-  PzWarpSmem *sm = (PzWarpSmem *)aligned_alloc(16, sizeof(PzWarpSmem));
-  memset(sm, 0xCD, sizeof(PzWarpSmem));
-  if (count_only) pz_inflate_stream<true>(buf + mis, in_len, out, out_cap, sm, res);
-  else pz_inflate_stream<false>(buf + mis, in_len, out, out_cap, sm, res);
+  PzStreamSmem *sm = (PzStreamSmem *)aligned_alloc(16, (sizeof(PzStreamSmem) + 15) & ~(size_t)15);
+  memset(sm, 0xCD, sizeof(PzStreamSmem));
+  /* a one-stream job through the same state machine the kernel runs */
+  uint64_t in_off[2] = {0, in_len}, out_off[2] = {0, out_cap};
+  PzJob job;
+  job.in_blob = buf + mis; job.in_off = in_off; job.out_blob = count_only ? nullptr : out; job.out_off = out_off;
+  job.res = res; job.first = 0; job.count = 1;
+  if (count_only) pz_inflate_group<true>(job, 0, 1, sm);
+  else pz_inflate_group<false>(job, 0, 1, sm);
   free(sm);
   free(buf);
   return 0;
 }
 
-extern "C" int hs_smem_bytes(void) { return (int)sizeof(PzWarpSmem); }
+extern "C" int hs_smem_bytes(void) { return (int)sizeof(PzStreamSmem); }

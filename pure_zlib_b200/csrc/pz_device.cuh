@@ -220,6 +220,13 @@ PZ_DEV uint32_t pz_peek(const uint32_t *ring, uint32_t bp) {
   uint32_t t = (bp >> 5) & (PZ_RING_WORDS - 1u);
   return pz_funnel_r(ring[t], ring[t + 1u], bp);
 }
+/* The 64 stream bits starting at bp: enough for a whole literal/length + distance pair. */
+PZ_DEV void pz_peek64(const uint32_t *ring, uint32_t bp, uint32_t &lo, uint32_t &hi) {
+  uint32_t t = (bp >> 5) & (PZ_RING_WORDS - 1u);
+  uint32_t w0 = ring[t], w1 = ring[t + 1u], w2 = ring[t + 2u];
+  lo = pz_funnel_r(w0, w1, bp);
+  hi = pz_funnel_r(w1, w2, bp);
+}
 PZ_DEV void pz_advance(PzCtx &c, PzStreamSmem *sm, uint32_t n) {
   c.bp += n;
   if ((c.bp >> PZ_QUARTER_SHIFT) != c.q) pz_cross(c, sm);
@@ -244,16 +251,17 @@ PZ_DEV void pz_align_byte(PzCtx &c, PzStreamSmem *sm) {
  * Consumes one bit per step and stops exactly where the reference's trie walk stops:
  * truncation if the input ends first, "Advanced to empty tree!" on an unused prefix. */
 PZ_DEV int pz_walk(PzCtx &c, PzStreamSmem *sm, const PzTree *t, const uint16_t *perm) {
+  const uint32_t av = pz_avail(c);
+  const uint32_t w = pz_peek(sm->ring, c.bp); /* only the first min(av, 15) bits are looked at */
   uint32_t code = 0, first = 0, index = 0;
-  for (int len = 1; len <= 15; len++) {
-    uint32_t bit;
-    if (!pz_take(c, sm, 1, bit)) return -1;
-    if (t->nsyms == 0) { pz_fail(c, PZ_ERR_HUFFMAN_TREE, PZ_D_ADVANCE_EMPTY_TREE); return -1; }
-    code |= bit;
+  for (uint32_t len = 1; len <= 15u; len++) {
+    if (len > av) { pz_advance(c, sm, len - 1u); pz_fail(c, PZ_ERR_DECOMPRESSION, PZ_D_RAN_OUT); return -1; }
+    if (t->nsyms == 0) { pz_advance(c, sm, len); pz_fail(c, PZ_ERR_HUFFMAN_TREE, PZ_D_ADVANCE_EMPTY_TREE); return -1; }
+    code |= (w >> (len - 1u)) & 1u;
     uint32_t count = t->cnt[len];
-    if (code - first < count) return perm[index + (code - first)];
+    if (code - first < count) { pz_advance(c, sm, len); return perm[index + (code - first)]; }
     index += count; first += count;
-    if (code - first >= t->used[len]) break;
+    if (code - first >= t->used[len]) { pz_advance(c, sm, len); break; } /* used[15] == 0 */
     first <<= 1; code <<= 1;
   }
   pz_fail(c, PZ_ERR_HUFFMAN_TREE, PZ_D_ADVANCED_TO_EMPTY);
@@ -504,84 +512,130 @@ PZ_DEV void pz_st8_if(bool p, uint8_t *a, uint32_t v) { if (p) *a = (uint8_t)v; 
 PZ_DEV uint32_t pz_ld8_if(bool p, const uint8_t *a, uint32_t old) { return p ? *a : old; }
 PZ_DEV void pz_syncwarp_all() {}
 #else
+/* The hot loop's global accesses are volatile asm WITHOUT a memory clobber: they keep their order
+ * among themselves (which is all the copy semantics need), while the compiler stays free to
+ * hoist the shared-memory table and window loads across them -- that freedom is what lets the
+ * next symbol's look-ahead overlap this symbol's copy. */
 PZ_DEV void pz_st8_if(bool p, uint8_t *a, uint32_t v) {
-  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %0, 0;\n\t@q st.global.u8 [%1], %2;\n\t}" ::"r"((int)p), "l"(a), "r"(v) : "memory");
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %0, 0;\n\t@q st.global.u8 [%1], %2;\n\t}" ::"r"((int)p), "l"(a), "r"(v));
 }
 PZ_DEV uint32_t pz_ld8_if(bool p, const uint8_t *a, uint32_t old) {
-  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t@q ld.global.u8 %0, [%2];\n\t}" : "+r"(old) : "r"((int)p), "l"(a) : "memory");
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t@q ld.global.u8 %0, [%2];\n\t}" : "+r"(old) : "r"((int)p), "l"(a));
   return old;
 }
-PZ_DEV void pz_syncwarp_all() { __syncwarp(); }
+/* warp barrier between the stores and the loads of one iteration (all 32 lanes are converged in
+ * the hot loop); same ordering rule as above */
+PZ_DEV void pz_syncwarp_all() { asm volatile("bar.warp.sync 0xffffffff;"); }
 #endif
+
+/* The bytes of one match in flight: this lane owns bytes lane, lane+G, lane+2G, lane+3G. */
+struct PzPend {
+  uint8_t *dst;
+  int32_t rem;    /* len - lane, or <= 0 when the slot is empty */
+  uint32_t start; /* output position of the match; 0xffffffff when empty (same in every lane) */
+  uint32_t v0, v1, v2, v3;
+};
+PZ_DEV void pz_pend_clear(PzPend &p, uint8_t *any) { p.dst = any; p.rem = 0; p.start = 0xffffffffu; p.v0 = p.v1 = p.v2 = p.v3 = 0; }
+PZ_DEV void pz_pend_store(PzPend &p) {
+  pz_st8_if(p.rem > 0, p.dst, p.v0);
+  pz_st8_if(p.rem > PZ_G, p.dst + PZ_G, p.v1);
+  pz_st8_if(p.rem > 2 * PZ_G, p.dst + 2 * PZ_G, p.v2);
+  pz_st8_if(p.rem > 3 * PZ_G, p.dst + 3 * PZ_G, p.v3);
+  p.rem = 0; p.start = 0xffffffffu;
+}
+
+struct PzFast { /* the registers of the hot loop */
+  uint32_t bp, pos, base, lim, safe_end;
+  uint32_t lo, hi, e; /* the 64-bit window at bp and its literal/length LUT entry (decoded ahead) */
+  uint8_t *out;
+  bool live;
+};
+
+PZ_DEV void pz_fast_fetch(PzFast &f, const PzStreamSmem *sm, uint32_t bp) {
+  pz_peek64(sm->ring, bp, f.lo, f.hi);
+  f.e = sm->lit_lut[f.lo & ((1u << PZ_LIT_BITS) - 1u)];
+}
+
+/* One iteration: returns this group's stop flag.  `mine` is the slot loaded PZ_DEPTH iterations
+ * ago (stored now, then reloaded); o1/o2 are the younger matches still in flight.
+ *
+ * The bit-position chain (window -> LUT -> bits -> next window) is the only serial part, so the
+ * NEXT symbol's window and LUT entry are requested as soon as this symbol's bit count is
+ * known -- speculatively: if this symbol turns out to be one the loop must not decide, the loop
+ * ends and the look-ahead is dropped -- and the copy/store work of this symbol is issued in the
+ * shadow of those shared-memory loads. */
+template <bool COUNT_ONLY>
+PZ_DEV bool pz_fast_step(PzFast &f, PzCtx &c, PzStreamSmem *sm, PzPend &mine, PzPend &o1, PzPend &o2) {
+  const int32_t lane = pz_lane();
+  const uint32_t lo = f.lo, e = f.e;
+  const uint32_t tb = e & 31u;
+  const bool is_lit = (int32_t)e < 0;
+  const uint32_t wd = pz_funnel_r(lo, f.hi, tb); /* the bits after the literal/length symbol (tb <= 15) */
+  const uint32_t d = sm->dist_lut[wd & ((1u << PZ_DIST_BITS) - 1u)];
+  const uint32_t tb2 = d & 31u;
+  const uint32_t nbp = f.bp + (is_lit ? tb : tb + tb2);
+  pz_fast_fetch(f, sm, nbp); /* look-ahead */
+  const uint32_t len = (e >> 16) + ((lo & ~(0xffffffffu << tb)) >> ((e >> 8) & 15u));
+  const uint32_t dist = (d >> 16) + ((wd & ~(0xffffffffu << tb2)) >> ((d >> 8) & 15u));
+  const uint32_t room = f.lim - f.pos;
+  const bool pre_ok = f.live && f.bp <= f.safe_end && room != 0u;
+  const bool m_ok = !is_lit && tb != 0u && tb2 != 0u && dist <= f.pos - f.base && len <= room && dist >= len && len <= 4u * PZ_G;
+  const bool do_lit = pre_ok && is_lit;
+  const bool do_m = pre_ok && m_ok;
+  uint8_t *const nd = f.out + f.pos + lane;
+  if (!COUNT_ONLY) {
+    pz_st8_if(do_lit && lane == 0, nd, e >> 16);
+    pz_pend_store(mine); /* its loads were issued PZ_DEPTH iterations ago */
+    /* a source that reaches into a match not yet stored: store everything first (rare) */
+    const uint32_t oldest = o1.start < o2.start ? o1.start : o2.start;
+    if (pz_warp_any(do_m && f.pos - dist + len > oldest)) { pz_pend_store(o1); pz_pend_store(o2); }
+    pz_syncwarp_all(); /* stores above are visible to the other lanes before the loads below */
+    const uint8_t *const ns = nd - dist;
+    mine.rem = do_m ? (int32_t)len - lane : 0;
+    mine.start = do_m ? f.pos : 0xffffffffu;
+    mine.dst = nd;
+    mine.v0 = pz_ld8_if(mine.rem > 0, ns, mine.v0);
+    mine.v1 = pz_ld8_if(mine.rem > PZ_G, ns + PZ_G, mine.v1);
+    mine.v2 = pz_ld8_if(mine.rem > 2 * PZ_G, ns + 2 * PZ_G, mine.v2);
+    mine.v3 = pz_ld8_if(mine.rem > 3 * PZ_G, ns + 3 * PZ_G, mine.v3);
+  }
+  const bool ok = do_lit || do_m;
+  if (ok) f.bp = nbp;
+  f.pos += do_lit ? 1u : (do_m ? len : 0u);
+  if (do_m && f.pos - f.base >= 2u * PZ_EXCESS) f.base += PZ_EXCESS; /* moveWindow after every match */
+  if (f.live && (f.bp >> PZ_QUARTER_SHIFT) != c.q) { c.bp = f.bp; pz_cross(c, sm); }
+  return f.live && !ok;
+}
 
 template <bool COUNT_ONLY>
 PZ_DEV void pz_fast_loop(PzCtx &c, PzStreamSmem *sm) {
-  const bool live = c.mode == PZ_M_FAST;
-  const uint32_t *ring = sm->ring;
-  const uint32_t *lit = sm->lit_lut;
-  const uint32_t *dl = sm->dist_lut;
-  const int32_t lane = pz_lane();
-  uint32_t bp = c.bp, pos = c.pos, base = c.base;
-  const uint32_t safe_end = c.safe_end;
+  PzFast f;
+  f.live = c.mode == PZ_M_FAST;
+  f.bp = c.bp; f.pos = c.pos; f.base = c.base; f.safe_end = c.safe_end; f.out = c.out;
   /* first position this run may not write at: a stale `base` only makes it conservative */
-  uint32_t lim = base + PZ_WINDOW;
-  if (c.cap < lim) lim = c.cap;
-  uint8_t *const out = c.out;
-  /* the match whose bytes are in flight: this lane owns bytes lane, lane+G, lane+2G, lane+3G */
-  uint8_t *pdst = out;
-  int32_t prem = 0;
-  uint32_t pv0 = 0, pv1 = 0, pv2 = 0, pv3 = 0;
+  f.lim = f.base + PZ_WINDOW;
+  if (c.cap < f.lim) f.lim = c.cap;
+  pz_fast_fetch(f, sm, f.bp);
+  PzPend p0, p1, p2;
+  pz_pend_clear(p0, f.out); pz_pend_clear(p1, f.out); pz_pend_clear(p2, f.out);
   bool stop;
-  do {
-    const uint32_t win = pz_peek(ring, bp);
-    const uint32_t e = lit[win & ((1u << PZ_LIT_BITS) - 1u)];
-    const uint32_t tb = e & 31u;
-    const bool is_lit = (int32_t)e < 0;
-    /* the distance code itself is still inside `win` (tb <= 15, index 8 bits); its extra
-     * bits may not be, so they come from a second window */
-    const uint32_t d = dl[(win >> tb) & ((1u << PZ_DIST_BITS) - 1u)];
-    const uint32_t bp2 = bp + tb;
-    const uint32_t win2 = pz_peek(ring, bp2);
-    const uint32_t tb2 = d & 31u;
-    const uint32_t len = (e >> 16) + ((win & ~(0xffffffffu << tb)) >> ((e >> 8) & 15u));
-    const uint32_t dist = (d >> 16) + ((win2 & ~(0xffffffffu << tb2)) >> ((d >> 8) & 15u));
-    const uint32_t room = lim - pos;
-    const bool pre_ok = live && bp <= safe_end && room != 0u;
-    const bool m_ok = !is_lit && tb != 0u && tb2 != 0u && dist <= pos - base && len <= room && dist >= len && len <= 4u * PZ_G;
-    const bool do_lit = pre_ok && is_lit;
-    const bool do_m = pre_ok && m_ok;
-    stop = live && !(do_lit || do_m);
-    uint8_t *const nd = out + pos + lane;
-    if (!COUNT_ONLY) {
-      pz_st8_if(do_lit && lane == 0, nd, e >> 16);
-      /* the previous iteration's match lands now ... */
-      pz_st8_if(prem > 0, pdst, pv0);
-      pz_st8_if(prem > PZ_G, pdst + PZ_G, pv1);
-      pz_st8_if(prem > 2 * PZ_G, pdst + 2 * PZ_G, pv2);
-      pz_st8_if(prem > 3 * PZ_G, pdst + 3 * PZ_G, pv3);
-      pz_syncwarp_all(); /* ... and is visible to the other lanes before this one's loads */
-      const uint8_t *const ns = nd - dist;
-      prem = do_m ? (int32_t)len - lane : 0;
-      pdst = nd;
-      pv0 = pz_ld8_if(prem > 0, ns, pv0);
-      pv1 = pz_ld8_if(prem > PZ_G, ns + PZ_G, pv1);
-      pv2 = pz_ld8_if(prem > 2 * PZ_G, ns + 2 * PZ_G, pv2);
-      pv3 = pz_ld8_if(prem > 3 * PZ_G, ns + 3 * PZ_G, pv3);
-    }
-    bp += do_lit ? tb : (do_m ? tb + tb2 : 0u);
-    pos += do_lit ? 1u : (do_m ? len : 0u);
-    if (do_m && pos - base >= 2u * PZ_EXCESS) base += PZ_EXCESS; /* moveWindow after every match */
-    if (live && (bp >> PZ_QUARTER_SHIFT) != c.q) { c.bp = bp; pz_cross(c, sm); }
-  } while (!pz_warp_any(stop));
-  if (!COUNT_ONLY) {
-    pz_st8_if(prem > 0, pdst, pv0);
-    pz_st8_if(prem > PZ_G, pdst + PZ_G, pv1);
-    pz_st8_if(prem > 2 * PZ_G, pdst + 2 * PZ_G, pv2);
-    pz_st8_if(prem > 3 * PZ_G, pdst + 3 * PZ_G, pv3);
-    pz_syncwarp_all();
+  for (;;) {
+    stop = pz_fast_step<COUNT_ONLY>(f, c, sm, p0, p1, p2);
+    if (pz_warp_any(stop)) break;
+    stop = pz_fast_step<COUNT_ONLY>(f, c, sm, p1, p2, p0);
+    if (pz_warp_any(stop)) break;
+    stop = pz_fast_step<COUNT_ONLY>(f, c, sm, p2, p0, p1);
+    if (pz_warp_any(stop)) break;
   }
-  if (live) {
-    c.bp = bp; c.pos = pos; c.base = base;
+  if (!COUNT_ONLY) {
+    pz_pend_store(p0); pz_pend_store(p1); pz_pend_store(p2);
+    pz_syncwarp_all();
+#ifndef PZ_HOSTSIM
+    __syncwarp(); /* and a compiler-level fence before the careful path's plain accesses */
+#endif
+  }
+  if (f.live) {
+    c.bp = f.bp; c.pos = f.pos; c.base = f.base;
     c.mode = PZ_M_SYMS;
     c.need_careful = stop;
   }

@@ -262,6 +262,19 @@ def main():
         _lib.check(L.pz_batch_run(batch_k1, d_in.data_ptr(), d_out.data_ptr(), st), "pz_batch_run")
     k1.record()
     barrier()
+    # the decoder warps alone (sizing pass: same bit-stream work, no tokens, no writer warps)
+    batch_dec = L.pz_batch_create(in_off.ctypes.data_as(p64), None, c.n, _lib.PZ_F_COUNT_ONLY)
+    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ms_dec = None
+    if batch_dec:
+        _lib.check(L.pz_batch_run(batch_dec, d_in.data_ptr(), None, st), "pz_batch_run")
+        d0.record()
+        for _ in range(a.steps):
+            _lib.check(L.pz_batch_run(batch_dec, d_in.data_ptr(), None, st), "pz_batch_run")
+        d1.record()
+        barrier()
+        ms_dec = d0.elapsed_time(d1) / a.steps
+        L.pz_batch_destroy(batch_dec)
     clocks = sampler.stop()
     ms_k1 = k0.elapsed_time(k1) / a.steps
     if distributed:
@@ -294,7 +307,7 @@ def main():
             "data": "synthetic", "config": config,
             "roofline": {"bound": "hbm", "kernel": "pz_inflate_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": load_traffic(a.config), "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": ms_k1,
+                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": ms_k1, "decoder_only_ms": ms_dec,
                          "note": "issue/latency-bound integer path: frac of HBM is expected to be small (SURVEY 7, hard part 1)"},
             "clocks": clocks, "gpu_launches": a.steps * L.pz_batch_launches(batch),
             "corpus_sha256": c.sha256_in, "compressed_bytes": c.in_bytes, "decoded_bytes": c.out_bytes}

@@ -1,34 +1,48 @@
 /*
  * pz_device.cuh -- the device-side inflate engine.
  *
- * Execution model: a warp is split into 32/PZ_G "groups" of PZ_G lanes; each group decodes one
+ * Execution model.  A warp is split into 32/PZ_G "groups" of PZ_G lanes and a group serves one
  * zlib stream, so a warp advances 32/PZ_G independent streams in lockstep and every issued
- * instruction does useful work for all of them (the decode chain of one stream is serial, so
- * the win is in sharing issue slots, not lanes).  All PZ_G lanes of a group hold the same
- * decoder state; lane 0 stores literals and LZ77 matches are copied by the whole group
- * (lane i moves bytes i, i+PZ_G, ...), straight into the stream's slice of the HBM output
- * blob -- the output itself is the history window.
+ * instruction does useful work for all of them (the decode chain of one stream is serial: the
+ * win is in sharing issue slots, not lanes).  A CTA is a PAIR of such warps working on the same
+ * streams:
  *
- * Each group runs a small state machine (IDLE -> HDR -> SYMS <-> FAST -> ... -> IDLE) so that
- * the groups of a warp meet in ONE hot loop (pz_fast_loop) no matter where their streams are;
- * everything that is rare or needs the reference's exact verdict order (block headers, table
- * construction, codes longer than the first-level LUT, the last bytes of the input or of the
- * output buffer) runs in the "slow" part, one group at a time.
+ *   decoder warp  owns the bit stream.  It parses headers, builds the Huffman LUTs in shared
+ *                 memory, and runs the serial bit-position chain (window -> LUT -> bits -> next
+ *                 window).  It never touches the output: every literal / match / stored run is
+ *                 pushed as one 32-bit token into the stream's shared-memory queue.  All of the
+ *                 reference's verdicts are decided here from counters alone.
+ *   writer warp   owns the output.  It pops tokens, stores literals and performs the LZ77
+ *                 copies straight into the stream's slice of the HBM output blob (the output
+ *                 itself is the history window).  Match bytes are loaded when the token is
+ *                 popped and stored three iterations later, so the L2/HBM round trip of a copy
+ *                 never stalls the warp.
+ *
+ * The two instruction streams are independent, which is what an in-order, one-warp-per-
+ * scheduler machine needs: the decoder's chain no longer waits behind copy instructions, and
+ * the writer's memory latencies no longer delay the next symbol.
+ *
+ * Each decoder group runs a small state machine (IDLE -> HDR -> SYMS <-> FAST -> ... -> IDLE) so
+ * that the groups of a warp meet in ONE hot loop (pz_fast_loop) no matter where their streams
+ * are; everything that is rare or needs the reference's exact verdict order (block headers,
+ * table construction, codes longer than the first-level LUT, the last bits of the input or the
+ * last bytes of the output buffer) runs in the "slow" part, one group at a time.
  *
  * What it replaces in the reference (file:line relative to the pure-zlib checkout):
  *   bit reader            Monad.hs:199-263   -> bit position over a cp.async-staged smem ring,
- *                                               32-bit windows assembled with a funnel shift
+ *                                               64-bit windows assembled with funnel shifts
  *   tree build + walk     HuffmanTree.hs:25-83, Deflate.hs:255-288 -> canonical counts + flat LUT
  *   block parser          Deflate.hs:65-156  -> pz_slow_step()
- *   symbol loop           Deflate.hs:106-120 -> pz_fast_loop() + exact bit-serial "careful" path
- *   output window         OutputWindow.hs:29-114 -> direct stores; the window is only *modelled*
- *                                              (fill/base counters) to reproduce its verdicts
+ *   symbol loop           Deflate.hs:106-120 -> pz_fast_loop() + exact "careful" path
+ *   output window         OutputWindow.hs:29-114 -> pz_writer_warp(): direct stores; the window
+ *                                              is only *modelled* (fill/base counters in the
+ *                                              decoder) to reproduce its verdicts
  *   zlib framing          Zlib.hs:53-69, Deflate.hs:52-63
  *
  * The file also compiles with a host C++ compiler when PZ_HOSTSIM is defined: a group is then
- * a single lane and a "warp" a single group.  That build exists only for tests/hostsim
- * (CPU-side differential fuzzing of this logic against the oracle); the product library never
- * contains it.
+ * a single lane, and every pushed token is applied to the output at once.  That build exists
+ * only for tests/hostsim (CPU-side differential fuzzing of this logic against the oracle); the
+ * product library never contains it.
  */
 #pragma once
 #include <stdint.h>
@@ -94,6 +108,19 @@ PZ_DEV void pz_async_wait_all() {
 #define PZ_STEP_BITS 48u  /* most bits one literal/length + distance pair can consume: 15+5+15+13 */
 #define PZ_MAX_IN_BYTES 0x1ffffff0ull /* bit positions are 32-bit: streams below 512 MiB */
 
+/* Token queue, decoder -> writer (one per stream, in shared memory).  A token is one 32-bit
+ * word: phase [31] | type [29,31) | payload.  The phase bit flips every time the ring wraps, so a
+ * slot is valid exactly when its phase matches the reader's lap: one store publishes a token. */
+#define PZ_QLEN 32u
+#define PZ_QSHIFT 5
+#define PZ_Q_LIT 0u   /* payload [0,8): the byte                                             */
+#define PZ_Q_MATCH 1u /* payload [16,25): length 3..258, [0,15): distance - 1                 */
+#define PZ_Q_CTRL 2u  /* payload [26,29): operation, followed by raw 31-bit argument tokens   */
+#define PZ_C_NEWSTREAM 1u /* + stream index: the writer switches to that stream's output slice */
+#define PZ_C_STORED 2u    /* + byte offset from the stream's first byte, + length (0..65535)  */
+#define PZ_C_EXIT 3u      /* the decoder group has no streams left                             */
+#define PZ_TOKEN(type, payload) (((uint32_t)(type) << 29) | (uint32_t)(payload))
+
 /* LUT entry: total bits [0,5) | code bits [8,12) | type [12,14) | value [16,31) | literal flag 31.
  * total == 0 marks an entry the hot loop must not act on (long code, dead prefix, end of
  * block, or a symbol the reference cannot index): the careful path decides. */
@@ -124,7 +151,12 @@ struct __attribute__((aligned(16))) PzStreamSmem {
   uint16_t pre_perm[24];
   PzTree lit, dist, pre;
   uint8_t lens[PZ_MAX_LENS];
+  uint32_t q[PZ_QLEN]; /* token queue: written by the decoder, read by the writer */
+  uint32_t qtail;      /* tokens consumed so far: written by the writer, read by the decoder */
 };
+/* 4 streams per CTA and 7 CTAs per SM only fit if a CTA stays within 32256 bytes (228 KiB per SM,
+ * 1 KiB reserved per resident CTA, 256-byte allocation granules): 8064 bytes per stream. */
+static_assert(sizeof(PzStreamSmem) <= 8064, "PzStreamSmem no longer fits 28 streams per SM");
 
 #ifdef PZ_HOSTSIM
 static const uint16_t PZ_LEN_BASE[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
@@ -162,7 +194,6 @@ struct PzCtx {
   uint32_t safe_end;    /* bp <= safe_end: a whole symbol pair (PZ_STEP_BITS) is available */
   uint32_t bp;          /* bit position of the reader, counted from in_al; bp <= end_bit   */
   uint32_t q;           /* ring quarter holding bp; quarters q and q+1 are resident        */
-  uint8_t *out;
   uint32_t pos;  /* bytes decoded                                                          */
   uint32_t base; /* bytes the reference would already have published (multiple of 32 KiB)  */
   uint32_t cap;
@@ -176,6 +207,12 @@ struct PzCtx {
   bool need_careful; /* the hot loop met something only the careful path may decide */
   uint32_t next;     /* next stream index of this group */
   pz_result *res;
+  /* token queue (decoder side) */
+  uint32_t qhead;  /* tokens pushed so far */
+  uint32_t qtailc; /* last value read from the writer's counter */
+#ifdef PZ_HOSTSIM
+  struct PzWriter *hw; /* host build: tokens are applied at once */
+#endif
 };
 
 PZ_DEV void pz_fail(PzCtx &c, int status, int detail, int64_t p0 = 0, int64_t p1 = 0) {
@@ -405,34 +442,45 @@ PZ_DEV int pz_build(const uint8_t *lens, int n, PzTree *t, uint16_t *perm, uint3
   return 0;
 }
 
-/* ---- output ---------------------------------------------------------------------------- */
-/* moveWindow / emitExcess (Monad.hs:338-347, OutputWindow.hs:45-54): at most one 32 KiB
- * chunk leaves the window per call, only once 64 KiB have accumulated. */
-PZ_DEV void pz_move_window(PzCtx &c) {
-  if (c.pos - c.base >= 2u * PZ_EXCESS) c.base += PZ_EXCESS;
+/* ---- output side: the writer ---------------------------------------------------------------- */
+#ifdef PZ_HOSTSIM
+PZ_DEV void pz_st8_if(bool p, uint8_t *a, uint32_t v) { if (p) *a = (uint8_t)v; }
+PZ_DEV uint32_t pz_ld8_if(bool p, const uint8_t *a) { return p ? *a : 0u; }
+PZ_DEV void pz_syncwarp_all() {}
+PZ_DEV uint32_t pz_vload(const uint32_t *p) { return *p; }
+PZ_DEV void pz_vstore(uint32_t *p, uint32_t v) { *p = v; }
+PZ_DEV void pz_backoff() {}
+#else
+/* The writer's hot-loop global accesses are volatile asm WITHOUT a memory clobber: they keep
+ * their order among themselves (which is all the copy semantics need), while the compiler
+ * stays free to move shared-memory loads across them. */
+PZ_DEV void pz_st8_if(bool p, uint8_t *a, uint32_t v) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %0, 0;\n\t@q st.global.u8 [%1], %2;\n\t}" ::"r"((int)p), "l"(a), "r"(v));
 }
+PZ_DEV uint32_t pz_ld8_if(bool p, const uint8_t *a) {
+  /* a fresh register with no other definition: nothing may read (and so wait for) the loaded
+   * byte before its store, and the store carries the same predicate as this load */
+  uint32_t v;
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t@q ld.global.u8 %0, [%2];\n\t}" : "=r"(v) : "r"((int)p), "l"(a));
+  return v;
+}
+/* warp barrier between the stores and the loads of one iteration (all 32 lanes are converged
+ * in the hot loops); same ordering rule as above */
+PZ_DEV void pz_syncwarp_all() { asm volatile("bar.warp.sync 0xffffffff;"); }
+PZ_DEV uint32_t pz_vload(const uint32_t *p) { return *(const volatile uint32_t *)p; }
+PZ_DEV void pz_vstore(uint32_t *p, uint32_t v) { *(volatile uint32_t *)p = v; }
+PZ_DEV void pz_backoff() { __nanosleep(64); }
+#endif
 
 /* The LZ77 copy (OutputWindow.hs:82-101: copyChunked = byte-serial replicate semantics) of
- * len bytes from dist back, all lanes of the group. */
+ * len bytes from dist back, all lanes of the group, no deferral: the general case. */
 PZ_DEV void pz_copy_match(uint8_t *out, uint32_t pos, uint32_t len, uint32_t dist) {
   const uint32_t lane = (uint32_t)pz_lane();
   uint8_t *dst = out + pos;
   const uint8_t *src = dst - dist;
   pz_syncwarp(); /* earlier stores by other lanes are ordered before the loads below */
   if (dist >= len) {
-    /* disjoint: up to 4*PZ_G bytes are loaded before any is stored (one memory round trip) */
-    const int32_t rem = (int32_t)len - (int32_t)lane;
-    uint8_t v0 = 0, v1 = 0, v2 = 0, v3 = 0;
-    if (rem > 0) v0 = src[lane];
-    if (rem > PZ_G) v1 = src[lane + PZ_G];
-    if (rem > 2 * PZ_G) v2 = src[lane + 2 * PZ_G];
-    if (rem > 3 * PZ_G) v3 = src[lane + 3 * PZ_G];
-    if (rem > 0) dst[lane] = v0;
-    if (rem > PZ_G) dst[lane + PZ_G] = v1;
-    if (rem > 2 * PZ_G) dst[lane + 2 * PZ_G] = v2;
-    if (rem > 3 * PZ_G) dst[lane + 3 * PZ_G] = v3;
-    if (len > 4u * PZ_G)
-      for (uint32_t i = lane + 4u * PZ_G; i < len; i += PZ_G) dst[i] = src[i];
+    for (uint32_t i = lane; i < len; i += PZ_G) dst[i] = src[i];
   } else if (dist >= PZ_G) {
     for (uint32_t i0 = 0; i0 < len; i0 += PZ_G) { /* each chunk may read the previous one */
       uint32_t i = i0 + lane;
@@ -448,17 +496,170 @@ PZ_DEV void pz_copy_match(uint8_t *out, uint32_t pos, uint32_t len, uint32_t dis
       if (m >= dist) m -= dist;
     }
   }
+  pz_syncwarp();
+}
+
+/* Writer state of one stream slot (registers; identical in every lane of the group). */
+struct PzWriter {
+  const PzJob *job;
+  uint8_t *out;      /* output slice of the current stream */
+  const uint8_t *in; /* its first compressed byte (stored runs copy from the input) */
+  uint32_t pos;      /* bytes written */
+  uint32_t op, need, a0; /* control message being assembled: `need` argument tokens to go */
+  bool exited;
+};
+PZ_DEV void pz_writer_init(PzWriter &w, const PzJob *job) {
+  w.job = job; w.out = nullptr; w.in = nullptr; w.pos = 0; w.op = 0; w.need = 0; w.a0 = 0; w.exited = false;
+}
+
+/* Applies one token completely (no deferral): the writer's path for everything that is not a
+ * literal or a short disjoint match.  `raw` is the token without its phase bit. */
+PZ_DEV void pz_writer_apply(PzWriter &w, uint32_t raw) {
+  const uint32_t lane = (uint32_t)pz_lane();
+  if (w.need) { /* argument of a control message */
+    if (w.op == PZ_C_NEWSTREAM) {
+      w.out = w.job->out_blob + w.job->out_off[raw];
+      w.in = w.job->in_blob + w.job->in_off[raw];
+      w.pos = 0; w.need = 0;
+    } else if (w.need == 2u) {
+      w.a0 = raw; w.need = 1;
+    } else { /* emitBlock (Monad.hs:317-322): raw bytes of a stored block */
+      const uint8_t *src = w.in + w.a0;
+      uint8_t *dst = w.out + w.pos;
+      pz_syncwarp();
+      for (uint32_t i = lane; i < raw; i += PZ_G) dst[i] = src[i];
+      pz_syncwarp();
+      w.pos += raw; w.need = 0;
+    }
+    return;
+  }
+  const uint32_t type = (raw >> 29) & 3u;
+  if (type == PZ_Q_LIT) {
+    if (lane == 0) w.out[w.pos] = (uint8_t)raw;
+    w.pos++;
+  } else if (type == PZ_Q_MATCH) {
+    const uint32_t len = (raw >> 16) & 0x1ffu, dist = (raw & 0x7fffu) + 1u;
+    pz_copy_match(w.out, w.pos, len, dist);
+    w.pos += len;
+  } else {
+    const uint32_t op = (raw >> 26) & 7u;
+    if (op == PZ_C_EXIT) w.exited = true;
+    else { w.op = op; w.need = op == PZ_C_NEWSTREAM ? 1u : 2u; }
+  }
+}
+
+#ifndef PZ_HOSTSIM
+/* The writer warp: runs until every group has seen its EXIT token.
+ *
+ * Each trip pops up to PZ_WB tokens per group.  Literals are stored at once; the bytes of every
+ * short disjoint match of the trip are LOADED first (this lane owns bytes lane, lane+G, lane+2G,
+ * lane+3G of each) and stored only after all the loads of the trip have been issued, so one
+ * L2/HBM round trip is shared by the whole batch instead of being paid per match.  A match
+ * whose source reaches into bytes produced earlier in the same trip ends the batch and opens
+ * the next one.  Everything else (overlapping or long copies, stored runs, control tokens)
+ * goes through pz_writer_apply(), one token per trip. */
+#define PZ_WB 6
+PZ_DEV void pz_writer_warp(const PzJob &job, PzStreamSmem *sm) {
+  PzWriter w;
+  pz_writer_init(w, &job);
+  const int32_t lane = pz_lane();
+  uint32_t tail = 0;
+  for (;;) {
+    pz_syncwarp_all(); /* the previous trip's stores are visible to the other lanes' loads */
+    uint32_t raw[PZ_WB];
+#pragma unroll
+    for (int j = 0; j < PZ_WB; j++) raw[j] = pz_vload(&sm->q[(tail + (uint32_t)j) & (PZ_QLEN - 1u)]);
+    { /* the general path, when the first token needs it */
+      const uint32_t r = raw[0];
+      const uint32_t type = (r >> 29) & 3u, len = (r >> 16) & 0x1ffu, dist = (r & 0x7fffu) + 1u;
+      const bool valid = !w.exited && (r >> 31) == ((tail >> PZ_QSHIFT) & 1u);
+      const bool fast = w.need == 0u && (type == PZ_Q_LIT || (type == PZ_Q_MATCH && dist >= len && len <= 4u * PZ_G));
+      const bool slow = valid && !fast;
+      if (pz_warp_any(slow)) {
+        if (slow) {
+          pz_writer_apply(w, r & 0x7fffffffu);
+          tail++;
+          pz_vstore(&sm->qtail, tail);
+        }
+        if (!pz_warp_any(!w.exited)) break;
+        continue;
+      }
+    }
+    const uint32_t start = w.pos;
+    uint32_t pos = w.pos, n = 0;
+    bool go = !w.exited;
+    uint8_t *dst[PZ_WB];
+    int32_t rem[PZ_WB];
+    uint32_t v[PZ_WB][4];
+#pragma unroll
+    for (int j = 0; j < PZ_WB; j++) {
+      const uint32_t r = raw[j];
+      const uint32_t type = (r >> 29) & 3u, len = (r >> 16) & 0x1ffu, dist = (r & 0x7fffu) + 1u;
+      const bool valid = (r >> 31) == (((tail + (uint32_t)j) >> PZ_QSHIFT) & 1u);
+      const bool is_lit = type == PZ_Q_LIT;
+      /* short, disjoint, and not reading what this trip has produced so far */
+      const bool is_m = type == PZ_Q_MATCH && dist >= len && len <= 4u * PZ_G && pos - dist + len <= start;
+      go = go && valid && (is_lit || is_m);
+      uint8_t *const nd = w.out + pos + lane;
+      const uint8_t *const ns = nd - dist;
+      pz_st8_if(go && is_lit && lane == 0, nd, r);
+      rem[j] = (go && !is_lit) ? (int32_t)len - lane : 0;
+      dst[j] = nd;
+      v[j][0] = pz_ld8_if(rem[j] > 0, ns);
+      v[j][1] = pz_ld8_if(rem[j] > PZ_G, ns + PZ_G);
+      v[j][2] = pz_ld8_if(rem[j] > 2 * PZ_G, ns + 2 * PZ_G);
+      v[j][3] = pz_ld8_if(rem[j] > 3 * PZ_G, ns + 3 * PZ_G);
+      pos += go ? (is_lit ? 1u : len) : 0u;
+      n += go ? 1u : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < PZ_WB; j++) {
+      pz_st8_if(rem[j] > 0, dst[j], v[j][0]);
+      pz_st8_if(rem[j] > PZ_G, dst[j] + PZ_G, v[j][1]);
+      pz_st8_if(rem[j] > 2 * PZ_G, dst[j] + 2 * PZ_G, v[j][2]);
+      pz_st8_if(rem[j] > 3 * PZ_G, dst[j] + 3 * PZ_G, v[j][3]);
+    }
+    w.pos = pos;
+    tail += n;
+    pz_vstore(&sm->qtail, tail);
+  }
+}
+#endif /* !PZ_HOSTSIM */
+
+/* ---- decoder side: emitting tokens --------------------------------------------------------- */
+/* Pushes one token (31 bits, phase added here); waits while the queue is full. */
+template <bool COUNT_ONLY>
+PZ_DEV void pz_push(PzCtx &c, PzStreamSmem *sm, uint32_t v) {
+#ifdef PZ_HOSTSIM
+  (void)sm;
+  if (!COUNT_ONLY) pz_writer_apply(*c.hw, v);
+#else
+  if (!COUNT_ONLY) {
+    while (c.qhead - c.qtailc >= PZ_QLEN) {
+      c.qtailc = pz_vload(&sm->qtail);
+      if (c.qhead - c.qtailc >= PZ_QLEN) pz_backoff();
+    }
+    pz_vstore(&sm->q[c.qhead & (PZ_QLEN - 1u)], v | (((c.qhead >> PZ_QSHIFT) & 1u) << 31));
+    c.qhead++;
+  }
+#endif
+}
+
+/* moveWindow / emitExcess (Monad.hs:338-347, OutputWindow.hs:45-54): at most one 32 KiB
+ * chunk leaves the window per call, only once 64 KiB have accumulated. */
+PZ_DEV void pz_move_window(PzCtx &c) {
+  if (c.pos - c.base >= 2u * PZ_EXCESS) c.base += PZ_EXCESS;
 }
 
 /* emitPastChunk (Monad.hs:324-333, OutputWindow.hs:82-101).  Returns false with the
  * verdict set when the reference would fault or the caller's buffer is full. */
 template <bool COUNT_ONLY>
-PZ_DEV bool pz_match(PzCtx &c, uint32_t len, uint32_t dist) {
+PZ_DEV bool pz_match(PzCtx &c, PzStreamSmem *sm, uint32_t len, uint32_t dist) {
   uint32_t fill = c.pos - c.base;
   if (dist > fill) { pz_fail(c, PZ_REF_BOTTOM, PZ_D_BOT_DIST_TOO_FAR, dist, fill); return false; }
   if (fill + len > PZ_WINDOW) { pz_fail(c, PZ_REF_BOTTOM, PZ_D_BOT_WINDOW_OVERFLOW); return false; }
   if (len > c.cap - c.pos) { pz_fail(c, PZ_OUTPUT_FULL, 0); return false; }
-  if (!COUNT_ONLY) pz_copy_match(c.out, c.pos, len, dist);
+  pz_push<COUNT_ONLY>(c, sm, PZ_TOKEN(PZ_Q_MATCH, (len << 16) | (dist - 1u)));
   c.pos += len;
   pz_move_window(c);
   return true;
@@ -466,10 +667,10 @@ PZ_DEV bool pz_match(PzCtx &c, uint32_t len, uint32_t dist) {
 
 /* emitByte (Monad.hs:309-315, OutputWindow.hs:64-68) with the window / capacity checks. */
 template <bool COUNT_ONLY>
-PZ_DEV bool pz_literal_checked(PzCtx &c, uint32_t b) {
+PZ_DEV bool pz_literal_checked(PzCtx &c, PzStreamSmem *sm, uint32_t b) {
   if (c.pos - c.base >= PZ_WINDOW) { pz_fail(c, PZ_REF_BOTTOM, PZ_D_BOT_WINDOW_OVERFLOW); return false; }
   if (c.pos >= c.cap) { pz_fail(c, PZ_OUTPUT_FULL, 0); return false; }
-  if (!COUNT_ONLY && pz_lane() == 0) c.out[c.pos] = (uint8_t)b;
+  pz_push<COUNT_ONLY>(c, sm, PZ_TOKEN(PZ_Q_LIT, b & 0xffu));
   c.pos++;
   return true;
 }
@@ -481,7 +682,7 @@ template <bool COUNT_ONLY>
 PZ_DEV int pz_symbol_careful(PzCtx &c, PzStreamSmem *sm) {
   int sym = pz_walk(c, sm, &sm->lit, sm->lit_perm);
   if (sym < 0) return -1;
-  if (sym < 256) return pz_literal_checked<COUNT_ONLY>(c, (uint32_t)sym) ? 1 : -1;
+  if (sym < 256) return pz_literal_checked<COUNT_ONLY>(c, sm, (uint32_t)sym) ? 1 : -1;
   if (sym == 256) return 0;
   if (sym > 285) { pz_fail(c, PZ_REF_BOTTOM, PZ_D_BOT_LENGTH_SYM, sym); return -1; }
   uint32_t ex;
@@ -491,63 +692,26 @@ PZ_DEV int pz_symbol_careful(PzCtx &c, PzStreamSmem *sm) {
   if (ds < 0) return -1;
   if (ds > 29) { pz_fail(c, PZ_REF_BOTTOM, PZ_D_BOT_DIST_SYM, ds); return -1; }
   if (!pz_take(c, sm, PZ_DIST_EXTRA[ds], ex)) return -1;
-  return pz_match<COUNT_ONLY>(c, len, PZ_DIST_BASE[ds] + ex) ? 1 : -1;
+  return pz_match<COUNT_ONLY>(c, sm, len, PZ_DIST_BASE[ds] + ex) ? 1 : -1;
 }
 
-/* ---- the hot loop (runInflate, Deflate.hs:106-120) ---------------------------------------
- * Every group in FAST mode decodes one symbol (a literal, or a length/distance pair with its
- * copy) per iteration.  The body is straight-line predicated code: the groups of a warp take
- * different "branches" (literal / match) in the same iteration, and a lone warp per scheduler
- * cannot afford branch latencies.  The bytes of a match are loaded in the iteration that
- * decodes it and stored one iteration later, so the L2 round trip of the copy overlaps the
- * decode of the next symbol; the stores precede the next iteration's loads in program order,
- * so no hazard analysis is needed.
+/* ---- the decoder's hot loop (runInflate, Deflate.hs:106-120) --------------------------------
+ * Every group in FAST mode decodes one symbol (a literal, or a length/distance pair) per
+ * iteration and pushes its token.  The body is straight-line predicated code: the groups of a
+ * warp take different "branches" (literal / match) in the same iteration, and a lone warp per
+ * scheduler cannot afford branch latencies.
  *
- * The loop ends as soon as ANY group of the warp meets something it must not decide here
- * (long code, end of block, end of input or output in sight, a verdict, an overlapping or very
- * long copy): that group has consumed nothing and sets need_careful.  Groups that are not in
- * FAST mode (no streams left) idle along. */
-#ifdef PZ_HOSTSIM
-PZ_DEV void pz_st8_if(bool p, uint8_t *a, uint32_t v) { if (p) *a = (uint8_t)v; }
-PZ_DEV uint32_t pz_ld8_if(bool p, const uint8_t *a, uint32_t old) { return p ? *a : old; }
-PZ_DEV void pz_syncwarp_all() {}
-#else
-/* The hot loop's global accesses are volatile asm WITHOUT a memory clobber: they keep their order
- * among themselves (which is all the copy semantics need), while the compiler stays free to
- * hoist the shared-memory table and window loads across them -- that freedom is what lets the
- * next symbol's look-ahead overlap this symbol's copy. */
-PZ_DEV void pz_st8_if(bool p, uint8_t *a, uint32_t v) {
-  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %0, 0;\n\t@q st.global.u8 [%1], %2;\n\t}" ::"r"((int)p), "l"(a), "r"(v));
-}
-PZ_DEV uint32_t pz_ld8_if(bool p, const uint8_t *a, uint32_t old) {
-  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t@q ld.global.u8 %0, [%2];\n\t}" : "+r"(old) : "r"((int)p), "l"(a));
-  return old;
-}
-/* warp barrier between the stores and the loads of one iteration (all 32 lanes are converged in
- * the hot loop); same ordering rule as above */
-PZ_DEV void pz_syncwarp_all() { asm volatile("bar.warp.sync 0xffffffff;"); }
-#endif
-
-/* The bytes of one match in flight: this lane owns bytes lane, lane+G, lane+2G, lane+3G. */
-struct PzPend {
-  uint8_t *dst;
-  int32_t rem;    /* len - lane, or <= 0 when the slot is empty */
-  uint32_t start; /* output position of the match; 0xffffffff when empty (same in every lane) */
-  uint32_t v0, v1, v2, v3;
-};
-PZ_DEV void pz_pend_clear(PzPend &p, uint8_t *any) { p.dst = any; p.rem = 0; p.start = 0xffffffffu; p.v0 = p.v1 = p.v2 = p.v3 = 0; }
-PZ_DEV void pz_pend_store(PzPend &p) {
-  pz_st8_if(p.rem > 0, p.dst, p.v0);
-  pz_st8_if(p.rem > PZ_G, p.dst + PZ_G, p.v1);
-  pz_st8_if(p.rem > 2 * PZ_G, p.dst + 2 * PZ_G, p.v2);
-  pz_st8_if(p.rem > 3 * PZ_G, p.dst + 3 * PZ_G, p.v3);
-  p.rem = 0; p.start = 0xffffffffu;
-}
-
+ * The bit-position chain (window -> LUT -> bits -> next window) is the only serial part, so the
+ * NEXT symbol's window and LUT entry are requested as soon as this symbol's bit count is
+ * known -- speculatively: if this symbol turns out to be one the loop must not decide, the loop
+ * ends and the look-ahead is dropped.
+ *
+ * The loop ends as soon as ANY group of the warp meets something it must not decide here (long
+ * code, end of block, end of input or output in sight, a verdict, a full token queue): that
+ * group has consumed nothing.  Groups that are not in FAST mode (no streams left) idle along. */
 struct PzFast { /* the registers of the hot loop */
-  uint32_t bp, pos, base, lim, safe_end;
+  uint32_t bp, pos, base, lim, safe_end, qhead, qtailc;
   uint32_t lo, hi, e; /* the 64-bit window at bp and its literal/length LUT entry (decoded ahead) */
-  uint8_t *out;
   bool live;
 };
 
@@ -556,17 +720,8 @@ PZ_DEV void pz_fast_fetch(PzFast &f, const PzStreamSmem *sm, uint32_t bp) {
   f.e = sm->lit_lut[f.lo & ((1u << PZ_LIT_BITS) - 1u)];
 }
 
-/* One iteration: returns this group's stop flag.  `mine` is the slot loaded PZ_DEPTH iterations
- * ago (stored now, then reloaded); o1/o2 are the younger matches still in flight.
- *
- * The bit-position chain (window -> LUT -> bits -> next window) is the only serial part, so the
- * NEXT symbol's window and LUT entry are requested as soon as this symbol's bit count is
- * known -- speculatively: if this symbol turns out to be one the loop must not decide, the loop
- * ends and the look-ahead is dropped -- and the copy/store work of this symbol is issued in the
- * shadow of those shared-memory loads. */
 template <bool COUNT_ONLY>
-PZ_DEV bool pz_fast_step(PzFast &f, PzCtx &c, PzStreamSmem *sm, PzPend &mine, PzPend &o1, PzPend &o2) {
-  const int32_t lane = pz_lane();
+PZ_DEV bool pz_fast_step(PzFast &f, PzCtx &c, PzStreamSmem *sm, bool &full) {
   const uint32_t lo = f.lo, e = f.e;
   const uint32_t tb = e & 31u;
   const bool is_lit = (int32_t)e < 0;
@@ -578,31 +733,26 @@ PZ_DEV bool pz_fast_step(PzFast &f, PzCtx &c, PzStreamSmem *sm, PzPend &mine, Pz
   const uint32_t len = (e >> 16) + ((lo & ~(0xffffffffu << tb)) >> ((e >> 8) & 15u));
   const uint32_t dist = (d >> 16) + ((wd & ~(0xffffffffu << tb2)) >> ((d >> 8) & 15u));
   const uint32_t room = f.lim - f.pos;
-  const bool pre_ok = f.live && f.bp <= f.safe_end && room != 0u;
-  const bool m_ok = !is_lit && tb != 0u && tb2 != 0u && dist <= f.pos - f.base && len <= room && dist >= len && len <= 4u * PZ_G;
-  const bool do_lit = pre_ok && is_lit;
-  const bool do_m = pre_ok && m_ok;
-  uint8_t *const nd = f.out + f.pos + lane;
+#ifdef PZ_HOSTSIM
+  full = false;
+#else
+  full = !COUNT_ONLY && f.qhead - f.qtailc >= PZ_QLEN;
+#endif
+  const bool pre_ok = f.live && f.bp <= f.safe_end && room != 0u && !full;
+  const bool m_ok = !is_lit && tb != 0u && tb2 != 0u && dist <= f.pos - f.base && len <= room;
+  const bool ok = pre_ok && (is_lit || m_ok);
   if (!COUNT_ONLY) {
-    pz_st8_if(do_lit && lane == 0, nd, e >> 16);
-    pz_pend_store(mine); /* its loads were issued PZ_DEPTH iterations ago */
-    /* a source that reaches into a match not yet stored: store everything first (rare) */
-    const uint32_t oldest = o1.start < o2.start ? o1.start : o2.start;
-    if (pz_warp_any(do_m && f.pos - dist + len > oldest)) { pz_pend_store(o1); pz_pend_store(o2); }
-    pz_syncwarp_all(); /* stores above are visible to the other lanes before the loads below */
-    const uint8_t *const ns = nd - dist;
-    mine.rem = do_m ? (int32_t)len - lane : 0;
-    mine.start = do_m ? f.pos : 0xffffffffu;
-    mine.dst = nd;
-    mine.v0 = pz_ld8_if(mine.rem > 0, ns, mine.v0);
-    mine.v1 = pz_ld8_if(mine.rem > PZ_G, ns + PZ_G, mine.v1);
-    mine.v2 = pz_ld8_if(mine.rem > 2 * PZ_G, ns + 2 * PZ_G, mine.v2);
-    mine.v3 = pz_ld8_if(mine.rem > 3 * PZ_G, ns + 3 * PZ_G, mine.v3);
+    const uint32_t tok = is_lit ? PZ_TOKEN(PZ_Q_LIT, (e >> 16) & 0xffu) : PZ_TOKEN(PZ_Q_MATCH, (len << 16) | (dist - 1u));
+#ifdef PZ_HOSTSIM
+    if (ok) pz_writer_apply(*c.hw, tok);
+#else
+    if (ok) pz_vstore(&sm->q[f.qhead & (PZ_QLEN - 1u)], tok | (((f.qhead >> PZ_QSHIFT) & 1u) << 31));
+    f.qhead += ok ? 1u : 0u;
+#endif
   }
-  const bool ok = do_lit || do_m;
   if (ok) f.bp = nbp;
-  f.pos += do_lit ? 1u : (do_m ? len : 0u);
-  if (do_m && f.pos - f.base >= 2u * PZ_EXCESS) f.base += PZ_EXCESS; /* moveWindow after every match */
+  f.pos += ok ? (is_lit ? 1u : len) : 0u;
+  if (ok && !is_lit && f.pos - f.base >= 2u * PZ_EXCESS) f.base += PZ_EXCESS; /* moveWindow after every match */
   if (f.live && (f.bp >> PZ_QUARTER_SHIFT) != c.q) { c.bp = f.bp; pz_cross(c, sm); }
   return f.live && !ok;
 }
@@ -611,33 +761,23 @@ template <bool COUNT_ONLY>
 PZ_DEV void pz_fast_loop(PzCtx &c, PzStreamSmem *sm) {
   PzFast f;
   f.live = c.mode == PZ_M_FAST;
-  f.bp = c.bp; f.pos = c.pos; f.base = c.base; f.safe_end = c.safe_end; f.out = c.out;
+  f.bp = c.bp; f.pos = c.pos; f.base = c.base; f.safe_end = c.safe_end;
+  f.qhead = c.qhead; f.qtailc = c.qtailc;
   /* first position this run may not write at: a stale `base` only makes it conservative */
   f.lim = f.base + PZ_WINDOW;
   if (c.cap < f.lim) f.lim = c.cap;
   pz_fast_fetch(f, sm, f.bp);
-  PzPend p0, p1, p2;
-  pz_pend_clear(p0, f.out); pz_pend_clear(p1, f.out); pz_pend_clear(p2, f.out);
-  bool stop;
+  bool stop, full;
   for (;;) {
-    stop = pz_fast_step<COUNT_ONLY>(f, c, sm, p0, p1, p2);
+    stop = pz_fast_step<COUNT_ONLY>(f, c, sm, full);
     if (pz_warp_any(stop)) break;
-    stop = pz_fast_step<COUNT_ONLY>(f, c, sm, p1, p2, p0);
+    stop = pz_fast_step<COUNT_ONLY>(f, c, sm, full);
     if (pz_warp_any(stop)) break;
-    stop = pz_fast_step<COUNT_ONLY>(f, c, sm, p2, p0, p1);
-    if (pz_warp_any(stop)) break;
-  }
-  if (!COUNT_ONLY) {
-    pz_pend_store(p0); pz_pend_store(p1); pz_pend_store(p2);
-    pz_syncwarp_all();
-#ifndef PZ_HOSTSIM
-    __syncwarp(); /* and a compiler-level fence before the careful path's plain accesses */
-#endif
   }
   if (f.live) {
-    c.bp = f.bp; c.pos = f.pos; c.base = f.base;
+    c.bp = f.bp; c.pos = f.pos; c.base = f.base; c.qhead = f.qhead;
     c.mode = PZ_M_SYMS;
-    c.need_careful = stop;
+    c.need_careful = stop && !full; /* a full queue is not the symbol's fault */
   }
 }
 
@@ -722,11 +862,9 @@ PZ_DEV bool pz_stored_block(PzCtx &c, PzStreamSmem *sm) {
   uint32_t fill = c.pos - c.base;
   if (fill + len > PZ_WINDOW) { pz_fail(c, PZ_REF_BOTTOM, PZ_D_BOT_WINDOW_OVERFLOW); return false; }
   if (len > c.cap - c.pos) { pz_fail(c, PZ_OUTPUT_FULL, 0); return false; }
-  if (!COUNT_ONLY) {
-    const uint8_t *src = c.in_al + boff;
-    uint8_t *dst = c.out + c.pos;
-    for (uint32_t i = (uint32_t)pz_lane(); i < len; i += PZ_G) dst[i] = src[i];
-  }
+  pz_push<COUNT_ONLY>(c, sm, PZ_TOKEN(PZ_Q_CTRL, PZ_C_STORED << 26));
+  pz_push<COUNT_ONLY>(c, sm, boff - (c.start_bit >> 3)); /* offset from the stream's first byte */
+  pz_push<COUNT_ONLY>(c, sm, len);
   c.pos += len;
   pz_seek(c, sm, (boff + len) * 8u);
   return true;
@@ -753,11 +891,11 @@ PZ_DEV void pz_finish(PzCtx &c) {
 }
 
 /* `decompress` for one single-chunk stream starts here: inflateWithHeaders (Zlib.hs:53-69). */
-PZ_DEV void pz_begin(PzCtx &c, PzStreamSmem *sm, const uint8_t *in, uint64_t in_len, uint8_t *out, uint64_t out_cap, pz_result *res) {
+template <bool COUNT_ONLY>
+PZ_DEV void pz_begin(PzCtx &c, PzStreamSmem *sm, uint32_t s, const uint8_t *in, uint64_t in_len, uint64_t out_cap, pz_result *res) {
   uint32_t mis = (uint32_t)((uintptr_t)in & 15u);
   c.in_al = in - mis;
   c.res = res;
-  c.out = out;
   c.pos = 0; c.base = 0;
   c.cap = out_cap > 0xfffdff00ull ? 0xfffdff00u : (uint32_t)out_cap; /* base + 128 KiB stays in 32 bits */
   c.status = PZ_OK; c.detail = 0; c.p0 = 0; c.p1 = 0;
@@ -772,6 +910,9 @@ PZ_DEV void pz_begin(PzCtx &c, PzStreamSmem *sm, const uint8_t *in, uint64_t in_
   c.in_al_bytes = (mis + (uint32_t)in_len + 15u) & ~15u;
   c.end_bit = (mis + (uint32_t)in_len) * 8u;
   c.safe_end = c.end_bit >= PZ_STEP_BITS ? c.end_bit - PZ_STEP_BITS : 0u; /* bp >= 16 once the header is read */
+  /* the writer switches to this stream's output slice */
+  pz_push<COUNT_ONLY>(c, sm, PZ_TOKEN(PZ_Q_CTRL, PZ_C_NEWSTREAM << 26));
+  pz_push<COUNT_ONLY>(c, sm, s);
   pz_seek(c, sm, c.start_bit);
   uint32_t cmf, flg;
   bool ok = pz_take(c, sm, 8, cmf) && pz_take(c, sm, 8, flg);
@@ -805,15 +946,19 @@ PZ_DEV void pz_block_end(PzCtx &c, PzStreamSmem *sm) {
 template <bool COUNT_ONLY>
 PZ_DEV void pz_slow_step(PzCtx &c, PzStreamSmem *sm, const PzJob &job, uint32_t stride) {
   if (c.mode == PZ_M_IDLE) {
-    if (c.next >= job.first + job.count) { c.mode = PZ_M_DEAD; return; }
+    if (c.next >= job.first + job.count) {
+      pz_push<COUNT_ONLY>(c, sm, PZ_TOKEN(PZ_Q_CTRL, PZ_C_EXIT << 26));
+      c.mode = PZ_M_DEAD;
+      return;
+    }
     const uint32_t s = c.next;
     c.next += stride;
     const uint64_t i0 = job.in_off[s], i1 = job.in_off[s + 1];
     if (COUNT_ONLY) {
-      pz_begin(c, sm, job.in_blob + i0, i1 - i0, nullptr, ~0ull, job.res + s);
+      pz_begin<true>(c, sm, s, job.in_blob + i0, i1 - i0, ~0ull, job.res + s);
     } else {
       const uint64_t o0 = job.out_off[s], o1 = job.out_off[s + 1];
-      pz_begin(c, sm, job.in_blob + i0, i1 - i0, job.out_blob + o0, o1 - o0, job.res + s);
+      pz_begin<false>(c, sm, s, job.in_blob + i0, i1 - i0, o1 - o0, job.res + s);
     }
   } else if (c.mode == PZ_M_HDR) { /* inflateBlock (Deflate.hs:65-104) */
     uint32_t btype;
@@ -836,7 +981,17 @@ PZ_DEV void pz_slow_step(PzCtx &c, PzStreamSmem *sm, const PzJob &job, uint32_t 
     if (!c.need_careful) {
       uint32_t lim = c.base + PZ_WINDOW;
       if (c.cap < lim) lim = c.cap;
-      if (c.bp <= c.safe_end && c.pos < lim) { c.mode = PZ_M_FAST; return; }
+      if (c.bp <= c.safe_end && c.pos < lim) {
+#ifndef PZ_HOSTSIM
+        /* enter the hot loop with room for a few tokens */
+        while (!COUNT_ONLY && c.qhead - c.qtailc > PZ_QLEN - 8u) {
+          c.qtailc = pz_vload(&sm->qtail);
+          if (c.qhead - c.qtailc > PZ_QLEN - 8u) pz_backoff();
+        }
+#endif
+        c.mode = PZ_M_FAST;
+        return;
+      }
     }
     c.need_careful = false;
     int r = pz_symbol_careful<COUNT_ONLY>(c, sm);
@@ -845,13 +1000,22 @@ PZ_DEV void pz_slow_step(PzCtx &c, PzStreamSmem *sm, const PzJob &job, uint32_t 
   }
 }
 
-/* All the streams of one group: streams first_stream, first_stream + stride, ... of the job. */
+/* The decoder warp: every group decodes streams first_stream, first_stream + stride, ... of the
+ * job (first_stream differs per group). */
 template <bool COUNT_ONLY>
-PZ_DEV void pz_inflate_group(const PzJob &job, uint32_t first_stream, uint32_t stride, PzStreamSmem *sm) {
+PZ_DEV void pz_decoder_warp(const PzJob &job, uint32_t first_stream, uint32_t stride, PzStreamSmem *sm
+#ifdef PZ_HOSTSIM
+                            , PzWriter *hw
+#endif
+) {
   PzCtx c;
   c.mode = PZ_M_IDLE;
   c.next = first_stream;
   c.in_al = nullptr; c.in_al_bytes = 0; c.bp = 0; c.q = 0; c.res = nullptr;
+  c.qhead = 0; c.qtailc = 0;
+#ifdef PZ_HOSTSIM
+  c.hw = hw;
+#endif
   for (;;) {
     while (c.mode != PZ_M_FAST && c.mode != PZ_M_DEAD) pz_slow_step<COUNT_ONLY>(c, sm, job, stride);
     if (!pz_warp_any(c.mode == PZ_M_FAST)) break; /* every group of the warp is out of streams */

@@ -8,8 +8,8 @@
 #ifndef PZ_GROUP
 #define PZ_GROUP 8 /* lanes per stream (pz_device.cuh) */
 #endif
-#define PZ_WARPS_PER_CTA 1
-#define PZ_GROUPS_PER_CTA (PZ_WARPS_PER_CTA * 32 / PZ_GROUP)
+#define PZ_THREADS_PER_CTA 64 /* decoder warp + writer warp */
+#define PZ_GROUPS_PER_CTA (32 / PZ_GROUP) /* streams a CTA works on at a time */
 #define PZ_MAX_STREAM_BYTES 0x1ffffff0ull /* == PZ_MAX_IN_BYTES in pz_device.cuh */
 #define PZ_ADLER_SEG 16384u /* bytes per checksum segment (one warp each) */
 

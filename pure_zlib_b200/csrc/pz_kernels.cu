@@ -1,8 +1,8 @@
 /*
  * pz_kernels.cu -- the sm_100a kernels of libpzcuda.so.
  *
- *   pz_inflate_kernel        K1: persistent CTAs, PZ_G lanes per zlib stream, 32/PZ_G streams
- *                            advancing in lockstep per warp (pz_device.cuh)
+ *   pz_inflate_kernel        K1: persistent CTAs of a decoder warp + a writer warp; PZ_G lanes per
+ *                            zlib stream, 32/PZ_G streams advancing in lockstep (pz_device.cuh)
  *   pz_adler_partial_kernel  K3a: one warp per 16 KiB segment of decoded output, dp4a sums
  *   pz_adler_finish_kernel   K3b: per stream, combines the segments (adler32-combine
  *                            identity) and compares with the stored trailer
@@ -12,15 +12,25 @@
 #include "pz_internal.h"
 
 template <bool COUNT_ONLY>
-__global__ void __launch_bounds__(PZ_WARPS_PER_CTA * 32)
+__global__ void __launch_bounds__(PZ_THREADS_PER_CTA, 7)
 pz_inflate_kernel(const PzJob job) {
   extern __shared__ __align__(16) unsigned char pz_smem_raw[];
-  const uint32_t g = threadIdx.x / PZ_G; /* group within the CTA */
-  PzStreamSmem *sm = reinterpret_cast<PzStreamSmem *>(pz_smem_raw) + g;
-  /* persistent groups: group gid takes streams gid, gid + stride, ... */
-  const uint32_t gid = blockIdx.x * PZ_GROUPS_PER_CTA + g;
-  const uint32_t stride = gridDim.x * PZ_GROUPS_PER_CTA;
-  pz_inflate_group<COUNT_ONLY>(job, job.first + gid, stride, sm);
+  PzStreamSmem *slots = reinterpret_cast<PzStreamSmem *>(pz_smem_raw);
+  /* empty token queues: every slot carries the phase the reader does NOT expect on lap 0 */
+  for (uint32_t i = threadIdx.x; i < PZ_GROUPS_PER_CTA * PZ_QLEN; i += PZ_THREADS_PER_CTA)
+    slots[i / PZ_QLEN].q[i % PZ_QLEN] = 0x80000000u;
+  if (threadIdx.x < PZ_GROUPS_PER_CTA) slots[threadIdx.x].qtail = 0;
+  __syncthreads();
+  const uint32_t g = (threadIdx.x & 31u) / PZ_G; /* group within the warp = stream slot of the CTA */
+  PzStreamSmem *sm = slots + g;
+  if (threadIdx.x < 32u) {
+    /* persistent groups: group gid takes streams gid, gid + stride, ... */
+    const uint32_t gid = blockIdx.x * PZ_GROUPS_PER_CTA + g;
+    const uint32_t stride = gridDim.x * PZ_GROUPS_PER_CTA;
+    pz_decoder_warp<COUNT_ONLY>(job, job.first + gid, stride, sm);
+  } else if (!COUNT_ONLY) {
+    pz_writer_warp(job, sm);
+  }
 }
 
 /* ---- Adler-32 (Adler32.hs:17-57) as a segmented reduction ------------------------------
@@ -138,9 +148,9 @@ cudaError_t pz_kernels_configure(void) {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(pz_inflate_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return e;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_inflate_ctas_per_sm[0], pz_inflate_kernel<false>, PZ_WARPS_PER_CTA * 32, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_inflate_ctas_per_sm[0], pz_inflate_kernel<false>, PZ_THREADS_PER_CTA, smem);
   if (e != cudaSuccess) return e;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_inflate_ctas_per_sm[1], pz_inflate_kernel<true>, PZ_WARPS_PER_CTA * 32, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_inflate_ctas_per_sm[1], pz_inflate_kernel<true>, PZ_THREADS_PER_CTA, smem);
   if (e != cudaSuccess) return e;
   if (g_inflate_ctas_per_sm[0] < 1 || g_inflate_ctas_per_sm[1] < 1) return cudaErrorLaunchOutOfResources;
   return cudaSuccess;
@@ -159,9 +169,9 @@ cudaError_t pz_launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uin
   job.in_blob = d_in; job.in_off = d_in_off; job.out_blob = d_out; job.out_off = d_out_off; job.res = d_res;
   job.first = first; job.count = count;
   if (count_only)
-    pz_inflate_kernel<true><<<grid, PZ_WARPS_PER_CTA * 32, smem, st>>>(job);
+    pz_inflate_kernel<true><<<grid, PZ_THREADS_PER_CTA, smem, st>>>(job);
   else
-    pz_inflate_kernel<false><<<grid, PZ_WARPS_PER_CTA * 32, smem, st>>>(job);
+    pz_inflate_kernel<false><<<grid, PZ_THREADS_PER_CTA, smem, st>>>(job);
   return cudaGetLastError();
 }
 

@@ -26,8 +26,10 @@ extern "C" int hs_inflate(const uint8_t *in, uint64_t in_len, uint8_t *out, uint
   PzJob job;
   job.in_blob = buf + mis; job.in_off = in_off; job.out_blob = count_only ? nullptr : out; job.out_off = out_off;
   job.res = res; job.first = 0; job.count = 1;
-  if (count_only) pz_inflate_group<true>(job, 0, 1, sm);
-  else pz_inflate_group<false>(job, 0, 1, sm);
+  PzWriter hw; /* tokens are applied as they are pushed */
+  pz_writer_init(hw, &job);
+  if (count_only) pz_decoder_warp<true>(job, 0, 1, sm, &hw);
+  else pz_decoder_warp<false>(job, 0, 1, sm, &hw);
   free(sm);
   free(buf);
   return 0;

@@ -563,7 +563,7 @@ PZ_DEV void pz_writer_warp(const PzJob &job, PzStreamSmem *sm) {
   PzWriter w;
   pz_writer_init(w, &job);
   const int32_t lane = pz_lane();
-  uint32_t tail = 0;
+  uint32_t tail = 0, naps = 0;
   for (;;) {
     pz_syncwarp_all(); /* the previous trip's stores are visible to the other lanes' loads */
     uint32_t raw[PZ_WB];
@@ -575,6 +575,13 @@ PZ_DEV void pz_writer_warp(const PzJob &job, PzStreamSmem *sm) {
       const bool valid = !w.exited && (r >> 31) == ((tail >> PZ_QSHIFT) & 1u);
       const bool fast = w.need == 0u && (type == PZ_Q_LIT || (type == PZ_Q_MATCH && dist >= len && len <= 4u * PZ_G));
       const bool slow = valid && !fast;
+      /* A trip costs the same whether it moves one token or PZ_WB per group, and the decoder
+       * warps need the issue slots: unless some group has a full batch (or a token for the
+       * general path) waiting, sleep a little -- but never for long. */
+      const uint32_t rl = raw[PZ_WB - 1];
+      const bool full_batch = !w.exited && (rl >> 31) == (((tail + PZ_WB - 1u) >> PZ_QSHIFT) & 1u);
+      if (naps < 8u && !pz_warp_any(full_batch || slow)) { naps++; __nanosleep(200); continue; }
+      naps = 0;
       if (pz_warp_any(slow)) {
         if (slow) {
           pz_writer_apply(w, r & 0x7fffffffu);
@@ -706,13 +713,17 @@ PZ_DEV int pz_symbol_careful(PzCtx &c, PzStreamSmem *sm) {
  * known -- speculatively: if this symbol turns out to be one the loop must not decide, the loop
  * ends and the look-ahead is dropped.
  *
- * The loop ends as soon as ANY group of the warp meets something it must not decide here (long
- * code, end of block, end of input or output in sight, a verdict, a full token queue): that
- * group has consumed nothing.  Groups that are not in FAST mode (no streams left) idle along. */
+ * The loop ends (at the end of a four-symbol trip) once ANY group of the warp has met something
+ * it must not decide here (long code, end of block, end of input or output in sight, a verdict,
+ * a full token queue): that group consumed nothing of it.  Groups that are not in FAST mode (no
+ * streams left) idle along. */
 struct PzFast { /* the registers of the hot loop */
   uint32_t bp, pos, base, lim, safe_end, qhead, qtailc;
   uint32_t lo, hi, e; /* the 64-bit window at bp and its literal/length LUT entry (decoded ahead) */
   bool live;
+#ifdef PZ_HOSTSIM
+  PzWriter *hw;
+#endif
 };
 
 PZ_DEV void pz_fast_fetch(PzFast &f, const PzStreamSmem *sm, uint32_t bp) {
@@ -721,7 +732,7 @@ PZ_DEV void pz_fast_fetch(PzFast &f, const PzStreamSmem *sm, uint32_t bp) {
 }
 
 template <bool COUNT_ONLY>
-PZ_DEV bool pz_fast_step(PzFast &f, PzCtx &c, PzStreamSmem *sm, bool &full) {
+PZ_DEV bool pz_fast_step(PzFast &f, PzStreamSmem *sm, bool &full) {
   const uint32_t lo = f.lo, e = f.e;
   const uint32_t tb = e & 31u;
   const bool is_lit = (int32_t)e < 0;
@@ -729,6 +740,7 @@ PZ_DEV bool pz_fast_step(PzFast &f, PzCtx &c, PzStreamSmem *sm, bool &full) {
   const uint32_t d = sm->dist_lut[wd & ((1u << PZ_DIST_BITS) - 1u)];
   const uint32_t tb2 = d & 31u;
   const uint32_t nbp = f.bp + (is_lit ? tb : tb + tb2);
+  const uint32_t hi0 = f.hi;
   pz_fast_fetch(f, sm, nbp); /* look-ahead */
   const uint32_t len = (e >> 16) + ((lo & ~(0xffffffffu << tb)) >> ((e >> 8) & 15u));
   const uint32_t dist = (d >> 16) + ((wd & ~(0xffffffffu << tb2)) >> ((d >> 8) & 15u));
@@ -744,16 +756,16 @@ PZ_DEV bool pz_fast_step(PzFast &f, PzCtx &c, PzStreamSmem *sm, bool &full) {
   if (!COUNT_ONLY) {
     const uint32_t tok = is_lit ? PZ_TOKEN(PZ_Q_LIT, (e >> 16) & 0xffu) : PZ_TOKEN(PZ_Q_MATCH, (len << 16) | (dist - 1u));
 #ifdef PZ_HOSTSIM
-    if (ok) pz_writer_apply(*c.hw, tok);
+    if (ok) pz_writer_apply(*f.hw, tok);
 #else
     if (ok) pz_vstore(&sm->q[f.qhead & (PZ_QLEN - 1u)], tok | (((f.qhead >> PZ_QSHIFT) & 1u) << 31));
     f.qhead += ok ? 1u : 0u;
 #endif
   }
   if (ok) f.bp = nbp;
+  else { f.lo = lo; f.hi = hi0; f.e = e; } /* a stopped group stays put until the trip ends */
   f.pos += ok ? (is_lit ? 1u : len) : 0u;
   if (ok && !is_lit && f.pos - f.base >= 2u * PZ_EXCESS) f.base += PZ_EXCESS; /* moveWindow after every match */
-  if (f.live && (f.bp >> PZ_QUARTER_SHIFT) != c.q) { c.bp = f.bp; pz_cross(c, sm); }
   return f.live && !ok;
 }
 
@@ -763,15 +775,22 @@ PZ_DEV void pz_fast_loop(PzCtx &c, PzStreamSmem *sm) {
   f.live = c.mode == PZ_M_FAST;
   f.bp = c.bp; f.pos = c.pos; f.base = c.base; f.safe_end = c.safe_end;
   f.qhead = c.qhead; f.qtailc = c.qtailc;
+#ifdef PZ_HOSTSIM
+  f.hw = c.hw;
+#endif
   /* first position this run may not write at: a stale `base` only makes it conservative */
   f.lim = f.base + PZ_WINDOW;
   if (c.cap < f.lim) f.lim = c.cap;
   pz_fast_fetch(f, sm, f.bp);
   bool stop, full;
   for (;;) {
-    stop = pz_fast_step<COUNT_ONLY>(f, c, sm, full);
-    if (pz_warp_any(stop)) break;
-    stop = pz_fast_step<COUNT_ONLY>(f, c, sm, full);
+    /* four symbols per trip: one vote and one ring check (4 x 48 bits stay inside the resident
+     * quarters); a group that stops early repeats its verdict until the trip ends */
+    pz_fast_step<COUNT_ONLY>(f, sm, full);
+    pz_fast_step<COUNT_ONLY>(f, sm, full);
+    pz_fast_step<COUNT_ONLY>(f, sm, full);
+    stop = pz_fast_step<COUNT_ONLY>(f, sm, full);
+    if (f.live && (f.bp >> PZ_QUARTER_SHIFT) != c.q) { c.bp = f.bp; pz_cross(c, sm); }
     if (pz_warp_any(stop)) break;
   }
   if (f.live) {

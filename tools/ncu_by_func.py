@@ -52,5 +52,5 @@ for title, pick in (("innermost function", lambda fs: fs[0]),
         agg[f][0] += int(r[sm]); agg[f][1] += int(r[ie])
     ts = sum(v[0] for v in agg.values()); ti = sum(v[1] for v in agg.values())
     print("--", title)
-    for f, (s_, n) in sorted(agg.items(), key=lambda x: -x[1][0])[:16]:
+    for f, (s_, n) in sorted(agg.items(), key=lambda x: -x[1][0])[:40]:
         print(f"{f:28s} samples {s_/ts:6.2%}  instr {n/ti:6.2%}")

@@ -193,7 +193,7 @@ pz_batch *pz_batch_create(const uint64_t *in_off, const uint64_t *out_off, size_
     }
   }
   if (e != cudaSuccess) { fail_cuda(e, "pz_batch_create"); pz_batch_destroy(b); return nullptr; }
-  b->launches = 1 + ((count_only || (flags & PZ_F_NO_ADLER)) ? 0 : (b->total_segs ? 2 : 1));
+  b->launches = (count_only ? 1 : 3) + ((count_only || (flags & PZ_F_NO_ADLER)) ? 0 : (b->total_segs ? 2 : 1)); /* K2 probe + K2 copy + K1, then K3a + K3b */
   return b;
 }
 

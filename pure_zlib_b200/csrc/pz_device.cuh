@@ -181,7 +181,9 @@ struct PzJob {
   const uint64_t *out_off;
   pz_result *res;
   uint32_t first, count; /* streams [first, first+count) */
+  uint32_t skip_done;    /* res[s].status != PZ_ST_PENDING: the stored-stream kernels dealt with s */
 };
+#define PZ_ST_PENDING (-1)
 
 /* ---- per-stream decoder state (registers; identical in every lane of the group) -------- */
 enum PzMode { PZ_M_IDLE = 0, PZ_M_HDR = 1, PZ_M_SYMS = 2, PZ_M_FAST = 3, PZ_M_DEAD = 4 };
@@ -918,7 +920,8 @@ PZ_DEV void pz_begin(PzCtx &c, PzStreamSmem *sm, uint32_t s, const uint8_t *in, 
   c.pos = 0; c.base = 0;
   c.cap = out_cap > 0xfffdff00ull ? 0xfffdff00u : (uint32_t)out_cap; /* base + 128 KiB stays in 32 bits */
   c.status = PZ_OK; c.detail = 0; c.p0 = 0; c.p1 = 0;
-  c.adler_stored = 0; c.bfinal = 0; c.fixed_ready = false; c.need_careful = false;
+  c.adler_stored = 0; c.bfinal = 0; c.need_careful = false;
+  /* c.fixed_ready survives: the fixed-code LUTs stay valid until a dynamic header overwrites them */
   c.start_bit = mis * 8u;
   if (in_len > PZ_MAX_IN_BYTES) { /* the C ABI refuses such streams before launching */
     c.in_al_bytes = 0; c.end_bit = c.start_bit; c.safe_end = 0; c.bp = c.start_bit; c.q = 0;
@@ -965,6 +968,7 @@ PZ_DEV void pz_block_end(PzCtx &c, PzStreamSmem *sm) {
 template <bool COUNT_ONLY>
 PZ_DEV void pz_slow_step(PzCtx &c, PzStreamSmem *sm, const PzJob &job, uint32_t stride) {
   if (c.mode == PZ_M_IDLE) {
+    while (job.skip_done && c.next < job.first + job.count && job.res[c.next].status != PZ_ST_PENDING) c.next += stride;
     if (c.next >= job.first + job.count) {
       pz_push<COUNT_ONLY>(c, sm, PZ_TOKEN(PZ_Q_CTRL, PZ_C_EXIT << 26));
       c.mode = PZ_M_DEAD;
@@ -1032,6 +1036,7 @@ PZ_DEV void pz_decoder_warp(const PzJob &job, uint32_t first_stream, uint32_t st
   c.next = first_stream;
   c.in_al = nullptr; c.in_al_bytes = 0; c.bp = 0; c.q = 0; c.res = nullptr;
   c.qhead = 0; c.qtailc = 0;
+  c.fixed_ready = false;
 #ifdef PZ_HOSTSIM
   c.hw = hw;
 #endif

@@ -3,6 +3,8 @@
  *
  *   pz_inflate_kernel        K1: persistent CTAs of a decoder warp + a writer warp; PZ_G lanes per
  *                            zlib stream, 32/PZ_G streams advancing in lockstep (pz_device.cuh)
+ *   pz_stored_probe_kernel,  K2: streams made of stored blocks only are copied with 16-byte
+ *   pz_stored_copy_kernel    accesses by whole CTAs before K1 runs (pz_stored.cuh)
  *   pz_adler_partial_kernel  K3a: one warp per 16 KiB segment of decoded output, dp4a sums
  *   pz_adler_finish_kernel   K3b: per stream, combines the segments (adler32-combine
  *                            identity) and compares with the stored trailer
@@ -10,6 +12,7 @@
  */
 #include "pz_device.cuh"
 #include "pz_internal.h"
+#include "pz_stored.cuh"
 
 template <bool COUNT_ONLY>
 __global__ void __launch_bounds__(PZ_THREADS_PER_CTA, 7)
@@ -178,11 +181,19 @@ cudaError_t pz_launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uin
   const size_t smem = sizeof(PzStreamSmem) * PZ_GROUPS_PER_CTA;
   PzJob job;
   job.in_blob = d_in; job.in_off = d_in_off; job.out_blob = d_out; job.out_off = d_out_off; job.res = d_res;
-  job.first = first; job.count = count;
-  if (count_only)
+  job.first = first; job.count = count; job.skip_done = count_only ? 0u : 1u;
+  if (count_only) {
     pz_inflate_kernel<true><<<grid, PZ_THREADS_PER_CTA, smem, st>>>(job);
-  else
+  } else {
+    /* K2 first: all-stored streams are copied at memory speed and marked done; K1 takes the rest */
+    pz_stored_probe_kernel<<<(count + 255u) / 256u, 256, 0, st>>>(job);
+    const unsigned ctas = (unsigned)g_sm_count * 4u;
+    unsigned tile = count / (ctas * 4u);
+    tile = tile < 1u ? 1u : (tile > PZ_ST_THREADS ? PZ_ST_THREADS : tile);
+    const unsigned tiles = (count + tile - 1u) / tile;
+    pz_stored_copy_kernel<<<tiles < ctas ? tiles : ctas, PZ_ST_THREADS, 0, st>>>(job, tile);
     pz_inflate_kernel<false><<<grid, PZ_THREADS_PER_CTA, smem, st>>>(job);
+  }
   return cudaGetLastError();
 }
 

@@ -97,11 +97,12 @@ PZ_DEV void pz_async_wait_all() {
 
 /* ---- geometry ------------------------------------------------------------------------ */
 #define PZ_LIT_BITS 10  /* first-level bits of the literal/length LUT */
-#define PZ_DIST_BITS 8  /* first-level bits of the distance LUT        */
+#define PZ_DIST_BITS 9  /* first-level bits of the distance LUT        */
 #define PZ_PRE_BITS 7   /* the code-length code never exceeds 7 bits    */
-#define PZ_RING_WORDS 256u /* staged input: four 256-byte quarters       */
-#define PZ_QUARTER_WORDS 64u
-#define PZ_QUARTER_SHIFT 11 /* log2(bits per quarter) */
+#define PZ_RING_WORDS 128u /* staged input: four 128-byte quarters       */
+#define PZ_QUARTER_WORDS 32u
+#define PZ_QUARTER_BYTES 128u
+#define PZ_QUARTER_SHIFT 10 /* log2(bits per quarter) */
 #define PZ_MAX_LENS 464 /* 288 + 32 + 137 overshoot (Deflate.hs:124-156), padded */
 #define PZ_WINDOW 131072u /* OutputWindow.hs:29-30 */
 #define PZ_EXCESS 32768u  /* OutputWindow.hs:42-43 */
@@ -130,6 +131,10 @@ PZ_DEV void pz_async_wait_all() {
 #define PZ_ENTRY(total, nbits, type, value) ((uint32_t)(total) | ((uint32_t)(nbits) << 8) | ((uint32_t)(type) << 12) | ((uint32_t)(value) << 16))
 #define PZ_SLOW_ENTRY PZ_ENTRY(0, 0, PZ_T_SLOW, 0)
 #define PZ_LIT_FLAG 0x80000000u
+/* Distance LUT entry (16 bits): total bits [0,5) | code bits [5,9) | extra bits [9,13) | m [13,15);
+ * distance = 1 + (m << extra) + extra-bit value (Deflate.hs:199-237: symbols 0,1 have m = 0,1 and
+ * every later pair of symbols m = 2,3).  0 = not for the hot loop. */
+#define PZ_DENTRY(nbits, extra, m) ((uint32_t)((nbits) + (extra)) | ((uint32_t)(nbits) << 5) | ((uint32_t)(extra) << 9) | ((uint32_t)(m) << 13))
 
 /* Canonical description of one prefix code: enough for the bit-serial walker to reproduce
  * the reference trie's accept / "Advanced to empty tree!" behaviour (HuffmanTree.hs:73-83). */
@@ -143,7 +148,7 @@ struct PzTree {
 /* Shared memory of one stream (one group). */
 struct __attribute__((aligned(16))) PzStreamSmem {
   uint32_t lit_lut[1 << PZ_LIT_BITS];
-  uint32_t dist_lut[1 << PZ_DIST_BITS]; /* the precode LUT aliases its first 128 entries */
+  uint16_t dist_lut[1 << PZ_DIST_BITS]; /* compact entries; the 128-entry 32-bit precode LUT aliases it */
   uint32_t ring[PZ_RING_WORDS + 4];     /* + a copy of words 0..3 so that ring[i+1] never wraps */
   uint32_t scratch[32]; /* [0,16) per-length counters, [16,32) per-length offsets */
   uint16_t lit_perm[288];
@@ -155,8 +160,11 @@ struct __attribute__((aligned(16))) PzStreamSmem {
   uint32_t qtail;      /* tokens consumed so far: written by the writer, read by the decoder */
 };
 /* 4 streams per CTA and 7 CTAs per SM only fit if a CTA stays within 32256 bytes (228 KiB per SM,
- * 1 KiB reserved per resident CTA, 256-byte allocation granules): 8064 bytes per stream. */
+ * 1 KiB reserved per resident CTA, 256-byte allocation granules): 8064 bytes per stream.  (With
+ * 4-lane groups -- 8 streams per CTA, 4 CTAs per SM -- the limit would be 7168; measured slower:
+ * twice the groups per warp means twice the shared-memory bank conflicts and loop exits.) */
 static_assert(sizeof(PzStreamSmem) <= 8064, "PzStreamSmem no longer fits 28 streams per SM");
+static_assert(sizeof(uint16_t) * (1 << PZ_DIST_BITS) >= sizeof(uint32_t) * (1 << PZ_PRE_BITS), "precode LUT must fit the distance LUT");
 
 #ifdef PZ_HOSTSIM
 static const uint16_t PZ_LEN_BASE[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
@@ -222,12 +230,12 @@ PZ_DEV void pz_fail(PzCtx &c, int status, int detail, int64_t p0 = 0, int64_t p1
 }
 
 /* ---- staged input ---------------------------------------------------------------------
- * Quarter k = bytes [256k, 256k+256) of in_al, staged into ring slot (k & 3) with cp.async
+ * Quarter k = bytes [128k, 128k+128) of in_al, staged into ring slot (k & 3) with cp.async
  * (16 bytes per request).  Invariant: quarters q and q+1 are resident, q+2 is in flight. */
 PZ_DEV void pz_ring_issue(PzCtx &c, PzStreamSmem *sm, uint32_t k) {
   uint32_t *dst = sm->ring + (k & 3u) * PZ_QUARTER_WORDS;
-  for (uint32_t p = (uint32_t)pz_lane(); p < 16u; p += PZ_G) {
-    uint32_t bo = k * 256u + p * 16u;
+  for (uint32_t p = (uint32_t)pz_lane(); p < PZ_QUARTER_BYTES / 16u; p += PZ_G) {
+    uint32_t bo = k * PZ_QUARTER_BYTES + p * 16u;
     if (bo < c.in_al_bytes) {
       pz_copy16_async(dst + p * 4u, c.in_al + bo);
       if (((k & 3u) | p) == 0u) pz_copy16_async(sm->ring + PZ_RING_WORDS, c.in_al + bo);
@@ -317,8 +325,8 @@ PZ_DEV uint32_t pz_make_entry(uint32_t sym, uint32_t nbits) {
     if (sym > 285u) return PZ_SLOW_ENTRY;  /* lengthArray ! 286/287 is a bounds error */
     return PZ_ENTRY(nbits + PZ_LEN_EXTRA[sym - 257u], nbits, PZ_T_BASE, PZ_LEN_BASE[sym - 257u]);
   }
-  if (sym > 29u) return PZ_SLOW_ENTRY; /* distanceArray ! >=30 is a bounds error */
-  return PZ_ENTRY(nbits + PZ_DIST_EXTRA[sym], nbits, PZ_T_BASE, PZ_DIST_BASE[sym]);
+  if (sym > 29u) return 0u; /* distanceArray ! >=30 is a bounds error */
+  return PZ_DENTRY(nbits, PZ_DIST_EXTRA[sym], sym < 2u ? sym : 2u + (sym & 1u));
 }
 
 /* computeCodeValues (Deflate.hs:261-288) from the sorted symbol list: codes[s] for every
@@ -378,8 +386,8 @@ PZ_DEV int pz_tree_error(const uint8_t *lens, int n, const PzTree *t, const uint
 /* computeHuffmanTree (Deflate.hs:255-259) for symbols 0..n-1 with lengths lens[]: canonical
  * counts, symbols sorted by (length, symbol), and the 2^BITS-entry LUT, all built
  * cooperatively by the group.  Returns 0, or the HuffmanTreeError detail with *val. */
-template <int BITS, int KIND>
-PZ_DEV int pz_build(const uint8_t *lens, int n, PzTree *t, uint16_t *perm, uint32_t *lut, uint32_t *scratch, int64_t *val) {
+template <int BITS, int KIND, typename LutT>
+PZ_DEV int pz_build(const uint8_t *lens, int n, PzTree *t, uint16_t *perm, LutT *lut, uint32_t *scratch, int64_t *val) {
   uint32_t *cnt32 = scratch, *offs = scratch + 16;
   const int lane = pz_lane();
   pz_syncwarp();
@@ -429,7 +437,7 @@ PZ_DEV int pz_build(const uint8_t *lens, int n, PzTree *t, uint16_t *perm, uint3
   if (over) return pz_tree_error(lens, n, t, perm, (uint16_t *)lut, val);
   /* LUT, entry-major: each lane walks the canonical code along the bits of its index */
   for (uint32_t e = (uint32_t)lane; e < (1u << BITS); e += PZ_G) {
-    uint32_t code = 0, first = 0, index = 0, entry = PZ_SLOW_ENTRY;
+    uint32_t code = 0, first = 0, index = 0, entry = KIND == 2 ? 0u : PZ_SLOW_ENTRY;
     for (int len = 1; len <= BITS; len++) {
       code |= (e >> (len - 1)) & 1u;
       uint32_t count = t->cnt[len];
@@ -438,7 +446,7 @@ PZ_DEV int pz_build(const uint8_t *lens, int n, PzTree *t, uint16_t *perm, uint3
       if (code - first >= t->used[len]) break; /* dead prefix: the careful path reports it */
       first <<= 1; code <<= 1;
     }
-    lut[e] = entry;
+    lut[e] = (LutT)entry;
   }
   pz_syncwarp();
   return 0;
@@ -555,12 +563,14 @@ PZ_DEV void pz_writer_apply(PzWriter &w, uint32_t raw) {
  *
  * Each trip pops up to PZ_WB tokens per group.  Literals are stored at once; the bytes of every
  * short disjoint match of the trip are LOADED first (this lane owns bytes lane, lane+G, lane+2G,
- * lane+3G of each) and stored only after all the loads of the trip have been issued, so one
+ * ... of each) and stored only after all the loads of the trip have been issued, so one
  * L2/HBM round trip is shared by the whole batch instead of being paid per match.  A match
  * whose source reaches into bytes produced earlier in the same trip ends the batch and opens
  * the next one.  Everything else (overlapping or long copies, stored runs, control tokens)
  * goes through pz_writer_apply(), one token per trip. */
 #define PZ_WB 6
+#define PZ_FAST_LEN 32u                    /* longest match the batched path copies */
+#define PZ_CHUNKS ((int)(PZ_FAST_LEN / PZ_G)) /* bytes of one match per lane */
 PZ_DEV void pz_writer_warp(const PzJob &job, PzStreamSmem *sm) {
   PzWriter w;
   pz_writer_init(w, &job);
@@ -575,7 +585,7 @@ PZ_DEV void pz_writer_warp(const PzJob &job, PzStreamSmem *sm) {
       const uint32_t r = raw[0];
       const uint32_t type = (r >> 29) & 3u, len = (r >> 16) & 0x1ffu, dist = (r & 0x7fffu) + 1u;
       const bool valid = !w.exited && (r >> 31) == ((tail >> PZ_QSHIFT) & 1u);
-      const bool fast = w.need == 0u && (type == PZ_Q_LIT || (type == PZ_Q_MATCH && dist >= len && len <= 4u * PZ_G));
+      const bool fast = w.need == 0u && (type == PZ_Q_LIT || (type == PZ_Q_MATCH && dist >= len && len <= PZ_FAST_LEN));
       const bool slow = valid && !fast;
       /* A trip costs the same whether it moves one token or PZ_WB per group, and the decoder
        * warps need the issue slots: unless some group has a full batch (or a token for the
@@ -599,7 +609,7 @@ PZ_DEV void pz_writer_warp(const PzJob &job, PzStreamSmem *sm) {
     bool go = !w.exited;
     uint8_t *dst[PZ_WB];
     int32_t rem[PZ_WB];
-    uint32_t v[PZ_WB][4];
+    uint32_t v[PZ_WB][PZ_CHUNKS];
 #pragma unroll
     for (int j = 0; j < PZ_WB; j++) {
       const uint32_t r = raw[j];
@@ -607,26 +617,22 @@ PZ_DEV void pz_writer_warp(const PzJob &job, PzStreamSmem *sm) {
       const bool valid = (r >> 31) == (((tail + (uint32_t)j) >> PZ_QSHIFT) & 1u);
       const bool is_lit = type == PZ_Q_LIT;
       /* short, disjoint, and not reading what this trip has produced so far */
-      const bool is_m = type == PZ_Q_MATCH && dist >= len && len <= 4u * PZ_G && pos - dist + len <= start;
+      const bool is_m = type == PZ_Q_MATCH && dist >= len && len <= PZ_FAST_LEN && pos - dist + len <= start;
       go = go && valid && (is_lit || is_m);
       uint8_t *const nd = w.out + pos + lane;
       const uint8_t *const ns = nd - dist;
       pz_st8_if(go && is_lit && lane == 0, nd, r);
       rem[j] = (go && !is_lit) ? (int32_t)len - lane : 0;
       dst[j] = nd;
-      v[j][0] = pz_ld8_if(rem[j] > 0, ns);
-      v[j][1] = pz_ld8_if(rem[j] > PZ_G, ns + PZ_G);
-      v[j][2] = pz_ld8_if(rem[j] > 2 * PZ_G, ns + 2 * PZ_G);
-      v[j][3] = pz_ld8_if(rem[j] > 3 * PZ_G, ns + 3 * PZ_G);
+#pragma unroll
+      for (int k = 0; k < PZ_CHUNKS; k++) v[j][k] = pz_ld8_if(rem[j] > k * PZ_G, ns + k * PZ_G);
       pos += go ? (is_lit ? 1u : len) : 0u;
       n += go ? 1u : 0u;
     }
 #pragma unroll
     for (int j = 0; j < PZ_WB; j++) {
-      pz_st8_if(rem[j] > 0, dst[j], v[j][0]);
-      pz_st8_if(rem[j] > PZ_G, dst[j] + PZ_G, v[j][1]);
-      pz_st8_if(rem[j] > 2 * PZ_G, dst[j] + 2 * PZ_G, v[j][2]);
-      pz_st8_if(rem[j] > 3 * PZ_G, dst[j] + 3 * PZ_G, v[j][3]);
+#pragma unroll
+      for (int k = 0; k < PZ_CHUNKS; k++) pz_st8_if(rem[j] > k * PZ_G, dst[j] + k * PZ_G, v[j][k]);
     }
     w.pos = pos;
     tail += n;
@@ -745,7 +751,8 @@ PZ_DEV bool pz_fast_step(PzFast &f, PzStreamSmem *sm, bool &full) {
   const uint32_t hi0 = f.hi;
   pz_fast_fetch(f, sm, nbp); /* look-ahead */
   const uint32_t len = (e >> 16) + ((lo & ~(0xffffffffu << tb)) >> ((e >> 8) & 15u));
-  const uint32_t dist = (d >> 16) + ((wd & ~(0xffffffffu << tb2)) >> ((d >> 8) & 15u));
+  const uint32_t dx = (d >> 9) & 15u; /* extra bits of the distance */
+  const uint32_t dist = 1u + ((d >> 13) << dx) + ((wd >> ((d >> 5) & 15u)) & ~(0xffffffffu << dx));
   const uint32_t room = f.lim - f.pos;
 #ifdef PZ_HOSTSIM
   full = false;
@@ -827,7 +834,7 @@ PZ_DEV bool pz_dynamic_header(PzCtx &c, PzStreamSmem *sm) {
     if (lane == 0) sm->lens[PZ_CL_ORDER[i]] = (uint8_t)v;
   }
   int64_t val = 0;
-  uint32_t *pre_lut = sm->dist_lut;
+  uint32_t *pre_lut = reinterpret_cast<uint32_t *>(sm->dist_lut);
   int e = pz_build<PZ_PRE_BITS, 0>(sm->lens, 19, &sm->pre, sm->pre_perm, pre_lut, sm->scratch, &val);
   if (e) { pz_fail(c, PZ_ERR_HUFFMAN_TREE, e, e == PZ_D_LEAF_IS_NODE ? val : 0); return false; }
   /* the code lengths; repeats are not clipped at hlit+hdist (Deflate.hs:153-156) */

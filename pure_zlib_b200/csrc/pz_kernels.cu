@@ -139,7 +139,7 @@ __global__ void pz_code_values_kernel(const uint8_t *lens, int n, uint16_t *code
   pz_syncwarp();
   int64_t val;
   (void)pz_build<PZ_LIT_BITS, 1>(sm.lens, n, &sm.lit, sm.lit_perm, sm.lit_lut, sm.scratch, &val);
-  uint16_t *c16 = reinterpret_cast<uint16_t *>(sm.dist_lut);
+  uint16_t *c16 = reinterpret_cast<uint16_t *>(sm.lit_lut); /* the LUT itself is not needed here */
   pz_canon_codes(sm.lens, &sm.lit, sm.lit_perm, c16, false);
   for (int i = threadIdx.x; i < n; i += PZ_G) codes[i] = sm.lens[i] ? c16[i] : 0;
 }

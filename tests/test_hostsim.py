@@ -63,6 +63,5 @@ def test_output_full():
 
 def test_smem_budget():
     # 28 resident streams per SM = 7 CTAs x 4 streams: 228 KiB of shared memory per SM, 1 KiB of
-    # it reserved by the driver for every resident CTA
-    # (and shared memory is handed out in 256-byte granules)
+    # it reserved by the driver for every resident CTA (and handed out in 256-byte granules)
     assert hostsim.lib().hs_smem_bytes() <= ((228 * 1024) // 7 - 1024) // 256 * 256 // 4

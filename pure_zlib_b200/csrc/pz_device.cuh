@@ -56,7 +56,15 @@
 #ifdef PZ_HOSTSIM
 #include <string.h>
 #define PZ_DEV static inline
+#define PZ_COLD static
 #define PZ_G 1
+PZ_DEV uint32_t pz_brev(uint32_t x) {
+  x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+  x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+  x = ((x >> 4) & 0x0f0f0f0fu) | ((x & 0x0f0f0f0fu) << 4);
+  x = ((x >> 8) & 0x00ff00ffu) | ((x & 0x00ff00ffu) << 8);
+  return (x >> 16) | (x << 16);
+}
 PZ_DEV int pz_lane() { return 0; }
 PZ_DEV void pz_syncwarp() {}
 PZ_DEV unsigned pz_ballot(int p) { return p ? 1u : 0u; }
@@ -72,7 +80,9 @@ PZ_DEV void pz_copy16_async(void *smem_dst, const void *gsrc) { memcpy(smem_dst,
 PZ_DEV void pz_async_wait_all() {}
 #else
 #define PZ_DEV __device__ __forceinline__
+#define PZ_COLD __device__ __noinline__ /* rare paths: kept out of line so the hot loops stay in the instruction cache */
 #define PZ_G PZ_GROUP
+PZ_DEV uint32_t pz_brev(uint32_t x) { return __brev(x); }
 PZ_DEV unsigned pz_gshift() { return (threadIdx.x & 31u) & ~(unsigned)(PZ_G - 1); }
 PZ_DEV unsigned pz_gmask() { return PZ_G == 32 ? 0xffffffffu : (((1u << (PZ_G & 31)) - 1u) << pz_gshift()); }
 PZ_DEV int pz_lane() { return (int)(threadIdx.x & (unsigned)(PZ_G - 1)); }
@@ -145,7 +155,20 @@ struct PzTree {
   uint16_t pad;
 };
 
-/* Shared memory of one stream (one group). */
+/* Hand-over block between a stream's service group and its lane of the hot warp (shared
+ * memory; one owner at a time, ownership moves with `state`). */
+#define PZ_MS_SERVICE 0u /* the service group owns the stream                         */
+#define PZ_MS_HOT 1u     /* posted: the hot lane decodes symbols                      */
+#define PZ_MS_DEAD 2u    /* the service group has no streams left                     */
+struct PzMail {
+  uint32_t state;
+  uint32_t bp, pos, base, lim, safe_end, qhead; /* travel with the ownership           */
+  uint32_t hot_bp;  /* hot lane -> service: bit position at the end of its last trip   */
+  uint32_t ring_hi; /* service -> hot lane: ring quarters < ring_hi are resident       */
+  uint32_t pad[3];
+};
+
+/* Shared memory of one stream (one slot of the CTA). */
 struct __attribute__((aligned(16))) PzStreamSmem {
   uint32_t lit_lut[1 << PZ_LIT_BITS];
   uint16_t dist_lut[1 << PZ_DIST_BITS]; /* compact entries; the 128-entry 32-bit precode LUT aliases it */
@@ -156,14 +179,16 @@ struct __attribute__((aligned(16))) PzStreamSmem {
   uint16_t pre_perm[24];
   PzTree lit, dist, pre;
   uint8_t lens[PZ_MAX_LENS];
-  uint32_t q[PZ_QLEN]; /* token queue: written by the decoder, read by the writer */
-  uint32_t qtail;      /* tokens consumed so far: written by the writer, read by the decoder */
+  uint32_t q[PZ_QLEN]; /* token queue: written by the decoder side, read by the writer */
+  uint32_t qtail;      /* tokens consumed so far: written by the writer, read by the decoder side */
+  uint32_t pad0[3];
+  PzMail mail;
+  uint32_t pad1[20]; /* slot stride = 16 (mod 128) bytes: the same field of consecutive slots falls
+                       into different banks when the hot warp's lanes (one per slot) read it */
 };
-/* 4 streams per CTA and 7 CTAs per SM only fit if a CTA stays within 32256 bytes (228 KiB per SM,
- * 1 KiB reserved per resident CTA, 256-byte allocation granules): 8064 bytes per stream.  (With
- * 4-lane groups -- 8 streams per CTA, 4 CTAs per SM -- the limit would be 7168; measured slower:
- * twice the groups per warp means twice the shared-memory bank conflicts and loop exits.) */
-static_assert(sizeof(PzStreamSmem) <= 8064, "PzStreamSmem no longer fits 28 streams per SM");
+/* One CTA per SM holds PZ_SLOTS = 28 streams: 28 slots must fit the 227 KiB a CTA may own. */
+static_assert(sizeof(PzStreamSmem) * 28 <= 232448, "PzStreamSmem no longer fits 28 streams per SM");
+static_assert(sizeof(PzStreamSmem) % 128 == 16, "slot stride must be 16 (mod 128) bytes");
 static_assert(sizeof(uint16_t) * (1 << PZ_DIST_BITS) >= sizeof(uint32_t) * (1 << PZ_PRE_BITS), "precode LUT must fit the distance LUT");
 
 #ifdef PZ_HOSTSIM
@@ -194,7 +219,7 @@ struct PzJob {
 #define PZ_ST_PENDING (-1)
 
 /* ---- per-stream decoder state (registers; identical in every lane of the group) -------- */
-enum PzMode { PZ_M_IDLE = 0, PZ_M_HDR = 1, PZ_M_SYMS = 2, PZ_M_FAST = 3, PZ_M_DEAD = 4 };
+enum PzMode { PZ_M_IDLE = 0, PZ_M_HDR = 1, PZ_M_SYMS = 2, PZ_M_FAST = 3, PZ_M_DEAD = 4, PZ_M_WAIT = 5 /* posted to the hot lane */ };
 
 struct PzCtx {
   const uint8_t *in_al; /* input, rounded down to 16 bytes                                */
@@ -204,6 +229,8 @@ struct PzCtx {
   uint32_t safe_end;    /* bp <= safe_end: a whole symbol pair (PZ_STEP_BITS) is available */
   uint32_t bp;          /* bit position of the reader, counted from in_al; bp <= end_bit   */
   uint32_t q;           /* ring quarter holding bp; quarters q and q+1 are resident        */
+  uint32_t next_q;      /* first quarter not requested yet (q+3 in steady state)           */
+  bool pending;         /* a quarter requested while the hot lane owns the stream has not been awaited */
   uint32_t pos;  /* bytes decoded                                                          */
   uint32_t base; /* bytes the reference would already have published (multiple of 32 KiB)  */
   uint32_t cap;
@@ -243,12 +270,12 @@ PZ_DEV void pz_ring_issue(PzCtx &c, PzStreamSmem *sm, uint32_t k) {
     /* past the stream: never consumed (every reader counts bits first), left as is */
   }
 }
-PZ_DEV void pz_cross(PzCtx &c, PzStreamSmem *sm) {
+PZ_COLD void pz_cross(PzCtx &c, PzStreamSmem *sm) {
   while (c.q != (c.bp >> PZ_QUARTER_SHIFT)) {
     c.q++;
     pz_async_wait_all(); /* quarter q+1 was requested one crossing ago */
     pz_syncwarp();
-    pz_ring_issue(c, sm, c.q + 2u);
+    while (c.next_q < c.q + 3u) pz_ring_issue(c, sm, c.next_q++);
   }
 }
 PZ_DEV void pz_seek(PzCtx &c, PzStreamSmem *sm, uint32_t bit) {
@@ -260,7 +287,7 @@ PZ_DEV void pz_seek(PzCtx &c, PzStreamSmem *sm, uint32_t bit) {
   pz_async_wait_all();
   pz_syncwarp();
   pz_ring_issue(c, sm, k + 2u);
-  c.q = k; c.bp = bit;
+  c.q = k; c.next_q = k + 3u; c.bp = bit;
 }
 /* The 32 stream bits starting at bit position bp (bits past end_bit are garbage). */
 PZ_DEV uint32_t pz_peek(const uint32_t *ring, uint32_t bp) {
@@ -297,7 +324,7 @@ PZ_DEV void pz_align_byte(PzCtx &c, PzStreamSmem *sm) {
 /* ---- exact bit-serial walk (nextCode / advanceTree, Monad.hs:295-302, HuffmanTree.hs:73-83)
  * Consumes one bit per step and stops exactly where the reference's trie walk stops:
  * truncation if the input ends first, "Advanced to empty tree!" on an unused prefix. */
-PZ_DEV int pz_walk(PzCtx &c, PzStreamSmem *sm, const PzTree *t, const uint16_t *perm) {
+PZ_COLD int pz_walk(PzCtx &c, PzStreamSmem *sm, const PzTree *t, const uint16_t *perm) {
   const uint32_t av = pz_avail(c);
   const uint32_t w = pz_peek(sm->ring, c.bp); /* only the first min(av, 15) bits are looked at */
   uint32_t code = 0, first = 0, index = 0;
@@ -358,7 +385,7 @@ PZ_DEV void pz_canon_codes(const uint8_t *lens, const PzTree *t, const uint16_t 
 /* createHuffmanTree's verdict when the lengths over-subscribe the code space: replay the
  * reference's insertion order (descending symbol, HuffmanTree.hs:29-34) on the canonical
  * codes and report the first collision.  `codes` is n uint16 scratch. */
-PZ_DEV int pz_tree_error(const uint8_t *lens, int n, const PzTree *t, const uint16_t *perm, uint16_t *codes, int64_t *val) {
+PZ_COLD int pz_tree_error(const uint8_t *lens, int n, const PzTree *t, const uint16_t *perm, uint16_t *codes, int64_t *val) {
   pz_canon_codes(lens, t, perm, codes, true);
   for (int i = n - 1; i >= 0; i--) {
     int li = lens[i];
@@ -387,7 +414,7 @@ PZ_DEV int pz_tree_error(const uint8_t *lens, int n, const PzTree *t, const uint
  * counts, symbols sorted by (length, symbol), and the 2^BITS-entry LUT, all built
  * cooperatively by the group.  Returns 0, or the HuffmanTreeError detail with *val. */
 template <int BITS, int KIND, typename LutT>
-PZ_DEV int pz_build(const uint8_t *lens, int n, PzTree *t, uint16_t *perm, LutT *lut, uint32_t *scratch, int64_t *val) {
+PZ_COLD int pz_build(const uint8_t *lens, int n, PzTree *t, uint16_t *perm, LutT *lut, uint32_t *scratch, int64_t *val) {
   uint32_t *cnt32 = scratch, *offs = scratch + 16;
   const int lane = pz_lane();
   pz_syncwarp();
@@ -416,10 +443,15 @@ PZ_DEV int pz_build(const uint8_t *lens, int n, PzTree *t, uint16_t *perm, LutT 
     used = (cl[l + 1] + used + 1u) >> 1;
     if (lane == 0) t->used[l] = (uint16_t)used;
   }
+  /* canonical code of the symbol at sorted position p with length l: cnt32[l] + p
+   * (computeCodeValues, Deflate.hs:261-288: next_code[l] minus the position of the first l-bit symbol) */
+  uint32_t code = 0, nshort = 0;
 #pragma unroll
   for (int l = 1; l <= 15; l++) {
-    if (lane == 0) { t->cnt[l] = (uint16_t)cl[l]; offs[l] = acc; }
+    code = (code + (l > 1 ? cl[l - 1] : 0u)) << 1;
+    if (lane == 0) { t->cnt[l] = (uint16_t)cl[l]; offs[l] = acc; cnt32[l] = code - acc; }
     acc += cl[l];
+    if (l <= BITS) nshort = acc;
   }
   if (lane == 0) t->nsyms = (uint16_t)acc;
   pz_syncwarp();
@@ -435,18 +467,16 @@ PZ_DEV int pz_build(const uint8_t *lens, int n, PzTree *t, uint16_t *perm, LutT 
     pz_syncwarp();
   }
   if (over) return pz_tree_error(lens, n, t, perm, (uint16_t *)lut, val);
-  /* LUT, entry-major: each lane walks the canonical code along the bits of its index */
-  for (uint32_t e = (uint32_t)lane; e < (1u << BITS); e += PZ_G) {
-    uint32_t code = 0, first = 0, index = 0, entry = KIND == 2 ? 0u : PZ_SLOW_ENTRY;
-    for (int len = 1; len <= BITS; len++) {
-      code |= (e >> (len - 1)) & 1u;
-      uint32_t count = t->cnt[len];
-      if (code - first < count) { entry = pz_make_entry<KIND>(perm[index + (code - first)], (uint32_t)len); break; }
-      index += count; first += count;
-      if (code - first >= t->used[len]) break; /* dead prefix: the careful path reports it */
-      first <<= 1; code <<= 1;
-    }
-    lut[e] = (LutT)entry;
+  /* LUT: every entry starts as "not for the hot loop" (long code or dead prefix: the careful path
+   * decides), then each code of at most BITS bits fills the entries that end in its reversed bits */
+  for (uint32_t e = (uint32_t)lane; e < (1u << BITS); e += PZ_G) lut[e] = (LutT)(KIND == 2 ? 0u : PZ_SLOW_ENTRY);
+  pz_syncwarp();
+  for (uint32_t p = (uint32_t)lane; p < nshort; p += PZ_G) {
+    const uint32_t sym = perm[p];
+    const uint32_t l = lens[sym];
+    const uint32_t rev = pz_brev(cnt32[l] + p) >> (32u - l);
+    const LutT entry = (LutT)pz_make_entry<KIND>(sym, l);
+    for (uint32_t e = rev; e < (1u << BITS); e += 1u << l) lut[e] = entry;
   }
   pz_syncwarp();
   return 0;
@@ -559,82 +589,110 @@ PZ_DEV void pz_writer_apply(PzWriter &w, uint32_t raw) {
 }
 
 #ifndef PZ_HOSTSIM
+/* The byte of a trip's output: a literal carried by the token word `inf` (bit 31 set, byte in
+ * [0,8)) or the byte `x` loaded from the history.  Select and store are one asm statement so the
+ * compiler cannot pull the use of `x` (and with it the wait for the load) ahead of later loads. */
+PZ_DEV void pz_st8_sel(bool p, uint8_t *a, uint32_t inf, uint32_t x) {
+  asm volatile(
+      "{\n\t.reg .pred q, l;\n\t.reg .b32 t, u;\n\tsetp.ne.b32 q, %0, 0;\n\tsetp.lt.s32 l, %2, 0;\n\t"
+      "and.b32 u, %2, 255;\n\tselp.b32 t, u, %3, l;\n\t@q st.global.u8 [%1], t;\n\t}" ::"r"((int)p),
+      "l"(a), "r"(inf), "r"(x));
+}
+
 /* The writer warp: runs until every group has seen its EXIT token.
  *
- * Each trip pops up to PZ_WB tokens per group.  Literals are stored at once; the bytes of every
- * short disjoint match of the trip are LOADED first (this lane owns bytes lane, lane+G, lane+2G,
- * ... of each) and stored only after all the loads of the trip have been issued, so one
- * L2/HBM round trip is shared by the whole batch instead of being paid per match.  A match
- * whose source reaches into bytes produced earlier in the same trip ends the batch and opens
- * the next one.  Everything else (overlapping or long copies, stored runs, control tokens)
- * goes through pz_writer_apply(), one token per trip. */
-#define PZ_WB 6
-#define PZ_FAST_LEN 32u                    /* longest match the batched path copies */
-#define PZ_CHUNKS ((int)(PZ_FAST_LEN / PZ_G)) /* bytes of one match per lane */
-PZ_DEV void pz_writer_warp(const PzJob &job, PzStreamSmem *sm) {
+ * A trip looks at the next PZ_G tokens of every stream, one token per lane.  The longest prefix
+ * of literals and short, disjoint matches whose sources lie entirely before the trip's first
+ * output byte (and whose bytes total at most PZ_TRIP_BYTES) forms the batch.  Its output bytes
+ * are then dealt out to the lanes by POSITION: lane l produces bytes l, l+G, l+2G, ... of the
+ * batch, finding the token that owns a byte with one popcount over the bitmap of token start
+ * offsets and one shuffle.  All history loads of the trip are issued before the first store, so
+ * one L2/HBM round trip is shared by the whole batch, and consecutive lanes touch consecutive
+ * bytes.  Everything else (overlapping or long copies, stored runs, control tokens) goes through
+ * pz_writer_apply(), one token per trip. */
+#define PZ_TRIP_BYTES 64u
+#define PZ_ROUNDS ((int)(PZ_TRIP_BYTES / PZ_G))
+PZ_DEV void pz_writer_warp(const PzJob &job, PzStreamSmem *sm, bool present) {
+  static_assert(PZ_G == 8, "the writer deals bytes to 8-lane groups");
   PzWriter w;
   pz_writer_init(w, &job);
-  const int32_t lane = pz_lane();
+  w.exited = !present;
+  const uint32_t lane = (uint32_t)pz_lane();
+  const unsigned gsh = pz_gshift();
+  const unsigned all = 0xffffffffu; /* the four groups run this loop converged: warp-wide collectives, group-sized segments */
   uint32_t tail = 0, naps = 0;
+  if (!pz_warp_any(!w.exited)) return;
   for (;;) {
     pz_syncwarp_all(); /* the previous trip's stores are visible to the other lanes' loads */
-    uint32_t raw[PZ_WB];
+    const uint32_t idx = tail + lane;
+    const uint32_t raw = pz_vload(&sm->q[idx & (PZ_QLEN - 1u)]);
+    const bool valid = !w.exited && (raw >> 31) == ((idx >> PZ_QSHIFT) & 1u);
+    const uint32_t type = (raw >> 29) & 3u, len = (raw >> 16) & 0x1ffu, dist = (raw & 0x7fffu) + 1u;
+    const bool is_lit = type == PZ_Q_LIT;
+    const bool fast = valid && w.need == 0u && (is_lit || (type == PZ_Q_MATCH && dist >= len && len <= PZ_TRIP_BYTES));
+    /* A trip costs the same whether it moves one token or PZ_G per group, and the other warps
+     * need the issue slots: unless some group has a full batch waiting (or a token that will not
+     * join a batch anyway), sleep a little -- but never for long. */
+    const unsigned vmask = (__ballot_sync(all, valid) >> gsh) & 0xffu;
+    const unsigned smask = (__ballot_sync(all, valid && !fast) >> gsh) & 0xffu;
+    if (naps < 8u && !pz_warp_any(vmask == 0xffu || smask != 0u)) { naps++; __nanosleep(1000); continue; }
+    const uint32_t L = fast ? (is_lit ? 1u : len) : 0u;
+    uint32_t E = L; /* inclusive prefix sum over the group: end offset of this lane's token */
 #pragma unroll
-    for (int j = 0; j < PZ_WB; j++) raw[j] = pz_vload(&sm->q[(tail + (uint32_t)j) & (PZ_QLEN - 1u)]);
-    { /* the general path, when the first token needs it */
-      const uint32_t r = raw[0];
-      const uint32_t type = (r >> 29) & 3u, len = (r >> 16) & 0x1ffu, dist = (r & 0x7fffu) + 1u;
-      const bool valid = !w.exited && (r >> 31) == ((tail >> PZ_QSHIFT) & 1u);
-      const bool fast = w.need == 0u && (type == PZ_Q_LIT || (type == PZ_Q_MATCH && dist >= len && len <= PZ_FAST_LEN));
-      const bool slow = valid && !fast;
-      /* A trip costs the same whether it moves one token or PZ_WB per group, and the decoder
-       * warps need the issue slots: unless some group has a full batch (or a token for the
-       * general path) waiting, sleep a little -- but never for long. */
-      const uint32_t rl = raw[PZ_WB - 1];
-      const bool full_batch = !w.exited && (rl >> 31) == (((tail + PZ_WB - 1u) >> PZ_QSHIFT) & 1u);
-      if (naps < 8u && !pz_warp_any(full_batch || slow)) { naps++; __nanosleep(200); continue; }
-      naps = 0;
-      if (pz_warp_any(slow)) {
-        if (slow) {
-          pz_writer_apply(w, r & 0x7fffffffu);
-          tail++;
-          pz_vstore(&sm->qtail, tail);
-        }
-        if (!pz_warp_any(!w.exited)) break;
-        continue;
+    for (int o = 1; o < PZ_G; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(all, E, o, PZ_G);
+      if ((int)lane >= o) E += t;
+    }
+    /* a match may not read what this trip produces: its source ends at E - dist <= 0 */
+    const bool ok = fast && (is_lit || dist >= E) && E <= PZ_TRIP_BYTES;
+    const unsigned bad = (__ballot_sync(all, !ok) >> gsh) & 0xffu;
+    const uint32_t n = bad ? (uint32_t)__ffs((int)bad) - 1u : (uint32_t)PZ_G;
+    const bool slow = n == 0u && (vmask & 1u);
+    naps = 0;
+    const uint32_t r0 = (uint32_t)__shfl_sync(all, (int)raw, 0, PZ_G);
+    if (pz_warp_any(slow)) {
+      if (slow) {
+        pz_writer_apply(w, r0 & 0x7fffffffu);
+        tail++;
+        pz_vstore(&sm->qtail, tail);
+      }
+      if (!pz_warp_any(!w.exited)) break;
+      continue;
+    }
+    const bool act = lane < n;
+    const uint32_t P = E - L; /* first output byte of this lane's token, relative to the trip */
+    const uint32_t Bn = (uint32_t)__shfl_sync(all, (int)E, (int)n - 1, PZ_G);
+    const uint32_t B = n ? Bn : 0u;
+    uint32_t s_lo = (act && P < 32u) ? (1u << P) : 0u; /* bitmap of the tokens' first bytes */
+    uint32_t s_hi = (act && P >= 32u) ? (1u << (P - 32u)) : 0u;
+#pragma unroll
+    for (int o = 1; o < PZ_G; o <<= 1) {
+      s_lo |= __shfl_xor_sync(all, s_lo, o, PZ_G);
+      s_hi |= __shfl_xor_sync(all, s_hi, o, PZ_G);
+    }
+    const uint32_t info = is_lit ? (0x80000000u | (raw & 0xffu)) : dist;
+    const uint32_t max_b = __reduce_max_sync(0xffffffffu, B);
+    const uint32_t c_lo = (uint32_t)__popc(s_lo);
+    uint8_t *const base = w.out + w.pos;
+    uint32_t x[PZ_ROUNDS], inf[PZ_ROUNDS];
+#pragma unroll
+    for (int r = 0; r < PZ_ROUNDS; r++) {
+      if ((uint32_t)(r * PZ_G) < max_b) { /* warp-uniform */
+        const uint32_t b = (uint32_t)(r * PZ_G) + lane;
+        const int t = r * PZ_G < 32 ? __popc(s_lo & ((2u << b) - 1u)) - 1
+                                    : (int)c_lo + __popc(s_hi & ((2u << (b - 32u)) - 1u)) - 1;
+        inf[r] = (uint32_t)__shfl_sync(all, (int)info, t, PZ_G);
+        x[r] = pz_ld8_if(b < B && (int32_t)inf[r] >= 0, base + (int32_t)(b - (inf[r] & 0xffffu)));
       }
     }
-    const uint32_t start = w.pos;
-    uint32_t pos = w.pos, n = 0;
-    bool go = !w.exited;
-    uint8_t *dst[PZ_WB];
-    int32_t rem[PZ_WB];
-    uint32_t v[PZ_WB][PZ_CHUNKS];
 #pragma unroll
-    for (int j = 0; j < PZ_WB; j++) {
-      const uint32_t r = raw[j];
-      const uint32_t type = (r >> 29) & 3u, len = (r >> 16) & 0x1ffu, dist = (r & 0x7fffu) + 1u;
-      const bool valid = (r >> 31) == (((tail + (uint32_t)j) >> PZ_QSHIFT) & 1u);
-      const bool is_lit = type == PZ_Q_LIT;
-      /* short, disjoint, and not reading what this trip has produced so far */
-      const bool is_m = type == PZ_Q_MATCH && dist >= len && len <= PZ_FAST_LEN && pos - dist + len <= start;
-      go = go && valid && (is_lit || is_m);
-      uint8_t *const nd = w.out + pos + lane;
-      const uint8_t *const ns = nd - dist;
-      pz_st8_if(go && is_lit && lane == 0, nd, r);
-      rem[j] = (go && !is_lit) ? (int32_t)len - lane : 0;
-      dst[j] = nd;
-#pragma unroll
-      for (int k = 0; k < PZ_CHUNKS; k++) v[j][k] = pz_ld8_if(rem[j] > k * PZ_G, ns + k * PZ_G);
-      pos += go ? (is_lit ? 1u : len) : 0u;
-      n += go ? 1u : 0u;
+    for (int r = 0; r < PZ_ROUNDS; r++) {
+      if ((uint32_t)(r * PZ_G) < max_b) {
+        const uint32_t b = (uint32_t)(r * PZ_G) + lane;
+        pz_st8_sel(b < B, base + b, inf[r], x[r]);
+      }
     }
-#pragma unroll
-    for (int j = 0; j < PZ_WB; j++) {
-#pragma unroll
-      for (int k = 0; k < PZ_CHUNKS; k++) pz_st8_if(rem[j] > k * PZ_G, dst[j] + k * PZ_G, v[j][k]);
-    }
-    w.pos = pos;
+    w.pos += B;
     tail += n;
     pz_vstore(&sm->qtail, tail);
   }
@@ -739,43 +797,60 @@ PZ_DEV void pz_fast_fetch(PzFast &f, const PzStreamSmem *sm, uint32_t bp) {
   f.e = sm->lit_lut[f.lo & ((1u << PZ_LIT_BITS) - 1u)];
 }
 
+/* One trip = PZ_TRIP symbols.  The bit-position chain (window -> literal/length LUT -> distance
+ * LUT -> bit count -> next window) runs SPECULATIVELY: it never waits for the verdict on the
+ * symbol it has just consumed.  The verdict (`alive`, sticky within the trip) only gates what is
+ * committed: the token, and the position registers in `f`.  Once a symbol fails -- something the
+ * loop must not decide, a full token queue -- the chain keeps running on garbage for the rest of
+ * the trip (all table and ring indices are masked, so that is harmless) and nothing more is
+ * committed.  Returns true if the stream stopped inside this trip; f.lo/hi/e are then stale. */
+#define PZ_TRIP 4
 template <bool COUNT_ONLY>
-PZ_DEV bool pz_fast_step(PzFast &f, PzStreamSmem *sm, bool &full) {
-  const uint32_t lo = f.lo, e = f.e;
-  const uint32_t tb = e & 31u;
-  const bool is_lit = (int32_t)e < 0;
-  const uint32_t wd = pz_funnel_r(lo, f.hi, tb); /* the bits after the literal/length symbol (tb <= 15) */
-  const uint32_t d = sm->dist_lut[wd & ((1u << PZ_DIST_BITS) - 1u)];
-  const uint32_t tb2 = d & 31u;
-  const uint32_t nbp = f.bp + (is_lit ? tb : tb + tb2);
-  const uint32_t hi0 = f.hi;
-  pz_fast_fetch(f, sm, nbp); /* look-ahead */
-  const uint32_t len = (e >> 16) + ((lo & ~(0xffffffffu << tb)) >> ((e >> 8) & 15u));
-  const uint32_t dx = (d >> 9) & 15u; /* extra bits of the distance */
-  const uint32_t dist = 1u + ((d >> 13) << dx) + ((wd >> ((d >> 5) & 15u)) & ~(0xffffffffu << dx));
-  const uint32_t room = f.lim - f.pos;
+PZ_DEV bool pz_fast_trip(PzFast &f, PzStreamSmem *sm, const bool run) {
+  uint32_t bp = f.bp, pos = f.pos, base = f.base, qhead = f.qhead;
+  uint32_t lo = f.lo, hi = f.hi, e = f.e;
+  bool alive = run;
+#pragma unroll
+  for (int k = 0; k < PZ_TRIP; k++) {
+    const uint32_t tb = e & 31u;
+    const bool is_lit = (int32_t)e < 0;
+    const uint32_t wd = pz_funnel_r(lo, hi, tb); /* the bits after the literal/length symbol (tb <= 20) */
+    const uint32_t d = sm->dist_lut[wd & ((1u << PZ_DIST_BITS) - 1u)];
+    const uint32_t tb2 = d & (is_lit ? 0u : 31u);
+    const uint32_t nbp = bp + tb + tb2;
+    uint32_t nlo, nhi;
+    pz_peek64(sm->ring, nbp, nlo, nhi);
+    const uint32_t ne = sm->lit_lut[nlo & ((1u << PZ_LIT_BITS) - 1u)];
+    /* off the chain: the symbol's values and its verdict */
+    const uint32_t len = (e >> 16) + ((lo & ~(0xffffffffu << tb)) >> ((e >> 8) & 15u));
+    const uint32_t dx = (d >> 9) & 15u; /* extra bits of the distance */
+    const uint32_t dist = 1u + ((d >> 13) << dx) + ((wd >> ((d >> 5) & 15u)) & ~(0xffffffffu << dx));
+    const uint32_t room = f.lim - pos;
 #ifdef PZ_HOSTSIM
-  full = false;
+    const bool full = false;
 #else
-  full = !COUNT_ONLY && f.qhead - f.qtailc >= PZ_QLEN;
+    const bool full = !COUNT_ONLY && qhead - f.qtailc >= PZ_QLEN;
 #endif
-  const bool pre_ok = f.live && f.bp <= f.safe_end && room != 0u && !full;
-  const bool m_ok = !is_lit && tb != 0u && tb2 != 0u && dist <= f.pos - f.base && len <= room;
-  const bool ok = pre_ok && (is_lit || m_ok);
-  if (!COUNT_ONLY) {
-    const uint32_t tok = is_lit ? PZ_TOKEN(PZ_Q_LIT, (e >> 16) & 0xffu) : PZ_TOKEN(PZ_Q_MATCH, (len << 16) | (dist - 1u));
+    const bool pre_ok = bp <= f.safe_end && room != 0u && !full;
+    const bool m_ok = tb != 0u && (d & 31u) != 0u && dist <= pos - base && len <= room;
+    alive = alive && pre_ok && (is_lit || m_ok);
+    const uint32_t adv = is_lit ? 1u : len;
+    if (!COUNT_ONLY) {
+      const uint32_t tok = is_lit ? PZ_TOKEN(PZ_Q_LIT, (e >> 16) & 0xffu) : PZ_TOKEN(PZ_Q_MATCH, (len << 16) | (dist - 1u));
 #ifdef PZ_HOSTSIM
-    if (ok) pz_writer_apply(*f.hw, tok);
+      if (alive) pz_writer_apply(*f.hw, tok);
 #else
-    if (ok) pz_vstore(&sm->q[f.qhead & (PZ_QLEN - 1u)], tok | (((f.qhead >> PZ_QSHIFT) & 1u) << 31));
-    f.qhead += ok ? 1u : 0u;
+      if (alive) pz_vstore(&sm->q[qhead & (PZ_QLEN - 1u)], tok | (((qhead >> PZ_QSHIFT) & 1u) << 31));
+      qhead += alive ? 1u : 0u;
 #endif
+    }
+    pos += adv;
+    if (!is_lit && pos - base >= 2u * PZ_EXCESS) base += PZ_EXCESS; /* moveWindow after every match */
+    bp = nbp; lo = nlo; hi = nhi; e = ne;
+    if (alive) { f.bp = bp; f.pos = pos; f.base = base; f.qhead = qhead; }
   }
-  if (ok) f.bp = nbp;
-  else { f.lo = lo; f.hi = hi0; f.e = e; } /* a stopped group stays put until the trip ends */
-  f.pos += ok ? (is_lit ? 1u : len) : 0u;
-  if (ok && !is_lit && f.pos - f.base >= 2u * PZ_EXCESS) f.base += PZ_EXCESS; /* moveWindow after every match */
-  return f.live && !ok;
+  if (alive) { f.lo = lo; f.hi = hi; f.e = e; } /* else: unchanged if the trip did not run, stale if it stopped */
+  return run && !alive;
 }
 
 template <bool COUNT_ONLY>
@@ -791,23 +866,129 @@ PZ_DEV void pz_fast_loop(PzCtx &c, PzStreamSmem *sm) {
   f.lim = f.base + PZ_WINDOW;
   if (c.cap < f.lim) f.lim = c.cap;
   pz_fast_fetch(f, sm, f.bp);
-  bool stop, full;
+  bool stop;
   for (;;) {
-    /* four symbols per trip: one vote and one ring check (4 x 48 bits stay inside the resident
-     * quarters); a group that stops early repeats its verdict until the trip ends */
-    pz_fast_step<COUNT_ONLY>(f, sm, full);
-    pz_fast_step<COUNT_ONLY>(f, sm, full);
-    pz_fast_step<COUNT_ONLY>(f, sm, full);
-    stop = pz_fast_step<COUNT_ONLY>(f, sm, full);
+    /* PZ_TRIP x 48 bits stay inside the resident quarters */
+    stop = pz_fast_trip<COUNT_ONLY>(f, sm, f.live);
     if (f.live && (f.bp >> PZ_QUARTER_SHIFT) != c.q) { c.bp = f.bp; pz_cross(c, sm); }
     if (pz_warp_any(stop)) break;
   }
   if (f.live) {
     c.bp = f.bp; c.pos = f.pos; c.base = f.base; c.qhead = f.qhead;
     c.mode = PZ_M_SYMS;
-    c.need_careful = stop && !full; /* a full queue is not the symbol's fault */
+    c.need_careful = true;
   }
 }
+
+#ifndef PZ_HOSTSIM
+/* ---- the hot warp ---------------------------------------------------------------------------
+ * ONE warp per CTA runs the symbol loop of every stream of the CTA, one lane per stream slot:
+ * the per-symbol chain (window -> LUT -> bits -> next window) is serial and the same for every
+ * stream, so this is the cheapest way to issue it.  A lane works on a stream only while its
+ * service group has posted it (PzMail.state == PZ_MS_HOT); as soon as the lane meets something
+ * the loop must not decide (long code, end of block, end of input or output in sight, a verdict)
+ * it writes the stream's position back and returns the ownership; the other lanes carry on.  The
+ * lane only READS the staged input: the service group keeps the ring filled, following the bit
+ * position the lane publishes after every trip. */
+template <bool COUNT_ONLY>
+PZ_DEV void pz_hot_warp(PzStreamSmem *slots, uint32_t n_slots) {
+  const uint32_t lane = threadIdx.x & 31u;
+  PzStreamSmem *sm = slots + (lane < n_slots ? lane : 0u);
+  PzFast f;
+  f.live = false;
+  f.bp = 0; f.pos = 0; f.base = 0; f.lim = 0; f.safe_end = 0; f.qhead = 0; f.qtailc = 0; f.lo = 0; f.hi = 0; f.e = 0;
+  bool dead = lane >= n_slots;
+  for (;;) {
+    if (!f.live && !dead) { /* anything posted? */
+      const uint32_t st = pz_vload(&sm->mail.state);
+      if (st == PZ_MS_HOT) {
+        __threadfence_block();
+        f.bp = pz_vload(&sm->mail.bp); f.pos = pz_vload(&sm->mail.pos); f.base = pz_vload(&sm->mail.base);
+        f.lim = pz_vload(&sm->mail.lim); f.safe_end = pz_vload(&sm->mail.safe_end); f.qhead = pz_vload(&sm->mail.qhead);
+        pz_fast_fetch(f, sm, f.bp);
+        f.live = true;
+      } else if (st == PZ_MS_DEAD) {
+        dead = true;
+      }
+    }
+    if (!__any_sync(0xffffffffu, f.live)) {
+      if (__all_sync(0xffffffffu, dead)) break;
+      __nanosleep(100);
+      continue;
+    }
+    /* four symbols per trip: the input the trip can touch (4 x 48 bits + the look-ahead) lies in
+     * quarters q and q+1, which must be resident; a lane whose input is late idles this trip */
+    const uint32_t ring_hi = pz_vload(&sm->mail.ring_hi);
+    if (!COUNT_ONLY) f.qtailc = pz_vload(&sm->qtail);
+    const bool run = f.live && (f.bp >> PZ_QUARTER_SHIFT) + 1u < ring_hi;
+    const bool stop = pz_fast_trip<COUNT_ONLY>(f, sm, run);
+    const bool full = !COUNT_ONLY && f.qhead - f.qtailc >= PZ_QLEN;
+    if (stop && full) pz_fast_fetch(f, sm, f.bp); /* stays live: the queue drains, the window is re-read */
+    if (f.live) pz_vstore(&sm->mail.hot_bp, f.bp);
+    if (stop && !full) { /* hand the stream back: the careful path decides the next symbol */
+      pz_vstore(&sm->mail.bp, f.bp); pz_vstore(&sm->mail.pos, f.pos); pz_vstore(&sm->mail.base, f.base);
+      pz_vstore(&sm->mail.qhead, f.qhead);
+      __threadfence_block();
+      pz_vstore(&sm->mail.state, PZ_MS_SERVICE);
+      f.live = false;
+    }
+  }
+}
+
+/* Service group: posts its stream to the hot lane.  Everything requested from the ring has
+ * landed before the ownership moves. */
+PZ_DEV void pz_post_hot(PzCtx &c, PzStreamSmem *sm) {
+  pz_async_wait_all();
+  pz_syncwarp();
+  if (pz_lane() == 0) {
+    uint32_t lim = c.base + PZ_WINDOW; /* first position this run may not write at */
+    if (c.cap < lim) lim = c.cap;
+    pz_vstore(&sm->mail.bp, c.bp); pz_vstore(&sm->mail.pos, c.pos); pz_vstore(&sm->mail.base, c.base);
+    pz_vstore(&sm->mail.lim, lim); pz_vstore(&sm->mail.safe_end, c.safe_end); pz_vstore(&sm->mail.qhead, c.qhead);
+    pz_vstore(&sm->mail.hot_bp, c.bp); pz_vstore(&sm->mail.ring_hi, c.next_q);
+    __threadfence_block();
+    pz_vstore(&sm->mail.state, PZ_MS_HOT);
+  }
+  pz_syncwarp();
+  c.pending = false;
+  c.mode = PZ_M_WAIT;
+}
+
+/* Service group while the hot lane owns the stream: one poll.  Takes the stream back if the lane
+ * has returned it, otherwise keeps the ring ahead of the lane (quarters up to hot_q + 3; the slot
+ * of quarter k is the slot of quarter k - 4, which the lane has left for good). */
+PZ_DEV void pz_service_poll(PzCtx &c, PzStreamSmem *sm) {
+  const uint32_t st = pz_vload(&sm->mail.state);
+  if (c.pending) {
+    pz_async_wait_all();
+    pz_syncwarp();
+    __threadfence_block();
+    if (pz_lane() == 0) pz_vstore(&sm->mail.ring_hi, c.next_q);
+    c.pending = false;
+  }
+  if (st == PZ_MS_SERVICE) {
+    __threadfence_block();
+    c.bp = pz_vload(&sm->mail.bp); c.pos = pz_vload(&sm->mail.pos); c.base = pz_vload(&sm->mail.base);
+    c.qhead = pz_vload(&sm->mail.qhead);
+    c.q = c.bp >> PZ_QUARTER_SHIFT;
+    /* the reader's invariant again: q and q+1 resident, q+2 requested */
+    if (c.next_q < c.q + 2u) {
+      while (c.next_q < c.q + 2u) pz_ring_issue(c, sm, c.next_q++);
+      pz_async_wait_all();
+      pz_syncwarp();
+    }
+    while (c.next_q < c.q + 3u) pz_ring_issue(c, sm, c.next_q++);
+    c.mode = PZ_M_SYMS;
+    c.need_careful = true;
+    return;
+  }
+  const uint32_t hq = pz_vload(&sm->mail.hot_bp) >> PZ_QUARTER_SHIFT;
+  if (c.next_q <= hq + 3u) {
+    pz_ring_issue(c, sm, c.next_q++);
+    c.pending = true;
+  }
+}
+#endif /* !PZ_HOSTSIM */
 
 /* One symbol of the code-length code (getCodeLengths, Deflate.hs:124-156). */
 PZ_DEV int pz_pre_symbol(PzCtx &c, PzStreamSmem *sm, const uint32_t *pre_lut) {
@@ -1012,13 +1193,6 @@ PZ_DEV void pz_slow_step(PzCtx &c, PzStreamSmem *sm, const PzJob &job, uint32_t 
       uint32_t lim = c.base + PZ_WINDOW;
       if (c.cap < lim) lim = c.cap;
       if (c.bp <= c.safe_end && c.pos < lim) {
-#ifndef PZ_HOSTSIM
-        /* enter the hot loop with room for a few tokens */
-        while (!COUNT_ONLY && c.qhead - c.qtailc > PZ_QLEN - 8u) {
-          c.qtailc = pz_vload(&sm->qtail);
-          if (c.qhead - c.qtailc > PZ_QLEN - 8u) pz_backoff();
-        }
-#endif
         c.mode = PZ_M_FAST;
         return;
       }
@@ -1030,27 +1204,55 @@ PZ_DEV void pz_slow_step(PzCtx &c, PzStreamSmem *sm, const PzJob &job, uint32_t 
   }
 }
 
-/* The decoder warp: every group decodes streams first_stream, first_stream + stride, ... of the
- * job (first_stream differs per group). */
+/* The service warp (device) / the whole decoder (host build): every group takes streams
+ * first_stream, first_stream + stride, ... of the job (first_stream differs per group) through
+ * the state machine.  On the device a stream that reaches the symbol loop is posted to its lane
+ * of the hot warp and the group only feeds the input ring until the lane returns it. */
 template <bool COUNT_ONLY>
 PZ_DEV void pz_decoder_warp(const PzJob &job, uint32_t first_stream, uint32_t stride, PzStreamSmem *sm
 #ifdef PZ_HOSTSIM
                             , PzWriter *hw
+#else
+                            , bool present
 #endif
 ) {
   PzCtx c;
   c.mode = PZ_M_IDLE;
   c.next = first_stream;
-  c.in_al = nullptr; c.in_al_bytes = 0; c.bp = 0; c.q = 0; c.res = nullptr;
+  c.in_al = nullptr; c.in_al_bytes = 0; c.bp = 0; c.q = 0; c.next_q = 0; c.pending = false; c.res = nullptr;
   c.qhead = 0; c.qtailc = 0;
   c.fixed_ready = false;
 #ifdef PZ_HOSTSIM
   c.hw = hw;
-#endif
   for (;;) {
     while (c.mode != PZ_M_FAST && c.mode != PZ_M_DEAD) pz_slow_step<COUNT_ONLY>(c, sm, job, stride);
     if (!pz_warp_any(c.mode == PZ_M_FAST)) break; /* every group of the warp is out of streams */
     pz_fast_loop<COUNT_ONLY>(c, sm);
   }
+#else
+  if (!present) c.mode = PZ_M_DEAD; /* a group without a slot */
+  for (;;) {
+    if (c.mode == PZ_M_WAIT) {
+      pz_service_poll(c, sm);
+    } else if (c.mode != PZ_M_DEAD) {
+      pz_slow_step<COUNT_ONLY>(c, sm, job, stride);
+      if (c.mode == PZ_M_FAST) pz_post_hot(c, sm);
+      else if (c.mode == PZ_M_DEAD && pz_lane() == 0) pz_vstore(&sm->mail.state, PZ_MS_DEAD);
+    }
+    if (!pz_warp_any(c.mode != PZ_M_WAIT && c.mode != PZ_M_DEAD)) {
+      if (!pz_warp_any(c.mode != PZ_M_DEAD)) break;
+      /* every group waits for its hot lane: doze until one of them needs something (its stream
+       * back, a ring quarter, or the end of a copy it has requested) */
+      for (;;) {
+        bool need = false;
+        if (c.mode == PZ_M_WAIT)
+          need = c.pending || pz_vload(&sm->mail.state) != PZ_MS_HOT ||
+                 c.next_q <= (pz_vload(&sm->mail.hot_bp) >> PZ_QUARTER_SHIFT) + 3u;
+        if (pz_warp_any(need)) break;
+        __nanosleep(1000);
+      }
+    }
+  }
+#endif
   pz_async_wait_all();
 }

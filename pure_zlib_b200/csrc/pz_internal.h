@@ -8,8 +8,12 @@
 #ifndef PZ_GROUP
 #define PZ_GROUP 8 /* lanes per stream (pz_device.cuh) */
 #endif
-#define PZ_THREADS_PER_CTA 64 /* decoder warp + writer warp */
-#define PZ_GROUPS_PER_CTA (32 / PZ_GROUP) /* streams a CTA works on at a time */
+#ifndef PZ_SLOTS
+#define PZ_SLOTS 28u /* streams a CTA works on at a time (one lane of the hot warp each) */
+#endif
+#define PZ_SERVICE_WARPS ((PZ_SLOTS + 3u) / 4u) /* four slots (8 lanes each) per service warp */
+#define PZ_WARPS_PER_CTA (1u + 2u * PZ_SERVICE_WARPS) /* hot + service + writer warps */
+#define PZ_THREADS_PER_CTA (32u * PZ_WARPS_PER_CTA)
 #define PZ_MAX_STREAM_BYTES 0x1ffffff0ull /* == PZ_MAX_IN_BYTES in pz_device.cuh */
 #define PZ_ADLER_SEG 16384u /* bytes per checksum segment (one warp each) */
 

@@ -1,8 +1,10 @@
 /*
  * pz_kernels.cu -- the sm_100a kernels of libpzcuda.so.
  *
- *   pz_inflate_kernel        K1: persistent CTAs of a decoder warp + a writer warp; PZ_G lanes per
- *                            zlib stream, 32/PZ_G streams advancing in lockstep (pz_device.cuh)
+ *   pz_inflate_kernel        K1: one persistent CTA per SM holding PZ_SLOTS zlib streams: a hot warp
+ *                            (one lane per stream) runs the symbol loops, service warps parse
+ *                            headers / build tables / feed the input rings, writer warps apply
+ *                            the tokens to the output (pz_device.cuh)
  *   pz_stored_probe_kernel,  K2: streams made of stored blocks only are copied with 16-byte
  *   pz_stored_copy_kernel    accesses by whole CTAs before K1 runs (pz_stored.cuh)
  *   pz_adler_partial_kernel  K3a: one warp per 16 KiB segment of decoded output, dp4a sums
@@ -14,36 +16,50 @@
 #include "pz_internal.h"
 #include "pz_stored.cuh"
 
+/* Warp roles.  A CTA owns PZ_SLOTS stream slots: warp 0 is the hot warp (one lane per slot),
+ * PZ_SERVICE_WARPS service warps and as many writer warps serve four slots each (8 lanes per
+ * slot).  A warp's scheduler is its index modulo 4 when the CTA has the SM to itself, so the
+ * multiples of four -- the hot warp's scheduler -- go to service warps, which sleep most of the
+ * time, and the writers are dealt over the other three schedulers first. */
+__device__ __forceinline__ void pz_role(uint32_t w, uint32_t &role, uint32_t &index) {
+  if (w == 0u) { role = 0u; index = 0u; return; }
+  if ((w & 3u) == 0u) { role = 1u; index = (w >> 2) - 1u; return; } /* 4, 8, 12, ... */
+  const uint32_t k = w - 1u - (w >> 2);                              /* rank among the other warps */
+  if (k < PZ_SERVICE_WARPS) { role = 2u; index = k; return; }        /* writers */
+  role = 1u;
+  index = (PZ_WARPS_PER_CTA - 1u) / 4u + (k - PZ_SERVICE_WARPS);
+}
+
 template <bool COUNT_ONLY>
-__global__ void __launch_bounds__(PZ_THREADS_PER_CTA, 7)
+__global__ void __launch_bounds__(PZ_THREADS_PER_CTA, 1)
 pz_inflate_kernel(const PzJob job) {
   extern __shared__ __align__(16) unsigned char pz_smem_raw[];
   PzStreamSmem *slots = reinterpret_cast<PzStreamSmem *>(pz_smem_raw);
   /* empty token queues: every slot carries the phase the reader does NOT expect on lap 0 */
-  for (uint32_t i = threadIdx.x; i < PZ_GROUPS_PER_CTA * PZ_QLEN; i += PZ_THREADS_PER_CTA)
+  for (uint32_t i = threadIdx.x; i < PZ_SLOTS * PZ_QLEN; i += PZ_THREADS_PER_CTA)
     slots[i / PZ_QLEN].q[i % PZ_QLEN] = 0x80000000u;
-  if (threadIdx.x < PZ_GROUPS_PER_CTA) slots[threadIdx.x].qtail = 0;
-  /* Which warp decodes and which writes.  A warp's scheduler is its hardware slot modulo 4, and a
-   * CTA takes two consecutive slots: with fixed roles every decoder warp of the SM would sit on
-   * schedulers 0 and 2 and every writer on 1 and 3.  Flipping the roles with bit 2 of the slot
-   * spreads the decoders over all four schedulers (slots 0, 2, 5, 7, 8, 10, 13 ...). */
-  if (threadIdx.x == 0) {
-    uint32_t wid;
-    asm("mov.u32 %0, %%warpid;" : "=r"(wid));
-    slots[0].scratch[31] = (wid >> 2) & 1u;
+  if (threadIdx.x < PZ_SLOTS) {
+    slots[threadIdx.x].qtail = 0;
+    slots[threadIdx.x].mail.state = PZ_MS_SERVICE;
+    slots[threadIdx.x].mail.ring_hi = 0;
+    slots[threadIdx.x].mail.hot_bp = 0;
   }
   __syncthreads();
-  const uint32_t flip = slots[0].scratch[31];
-  __syncthreads(); /* scratch is free again before any table is built */
-  const uint32_t g = (threadIdx.x & 31u) / PZ_G; /* group within the warp = stream slot of the CTA */
-  PzStreamSmem *sm = slots + g;
-  if (((threadIdx.x >> 5) ^ flip) == 0u) {
-    /* persistent groups: group gid takes streams gid, gid + stride, ... */
-    const uint32_t gid = blockIdx.x * PZ_GROUPS_PER_CTA + g;
-    const uint32_t stride = gridDim.x * PZ_GROUPS_PER_CTA;
-    pz_decoder_warp<COUNT_ONLY>(job, job.first + gid, stride, sm);
+  uint32_t role, index;
+  pz_role(threadIdx.x >> 5, role, index);
+  if (role == 0u) {
+    pz_hot_warp<COUNT_ONLY>(slots, PZ_SLOTS);
+    return;
+  }
+  /* slot s of CTA b takes streams b + grid * (s + PZ_SLOTS * k): a batch spreads over the SMs
+   * before it fills the slots of any of them */
+  const uint32_t slot = index * 4u + (threadIdx.x & 31u) / PZ_G;
+  const bool present = slot < PZ_SLOTS;
+  PzStreamSmem *sm = slots + (present ? slot : 0u);
+  if (role == 1u) {
+    pz_decoder_warp<COUNT_ONLY>(job, job.first + blockIdx.x + gridDim.x * slot, gridDim.x * PZ_SLOTS, sm, present);
   } else if (!COUNT_ONLY) {
-    pz_writer_warp(job, sm);
+    pz_writer_warp(job, sm, present);
   }
 }
 
@@ -150,7 +166,7 @@ static int g_sm_count = 0;
 
 cudaError_t pz_kernels_configure(void) {
   cudaError_t e;
-  const size_t smem = sizeof(PzStreamSmem) * PZ_GROUPS_PER_CTA;
+  const size_t smem = sizeof(PzStreamSmem) * PZ_SLOTS;
   int dev = 0;
   if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
   if ((e = cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
@@ -170,15 +186,14 @@ cudaError_t pz_kernels_configure(void) {
   return cudaSuccess;
 }
 
-/* One resident wave of persistent CTAs: 148 SMs x CTAs/SM on B200, fewer for small batches. */
+/* One resident wave of persistent CTAs: one per SM (148 on B200), fewer for small batches. */
 cudaError_t pz_launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uint8_t *d_out, const uint64_t *d_out_off,
                               uint32_t first, uint32_t count, pz_result *d_res, cudaStream_t st) {
   if (count == 0) return cudaSuccess;
   const bool count_only = d_out == nullptr;
-  const unsigned want = (count + PZ_GROUPS_PER_CTA - 1) / PZ_GROUPS_PER_CTA;
   const unsigned wave = (unsigned)(g_sm_count * g_inflate_ctas_per_sm[count_only ? 1 : 0]);
-  const unsigned grid = want < wave ? want : wave;
-  const size_t smem = sizeof(PzStreamSmem) * PZ_GROUPS_PER_CTA;
+  const unsigned grid = count < wave ? count : wave; /* one stream per CTA before any CTA gets two */
+  const size_t smem = sizeof(PzStreamSmem) * PZ_SLOTS;
   PzJob job;
   job.in_blob = d_in; job.in_off = d_in_off; job.out_blob = d_out; job.out_off = d_out_off; job.res = d_res;
   job.first = first; job.count = count; job.skip_done = count_only ? 0u : 1u;

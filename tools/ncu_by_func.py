@@ -16,8 +16,8 @@ if not dis:
 dev = os.path.join(root, "pure_zlib_b200", "csrc", "pz_device.cuh")
 starts = []
 for n, line in enumerate(open(dev), 1):
-    m = re.match(r"(?:PZ_DEV|template).*?\b(pz_\w+)\s*\(", line)
-    if m and line.startswith("PZ_DEV"):
+    m = re.match(r"(?:PZ_DEV|PZ_COLD).*?\b(pz_\w+)\s*\(", line)
+    if m:
         starts.append((n, m.group(1)))
 def func_of(path, line):
     if not path.endswith("pz_device.cuh"): return os.path.basename(path)
@@ -27,6 +27,7 @@ def func_of(path, line):
 lines = dis.splitlines()
 kern = "ILb1" if len(sys.argv) > 2 and sys.argv[2] == "count" else "ILb0"
 i0 = next(i for i, l in enumerate(lines) if l.startswith(".text._Z17pz_inflate_kernel" + kern))
+ONLY_KERNEL = False
 chain = []; last = [("?", 0)]; per_instr = []
 for l in lines[i0 + 1:]:
     if l.startswith(".text.") or l.startswith(".section"): break

@@ -93,6 +93,8 @@ typedef struct pz_result {
 /* Flags for the batch calls. */
 #define PZ_F_NO_ADLER 0x1u    /* skip the Adler-32 pass (verdicts then stop before the trailer compare) */
 #define PZ_F_COUNT_ONLY 0x2u  /* sizing pass: decode symbols, write nothing */
+#define PZ_F_INPUT_IN_PLACE 0x4u /* host blobs: let the kernel read a pinned, mapped in_blob over PCIe instead of copying it */
+#define PZ_F_NO_DRAIN 0x8u    /* host blobs: copy the output only after the kernel (no progressive 2-D copies) */
 
 typedef struct pz_config {
   int32_t device;          /* CUDA device ordinal, -1 = current device */

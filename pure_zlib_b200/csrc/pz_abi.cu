@@ -10,11 +10,14 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "pz_internal.h"
@@ -71,6 +74,19 @@ bool is_device_ptr(const void *p) {
   return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
 }
 
+/* The device-side address of [p, p+len) if that host range is pinned and mapped (cudaHostAlloc /
+ * cudaHostRegister), else nullptr. */
+const uint8_t *mapped_device_ptr(const uint8_t *p, uint64_t len) {
+  cudaPointerAttributes a0, a1;
+  if (cudaPointerGetAttributes(&a0, p) != cudaSuccess || cudaPointerGetAttributes(&a1, p + (len ? len - 1 : 0)) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  if (a0.type != cudaMemoryTypeHost || a1.type != cudaMemoryTypeHost || !a0.devicePointer || !a1.devicePointer) return nullptr;
+  if ((const uint8_t *)a1.devicePointer - (const uint8_t *)a0.devicePointer != (ptrdiff_t)(len ? len - 1 : 0)) return nullptr;
+  return (const uint8_t *)a0.devicePointer;
+}
+
 /* Grow-only device / pinned buffers kept per host thread, so repeated calls do not pay
  * cudaMalloc.  Freed at thread exit. */
 struct Buf {
@@ -93,15 +109,19 @@ struct Buf {
 };
 
 constexpr int kStreams = 4;
+constexpr int kGroups = 8; /* pieces a host batch travels in (progressive input) */
+constexpr uint64_t kColumnBytes = 32768; /* granularity of the progress words (PZ_PROG_SHIFT) */
 constexpr size_t PZ_EXCESS_CHUNK = 32768; /* excessChunkSize (OutputWindow.hs:42-43) */
 
 struct Workspace {
   Buf d_in, d_out, d_in_off, d_out_off, d_seg_off, d_res, d_parts;
   Buf h_in, h_out; /* pinned staging for the pointer-array entry point */
   Buf h_res;       /* pinned landing zone for the verdicts: a D2H copy into pageable memory would block the host */
+  Buf h_prog;      /* pinned, mapped: the kernel's progress words (PzJob::prog) */
+  Buf d_ready;     /* device word: PzJob::in_ready */
   cudaStream_t streams[kStreams] = {};
   bool have_streams = false;
-  Workspace() { h_in.pinned = true; h_out.pinned = true; h_res.pinned = true; }
+  Workspace() { h_in.pinned = true; h_out.pinned = true; h_res.pinned = true; h_prog.pinned = true; }
   int ensure_streams() {
     if (have_streams) return PZ_E_OK;
     for (int i = 0; i < kStreams; i++) PZ_CUDA(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking));
@@ -111,7 +131,7 @@ struct Workspace {
   ~Workspace() {
     /* the CUDA context may already be gone at process exit; errors are ignored */
     d_in.release(); d_out.release(); d_in_off.release(); d_out_off.release(); d_seg_off.release();
-    d_res.release(); d_parts.release(); h_in.release(); h_out.release(); h_res.release();
+    d_res.release(); d_parts.release(); h_in.release(); h_out.release(); h_res.release(); h_prog.release(); d_ready.release();
     if (have_streams) for (int i = 0; i < kStreams; i++) cudaStreamDestroy(streams[i]);
   }
 };
@@ -277,68 +297,155 @@ int pz_inflate_batch_contig(const uint8_t *in_blob, const uint64_t *in_off, uint
     return PZ_E_OK;
   }
 
-  /* host blobs: slices of the batch pipelined over kStreams CUDA streams */
+  /* Host blobs.  The decode of a stream is one serial chain, so the whole batch goes to the device
+   * in ONE launch (slices would each take as long as the batch) and the PCIe traffic is overlapped
+   * with it instead:
+   *   input   a pinned, mapped in_blob is read by the kernel in place (its input rings are filled
+   *           with 16-byte asynchronous copies, issued far ahead of the decoder, so PCIe latency is
+   *           hidden); anything else is copied to the device first.
+   *   output  the kernel announces the finished part of every stream (PzJob::prog, 32 KiB steps) in
+   *           mapped host memory.  When all streams have the same capacity the output is a matrix
+   *           of n rows; this thread polls the progress words and sends every finished block of
+   *           columns home with one 2-D copy while the kernel is still decoding the next one.
+   *           Otherwise the output is copied after the kernel, overlapped only with the checksum. */
   if ((rc = ws.ensure_streams()) != PZ_E_OK) return rc;
   const uint64_t in_base = in_off[0] & ~(uint64_t)15, in_end = in_off[n];
   const uint64_t out_base = count_only ? 0 : (out_off[0] & ~(uint64_t)15), out_end = count_only ? 0 : out_off[n];
-  if ((rc = ws.d_in.reserve(in_end - in_base + 64)) != PZ_E_OK) return rc;
-  if (!count_only && (rc = ws.d_out.reserve(out_end - out_base + 64)) != PZ_E_OK) return rc;
-  /* device copies keep the host blobs' offsets modulo 16, so the offset tables are shared */
-  const uint8_t *d_in = (const uint8_t *)ws.d_in.p - in_base;
-  uint8_t *d_out = count_only ? nullptr : (uint8_t *)ws.d_out.p - out_base;
+  cudaStream_t s0 = ws.streams[0], s1 = ws.streams[1], s2 = ws.streams[2];
 
-  cudaStream_t s0 = ws.streams[0];
-  PZ_CUDA(cudaMemcpyAsync(d_in_off, in_off, ob, cudaMemcpyHostToDevice, s0));
-  if (!count_only) PZ_CUDA(cudaMemcpyAsync(d_out_off, out_off, ob, cudaMemcpyHostToDevice, s0));
-  if (adler) PZ_CUDA(cudaMemcpyAsync(d_seg_off, seg.data(), ob, cudaMemcpyHostToDevice, s0));
-  cudaEvent_t tables_ready;
-  PZ_CUDA(cudaEventCreateWithFlags(&tables_ready, cudaEventDisableTiming));
-  PZ_CUDA(cudaEventRecord(tables_ready, s0));
-
-  /* A stream's decode is one serial chain, so a slice of the batch takes about as long on the
-   * device as the whole batch: slicing only pays for overlapping the PCIe copies of one slice
-   * with the decode of the next.  A few big slices, one CUDA stream each. */
-  const uint64_t total_bytes = (in_end - in_off[0]) + (count_only ? 0 : out_end - out_off[0]);
-  const int n_slices = (n >= 64 && total_bytes >= (64ull << 20)) ? kStreams : 1;
-  const uint64_t slice_bytes = total_bytes / n_slices + 1;
-  if ((rc = ws.h_res.reserve(n * sizeof(pz_result))) != PZ_E_OK) { cudaEventDestroy(tables_ready); return rc; }
-  pz_result *h_res = (pz_result *)ws.h_res.p;
-  size_t first = 0;
-  int k = 0;
-  rc = PZ_E_OK;
-  while (first < n && rc == PZ_E_OK) {
-    size_t last = first;
-    uint64_t acc = 0;
-    while (last < n && (acc < slice_bytes || last == first)) {
-      acc += (in_off[last + 1] - in_off[last]) + (count_only ? 0 : out_off[last + 1] - out_off[last]);
-      last++;
-    }
-    if (k == n_slices - 1) last = n;
-    cudaStream_t st = ws.streams[k % kStreams];
-    k++;
-    auto step = [&]() -> int {
-      PZ_CUDA(cudaStreamWaitEvent(st, tables_ready, 0));
-      const uint64_t i0 = in_off[first], i1 = in_off[last];
-      if (i1 > i0) PZ_CUDA(cudaMemcpyAsync((void *)(d_in + i0), in_blob + i0, i1 - i0, cudaMemcpyHostToDevice, st));
-      PZ_CUDA(pz_launch_inflate(d_in, d_in_off, d_out, d_out_off, (uint32_t)first, (uint32_t)(last - first), d_res, st));
-      if (adler)
-        PZ_CUDA(pz_launch_adler(d_out, d_out_off, d_seg_off, (uint32_t)n, (uint32_t)first, (uint32_t)(last - first), seg[first],
-                                seg[last] - seg[first], d_res, d_parts, st));
-      if (!count_only) {
-        const uint64_t o0 = out_off[first], o1 = out_off[last];
-        if (o1 > o0) PZ_CUDA(cudaMemcpyAsync(out_blob + o0, d_out + o0, o1 - o0, cudaMemcpyDeviceToHost, st));
-      }
-      PZ_CUDA(cudaMemcpyAsync(h_res + first, d_res + first, (last - first) * sizeof(pz_result), cudaMemcpyDeviceToHost, st));
-      return PZ_E_OK;
-    };
-    rc = step();
-    first = last;
+  /* column mode: equal capacities (rows of a matrix), big enough to be worth the polling */
+  const uint64_t pitch = count_only ? 0 : out_off[1] - out_off[0];
+  bool columns = !count_only && n >= 64 && pitch >= 4 * kColumnBytes && pitch < (1ull << 31) && !(flags & PZ_F_NO_DRAIN);
+  for (size_t i = 1; columns && i < n; i++) columns = out_off[i + 1] - out_off[i] == pitch;
+  /* progressive input: the batch travels in kGroups pieces and the kernel starts the streams of a
+   * piece as soon as it has landed.  K2 cannot take part (it would read all inputs at once), so
+   * batches with stored-block streams -- recognisable from their first block header -- wait for
+   * the whole input instead. */
+  const bool in_place = (flags & PZ_F_INPUT_IN_PLACE) != 0;
+  bool progressive = columns && !in_place && n >= 8 * kGroups;
+  for (size_t i = 0; progressive && i < n; i++) {
+    const uint64_t len = in_off[i + 1] - in_off[i];
+    const uint8_t *p = in_blob + in_off[i];
+    progressive = len >= 3 && ((p[(p[1] & 0x20u) && len >= 7 ? 6 : 2] >> 1) & 3u) != 0u;
   }
-  for (int i = 0; i < kStreams; i++) {
-    cudaError_t e = cudaStreamSynchronize(ws.streams[i]);
+
+  const uint8_t *d_in = nullptr;
+  if (in_place) d_in = mapped_device_ptr(in_blob + in_base, in_end - in_base);
+  const bool staged = d_in == nullptr;
+  if (!staged) {
+    d_in -= in_base; /* the kernel indexes with the caller's offsets */
+  } else {
+    if ((rc = ws.d_in.reserve(in_end - in_base + 64)) != PZ_E_OK) return rc;
+    d_in = (const uint8_t *)ws.d_in.p - in_base; /* keeps the host blob's offsets modulo 16 */
+  }
+  uint8_t *d_out = nullptr;
+  if (!count_only) {
+    if ((rc = ws.d_out.reserve(out_end - out_base + 64)) != PZ_E_OK) return rc;
+    d_out = (uint8_t *)ws.d_out.p - out_base;
+  }
+  if ((rc = ws.h_res.reserve(n * sizeof(pz_result))) != PZ_E_OK) return rc;
+  pz_result *h_res = (pz_result *)ws.h_res.p;
+  volatile uint32_t *h_prog = nullptr;
+  uint32_t *d_prog = nullptr, *d_ready = nullptr, *h_ready = nullptr;
+  if (columns) {
+    if ((rc = ws.h_prog.reserve((n + kGroups) * sizeof(uint32_t))) != PZ_E_OK) return rc;
+    memset(ws.h_prog.p, 0, n * sizeof(uint32_t));
+    h_prog = (volatile uint32_t *)ws.h_prog.p;
+    h_ready = (uint32_t *)ws.h_prog.p + n; /* the values the ready word takes, one per piece */
+    PZ_CUDA(cudaHostGetDevicePointer((void **)&d_prog, ws.h_prog.p, 0));
+  }
+  if (progressive) {
+    if ((rc = ws.d_ready.reserve(sizeof(uint32_t))) != PZ_E_OK) return rc;
+    d_ready = (uint32_t *)ws.d_ready.p;
+  }
+  const int groups = progressive ? kGroups : 1;
+  auto group_lo = [&](int g) { return (size_t)((uint64_t)n * g / groups); };
+
+  /* PZ_TRACE=1: a timeline of this call on stderr (host clock for the copies, device clock for the kernel) */
+  static const bool trace = getenv("PZ_TRACE") != nullptr;
+  const auto t_start = std::chrono::steady_clock::now();
+  auto now_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
+  cudaEvent_t k1_start, k1_done, ready_zero;
+  PZ_CUDA(cudaEventCreateWithFlags(&k1_start, trace ? cudaEventDefault : cudaEventDisableTiming));
+  PZ_CUDA(cudaEventCreateWithFlags(&k1_done, trace ? cudaEventDefault : cudaEventDisableTiming));
+  PZ_CUDA(cudaEventCreateWithFlags(&ready_zero, cudaEventDisableTiming));
+  auto run = [&]() -> int {
+    PZ_CUDA(cudaMemcpyAsync(d_in_off, in_off, ob, cudaMemcpyHostToDevice, s0));
+    if (!count_only) PZ_CUDA(cudaMemcpyAsync(d_out_off, out_off, ob, cudaMemcpyHostToDevice, s0));
+    if (adler) PZ_CUDA(cudaMemcpyAsync(d_seg_off, seg.data(), ob, cudaMemcpyHostToDevice, s0));
+    if (progressive) {
+      /* the copies go on their own stream: the kernel (on s0) waits for them, never the reverse */
+      PZ_CUDA(cudaMemsetAsync(d_ready, 0, sizeof(uint32_t), s0));
+      PZ_CUDA(cudaEventRecord(ready_zero, s0));
+      PZ_CUDA(cudaStreamWaitEvent(s2, ready_zero, 0));
+      for (int g = 0; g < groups; g++) {
+        const uint64_t i0 = in_off[group_lo(g)], i1 = in_off[group_lo(g + 1)];
+        if (i1 > i0) PZ_CUDA(cudaMemcpyAsync((void *)(d_in + i0), in_blob + i0, i1 - i0, cudaMemcpyHostToDevice, s2));
+        h_ready[g] = (uint32_t)group_lo(g + 1);
+        PZ_CUDA(cudaMemcpyAsync(d_ready, h_ready + g, sizeof(uint32_t), cudaMemcpyHostToDevice, s2));
+      }
+    } else if (staged && in_end > in_off[0]) {
+      PZ_CUDA(cudaMemcpyAsync((void *)(d_in + in_off[0]), in_blob + in_off[0], in_end - in_off[0], cudaMemcpyHostToDevice, s0));
+    }
+    PZ_CUDA(cudaEventRecord(k1_start, s0));
+    PZ_CUDA(pz_launch_inflate(d_in, d_in_off, d_out, d_out_off, 0, (uint32_t)n, d_res, s0, d_prog, d_ready));
+    PZ_CUDA(cudaEventRecord(k1_done, s0));
+    if (adler) PZ_CUDA(pz_launch_adler(d_out, d_out_off, d_seg_off, (uint32_t)n, 0, (uint32_t)n, 0, total_segs, d_res, d_parts, s0));
+    PZ_CUDA(cudaMemcpyAsync(h_res, d_res, n * sizeof(pz_result), cudaMemcpyDeviceToHost, s0));
+    if (count_only) return PZ_E_OK;
+    if (!columns) {
+      PZ_CUDA(cudaStreamWaitEvent(s1, k1_done, 0));
+      PZ_CUDA(cudaMemcpyAsync(out_blob + out_off[0], d_out + out_off[0], out_end - out_off[0], cudaMemcpyDeviceToHost, s1));
+      return PZ_E_OK;
+    }
+    /* drain: columns [0, sent[g]) of the rows of piece g are on their way home */
+    uint64_t sent[kGroups] = {};
+    bool finished = false;
+    for (;;) {
+      bool all_sent = true, progress = false;
+      uint32_t lo[kGroups];
+      for (int g = 0; g < groups; g++) {
+        lo[g] = 0xffffffffu;
+        if (sent[g] >= pitch || finished) continue;
+        for (size_t i = group_lo(g), e = group_lo(g + 1); i < e; i++) { const uint32_t v = h_prog[i]; lo[g] = v < lo[g] ? v : lo[g]; }
+      }
+      for (int g = 0; g < groups; g++) {
+        if (sent[g] >= pitch) continue;
+        uint64_t ready = lo[g] == 0xffffffffu ? pitch : std::min<uint64_t>(lo[g], pitch) / kColumnBytes * kColumnBytes;
+        if (ready > sent[g]) {
+          const size_t r0 = group_lo(g), rows = group_lo(g + 1) - r0;
+          PZ_CUDA(cudaMemcpy2DAsync(out_blob + out_off[r0] + sent[g], pitch, d_out + out_off[r0] + sent[g], pitch, ready - sent[g], rows,
+                                    cudaMemcpyDeviceToHost, s1));
+          if (trace) fprintf(stderr, "[pz] %8.3f ms: piece %d columns [%llu, %llu) issued\n", now_ms(), g, (unsigned long long)sent[g], (unsigned long long)ready);
+          sent[g] = ready;
+          progress = true;
+        }
+        all_sent = all_sent && sent[g] >= pitch;
+      }
+      if (all_sent) break;
+      if (progress) continue;
+      const cudaError_t q = cudaEventQuery(k1_done);
+      if (q == cudaSuccess) finished = true; /* whatever is left is final now */
+      else if (q != cudaErrorNotReady) return fail_cuda(q, "cudaEventQuery");
+      else std::this_thread::yield();
+    }
+    return PZ_E_OK;
+  };
+  rc = run();
+  for (cudaStream_t st : {s0, s1, s2}) {
+    cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess && rc == PZ_E_OK) rc = fail_cuda(e, "cudaStreamSynchronize");
   }
-  cudaEventDestroy(tables_ready);
+  if (trace && rc == PZ_E_OK) {
+    float k = 0;
+    cudaEventElapsedTime(&k, k1_start, k1_done);
+    fprintf(stderr, "[pz] %8.3f ms: call done; K1(+K2) %.3f ms on the device; input %s, output %s\n", now_ms(), k,
+            !staged ? "read in place" : progressive ? "copied in pieces while the kernel runs" : "copied first",
+            columns ? "drained in column blocks" : "copied after the kernel");
+  }
+  cudaEventDestroy(k1_start);
+  cudaEventDestroy(k1_done);
+  cudaEventDestroy(ready_zero);
   if (rc == PZ_E_OK) memcpy(res, h_res, n * sizeof(pz_result));
   return rc;
 }

@@ -215,7 +215,14 @@ struct PzJob {
   pz_result *res;
   uint32_t first, count; /* streams [first, first+count) */
   uint32_t skip_done;    /* res[s].status != PZ_ST_PENDING: the stored-stream kernels dealt with s */
+  uint32_t *prog;        /* optional (host-mapped): prog[s] = decoded bytes of stream s that are final, in
+                            32 KiB steps, 0xffffffff once the stream is finished: the host driver drains
+                            finished parts of the output over PCIe while the kernel is still running */
+  const uint32_t *in_ready; /* optional: streams [0, *in_ready) have their input in device memory; the
+                               host driver raises it while it is still copying the rest of the batch */
 };
+#define PZ_PROG_SHIFT 15
+#define PZ_PROG_DONE 0xffffffffu
 #define PZ_ST_PENDING (-1)
 
 /* ---- per-stream decoder state (registers; identical in every lane of the group) -------- */
@@ -231,6 +238,7 @@ struct PzCtx {
   uint32_t q;           /* ring quarter holding bp; quarters q and q+1 are resident        */
   uint32_t next_q;      /* first quarter not requested yet (q+3 in steady state)           */
   bool pending;         /* a quarter requested while the hot lane owns the stream has not been awaited */
+  bool starved;         /* idle because the next stream's input has not reached the device yet */
   uint32_t pos;  /* bytes decoded                                                          */
   uint32_t base; /* bytes the reference would already have published (multiple of 32 KiB)  */
   uint32_t cap;
@@ -546,10 +554,22 @@ struct PzWriter {
   const uint8_t *in; /* its first compressed byte (stored runs copy from the input) */
   uint32_t pos;      /* bytes written */
   uint32_t op, need, a0; /* control message being assembled: `need` argument tokens to go */
+  uint32_t sidx, pub;    /* current stream; 32 KiB steps of it already published in job->prog */
   bool exited;
 };
+#ifdef PZ_HOSTSIM
+PZ_DEV void pz_publish(PzWriter &, uint32_t) {}
+#else
+/* Tells the host driver that the first `value` bytes of the current stream are final. */
+PZ_DEV void pz_publish(PzWriter &w, uint32_t value) {
+  if (w.job->prog == nullptr || w.out == nullptr) return;
+  pz_syncwarp();
+  __threadfence_system(); /* the bytes first, then the word that announces them */
+  if (pz_lane() == 0) *(volatile uint32_t *)(w.job->prog + w.sidx) = value;
+}
+#endif
 PZ_DEV void pz_writer_init(PzWriter &w, const PzJob *job) {
-  w.job = job; w.out = nullptr; w.in = nullptr; w.pos = 0; w.op = 0; w.need = 0; w.a0 = 0; w.exited = false;
+  w.job = job; w.out = nullptr; w.in = nullptr; w.pos = 0; w.op = 0; w.need = 0; w.a0 = 0; w.sidx = 0; w.pub = 0; w.exited = false;
 }
 
 /* Applies one token completely (no deferral): the writer's path for everything that is not a
@@ -558,6 +578,8 @@ PZ_DEV void pz_writer_apply(PzWriter &w, uint32_t raw) {
   const uint32_t lane = (uint32_t)pz_lane();
   if (w.need) { /* argument of a control message */
     if (w.op == PZ_C_NEWSTREAM) {
+      pz_publish(w, PZ_PROG_DONE); /* the previous stream of this slot is complete */
+      w.sidx = raw; w.pub = 0;
       w.out = w.job->out_blob + w.job->out_off[raw];
       w.in = w.job->in_blob + w.job->in_off[raw];
       w.pos = 0; w.need = 0;
@@ -583,7 +605,7 @@ PZ_DEV void pz_writer_apply(PzWriter &w, uint32_t raw) {
     w.pos += len;
   } else {
     const uint32_t op = (raw >> 26) & 7u;
-    if (op == PZ_C_EXIT) w.exited = true;
+    if (op == PZ_C_EXIT) { pz_publish(w, PZ_PROG_DONE); w.exited = true; }
     else { w.op = op; w.need = op == PZ_C_NEWSTREAM ? 1u : 2u; }
   }
 }
@@ -655,6 +677,7 @@ PZ_DEV void pz_writer_warp(const PzJob &job, PzStreamSmem *sm, bool present) {
         pz_writer_apply(w, r0 & 0x7fffffffu);
         tail++;
         pz_vstore(&sm->qtail, tail);
+        if (!w.exited && (w.pos >> PZ_PROG_SHIFT) != w.pub) { w.pub = w.pos >> PZ_PROG_SHIFT; pz_publish(w, w.pub << PZ_PROG_SHIFT); }
       }
       if (!pz_warp_any(!w.exited)) break;
       continue;
@@ -695,6 +718,9 @@ PZ_DEV void pz_writer_warp(const PzJob &job, PzStreamSmem *sm, bool present) {
     w.pos += B;
     tail += n;
     pz_vstore(&sm->qtail, tail);
+    if (job.prog != nullptr && pz_warp_any((w.pos >> PZ_PROG_SHIFT) != w.pub)) {
+      if ((w.pos >> PZ_PROG_SHIFT) != w.pub) { w.pub = w.pos >> PZ_PROG_SHIFT; pz_publish(w, w.pub << PZ_PROG_SHIFT); }
+    }
   }
 }
 #endif /* !PZ_HOSTSIM */
@@ -1156,13 +1182,23 @@ PZ_DEV void pz_block_end(PzCtx &c, PzStreamSmem *sm) {
 template <bool COUNT_ONLY>
 PZ_DEV void pz_slow_step(PzCtx &c, PzStreamSmem *sm, const PzJob &job, uint32_t stride) {
   if (c.mode == PZ_M_IDLE) {
-    while (job.skip_done && c.next < job.first + job.count && job.res[c.next].status != PZ_ST_PENDING) c.next += stride;
+    while (job.skip_done && c.next < job.first + job.count && job.res[c.next].status != PZ_ST_PENDING) {
+#ifndef PZ_HOSTSIM
+      if (job.prog != nullptr && pz_lane() == 0) *(volatile uint32_t *)(job.prog + c.next) = PZ_PROG_DONE; /* K2 wrote it before K1 started */
+#endif
+      c.next += stride;
+    }
     if (c.next >= job.first + job.count) {
       pz_push<COUNT_ONLY>(c, sm, PZ_TOKEN(PZ_Q_CTRL, PZ_C_EXIT << 26));
       c.mode = PZ_M_DEAD;
       return;
     }
     const uint32_t s = c.next;
+#ifndef PZ_HOSTSIM
+    /* the stream's input may still be on its way to the device: stay idle, the warp loop dozes */
+    c.starved = job.in_ready != nullptr && *(const volatile uint32_t *)job.in_ready <= s;
+    if (c.starved) return;
+#endif
     c.next += stride;
     const uint64_t i0 = job.in_off[s], i1 = job.in_off[s + 1];
     if (COUNT_ONLY) {
@@ -1219,7 +1255,7 @@ PZ_DEV void pz_decoder_warp(const PzJob &job, uint32_t first_stream, uint32_t st
   PzCtx c;
   c.mode = PZ_M_IDLE;
   c.next = first_stream;
-  c.in_al = nullptr; c.in_al_bytes = 0; c.bp = 0; c.q = 0; c.next_q = 0; c.pending = false; c.res = nullptr;
+  c.in_al = nullptr; c.in_al_bytes = 0; c.bp = 0; c.q = 0; c.next_q = 0; c.pending = false; c.starved = false; c.res = nullptr;
   c.qhead = 0; c.qtailc = 0;
   c.fixed_ready = false;
 #ifdef PZ_HOSTSIM
@@ -1239,7 +1275,7 @@ PZ_DEV void pz_decoder_warp(const PzJob &job, uint32_t first_stream, uint32_t st
       if (c.mode == PZ_M_FAST) pz_post_hot(c, sm);
       else if (c.mode == PZ_M_DEAD && pz_lane() == 0) pz_vstore(&sm->mail.state, PZ_MS_DEAD);
     }
-    if (!pz_warp_any(c.mode != PZ_M_WAIT && c.mode != PZ_M_DEAD)) {
+    if (!pz_warp_any(c.mode != PZ_M_WAIT && c.mode != PZ_M_DEAD && !(c.mode == PZ_M_IDLE && c.starved))) {
       if (!pz_warp_any(c.mode != PZ_M_DEAD)) break;
       /* every group waits for its hot lane: doze until one of them needs something (its stream
        * back, a ring quarter, or the end of a copy it has requested) */
@@ -1248,6 +1284,8 @@ PZ_DEV void pz_decoder_warp(const PzJob &job, uint32_t first_stream, uint32_t st
         if (c.mode == PZ_M_WAIT)
           need = c.pending || pz_vload(&sm->mail.state) != PZ_MS_HOT ||
                  c.next_q <= (pz_vload(&sm->mail.hot_bp) >> PZ_QUARTER_SHIFT) + 3u;
+        else if (c.mode == PZ_M_IDLE)
+          need = *(const volatile uint32_t *)job.in_ready > c.next;
         if (pz_warp_any(need)) break;
         __nanosleep(1000);
       }

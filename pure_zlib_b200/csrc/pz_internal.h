@@ -18,9 +18,12 @@
 #define PZ_ADLER_SEG 16384u /* bytes per checksum segment (one warp each) */
 
 /* Stream s = first + k decodes in_blob[in_off[s], in_off[s+1]) into out_blob[out_off[s], out_off[s+1]).
- * d_out == nullptr selects the sizing pass. */
+ * d_out == nullptr selects the sizing pass.  d_prog (optional, host-mapped, one word per stream, zeroed by
+ * the caller) receives the progress words described at PzJob::prog.  d_in_ready (optional, device word): see
+ * PzJob::in_ready; K2 is skipped then. */
 cudaError_t pz_launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uint8_t *d_out, const uint64_t *d_out_off,
-                              uint32_t first, uint32_t count, pz_result *d_res, cudaStream_t st);
+                              uint32_t first, uint32_t count, pz_result *d_res, cudaStream_t st, uint32_t *d_prog = nullptr,
+                              const uint32_t *d_in_ready = nullptr);
 /* Adler-32 of each decoded stream (segments [seg_off[first], seg_off[first+count])), then the
  * trailer comparison that completes the verdict (Deflate.hs:52-63). */
 cudaError_t pz_launch_adler(const uint8_t *d_out, const uint64_t *d_out_off, const uint64_t *d_seg_off, uint32_t n_total,

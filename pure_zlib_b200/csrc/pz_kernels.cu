@@ -188,7 +188,8 @@ cudaError_t pz_kernels_configure(void) {
 
 /* One resident wave of persistent CTAs: one per SM (148 on B200), fewer for small batches. */
 cudaError_t pz_launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uint8_t *d_out, const uint64_t *d_out_off,
-                              uint32_t first, uint32_t count, pz_result *d_res, cudaStream_t st) {
+                              uint32_t first, uint32_t count, pz_result *d_res, cudaStream_t st, uint32_t *d_prog,
+                              const uint32_t *d_in_ready) {
   if (count == 0) return cudaSuccess;
   const bool count_only = d_out == nullptr;
   const unsigned wave = (unsigned)(g_sm_count * g_inflate_ctas_per_sm[count_only ? 1 : 0]);
@@ -197,8 +198,13 @@ cudaError_t pz_launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uin
   PzJob job;
   job.in_blob = d_in; job.in_off = d_in_off; job.out_blob = d_out; job.out_off = d_out_off; job.res = d_res;
   job.first = first; job.count = count; job.skip_done = count_only ? 0u : 1u;
+  job.prog = count_only ? nullptr : d_prog;
+  job.in_ready = d_in_ready;
+  if (d_in_ready) job.skip_done = 0; /* K2 would read input that is not there yet: K1 decodes every stream */
   if (count_only) {
     pz_inflate_kernel<true><<<grid, PZ_THREADS_PER_CTA, smem, st>>>(job);
+  } else if (d_in_ready) {
+    pz_inflate_kernel<false><<<grid, PZ_THREADS_PER_CTA, smem, st>>>(job);
   } else {
     /* K2 first: all-stored streams are copied at memory speed and marked done; K1 takes the rest */
     pz_stored_probe_kernel<<<(count + 255u) / 256u, 256, 0, st>>>(job);

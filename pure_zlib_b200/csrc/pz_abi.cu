@@ -109,6 +109,7 @@ struct Buf {
 };
 
 constexpr int kStreams = 4;
+constexpr int kSlices = 8; /* slices of a host batch whose copies and kernels are pipelined */
 constexpr int kGroups = 8; /* pieces a host batch travels in (progressive input) */
 constexpr uint64_t kColumnBytes = 32768; /* granularity of the progress words (PZ_PROG_SHIFT) */
 constexpr size_t PZ_EXCESS_CHUNK = 32768; /* excessChunkSize (OutputWindow.hs:42-43) */
@@ -322,12 +323,18 @@ int pz_inflate_batch_contig(const uint8_t *in_blob, const uint64_t *in_off, uint
    * batches with stored-block streams -- recognisable from their first block header -- wait for
    * the whole input instead. */
   const bool in_place = (flags & PZ_F_INPUT_IN_PLACE) != 0;
-  bool progressive = columns && !in_place && n >= 8 * kGroups;
+  bool progressive = columns && !in_place && n >= 8 * kGroups && n <= 2 * (size_t)pz_inflate_slots();
   for (size_t i = 0; progressive && i < n; i++) {
     const uint64_t len = in_off[i + 1] - in_off[i];
     const uint8_t *p = in_blob + in_off[i];
     progressive = len >= 3 && ((p[(p[1] & 0x20u) && len >= 7 ? 6 : 2] >> 1) & 3u) != 0u;
   }
+  /* Everything else -- many more streams than the device has slots, stored-block streams, ragged
+   * capacities -- is cut into slices of consecutive streams: the kernels of the slices follow each
+   * other on one CUDA stream while the copies of their neighbours run on two others. */
+  columns = columns && progressive;
+  const uint64_t total_bytes = (in_end - in_off[0]) + (count_only ? 0 : out_end - out_off[0]);
+  const int n_slices = (!progressive && n >= 64 && total_bytes >= (64ull << 20)) ? kSlices : 1;
 
   const uint8_t *d_in = nullptr;
   if (in_place) d_in = mapped_device_ptr(in_blob + in_base, in_end - in_base);
@@ -384,8 +391,48 @@ int pz_inflate_batch_contig(const uint8_t *in_blob, const uint64_t *in_off, uint
         h_ready[g] = (uint32_t)group_lo(g + 1);
         PZ_CUDA(cudaMemcpyAsync(d_ready, h_ready + g, sizeof(uint32_t), cudaMemcpyHostToDevice, s2));
       }
-    } else if (staged && in_end > in_off[0]) {
-      PZ_CUDA(cudaMemcpyAsync((void *)(d_in + in_off[0]), in_blob + in_off[0], in_end - in_off[0], cudaMemcpyHostToDevice, s0));
+    } else {
+      /* sliced: H2D on s2, kernels on s0, D2H on s1 */
+      PZ_CUDA(cudaEventRecord(k1_start, s0));
+      PZ_CUDA(cudaEventRecord(ready_zero, s0)); /* the offset tables are queued: s2 may not overtake a previous call's kernels */
+      PZ_CUDA(cudaStreamWaitEvent(s2, ready_zero, 0));
+      const uint64_t slice_bytes = total_bytes / n_slices + 1;
+      std::vector<cudaEvent_t> evs;
+      size_t first = 0;
+      for (int k = 0; first < n; k++) {
+        size_t last = first;
+        uint64_t acc = 0;
+        while (last < n && (acc < slice_bytes || last == first)) {
+          acc += (in_off[last + 1] - in_off[last]) + (count_only ? 0 : out_off[last + 1] - out_off[last]);
+          last++;
+        }
+        if (k == n_slices - 1) last = n;
+        cudaEvent_t ev_in, ev_k;
+        PZ_CUDA(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
+        evs.push_back(ev_in);
+        PZ_CUDA(cudaEventCreateWithFlags(&ev_k, cudaEventDisableTiming));
+        evs.push_back(ev_k);
+        const uint64_t i0 = in_off[first], i1 = in_off[last];
+        if (staged && i1 > i0) PZ_CUDA(cudaMemcpyAsync((void *)(d_in + i0), in_blob + i0, i1 - i0, cudaMemcpyHostToDevice, s2));
+        PZ_CUDA(cudaEventRecord(ev_in, s2));
+        PZ_CUDA(cudaStreamWaitEvent(s0, ev_in, 0));
+        PZ_CUDA(pz_launch_inflate(d_in, d_in_off, d_out, d_out_off, (uint32_t)first, (uint32_t)(last - first), d_res, s0));
+        if (adler)
+          PZ_CUDA(pz_launch_adler(d_out, d_out_off, d_seg_off, (uint32_t)n, (uint32_t)first, (uint32_t)(last - first), seg[first],
+                                  seg[last] - seg[first], d_res, d_parts, s0));
+        PZ_CUDA(cudaEventRecord(ev_k, s0));
+        if (!count_only) {
+          const uint64_t o0 = out_off[first], o1 = out_off[last];
+          PZ_CUDA(cudaStreamWaitEvent(s1, ev_k, 0));
+          if (o1 > o0) PZ_CUDA(cudaMemcpyAsync(out_blob + o0, d_out + o0, o1 - o0, cudaMemcpyDeviceToHost, s1));
+        }
+        first = last;
+      }
+      PZ_CUDA(cudaEventRecord(k1_done, s0));
+      PZ_CUDA(cudaMemcpyAsync(h_res, d_res, n * sizeof(pz_result), cudaMemcpyDeviceToHost, s0));
+      for (cudaStream_t st : {s0, s1, s2}) PZ_CUDA(cudaStreamSynchronize(st));
+      for (cudaEvent_t e : evs) cudaEventDestroy(e);
+      return PZ_E_OK;
     }
     PZ_CUDA(cudaEventRecord(k1_start, s0));
     PZ_CUDA(pz_launch_inflate(d_in, d_in_off, d_out, d_out_off, 0, (uint32_t)n, d_res, s0, d_prog, d_ready));
@@ -393,11 +440,6 @@ int pz_inflate_batch_contig(const uint8_t *in_blob, const uint64_t *in_off, uint
     if (adler) PZ_CUDA(pz_launch_adler(d_out, d_out_off, d_seg_off, (uint32_t)n, 0, (uint32_t)n, 0, total_segs, d_res, d_parts, s0));
     PZ_CUDA(cudaMemcpyAsync(h_res, d_res, n * sizeof(pz_result), cudaMemcpyDeviceToHost, s0));
     if (count_only) return PZ_E_OK;
-    if (!columns) {
-      PZ_CUDA(cudaStreamWaitEvent(s1, k1_done, 0));
-      PZ_CUDA(cudaMemcpyAsync(out_blob + out_off[0], d_out + out_off[0], out_end - out_off[0], cudaMemcpyDeviceToHost, s1));
-      return PZ_E_OK;
-    }
     /* drain: columns [0, sent[g]) of the rows of piece g are on their way home */
     uint64_t sent[kGroups] = {};
     bool finished = false;
@@ -440,8 +482,8 @@ int pz_inflate_batch_contig(const uint8_t *in_blob, const uint64_t *in_off, uint
     float k = 0;
     cudaEventElapsedTime(&k, k1_start, k1_done);
     fprintf(stderr, "[pz] %8.3f ms: call done; K1(+K2) %.3f ms on the device; input %s, output %s\n", now_ms(), k,
-            !staged ? "read in place" : progressive ? "copied in pieces while the kernel runs" : "copied first",
-            columns ? "drained in column blocks" : "copied after the kernel");
+            !staged ? "read in place" : progressive ? "copied in pieces while the kernel runs" : "copied slice by slice",
+            columns ? "drained in column blocks" : "copied slice by slice");
   }
   cudaEventDestroy(k1_start);
   cudaEventDestroy(k1_done);

@@ -32,3 +32,5 @@ cudaError_t pz_launch_adler(const uint8_t *d_out, const uint64_t *d_out_off, con
 /* canonical codes of lens[0..n) (n <= 288) into codes[0..n) */
 cudaError_t pz_launch_code_values(const uint8_t *d_lens, int n, uint16_t *d_codes, cudaStream_t st);
 cudaError_t pz_kernels_configure(void);
+/* streams K1 decodes at the same time on this device (SMs x slots per CTA) */
+int pz_inflate_slots(void);

@@ -186,6 +186,8 @@ cudaError_t pz_kernels_configure(void) {
   return cudaSuccess;
 }
 
+int pz_inflate_slots(void) { return g_sm_count * g_inflate_ctas_per_sm[0] * (int)PZ_SLOTS; }
+
 /* One resident wave of persistent CTAs: one per SM (148 on B200), fewer for small batches. */
 cudaError_t pz_launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uint8_t *d_out, const uint64_t *d_out_off,
                               uint32_t first, uint32_t count, pz_result *d_res, cudaStream_t st, uint32_t *d_prog,

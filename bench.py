@@ -35,6 +35,8 @@ CONFIGS = {
     "text256k": dict(workload="4096 x 256 KiB synthetic text, system zlib level 6 (BASELINE configs[1])", n=4096),
     "records4k": dict(workload="2^20 x 4 KiB text records, 75% Z_FIXED / 25% dynamic (BASELINE configs[2])", n=1 << 20),
     "stored16m": dict(workload="512 x 16 MiB random bytes, zlib level 6 => stored blocks (BASELINE configs[4])", n=512),
+    "huge": dict(workload="ONE zlib stream of --streams MiB (default 1024) of synthetic text, level 9, compressed in 16 MiB pieces "
+                          "and stitched (BASELINE configs[3]); block-parallel path K4", n=1024),
 }
 
 
@@ -177,7 +179,9 @@ def main():
     config = {"workload": cfg["workload"], "config": a.config, "streams_per_gpu": n,
               "l2": "per-step working set (compressed + decoded batch) exceeds the 126 MB L2; no flush needed",
               "parallelism": f"{world} independent shard(s), no collective on the data path"}
-    if a.streams:
+    if a.config == "huge":
+        config["streams_per_gpu"], config["stream_mib"] = 1, n
+    elif a.streams:
         config["workload"] += f" [DEBUG: {n} streams]"
 
     if a.impl == "reference":
@@ -264,7 +268,8 @@ def main():
     k1.record()
     barrier()
     # the decoder warps alone (sizing pass: same bit-stream work, no tokens, no writer warps)
-    batch_dec = L.pz_batch_create(in_off.ctypes.data_as(p64), None, c.n, _lib.PZ_F_COUNT_ONLY)
+    # (not for the one huge stream: its sizing pass is the serial chain K4 exists to avoid)
+    batch_dec = None if a.config == "huge" else L.pz_batch_create(in_off.ctypes.data_as(p64), None, c.n, _lib.PZ_F_COUNT_ONLY)
     d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ms_dec = None
     if batch_dec:
@@ -293,9 +298,17 @@ def main():
     if a.verify:
         from pure_zlib_b200 import corpus as corpus_mod
         host = d_out.cpu().numpy()
-        for i in np.linspace(0, c.n - 1, min(a.verify, c.n)).astype(int):
-            o = int(c.out_off[i])
-            assert host[o:o + int(c.out_len[i])].tobytes() == corpus_mod.decoded(c, int(i)), f"stream {i} differs"
+        if a.config == "huge":  # three 16 MiB pieces of the one stream, regenerated
+            piece = 16 << 20
+            n_pieces = (int(c.out_len[0]) + piece - 1) // piece
+            for k in sorted({0, n_pieces // 2, n_pieces - 1}):
+                want = corpus_mod.decoded_piece(k, min(piece, int(c.out_len[0]) - k * piece))
+                o = int(c.out_off[0]) + k * piece
+                assert host[o:o + len(want)].tobytes() == want, f"piece {k} differs"
+        else:
+            for i in np.linspace(0, c.n - 1, min(a.verify, c.n)).astype(int):
+                o = int(c.out_off[i])
+                assert host[o:o + int(c.out_len[i])].tobytes() == corpus_mod.decoded(c, int(i)), f"stream {i} differs"
         del host
 
     out_bytes_total = c.out_bytes * world
@@ -341,7 +354,10 @@ def main():
         i = c.n // 2
         o = int(c.out_off[i])
         from pure_zlib_b200 import corpus as corpus_mod
-        assert hview[o:o + int(c.out_len[i])].tobytes() == corpus_mod.decoded(c, i)
+        if a.config == "huge":
+            assert hview[o:o + (1 << 20)].tobytes() == corpus_mod.decoded_piece(0)[: 1 << 20]
+        else:
+            assert hview[o:o + int(c.out_len[i])].tobytes() == corpus_mod.decoded(c, i)
         line["e2e"] = {"value": out_bytes_total * e2e_steps / sec / 1e9, "unit": "GB/s",
                        "h2d_bytes_per_step": int(c.in_off[-1]) + 3 * 8 * (c.n + 1),
                        "d2h_bytes_per_step": int(c.out_off[-1]) + 48 * c.n, "steps": e2e_steps,

@@ -94,6 +94,7 @@ typedef struct pz_result {
 #define PZ_F_NO_ADLER 0x1u    /* skip the Adler-32 pass (verdicts then stop before the trailer compare) */
 #define PZ_F_COUNT_ONLY 0x2u  /* sizing pass: decode symbols, write nothing */
 #define PZ_F_INPUT_IN_PLACE 0x4u /* host blobs: let the kernel read a pinned, mapped in_blob over PCIe instead of copying it */
+#define PZ_F_NO_HUGE 0x10u   /* never use the block-parallel path (K4) for huge streams */
 #define PZ_F_NO_DRAIN 0x8u    /* host blobs: copy the output only after the kernel (no progressive 2-D copies) */
 
 typedef struct pz_config {
@@ -107,6 +108,14 @@ typedef struct pz_config {
 int pz_init(const pz_config *cfg);
 void pz_shutdown(void);
 int pz_abi_version(void);
+/* Tuning knobs.  PZ_OPT_HUGE_BYTES: compressed size from which a stream is decoded block-parallel
+ * (K4) instead of as one serial chain; default 4 MiB, environment PZ_HUGE_BYTES at start-up. */
+#define PZ_OPT_HUGE_BYTES 1
+int pz_set_option(int key, uint64_t value);
+/* Process-wide counters (diagnostics, tests): streams the block-parallel path decoded / declined. */
+#define PZ_CTR_HUGE_DONE 1
+#define PZ_CTR_HUGE_DECLINED 2
+uint64_t pz_get_counter(int which);
 /* Human-readable text of the last CUDA failure on this thread. */
 const char *pz_last_error(void);
 

@@ -22,10 +22,15 @@ class PzResult(C.Structure):
 
 
 # every symbol include/pzcuda.h declares: (name, restype, argtypes)
+PZ_OPT_HUGE_BYTES = 1
+PZ_F_NO_HUGE = 0x10
+
 SYMBOLS = [
     ("pz_init", C.c_int, [C.c_void_p]),
     ("pz_shutdown", None, []),
     ("pz_abi_version", C.c_int, []),
+    ("pz_set_option", C.c_int, [C.c_int, C.c_uint64]),
+    ("pz_get_counter", C.c_uint64, [C.c_int]),
     ("pz_last_error", C.c_char_p, []),
     ("pz_inflate_batch", C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p),
                                    C.POINTER(C.c_size_t), C.c_size_t, C.POINTER(PzResult), C.c_uint32]),

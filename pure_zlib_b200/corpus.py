@@ -7,6 +7,12 @@ them BEFORE the process initialises CUDA.
   config 2  text256k : 4096 x 256 KiB synthetic text, zlib level 6 (dynamic Huffman)
   config 3  records4k: 2^20 x 4 KiB text records, 75 % Z_FIXED / 25 % default strategy
   config 5  stored16m: 512 x 16 MiB random bytes, level 6 (=> ~16 KiB stored blocks)
+  config 4  huge     : ONE zlib stream of n MiB of the same text at level 9.  A single-threaded
+                       level-9 pass over 1 GiB takes minutes, so the text is compressed in 16 MiB
+                       pieces on all cores (raw deflate, each piece ended with Z_FULL_FLUSH) and
+                       the pieces are concatenated behind one zlib header, with one Adler-32
+                       trailer: a valid single stream (what pigz -i writes) whose only difference
+                       from a one-pass stream is an empty stored block every 16 MiB
 """
 from __future__ import annotations
 
@@ -88,6 +94,17 @@ def _job_records4k(args):
     return out
 
 
+_HUGE_PIECE = 16 << 20
+
+
+def _job_huge(args):
+    k, nbytes, level, last = args
+    d = text(nbytes, 3_000_000 + k)
+    co = zlib.compressobj(level, zlib.DEFLATED, -15)
+    z = co.compress(d) + (co.flush(zlib.Z_FINISH) if last else co.flush(zlib.Z_FULL_FLUSH))
+    return z, zlib.adler32(d), len(d)
+
+
 def _job_stored16m(args):
     i, nbytes = args
     d = np.random.default_rng(5_000_000 + i).integers(0, 256, nbytes, dtype=np.uint8).tobytes()
@@ -160,6 +177,26 @@ def stored16m(n: int = 512, nbytes: int = 16 << 20, workers: int | None = None) 
     with _pool(workers) as p:
         items = p.map(_job_stored16m, [(i, nbytes) for i in range(n)])
     return _pack("stored16m", items, [nbytes] * n)
+
+
+def huge(n_mib: int = 1024, level: int = 9, workers: int | None = None) -> Corpus:
+    """One stream of n_mib MiB (see the module docstring for how it is put together)."""
+    total = n_mib << 20
+    pieces = [(k, min(_HUGE_PIECE, total - k * _HUGE_PIECE), level, (k + 1) * _HUGE_PIECE >= total)
+              for k in range((total + _HUGE_PIECE - 1) // _HUGE_PIECE)]
+    with _pool(workers) as p:
+        parts = p.map(_job_huge, pieces)
+    adler = 1
+    for _, a, ln in parts:  # adler32_combine: A = A1 + A2 - 1, B = B1 + B2 + len2 * (A1 - 1)  (mod 65521)
+        a1, b1, a2, b2 = adler & 0xffff, adler >> 16, a & 0xffff, a >> 16
+        adler = (((b1 + b2 + ln % 65521 * ((a1 + 65520) % 65521)) % 65521) << 16) | ((a1 + a2 + 65520) % 65521)
+    z = b"\x78\xda" + b"".join(zz for zz, _, _ in parts) + adler.to_bytes(4, "big")
+    return _pack(f"huge{n_mib}m-l{level}", [(z, adler)], [total])
+
+
+def decoded_piece(k: int, nbytes: int = _HUGE_PIECE) -> bytes:
+    """Plain text of piece k of the huge stream."""
+    return text(nbytes, 3_000_000 + k)
 
 
 def decoded(corpus: Corpus, i: int) -> bytes:

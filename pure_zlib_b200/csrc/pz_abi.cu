@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdlib>
 #include <cstdio>
@@ -39,6 +40,8 @@ int fail_cuda(cudaError_t e, const char *what) {
     if (e__ != cudaSuccess) return fail_cuda(e__, #call); \
   } while (0)
 
+uint64_t g_huge_bytes = 4ull << 20; /* compressed size from which a stream goes to K4 (PZ_HUGE_BYTES overrides) */
+std::atomic<uint64_t> g_huge_done{0}, g_huge_declined{0};
 std::once_flag g_once;
 int g_init_rc = PZ_E_STATE;
 int g_device = -1;
@@ -57,6 +60,7 @@ void do_init(const pz_config *cfg) {
   cudaGetDevice(&g_device);
   e = pz_kernels_configure();
   if (e != cudaSuccess) { g_init_rc = fail_cuda(e, "pz_kernels_configure"); return; }
+  if (const char *h = getenv("PZ_HUGE_BYTES")) { const long long v = atoll(h); if (v > 0) g_huge_bytes = (uint64_t)v; }
   g_init_rc = PZ_E_OK;
 }
 
@@ -120,6 +124,7 @@ struct Workspace {
   Buf h_res;       /* pinned landing zone for the verdicts: a D2H copy into pageable memory would block the host */
   Buf h_prog;      /* pinned, mapped: the kernel's progress words (PzJob::prog) */
   Buf d_ready;     /* device word: PzJob::in_ready */
+  Buf k4_cand, k4_keep, k4_start, k4_off, k4_len, k4_res, k4_sym, k4_word, k4_grp, k4_gfirst, k4_gw; /* K4 scratch (one huge stream at a time) */
   cudaStream_t streams[kStreams] = {};
   bool have_streams = false;
   Workspace() { h_in.pinned = true; h_out.pinned = true; h_res.pinned = true; h_prog.pinned = true; }
@@ -133,6 +138,7 @@ struct Workspace {
     /* the CUDA context may already be gone at process exit; errors are ignored */
     d_in.release(); d_out.release(); d_in_off.release(); d_out_off.release(); d_seg_off.release();
     d_res.release(); d_parts.release(); h_in.release(); h_out.release(); h_res.release(); h_prog.release(); d_ready.release();
+    k4_cand.release(); k4_keep.release(); k4_start.release(); k4_off.release(); k4_len.release(); k4_res.release(); k4_sym.release(); k4_word.release(); k4_grp.release(); k4_gfirst.release(); k4_gw.release();
     if (have_streams) for (int i = 0; i < kStreams; i++) cudaStreamDestroy(streams[i]);
   }
 };
@@ -161,6 +167,178 @@ bool in_sizes_ok(const uint64_t *off, size_t n) {
   return true;
 }
 
+
+/* ---- K4 driver: one huge stream, block-parallel (kernels: pz_huge.cuh, block jobs on K1) --------
+ * Returns 1 with *out filled when the stream was decoded, 0 when K4 declines (the caller then leaves
+ * the stream to the serial path, which reproduces every verdict of the reference), < 0 on errors.
+ * Declining is always safe, so every doubt -- an odd header, a block the search cannot see more
+ * than a few times, any verdict other than success inside a block, a reference before the stream's
+ * first byte -- ends here. */
+constexpr uint32_t kBlockCap = 32u << 20; /* most bytes one speculative block may produce */
+constexpr int kMaxGaps = 256; /* blocks the search cannot see (stored, fixed) that K4 will size one by one before giving up */
+
+int huge_stream(const uint8_t *d_in_blob, const uint64_t *d_in_off_i, uint64_t in_byte_off, uint64_t in_len, uint8_t *d_out_i,
+                uint64_t out_cap, pz_result *out, cudaStream_t st) {
+  Workspace &ws = g_ws;
+  if (in_len < 16 || in_len > PZ_MAX_STREAM_BYTES) return 0;
+  static const bool trace = getenv("PZ_TRACE") != nullptr;
+  const auto t_start = std::chrono::steady_clock::now();
+  auto now_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
+  const uint8_t *d_stream = d_in_blob + in_byte_off;
+  uint8_t head[8];
+  PZ_CUDA(cudaMemcpyAsync(head, d_stream, 8, cudaMemcpyDeviceToHost, st));
+  PZ_CUDA(cudaStreamSynchronize(st));
+  const uint32_t cmf = head[0], flg = head[1];
+  if (((cmf << 8) | flg) % 31u != 0u || (cmf & 15u) != 8u || (cmf >> 4) > 7u) return 0; /* Zlib.hs:53-69: the serial path words the verdict */
+  const uint64_t first_bit = (flg & 0x20u) ? 48u : 16u;
+  const uint64_t total_bits = in_len * 8u, last_bit = total_bits - 32u; /* four trailer bytes must follow the last block */
+  int rc;
+  /* K4a: candidates */
+  const uint32_t cap = (uint32_t)(total_bits / 128u + 4096u);
+  if ((rc = ws.k4_cand.reserve((size_t)cap * 4u)) != PZ_E_OK || (rc = ws.k4_keep.reserve(cap)) != PZ_E_OK || (rc = ws.k4_word.reserve(64)) != PZ_E_OK) return rc;
+  uint32_t *d_word = (uint32_t *)ws.k4_word.p;
+  PZ_CUDA(cudaMemsetAsync(d_word, 0, 8, st));
+  PZ_CUDA(pz_launch_blk_search(d_stream, in_len, first_bit, last_bit, (uint32_t *)ws.k4_cand.p, d_word, cap, st));
+  uint32_t ncand = 0;
+  PZ_CUDA(cudaMemcpyAsync(&ncand, d_word, 4, cudaMemcpyDeviceToHost, st));
+  PZ_CUDA(cudaStreamSynchronize(st));
+  if (ncand > cap) return 0;
+  PZ_CUDA(pz_launch_blk_verify(d_stream, in_len, last_bit, (const uint32_t *)ws.k4_cand.p, ncand, (uint8_t *)ws.k4_keep.p, st));
+  std::vector<uint32_t> cand(ncand);
+  std::vector<uint8_t> keep(ncand);
+  if (ncand) {
+    PZ_CUDA(cudaMemcpyAsync(cand.data(), ws.k4_cand.p, (size_t)ncand * 4u, cudaMemcpyDeviceToHost, st));
+    PZ_CUDA(cudaMemcpyAsync(keep.data(), ws.k4_keep.p, ncand, cudaMemcpyDeviceToHost, st));
+  }
+  PZ_CUDA(cudaStreamSynchronize(st));
+  std::vector<uint32_t> starts;
+  starts.reserve(ncand / 64 + 16);
+  if (trace) fprintf(stderr, "[pz-k4] %8.3f ms: search done, %u first-stage candidates\n", now_ms(), ncand);
+  starts.push_back((uint32_t)first_bit); /* the first block is known, whatever its type */
+  for (uint32_t i = 0; i < ncand; i++) if (keep[i] && cand[i] != first_bit) starts.push_back(cand[i]);
+  std::sort(starts.begin(), starts.end());
+  /* sizing pass over every candidate */
+  std::vector<pz_result> sized(starts.size());
+  auto size_jobs = [&](const uint32_t *h_start, size_t count, pz_result *h_res) -> int {
+    int r;
+    if ((r = ws.k4_start.reserve(count * 4u)) != PZ_E_OK || (r = ws.k4_res.reserve(count * sizeof(pz_result))) != PZ_E_OK) return r;
+    PZ_CUDA(cudaMemcpyAsync(ws.k4_start.p, h_start, count * 4u, cudaMemcpyHostToDevice, st));
+    PZ_CUDA(pz_launch_blk_jobs(d_in_blob, d_in_off_i, (const uint32_t *)ws.k4_start.p, nullptr, nullptr, kBlockCap, nullptr, (uint32_t)count,
+                               (pz_result *)ws.k4_res.p, st));
+    PZ_CUDA(cudaMemcpyAsync(h_res, ws.k4_res.p, count * sizeof(pz_result), cudaMemcpyDeviceToHost, st));
+    PZ_CUDA(cudaStreamSynchronize(st));
+    return PZ_E_OK;
+  };
+  if ((rc = size_jobs(starts.data(), starts.size(), sized.data())) != PZ_E_OK) return rc;
+  if (trace) fprintf(stderr, "[pz-k4] %8.3f ms: %zu candidates sized\n", now_ms(), starts.size());
+  /* the chain: block k+1 starts at the bit where block k ended */
+  std::vector<uint32_t> c_start;
+  std::vector<uint32_t> c_len;
+  std::vector<uint64_t> c_off;
+  uint64_t total = 0, end_bit = 0;
+  uint32_t at = (uint32_t)first_bit;
+  int gaps = 0;
+  for (;;) {
+    pz_result r;
+    auto it = std::lower_bound(starts.begin(), starts.end(), at);
+    if (it != starts.end() && *it == at) {
+      r = sized[it - starts.begin()];
+    } else { /* a block the search did not see (fixed or stored block, unusual trees): size it alone */
+      if (++gaps > kMaxGaps) return 0;
+      if ((rc = size_jobs(&at, 1, &r)) != PZ_E_OK) return rc;
+    }
+    if (r.status != PZ_OK) return 0;
+    if (r.out_len > 0xffffffffull || total + r.out_len > out_cap) return 0; /* PZ_OUTPUT_FULL is the serial path's to report */
+    c_start.push_back(at);
+    c_off.push_back(total);
+    c_len.push_back((uint32_t)r.out_len);
+    total += r.out_len;
+    end_bit = r.err_bitpos;
+    if (r.detail != 0) break; /* BFINAL */
+    if (end_bit >= last_bit || end_bit > 0xffffffffull) return 0;
+    at = (uint32_t)end_bit;
+  }
+  const uint64_t tb = (end_bit + 7u) / 8u;
+  if (tb + 4u > in_len) return 0;
+  if (trace) fprintf(stderr, "[pz-k4] %8.3f ms: chain of %zu blocks, %llu bytes, %d found one by one\n", now_ms(), c_start.size(), (unsigned long long)total, gaps);
+  uint8_t trailer[4];
+  PZ_CUDA(cudaMemcpyAsync(trailer, d_stream + tb, 4, cudaMemcpyDeviceToHost, st));
+  /* decode pass: 16-bit symbols of every chain block, at its final position */
+  const size_t nb = c_start.size();
+  if ((rc = ws.k4_start.reserve(nb * 4u)) != PZ_E_OK || (rc = ws.k4_len.reserve(nb * 4u)) != PZ_E_OK || (rc = ws.k4_off.reserve(nb * 8u)) != PZ_E_OK ||
+      (rc = ws.k4_res.reserve(nb * sizeof(pz_result))) != PZ_E_OK || (rc = ws.k4_sym.reserve(total * 2u + 64u)) != PZ_E_OK)
+    return rc == PZ_E_NOMEM ? 0 : rc; /* no room for the symbol buffer: the serial path needs none */
+  PZ_CUDA(cudaMemcpyAsync(ws.k4_start.p, c_start.data(), nb * 4u, cudaMemcpyHostToDevice, st));
+  PZ_CUDA(cudaMemcpyAsync(ws.k4_len.p, c_len.data(), nb * 4u, cudaMemcpyHostToDevice, st));
+  PZ_CUDA(cudaMemcpyAsync(ws.k4_off.p, c_off.data(), nb * 8u, cudaMemcpyHostToDevice, st));
+  PZ_CUDA(pz_launch_blk_jobs(d_in_blob, d_in_off_i, (const uint32_t *)ws.k4_start.p, (const uint64_t *)ws.k4_off.p, (const uint32_t *)ws.k4_len.p, 0,
+                             (uint16_t *)ws.k4_sym.p, (uint32_t)nb, (pz_result *)ws.k4_res.p, st));
+  if (trace) { cudaStreamSynchronize(st); fprintf(stderr, "[pz-k4] %8.3f ms: symbols written\n", now_ms()); }
+  /* groups for the two-level walk over the tails: about sqrt(2 * blocks) of them balances the two levels */
+  uint32_t ngrp = 1;
+  while ((uint64_t)ngrp * ngrp < 2u * nb) ngrp++;
+  ngrp = (uint32_t)std::min<size_t>(std::min<uint32_t>(ngrp, 1024u), nb);
+  std::vector<uint32_t> g_first(ngrp + 1), b_grp(nb);
+  for (uint32_t g = 0; g <= ngrp; g++) g_first[g] = (uint32_t)((uint64_t)nb * g / ngrp);
+  for (uint32_t g = 0; g < ngrp; g++) for (uint32_t k = g_first[g]; k < g_first[g + 1]; k++) b_grp[k] = g;
+  if ((rc = ws.k4_grp.reserve(nb * 4u)) != PZ_E_OK || (rc = ws.k4_gfirst.reserve((ngrp + 1) * 4u)) != PZ_E_OK || (rc = ws.k4_gw.reserve((size_t)ngrp * 32768u)) != PZ_E_OK) return rc;
+  PZ_CUDA(cudaMemcpyAsync(ws.k4_grp.p, b_grp.data(), nb * 4u, cudaMemcpyHostToDevice, st));
+  PZ_CUDA(cudaMemcpyAsync(ws.k4_gfirst.p, g_first.data(), (ngrp + 1) * 4u, cudaMemcpyHostToDevice, st));
+  PZ_CUDA(cudaMemsetAsync(d_word + 1, 0, 4, st));
+  PZ_CUDA(pz_launch_blk_resolve((uint16_t *)ws.k4_sym.p, d_out_i, (const uint64_t *)ws.k4_off.p, (const uint32_t *)ws.k4_len.p, (const uint32_t *)ws.k4_grp.p,
+                                (const uint32_t *)ws.k4_gfirst.p, ngrp, (uint32_t)nb, total, (uint8_t *)ws.k4_gw.p, d_word + 1, st));
+  std::vector<pz_result> done(nb);
+  uint32_t err = 0;
+  PZ_CUDA(cudaMemcpyAsync(done.data(), ws.k4_res.p, nb * sizeof(pz_result), cudaMemcpyDeviceToHost, st));
+  PZ_CUDA(cudaMemcpyAsync(&err, d_word + 1, 4, cudaMemcpyDeviceToHost, st));
+  PZ_CUDA(cudaStreamSynchronize(st));
+  if (trace) fprintf(stderr, "[pz-k4] %8.3f ms: decoded and resolved (err %u)\n", now_ms(), err);
+  if (err) return 0;
+  for (size_t k = 0; k < nb; k++)
+    if (done[k].status != PZ_OK || done[k].out_len != c_len[k]) return 0;
+  memset(out, 0, sizeof *out);
+  out->status = PZ_OK;
+  out->out_len = total;
+  out->adler_stored = ((uint32_t)trailer[0] << 24) | ((uint32_t)trailer[1] << 16) | ((uint32_t)trailer[2] << 8) | trailer[3];
+  out->err_bitpos = tb * 8u + 32u;
+  /* bytes the reference has published as 32 KiB chunks when it reaches the trailer: one chunk per
+   * moveWindow call that finds 64 KiB in the window (Monad.hs:338-347); with calls after every match
+   * that is every threshold 64 KiB + 32 KiB * j up to the final length */
+  out->payload[1] = total >= 65536u ? (int64_t)(32768u * ((total - 65536u) / 32768u + 1u)) : 0;
+  return 1;
+}
+
+/* K2, then K4 for every huge stream K2 left pending, then K1 for whatever is still pending. */
+int run_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uint8_t *d_out, const uint64_t *d_out_off, uint32_t first, uint32_t count,
+                pz_result *d_res, cudaStream_t st, const uint64_t *h_in_off, const uint64_t *h_out_off, uint32_t flags) {
+  const bool count_only = d_out == nullptr;
+  std::vector<uint32_t> huge;
+  if (!count_only && !(flags & PZ_F_NO_HUGE) && h_in_off && h_out_off)
+    for (uint32_t i = first; i < first + count; i++)
+      if (h_in_off[i + 1] - h_in_off[i] >= g_huge_bytes) huge.push_back(i);
+  if (huge.empty()) {
+    PZ_CUDA(pz_launch_inflate(d_in, d_in_off, d_out, d_out_off, first, count, d_res, st));
+    return PZ_E_OK;
+  }
+  PZ_CUDA(pz_launch_inflate(d_in, d_in_off, d_out, d_out_off, first, count, d_res, st, nullptr, nullptr, PZ_PHASE_K2));
+  for (uint32_t i : huge) {
+    int32_t status = 0;
+    PZ_CUDA(cudaMemcpyAsync(&status, &d_res[i].status, 4, cudaMemcpyDeviceToHost, st));
+    PZ_CUDA(cudaStreamSynchronize(st));
+    if (status != PZ_ST_PENDING_HOST) continue; /* a stored-block stream: K2 has copied it */
+    pz_result r;
+    const int k = huge_stream(d_in, d_in_off + i, h_in_off[i], h_in_off[i + 1] - h_in_off[i], d_out + h_out_off[i], h_out_off[i + 1] - h_out_off[i], &r, st);
+    if (k < 0) return k;
+    (k == 1 ? g_huge_done : g_huge_declined)++;
+    if (k == 1) {
+      PZ_CUDA(cudaMemcpyAsync(&d_res[i], &r, sizeof r, cudaMemcpyHostToDevice, st));
+      PZ_CUDA(cudaStreamSynchronize(st)); /* r lives on this stack frame */
+    }
+  }
+  PZ_CUDA(pz_launch_inflate(d_in, d_in_off, d_out, d_out_off, first, count, d_res, st, nullptr, nullptr, PZ_PHASE_K1));
+  return PZ_E_OK;
+}
+
 }  // namespace
 
 struct pz_batch {
@@ -171,11 +349,21 @@ struct pz_batch {
   uint2 *d_parts = nullptr;
   uint64_t total_segs = 0;
   int launches = 0;
+  std::vector<uint64_t> h_in_off, h_out_off; /* host copies: the K4 driver works from them */
 };
 
 extern "C" {
 
 int pz_abi_version(void) { return PZ_ABI_VERSION; }
+
+uint64_t pz_get_counter(int which) {
+  return which == PZ_CTR_HUGE_DONE ? g_huge_done.load() : which == PZ_CTR_HUGE_DECLINED ? g_huge_declined.load() : 0;
+}
+
+int pz_set_option(int key, uint64_t value) {
+  if (key == PZ_OPT_HUGE_BYTES && value > 0) { g_huge_bytes = value; return PZ_E_OK; }
+  return PZ_E_ARG;
+}
 
 const char *pz_last_error(void) { return g_last_error.c_str(); }
 
@@ -198,6 +386,8 @@ pz_batch *pz_batch_create(const uint64_t *in_off, const uint64_t *out_off, size_
   pz_batch *b = new (std::nothrow) pz_batch();
   if (!b) return nullptr;
   b->n = n; b->flags = flags;
+  b->h_in_off.assign(in_off, in_off + n + 1);
+  if (!count_only) b->h_out_off.assign(out_off, out_off + n + 1);
   const size_t ob = (n + 1) * sizeof(uint64_t);
   cudaError_t e = cudaMalloc(&b->d_in_off, ob);
   if (e == cudaSuccess) e = cudaMalloc(&b->d_res, std::max<size_t>(n, 1) * sizeof(pz_result));
@@ -223,7 +413,11 @@ int pz_batch_run(pz_batch *b, const uint8_t *d_in, uint8_t *d_out, void *stream)
   cudaStream_t st = (cudaStream_t)stream;
   const bool count_only = (b->flags & PZ_F_COUNT_ONLY) != 0;
   if (!count_only && !d_out) return PZ_E_ARG;
-  PZ_CUDA(pz_launch_inflate(d_in, b->d_in_off, count_only ? nullptr : d_out, b->d_out_off, 0, (uint32_t)b->n, b->d_res, st));
+  {
+    const int rc = run_inflate(d_in, b->d_in_off, count_only ? nullptr : d_out, b->d_out_off, 0, (uint32_t)b->n, b->d_res, st, b->h_in_off.data(),
+                               count_only ? nullptr : b->h_out_off.data(), b->flags);
+    if (rc != PZ_E_OK) return rc;
+  }
   if (!count_only && !(b->flags & PZ_F_NO_ADLER))
     PZ_CUDA(pz_launch_adler(d_out, b->d_out_off, b->d_seg_off, (uint32_t)b->n, 0, (uint32_t)b->n, 0, b->total_segs, b->d_res, b->d_parts, st));
   return PZ_E_OK;
@@ -291,7 +485,7 @@ int pz_inflate_batch_contig(const uint8_t *in_blob, const uint64_t *in_off, uint
     PZ_CUDA(cudaMemcpyAsync(d_in_off, in_off, ob, cudaMemcpyHostToDevice, st));
     if (!count_only) PZ_CUDA(cudaMemcpyAsync(d_out_off, out_off, ob, cudaMemcpyHostToDevice, st));
     if (adler) PZ_CUDA(cudaMemcpyAsync(d_seg_off, seg.data(), ob, cudaMemcpyHostToDevice, st));
-    PZ_CUDA(pz_launch_inflate(in_blob, d_in_off, count_only ? nullptr : out_blob, d_out_off, 0, (uint32_t)n, d_res, st));
+    if ((rc = run_inflate(in_blob, d_in_off, count_only ? nullptr : out_blob, d_out_off, 0, (uint32_t)n, d_res, st, in_off, out_off, flags)) != PZ_E_OK) return rc;
     if (adler) PZ_CUDA(pz_launch_adler(out_blob, d_out_off, d_seg_off, (uint32_t)n, 0, (uint32_t)n, 0, total_segs, d_res, d_parts, st));
     PZ_CUDA(cudaMemcpyAsync(res, d_res, n * sizeof(pz_result), cudaMemcpyDeviceToHost, st));
     PZ_CUDA(cudaStreamSynchronize(st));
@@ -327,7 +521,7 @@ int pz_inflate_batch_contig(const uint8_t *in_blob, const uint64_t *in_off, uint
   for (size_t i = 0; progressive && i < n; i++) {
     const uint64_t len = in_off[i + 1] - in_off[i];
     const uint8_t *p = in_blob + in_off[i];
-    progressive = len >= 3 && ((p[(p[1] & 0x20u) && len >= 7 ? 6 : 2] >> 1) & 3u) != 0u;
+    progressive = len >= 3 && len < g_huge_bytes && ((p[(p[1] & 0x20u) && len >= 7 ? 6 : 2] >> 1) & 3u) != 0u;
   }
   /* Everything else -- many more streams than the device has slots, stored-block streams, ragged
    * capacities -- is cut into slices of consecutive streams: the kernels of the slices follow each
@@ -416,7 +610,10 @@ int pz_inflate_batch_contig(const uint8_t *in_blob, const uint64_t *in_off, uint
         if (staged && i1 > i0) PZ_CUDA(cudaMemcpyAsync((void *)(d_in + i0), in_blob + i0, i1 - i0, cudaMemcpyHostToDevice, s2));
         PZ_CUDA(cudaEventRecord(ev_in, s2));
         PZ_CUDA(cudaStreamWaitEvent(s0, ev_in, 0));
-        PZ_CUDA(pz_launch_inflate(d_in, d_in_off, d_out, d_out_off, (uint32_t)first, (uint32_t)(last - first), d_res, s0));
+        {
+          const int r2 = run_inflate(d_in, d_in_off, d_out, d_out_off, (uint32_t)first, (uint32_t)(last - first), d_res, s0, in_off, out_off, flags);
+          if (r2 != PZ_E_OK) return r2;
+        }
         if (adler)
           PZ_CUDA(pz_launch_adler(d_out, d_out_off, d_seg_off, (uint32_t)n, (uint32_t)first, (uint32_t)(last - first), seg[first],
                                   seg[last] - seg[first], d_res, d_parts, s0));
@@ -581,7 +778,7 @@ static int stream_decode(pz_stream *s) {
     static const uint8_t empty = 0;
     if (!inp) inp = &empty;
     pz_result r;
-    int rc = pz_inflate_batch(&inp, &in_len, &outp, &cap, 1, &r, 0);
+    int rc = pz_inflate_batch(&inp, &in_len, &outp, &cap, 1, &r, PZ_F_NO_HUGE); /* the event sequence needs the exact window model */
     if (rc != PZ_E_OK) return rc;
     if (r.status == PZ_OUTPUT_FULL) { s->cap_hint *= 4; continue; }
     s->verdict = r;

@@ -220,7 +220,19 @@ struct PzJob {
                             finished parts of the output over PCIe while the kernel is still running */
   const uint32_t *in_ready; /* optional: streams [0, *in_ready) have their input in device memory; the
                                host driver raises it while it is still copying the rest of the batch */
+  /* Block jobs (K4, one huge stream decoded block-parallel): when blk_start != nullptr, unit j of
+   * [first, first+count) is ONE deflate block of stream blk_stream, beginning at bit blk_start[j]
+   * of that stream.  It is decoded from its header to its end-of-block symbol with an unknown
+   * history: the writers produce 16-bit symbols (a byte, or 256 + index into the 32 KiB that
+   * precede the block) at out16 + blk_out[j].  res[j] receives the block's verdict. */
+  const uint32_t *blk_start;
+  const uint64_t *blk_out; /* element offsets into out16 (nullptr in the sizing pass)            */
+  const uint32_t *blk_len; /* exact decoded length of block j (nullptr: blk_cap bounds every block) */
+  uint16_t *out16;
+  uint32_t blk_stream, blk_cap;
 };
+#define PZ_BLK_BIAS 65536u /* a block job counts its output from here: the window model then always
+                              sees at least 32 KiB of history, as it would inside a long stream */
 #define PZ_PROG_SHIFT 15
 #define PZ_PROG_DONE 0xffffffffu
 #define PZ_ST_PENDING (-1)
@@ -239,6 +251,7 @@ struct PzCtx {
   uint32_t next_q;      /* first quarter not requested yet (q+3 in steady state)           */
   bool pending;         /* a quarter requested while the hot lane owns the stream has not been awaited */
   bool starved;         /* idle because the next stream's input has not reached the device yet */
+  bool block_job;       /* the unit is one deflate block (PzJob::blk_start), not a zlib stream     */
   uint32_t pos;  /* bytes decoded                                                          */
   uint32_t base; /* bytes the reference would already have published (multiple of 32 KiB)  */
   uint32_t cap;
@@ -512,6 +525,11 @@ PZ_DEV uint32_t pz_ld8_if(bool p, const uint8_t *a) {
   asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t@q ld.global.u8 %0, [%2];\n\t}" : "=r"(v) : "r"((int)p), "l"(a));
   return v;
 }
+PZ_DEV uint32_t pz_ld16_if(bool p, const uint16_t *a) {
+  uint32_t v;
+  asm volatile("{\n\t.reg .pred q;\n\t.reg .b16 h;\n\tmov.b16 h, 0;\n\tsetp.ne.b32 q, %1, 0;\n\t@q ld.global.u16 h, [%2];\n\tcvt.u32.u16 %0, h;\n\t}" : "=r"(v) : "r"((int)p), "l"(a));
+  return v;
+}
 /* warp barrier between the stores and the loads of one iteration (all 32 lanes are converged
  * in the hot loops); same ordering rule as above */
 PZ_DEV void pz_syncwarp_all() { asm volatile("bar.warp.sync 0xffffffff;"); }
@@ -522,24 +540,38 @@ PZ_DEV void pz_backoff() { __nanosleep(64); }
 
 /* The LZ77 copy (OutputWindow.hs:82-101: copyChunked = byte-serial replicate semantics) of
  * len bytes from dist back, all lanes of the group, no deferral: the general case. */
-PZ_DEV void pz_copy_match(uint8_t *out, uint32_t pos, uint32_t len, uint32_t dist) {
+/* Symbol i of a block job's output (i relative to the block; negative = one of the 32768 bytes
+ * before it, which only the resolution pass knows: a marker 256 + index stands in for it). */
+#define PZ_MARK(i) ((uint16_t)(256 + 32768 + (i)))
+PZ_DEV uint16_t pz_sym16(const uint16_t *out16, int32_t i) { return i < 0 ? PZ_MARK(i) : out16[i]; }
+
+template <bool WIDE>
+PZ_DEV void pz_copy_match(uint8_t *out, uint16_t *out16, uint32_t pos, uint32_t len, uint32_t dist) {
   const uint32_t lane = (uint32_t)pz_lane();
   uint8_t *dst = out + pos;
   const uint8_t *src = dst - dist;
+  const int32_t s16 = (int32_t)pos - (int32_t)dist;
   pz_syncwarp(); /* earlier stores by other lanes are ordered before the loads below */
   if (dist >= len) {
-    for (uint32_t i = lane; i < len; i += PZ_G) dst[i] = src[i];
+    for (uint32_t i = lane; i < len; i += PZ_G) {
+      if (WIDE) out16[pos + i] = pz_sym16(out16, s16 + (int32_t)i);
+      else dst[i] = src[i];
+    }
   } else if (dist >= PZ_G) {
     for (uint32_t i0 = 0; i0 < len; i0 += PZ_G) { /* each chunk may read the previous one */
       uint32_t i = i0 + lane;
-      if (i < len) dst[i] = src[i];
+      if (i < len) {
+        if (WIDE) out16[pos + i] = pz_sym16(out16, s16 + (int32_t)i);
+        else dst[i] = src[i];
+      }
       pz_syncwarp();
     }
   } else { /* dist < PZ_G and dist < len: replicate the dist-byte pattern */
     uint32_t m = lane % dist;
     const uint32_t step = PZ_G % dist;
     for (uint32_t i = lane; i < len; i += PZ_G) {
-      dst[i] = src[m];
+      if (WIDE) out16[pos + i] = pz_sym16(out16, s16 + (int32_t)m);
+      else dst[i] = src[m];
       m += step;
       if (m >= dist) m -= dist;
     }
@@ -551,6 +583,7 @@ PZ_DEV void pz_copy_match(uint8_t *out, uint32_t pos, uint32_t len, uint32_t dis
 struct PzWriter {
   const PzJob *job;
   uint8_t *out;      /* output slice of the current stream */
+  uint16_t *out16;   /* block jobs: 16-bit symbols of the current block */
   const uint8_t *in; /* its first compressed byte (stored runs copy from the input) */
   uint32_t pos;      /* bytes written */
   uint32_t op, need, a0; /* control message being assembled: `need` argument tokens to go */
@@ -569,19 +602,25 @@ PZ_DEV void pz_publish(PzWriter &w, uint32_t value) {
 }
 #endif
 PZ_DEV void pz_writer_init(PzWriter &w, const PzJob *job) {
-  w.job = job; w.out = nullptr; w.in = nullptr; w.pos = 0; w.op = 0; w.need = 0; w.a0 = 0; w.sidx = 0; w.pub = 0; w.exited = false;
+  w.job = job; w.out = nullptr; w.out16 = nullptr; w.in = nullptr; w.pos = 0; w.op = 0; w.need = 0; w.a0 = 0; w.sidx = 0; w.pub = 0; w.exited = false;
 }
 
 /* Applies one token completely (no deferral): the writer's path for everything that is not a
  * literal or a short disjoint match.  `raw` is the token without its phase bit. */
+template <bool WIDE>
 PZ_DEV void pz_writer_apply(PzWriter &w, uint32_t raw) {
   const uint32_t lane = (uint32_t)pz_lane();
   if (w.need) { /* argument of a control message */
     if (w.op == PZ_C_NEWSTREAM) {
       pz_publish(w, PZ_PROG_DONE); /* the previous stream of this slot is complete */
       w.sidx = raw; w.pub = 0;
-      w.out = w.job->out_blob + w.job->out_off[raw];
-      w.in = w.job->in_blob + w.job->in_off[raw];
+      if (WIDE) {
+        w.out16 = w.job->out16 + w.job->blk_out[raw];
+        w.in = w.job->in_blob + w.job->in_off[w.job->blk_stream];
+      } else {
+        w.out = w.job->out_blob + w.job->out_off[raw];
+        w.in = w.job->in_blob + w.job->in_off[raw];
+      }
       w.pos = 0; w.need = 0;
     } else if (w.need == 2u) {
       w.a0 = raw; w.need = 1;
@@ -589,7 +628,10 @@ PZ_DEV void pz_writer_apply(PzWriter &w, uint32_t raw) {
       const uint8_t *src = w.in + w.a0;
       uint8_t *dst = w.out + w.pos;
       pz_syncwarp();
-      for (uint32_t i = lane; i < raw; i += PZ_G) dst[i] = src[i];
+      for (uint32_t i = lane; i < raw; i += PZ_G) {
+        if (WIDE) w.out16[w.pos + i] = src[i];
+        else dst[i] = src[i];
+      }
       pz_syncwarp();
       w.pos += raw; w.need = 0;
     }
@@ -597,11 +639,14 @@ PZ_DEV void pz_writer_apply(PzWriter &w, uint32_t raw) {
   }
   const uint32_t type = (raw >> 29) & 3u;
   if (type == PZ_Q_LIT) {
-    if (lane == 0) w.out[w.pos] = (uint8_t)raw;
+    if (lane == 0) {
+      if (WIDE) w.out16[w.pos] = (uint16_t)(raw & 0xffu);
+      else w.out[w.pos] = (uint8_t)raw;
+    }
     w.pos++;
   } else if (type == PZ_Q_MATCH) {
     const uint32_t len = (raw >> 16) & 0x1ffu, dist = (raw & 0x7fffu) + 1u;
-    pz_copy_match(w.out, w.pos, len, dist);
+    pz_copy_match<WIDE>(w.out, w.out16, w.pos, len, dist);
     w.pos += len;
   } else {
     const uint32_t op = (raw >> 26) & 7u;
@@ -620,6 +665,14 @@ PZ_DEV void pz_st8_sel(bool p, uint8_t *a, uint32_t inf, uint32_t x) {
       "and.b32 u, %2, 255;\n\tselp.b32 t, u, %3, l;\n\t@q st.global.u8 [%1], t;\n\t}" ::"r"((int)p),
       "l"(a), "r"(inf), "r"(x));
 }
+/* 16-bit flavour (block jobs): `alt` (a literal byte or a marker for a byte before the block) wins
+ * over the loaded symbol `x` when bit 31 of alt is set. */
+PZ_DEV void pz_st16_sel(bool p, uint16_t *a, uint32_t alt, uint32_t x) {
+  asm volatile(
+      "{\n\t.reg .pred q, l;\n\t.reg .b32 t, u;\n\t.reg .b16 h;\n\tsetp.ne.b32 q, %0, 0;\n\tsetp.lt.s32 l, %2, 0;\n\t"
+      "and.b32 u, %2, 65535;\n\tselp.b32 t, u, %3, l;\n\tcvt.u16.u32 h, t;\n\t@q st.global.u16 [%1], h;\n\t}" ::"r"((int)p),
+      "l"(a), "r"(alt), "r"(x));
+}
 
 /* The writer warp: runs until every group has seen its EXIT token.
  *
@@ -634,6 +687,7 @@ PZ_DEV void pz_st8_sel(bool p, uint8_t *a, uint32_t inf, uint32_t x) {
  * pz_writer_apply(), one token per trip. */
 #define PZ_TRIP_BYTES 64u
 #define PZ_ROUNDS ((int)(PZ_TRIP_BYTES / PZ_G))
+template <bool WIDE>
 PZ_DEV void pz_writer_warp(const PzJob &job, PzStreamSmem *sm, bool present) {
   static_assert(PZ_G == 8, "the writer deals bytes to 8-lane groups");
   PzWriter w;
@@ -674,7 +728,7 @@ PZ_DEV void pz_writer_warp(const PzJob &job, PzStreamSmem *sm, bool present) {
     const uint32_t r0 = (uint32_t)__shfl_sync(all, (int)raw, 0, PZ_G);
     if (pz_warp_any(slow)) {
       if (slow) {
-        pz_writer_apply(w, r0 & 0x7fffffffu);
+        pz_writer_apply<WIDE>(w, r0 & 0x7fffffffu);
         tail++;
         pz_vstore(&sm->qtail, tail);
         if (!w.exited && (w.pos >> PZ_PROG_SHIFT) != w.pub) { w.pub = w.pos >> PZ_PROG_SHIFT; pz_publish(w, w.pub << PZ_PROG_SHIFT); }
@@ -705,14 +759,23 @@ PZ_DEV void pz_writer_warp(const PzJob &job, PzStreamSmem *sm, bool present) {
         const int t = r * PZ_G < 32 ? __popc(s_lo & ((2u << b) - 1u)) - 1
                                     : (int)c_lo + __popc(s_hi & ((2u << (b - 32u)) - 1u)) - 1;
         inf[r] = (uint32_t)__shfl_sync(all, (int)info, t, PZ_G);
-        x[r] = pz_ld8_if(b < B && (int32_t)inf[r] >= 0, base + (int32_t)(b - (inf[r] & 0xffffu)));
+        if (WIDE) {
+          /* a source before the block is not loaded: its marker takes the literal's place */
+          const int32_t si = (int32_t)(w.pos + b) - (int32_t)(inf[r] & 0xffffu);
+          const bool lit = (int32_t)inf[r] < 0;
+          x[r] = pz_ld16_if(b < B && !lit && si >= 0, w.out16 + si);
+          if (!lit && si < 0) inf[r] = 0x80000000u | PZ_MARK(si);
+        } else {
+          x[r] = pz_ld8_if(b < B && (int32_t)inf[r] >= 0, base + (int32_t)(b - (inf[r] & 0xffffu)));
+        }
       }
     }
 #pragma unroll
     for (int r = 0; r < PZ_ROUNDS; r++) {
       if ((uint32_t)(r * PZ_G) < max_b) {
         const uint32_t b = (uint32_t)(r * PZ_G) + lane;
-        pz_st8_sel(b < B, base + b, inf[r], x[r]);
+        if (WIDE) pz_st16_sel(b < B, w.out16 + w.pos + b, inf[r], x[r]);
+        else pz_st8_sel(b < B, base + b, inf[r], x[r]);
       }
     }
     w.pos += B;
@@ -731,7 +794,7 @@ template <bool COUNT_ONLY>
 PZ_DEV void pz_push(PzCtx &c, PzStreamSmem *sm, uint32_t v) {
 #ifdef PZ_HOSTSIM
   (void)sm;
-  if (!COUNT_ONLY) pz_writer_apply(*c.hw, v);
+  if (!COUNT_ONLY) pz_writer_apply<false>(*c.hw, v);
 #else
   if (!COUNT_ONLY) {
     while (c.qhead - c.qtailc >= PZ_QLEN) {
@@ -864,7 +927,7 @@ PZ_DEV bool pz_fast_trip(PzFast &f, PzStreamSmem *sm, const bool run) {
     if (!COUNT_ONLY) {
       const uint32_t tok = is_lit ? PZ_TOKEN(PZ_Q_LIT, (e >> 16) & 0xffu) : PZ_TOKEN(PZ_Q_MATCH, (len << 16) | (dist - 1u));
 #ifdef PZ_HOSTSIM
-      if (alive) pz_writer_apply(*f.hw, tok);
+      if (alive) pz_writer_apply<false>(*f.hw, tok);
 #else
       if (alive) pz_vstore(&sm->q[qhead & (PZ_QLEN - 1u)], tok | (((qhead >> PZ_QSHIFT) & 1u) << 31));
       qhead += alive ? 1u : 0u;
@@ -1112,8 +1175,8 @@ PZ_DEV void pz_finish(PzCtx &c) {
   if (pz_lane() == 0) {
     pz_result *res = c.res;
     res->status = c.status;
-    res->detail = c.detail;
-    res->out_len = c.pos;
+    res->detail = c.block_job && c.status == PZ_OK ? (int32_t)c.bfinal : c.detail;
+    res->out_len = c.block_job ? c.pos - PZ_BLK_BIAS : c.pos;
     res->adler_computed = 0;
     res->adler_stored = c.adler_stored;
     res->err_bitpos = c.bp - c.start_bit;
@@ -1165,10 +1228,32 @@ PZ_DEV void pz_begin(PzCtx &c, PzStreamSmem *sm, uint32_t s, const uint8_t *in, 
   c.mode = PZ_M_HDR;
 }
 
+/* A block job starts at a block header somewhere inside its stream (no zlib framing). */
+template <bool COUNT_ONLY>
+PZ_DEV void pz_begin_block(PzCtx &c, PzStreamSmem *sm, uint32_t j, const uint8_t *in, uint64_t in_len, uint32_t bit, uint32_t cap, pz_result *res) {
+  uint32_t mis = (uint32_t)((uintptr_t)in & 15u);
+  c.in_al = in - mis;
+  c.res = res;
+  c.pos = PZ_BLK_BIAS; c.base = 0;
+  c.cap = PZ_BLK_BIAS + cap;
+  c.status = PZ_OK; c.detail = 0; c.p0 = 0; c.p1 = 0;
+  c.adler_stored = 0; c.bfinal = 0; c.need_careful = false;
+  c.start_bit = mis * 8u;
+  c.in_al_bytes = (mis + (uint32_t)in_len + 15u) & ~15u;
+  c.end_bit = (mis + (uint32_t)in_len) * 8u;
+  c.safe_end = c.end_bit >= PZ_STEP_BITS ? c.end_bit - PZ_STEP_BITS : 0u;
+  pz_push<COUNT_ONLY>(c, sm, PZ_TOKEN(PZ_Q_CTRL, PZ_C_NEWSTREAM << 26));
+  pz_push<COUNT_ONLY>(c, sm, j);
+  if (bit > c.end_bit - c.start_bit) bit = c.end_bit - c.start_bit; /* the header read then reports the truncation */
+  pz_seek(c, sm, c.start_bit + bit);
+  c.mode = PZ_M_HDR;
+}
+
 /* End of a block (Deflate.hs:45-50): moveWindow, then either the next block or the trailer
  * (checkChecksum, Deflate.hs:52-63: align, four bytes, most significant first). */
 PZ_DEV void pz_block_end(PzCtx &c, PzStreamSmem *sm) {
   pz_move_window(c);
+  if (c.block_job) { pz_finish(c); return; } /* err_bitpos = first bit after the block */
   if (!c.bfinal) { c.mode = PZ_M_HDR; return; }
   pz_align_byte(c, sm);
   uint32_t hi, lo;
@@ -1200,6 +1285,12 @@ PZ_DEV void pz_slow_step(PzCtx &c, PzStreamSmem *sm, const PzJob &job, uint32_t 
     if (c.starved) return;
 #endif
     c.next += stride;
+    if (job.blk_start != nullptr) {
+      const uint64_t b0 = job.in_off[job.blk_stream], b1 = job.in_off[job.blk_stream + 1];
+      c.block_job = true;
+      pz_begin_block<COUNT_ONLY>(c, sm, s, job.in_blob + b0, b1 - b0, job.blk_start[s], job.blk_len ? job.blk_len[s] : job.blk_cap, job.res + s);
+      return;
+    }
     const uint64_t i0 = job.in_off[s], i1 = job.in_off[s + 1];
     if (COUNT_ONLY) {
       pz_begin<true>(c, sm, s, job.in_blob + i0, i1 - i0, ~0ull, job.res + s);
@@ -1255,7 +1346,7 @@ PZ_DEV void pz_decoder_warp(const PzJob &job, uint32_t first_stream, uint32_t st
   PzCtx c;
   c.mode = PZ_M_IDLE;
   c.next = first_stream;
-  c.in_al = nullptr; c.in_al_bytes = 0; c.bp = 0; c.q = 0; c.next_q = 0; c.pending = false; c.starved = false; c.res = nullptr;
+  c.in_al = nullptr; c.in_al_bytes = 0; c.bp = 0; c.q = 0; c.next_q = 0; c.pending = false; c.starved = false; c.block_job = false; c.res = nullptr;
   c.qhead = 0; c.qtailc = 0;
   c.fixed_ready = false;
 #ifdef PZ_HOSTSIM

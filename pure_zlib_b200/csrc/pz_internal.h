@@ -23,7 +23,22 @@
  * PzJob::in_ready; K2 is skipped then. */
 cudaError_t pz_launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uint8_t *d_out, const uint64_t *d_out_off,
                               uint32_t first, uint32_t count, pz_result *d_res, cudaStream_t st, uint32_t *d_prog = nullptr,
-                              const uint32_t *d_in_ready = nullptr);
+                              const uint32_t *d_in_ready = nullptr, int phase = 0);
+#define PZ_PHASE_ALL 0
+#define PZ_PHASE_K2 1 /* only the stored-stream kernels (they also mark every other stream PENDING) */
+#define PZ_PHASE_K1 2 /* only K1: decodes the streams that are still PENDING */
+#define PZ_ST_PENDING_HOST (-1) /* == PZ_ST_PENDING in pz_device.cuh */
+/* K4 (pz_huge.cuh): one huge stream decoded block-parallel; see pz_abi.cu for the driver */
+cudaError_t pz_launch_blk_search(const uint8_t *d_stream, uint64_t nbytes, uint64_t first_bit, uint64_t last_bit, uint32_t *d_cand,
+                                 uint32_t *d_ncand, uint32_t cap, cudaStream_t st);
+cudaError_t pz_launch_blk_verify(const uint8_t *d_stream, uint64_t nbytes, uint64_t last_bit, const uint32_t *d_cand, uint32_t ncand,
+                                 uint8_t *d_keep, cudaStream_t st);
+cudaError_t pz_launch_blk_jobs(const uint8_t *d_in_blob, const uint64_t *d_in_off2, const uint32_t *d_blk_start, const uint64_t *d_blk_out,
+                               const uint32_t *d_blk_len, uint32_t cap, uint16_t *d_sym16, uint32_t count, pz_result *d_res, cudaStream_t st);
+/* groups of consecutive chain blocks: d_grp_first[ngrp + 1] (first block of each group), d_blk_grp[nblk]; d_gw = ngrp * 32768 bytes */
+cudaError_t pz_launch_blk_resolve(uint16_t *d_sym16, uint8_t *d_out, const uint64_t *d_blk_off, const uint32_t *d_blk_len, const uint32_t *d_blk_grp,
+                                  const uint32_t *d_grp_first, uint32_t ngrp, uint32_t nblk, uint64_t total, uint8_t *d_gw, uint32_t *d_err,
+                                  cudaStream_t st);
 /* Adler-32 of each decoded stream (segments [seg_off[first], seg_off[first+count])), then the
  * trailer comparison that completes the verdict (Deflate.hs:52-63). */
 cudaError_t pz_launch_adler(const uint8_t *d_out, const uint64_t *d_out_off, const uint64_t *d_seg_off, uint32_t n_total,

@@ -12,9 +12,13 @@
  *                            identity) and compares with the stored trailer
  *   pz_code_values_kernel    canonical-code KAT hook (test/Test.hs:107-120)
  */
+#include <cstdio>
+#include <cstdlib>
+
 #include "pz_device.cuh"
 #include "pz_internal.h"
 #include "pz_stored.cuh"
+#include "pz_huge.cuh"
 
 /* Warp roles.  A CTA owns PZ_SLOTS stream slots: warp 0 is the hot warp (one lane per slot),
  * PZ_SERVICE_WARPS service warps and as many writer warps serve four slots each (8 lanes per
@@ -30,7 +34,7 @@ __device__ __forceinline__ void pz_role(uint32_t w, uint32_t &role, uint32_t &in
   index = (PZ_WARPS_PER_CTA - 1u) / 4u + (k - PZ_SERVICE_WARPS);
 }
 
-template <bool COUNT_ONLY>
+template <bool COUNT_ONLY, bool WIDE = false>
 __global__ void __launch_bounds__(PZ_THREADS_PER_CTA, 1)
 pz_inflate_kernel(const PzJob job) {
   extern __shared__ __align__(16) unsigned char pz_smem_raw[];
@@ -59,7 +63,7 @@ pz_inflate_kernel(const PzJob job) {
   if (role == 1u) {
     pz_decoder_warp<COUNT_ONLY>(job, job.first + blockIdx.x + gridDim.x * slot, gridDim.x * PZ_SLOTS, sm, present);
   } else if (!COUNT_ONLY) {
-    pz_writer_warp(job, sm, present);
+    pz_writer_warp<WIDE>(job, sm, present);
   }
 }
 
@@ -174,6 +178,10 @@ cudaError_t pz_kernels_configure(void) {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(pz_inflate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute((pz_inflate_kernel<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute((pz_inflate_kernel<false, true>), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(pz_inflate_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(pz_inflate_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -191,7 +199,7 @@ int pz_inflate_slots(void) { return g_sm_count * g_inflate_ctas_per_sm[0] * (int
 /* One resident wave of persistent CTAs: one per SM (148 on B200), fewer for small batches. */
 cudaError_t pz_launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uint8_t *d_out, const uint64_t *d_out_off,
                               uint32_t first, uint32_t count, pz_result *d_res, cudaStream_t st, uint32_t *d_prog,
-                              const uint32_t *d_in_ready) {
+                              const uint32_t *d_in_ready, int phase) {
   if (count == 0) return cudaSuccess;
   const bool count_only = d_out == nullptr;
   const unsigned wave = (unsigned)(g_sm_count * g_inflate_ctas_per_sm[count_only ? 1 : 0]);
@@ -202,6 +210,7 @@ cudaError_t pz_launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uin
   job.first = first; job.count = count; job.skip_done = count_only ? 0u : 1u;
   job.prog = count_only ? nullptr : d_prog;
   job.in_ready = d_in_ready;
+  job.blk_start = nullptr; job.blk_out = nullptr; job.blk_len = nullptr; job.out16 = nullptr; job.blk_stream = 0; job.blk_cap = 0;
   if (d_in_ready) job.skip_done = 0; /* K2 would read input that is not there yet: K1 decodes every stream */
   if (count_only) {
     pz_inflate_kernel<true><<<grid, PZ_THREADS_PER_CTA, smem, st>>>(job);
@@ -209,14 +218,66 @@ cudaError_t pz_launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uin
     pz_inflate_kernel<false><<<grid, PZ_THREADS_PER_CTA, smem, st>>>(job);
   } else {
     /* K2 first: all-stored streams are copied at memory speed and marked done; K1 takes the rest */
-    pz_stored_probe_kernel<<<(count + 255u) / 256u, 256, 0, st>>>(job);
-    const unsigned ctas = (unsigned)g_sm_count * 4u;
-    unsigned tile = count / (ctas * 4u);
-    tile = tile < 1u ? 1u : (tile > PZ_ST_THREADS ? PZ_ST_THREADS : tile);
-    const unsigned tiles = (count + tile - 1u) / tile;
-    pz_stored_copy_kernel<<<tiles < ctas ? tiles : ctas, PZ_ST_THREADS, 0, st>>>(job, tile);
-    pz_inflate_kernel<false><<<grid, PZ_THREADS_PER_CTA, smem, st>>>(job);
+    if (phase != PZ_PHASE_K1) {
+      pz_stored_probe_kernel<<<(count + 255u) / 256u, 256, 0, st>>>(job);
+      const unsigned ctas = (unsigned)g_sm_count * 4u;
+      unsigned tile = count / (ctas * 4u);
+      tile = tile < 1u ? 1u : (tile > PZ_ST_THREADS ? PZ_ST_THREADS : tile);
+      const unsigned tiles = (count + tile - 1u) / tile;
+      pz_stored_copy_kernel<<<tiles < ctas ? tiles : ctas, PZ_ST_THREADS, 0, st>>>(job, tile);
+    }
+    if (phase != PZ_PHASE_K2) pz_inflate_kernel<false><<<grid, PZ_THREADS_PER_CTA, smem, st>>>(job);
   }
+  return cudaGetLastError();
+}
+
+/* ---- K4 launchers (pz_huge.cuh; block jobs run on K1) ---------------------------------------- */
+cudaError_t pz_launch_blk_search(const uint8_t *d_stream, uint64_t nbytes, uint64_t first_bit, uint64_t last_bit, uint32_t *d_cand,
+                                 uint32_t *d_ncand, uint32_t cap, cudaStream_t st) {
+  const uint64_t bytes = (last_bit + 7u) / 8u - first_bit / 8u;
+  if (bytes == 0) return cudaSuccess;
+  const uint64_t grid = (bytes + PZ_HUGE_THREADS - 1) / PZ_HUGE_THREADS;
+  pz_blk_search_kernel<<<(unsigned)grid, PZ_HUGE_THREADS, 0, st>>>(d_stream, nbytes, first_bit, last_bit, d_cand, d_ncand, cap);
+  return cudaGetLastError();
+}
+cudaError_t pz_launch_blk_verify(const uint8_t *d_stream, uint64_t nbytes, uint64_t last_bit, const uint32_t *d_cand, uint32_t ncand,
+                                 uint8_t *d_keep, cudaStream_t st) {
+  if (ncand == 0) return cudaSuccess;
+  pz_blk_verify_kernel<<<(ncand + PZ_HUGE_THREADS - 1) / PZ_HUGE_THREADS, PZ_HUGE_THREADS, 0, st>>>(d_stream, nbytes, last_bit, d_cand, ncand, d_keep);
+  return cudaGetLastError();
+}
+/* d_in_off2 = {offset of the stream in d_in_blob, its end}.  d_blk_out == nullptr: sizing pass (every block bounded by
+ * cap); else 16-bit symbols of block j go to d_sym16 + d_blk_out[j], bounded by d_blk_len[j]. */
+cudaError_t pz_launch_blk_jobs(const uint8_t *d_in_blob, const uint64_t *d_in_off2, const uint32_t *d_blk_start, const uint64_t *d_blk_out,
+                               const uint32_t *d_blk_len, uint32_t cap, uint16_t *d_sym16, uint32_t count, pz_result *d_res, cudaStream_t st) {
+  if (count == 0) return cudaSuccess;
+  const bool count_only = d_blk_out == nullptr;
+  const unsigned wave = (unsigned)(g_sm_count * g_inflate_ctas_per_sm[count_only ? 1 : 0]);
+  const unsigned grid = count < wave ? count : wave;
+  const size_t smem = sizeof(PzStreamSmem) * PZ_SLOTS;
+  PzJob job;
+  job.in_blob = d_in_blob; job.in_off = d_in_off2; job.out_blob = nullptr; job.out_off = nullptr; job.res = d_res;
+  job.first = 0; job.count = count; job.skip_done = 0; job.prog = nullptr; job.in_ready = nullptr;
+  job.blk_start = d_blk_start; job.blk_out = d_blk_out; job.blk_len = d_blk_len; job.out16 = d_sym16; job.blk_stream = 0; job.blk_cap = cap;
+  if (count_only) pz_inflate_kernel<true><<<grid, PZ_THREADS_PER_CTA, smem, st>>>(job);
+  else pz_inflate_kernel<false, true><<<grid, PZ_THREADS_PER_CTA, smem, st>>>(job);
+  return cudaGetLastError();
+}
+cudaError_t pz_launch_blk_resolve(uint16_t *d_sym16, uint8_t *d_out, const uint64_t *d_blk_off, const uint32_t *d_blk_len, const uint32_t *d_blk_grp,
+                                  const uint32_t *d_grp_first, uint32_t ngrp, uint32_t nblk, uint64_t total, uint8_t *d_gw, uint32_t *d_err,
+                                  cudaStream_t st) {
+  if (nblk == 0 || total == 0) return cudaSuccess;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(pz_blk_tails_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PZ_TAIL * sizeof(uint16_t)));
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  pz_blk_tails_kernel<<<ngrp, PZ_TAILS_THREADS, PZ_TAIL * sizeof(uint16_t), st>>>(d_sym16, d_blk_off, d_blk_len, d_grp_first, ngrp);
+  pz_blk_windows_kernel<<<1, PZ_TAILS_THREADS, 0, st>>>(d_sym16, d_blk_off, d_grp_first, ngrp, total, d_gw, d_err);
+  const uint64_t per_cta = PZ_HUGE_THREADS * 8u;
+  pz_blk_resolve_kernel<<<(unsigned)((total + per_cta - 1) / per_cta), PZ_HUGE_THREADS, 0, st>>>(d_sym16, d_out, d_blk_off, d_blk_len, d_blk_grp, d_grp_first,
+                                                                                               nblk, total, d_gw, d_err);
   return cudaGetLastError();
 }
 

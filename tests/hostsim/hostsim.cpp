@@ -25,7 +25,7 @@ extern "C" int hs_inflate(const uint8_t *in, uint64_t in_len, uint8_t *out, uint
   uint64_t in_off[2] = {0, in_len}, out_off[2] = {0, out_cap};
   PzJob job;
   job.in_blob = buf + mis; job.in_off = in_off; job.out_blob = count_only ? nullptr : out; job.out_off = out_off;
-  job.res = res; job.first = 0; job.count = 1; job.skip_done = 0; job.prog = nullptr; job.in_ready = nullptr;
+  job.res = res; job.first = 0; job.count = 1; job.skip_done = 0; job.prog = nullptr; job.in_ready = nullptr; job.blk_start = nullptr; job.blk_out = nullptr; job.blk_len = nullptr; job.out16 = nullptr; job.blk_stream = 0; job.blk_cap = 0;
   PzWriter hw; /* tokens are applied as they are pushed */
   pz_writer_init(hw, &job);
   if (count_only) pz_decoder_warp<true>(job, 0, 1, sm, &hw);

@@ -357,3 +357,96 @@ def test_sizing_pass_matches_decode(pz):
     for i in range(n):
         want_status = 0 if res[i].status == 5 else res[i].status  # the sizing pass stops before the checksum compare
         assert (sz[i].status, sz[i].out_len) == (want_status, res[i].out_len), (i, sz[i].status, res[i].status)
+
+
+# ---- K4: one huge stream decoded block-parallel -------------------------------------------------
+@pytest.fixture()
+def huge_threshold():
+    """Lowers the size from which a stream takes the block-parallel path, so that streams the
+    oracle finishes in seconds exercise it; restores the default afterwards."""
+    from pure_zlib_b200 import _lib
+    L = _lib.load()
+    _lib.check(L.pz_init(None), "pz_init")
+    assert L.pz_set_option(_lib.PZ_OPT_HUGE_BYTES, 64 * 1024) == 0
+    yield
+    assert L.pz_set_option(_lib.PZ_OPT_HUGE_BYTES, 4 << 20) == 0
+
+
+def _huge_cases():
+    from pure_zlib_b200 import corpus
+    text = corpus.text(6 << 20, 77)
+    cases = [("text-l9", zlib.compress(text, 9)), ("text-l6", zlib.compress(text, 6)), ("text-l1", zlib.compress(text[: 2 << 20], 1))]
+    # a fixed-Huffman block and a stored block in the middle: blocks the header search cannot see
+    co = zlib.compressobj(9)
+    z = co.compress(text[: 1 << 20]) + co.flush(zlib.Z_FULL_FLUSH)
+    z += co.compress(text[1 << 20: 2 << 20]) + co.flush()
+    cases.append(("sync-flush", z))
+    cf = zlib.compressobj(6, zlib.DEFLATED, 15, 8, zlib.Z_FIXED)
+    cases.append(("all-fixed", cf.compress(text[: 1 << 20]) + cf.flush()))
+    rng = np.random.default_rng(5)
+    mixed = text[: 1 << 20] + rng.integers(0, 256, 200_000, dtype=np.uint8).tobytes() + text[1 << 20: 2 << 20]
+    cases.append(("mixed-random", zlib.compress(mixed, 9)))
+    # faults: truncated, corrupted in the middle, bad checksum, trailing garbage
+    good = cases[0][1]
+    cases.append(("truncated", good[: len(good) // 2]))
+    bad = bytearray(good); bad[len(bad) // 3] ^= 0x40
+    cases.append(("corrupt", bytes(bad)))
+    bad = bytearray(good); bad[-1] ^= 1
+    cases.append(("checksum", bytes(bad)))
+    cases.append(("trailing", good + b"xyz"))
+    # references before the start of the stream: a valid tail glued behind a fresh header
+    return cases
+
+
+def test_huge_stream_block_parallel(pz, oracle, huge_threshold):
+    """Streams above the threshold take K4 (or fall back): bytes, verdict and the published-bytes
+    model must equal the oracle's, and equal the serial path's (PZ_F_NO_HUGE)."""
+    from pure_zlib_b200 import _lib
+    cases = _huge_cases()
+    L = _lib.load()
+    done0, declined0 = L.pz_get_counter(1), L.pz_get_counter(2)
+    res, outs = pz.zlib.inflate_batch_raw([z for _, z in cases])
+    # the six well-formed streams, the one with a bad checksum and the one with bytes after its trailer take K4
+    # (inflate_batch_raw decodes twice: sizing pass without K4, then the decode); the broken ones are declined
+    # (a flipped bit may leave every block decodable -- then K4 finishes and the checksum fails -- or not)
+    done, declined = L.pz_get_counter(1) - done0, L.pz_get_counter(2) - declined0
+    assert done + declined == len(cases) and done >= 8 and declined >= 1, (done, declined)
+    res0, outs0 = pz.zlib.inflate_batch_raw([z for _, z in cases], flags=_lib.PZ_F_NO_HUGE)
+    for (name, z), r, out, r0, out0 in zip(cases, res, outs, res0, outs0):
+        o = oracle.decompress(z)
+        assert (r.status, r.detail, r.out_len) == (o.status, o.detail, o.out_len), (name, r.status, r.detail, o.message)
+        assert (r0.status, r0.detail, r0.out_len) == (o.status, o.detail, o.out_len), name
+        assert out == o.data and out0 == o.data, name
+        if o.status == 0:
+            assert r.adler_computed == o.adler_computed == r0.adler_computed, name
+            assert r.payload[1] == r0.payload[1], (name, r.payload[1], r0.payload[1])  # published-bytes model (serial path = hostsim-checked)
+            assert r.err_bitpos == r0.err_bitpos, name
+        else:
+            assert _lib.strerror(r) == o.message, name
+
+
+def test_huge_stream_in_a_batch_and_device_pointers(pz, huge_threshold):
+    """A huge stream among small ones, through the contiguous entry point with device pointers."""
+    import torch
+    from pure_zlib_b200 import _lib, corpus
+    L = _lib.load()
+    datas = [corpus.text(3 << 20, 5), b"small one" * 10, corpus.text(1 << 20, 6), b""]
+    zs = [zlib.compress(d, 9) for d in datas]
+    n = len(zs)
+    in_off = np.zeros(n + 1, dtype=np.uint64); out_off = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum([(len(z) + 15) & ~15 for z in zs], out=in_off[1:])
+    np.cumsum([(len(d) + 15) & ~15 for d in datas], out=out_off[1:])
+    blob = np.zeros(int(in_off[-1]) + 64, dtype=np.uint8)
+    for i, z in enumerate(zs):
+        blob[int(in_off[i]): int(in_off[i]) + len(z)] = np.frombuffer(z, dtype=np.uint8)
+    # in_off[i+1]-in_off[i] includes padding: the padding bytes are "data after the trailer", ignored like the reference does
+    d_in = torch.from_numpy(blob).cuda()
+    d_out = torch.zeros(int(out_off[-1]) + 64, dtype=torch.uint8, device="cuda")
+    res = (_lib.PzResult * n)()
+    p64 = C.POINTER(C.c_uint64)
+    _lib.check(L.pz_inflate_batch_contig(d_in.data_ptr(), in_off.ctypes.data_as(p64), d_out.data_ptr(), out_off.ctypes.data_as(p64), n, res, None, 0),
+               "pz_inflate_batch_contig")
+    host = d_out.cpu().numpy()
+    for i, d in enumerate(datas):
+        assert res[i].status == 0 and res[i].out_len == len(d) and res[i].adler_computed == zlib.adler32(d), i
+        assert host[int(out_off[i]): int(out_off[i]) + len(d)].tobytes() == d, i

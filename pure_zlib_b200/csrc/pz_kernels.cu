@@ -127,24 +127,46 @@ pz_adler_partial_kernel(const uint8_t *__restrict__ out_blob, const uint64_t *__
   if (lane == 0) parts[g] = make_uint2(s1 % PZ_ADLER_MOD, (uint32_t)(s2 % PZ_ADLER_MOD));
 }
 
+/* One warp per stream.  A range of the stream is summarised as (s1, s2, n): s1 = sum of its bytes,
+ * s2 = sum of (n - i) * byte_i, both mod 65521; appending range Y to range X gives
+ * (s1x + s1y, s2x + n_y * s1x + s2y, n_x + n_y).  Each lane folds a contiguous run of segments, the
+ * 32 partial summaries are folded with shuffles, and Adler = ((n + s2) mod p) << 16 | (1 + s1) mod p
+ * (initialAdlerState a = 1, b = 0: Adler32.hs:19-20). */
 __global__ void __launch_bounds__(128)
 pz_adler_finish_kernel(const uint64_t *__restrict__ seg_off, uint32_t first, uint32_t count, pz_result *res,
                        const uint2 *__restrict__ parts) {
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31u;
   if (k >= count) return;
   const uint32_t i = first + k;
   if (res[i].status != PZ_OK) return;
   const uint64_t len = res[i].out_len;
   const uint64_t nseg = (len + PZ_ADLER_SEG - 1) / PZ_ADLER_SEG;
   const uint2 *p = parts + seg_off[i];
-  uint32_t a = 1, b = 0; /* initialAdlerState (Adler32.hs:19-20) */
-  for (uint64_t j = 0; j < nseg; j++) {
+  const uint64_t per = (nseg + 31u) / 32u;
+  const uint64_t j0 = per * lane < nseg ? per * lane : nseg, j1 = j0 + per < nseg ? j0 + per : nseg;
+  uint32_t s1 = 0, s2 = 0;
+  uint64_t n = 0; /* bytes summarised by this lane */
+  for (uint64_t j = j0; j < j1; j++) {
     const uint64_t rest = len - j * PZ_ADLER_SEG;
     const uint32_t L = (uint32_t)(rest < PZ_ADLER_SEG ? rest : PZ_ADLER_SEG);
     const uint2 s = p[j];
-    b = (uint32_t)(((uint64_t)b + (uint64_t)L * a + s.y) % PZ_ADLER_MOD);
-    a = (a + s.x) % PZ_ADLER_MOD;
+    s2 = (uint32_t)(((uint64_t)s2 + (uint64_t)L * s1 + s.y) % PZ_ADLER_MOD);
+    s1 = (s1 + s.x) % PZ_ADLER_MOD;
+    n += L;
   }
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { /* lane l absorbs the summary of the 'o' lanes to its right, pairwise */
+    const uint32_t t1 = __shfl_down_sync(0xffffffffu, s1, o), t2 = __shfl_down_sync(0xffffffffu, s2, o);
+    const uint64_t tn = __shfl_down_sync(0xffffffffu, n, o);
+    if ((lane & (2u * (uint32_t)o - 1u)) == 0u) {
+      s2 = (uint32_t)(((uint64_t)s2 + (tn % PZ_ADLER_MOD) * s1 + t2) % PZ_ADLER_MOD);
+      s1 = (s1 + t1) % PZ_ADLER_MOD;
+      n += tn;
+    }
+  }
+  if (lane != 0) return;
+  const uint32_t a = (1u + s1) % PZ_ADLER_MOD, b = (uint32_t)((len % PZ_ADLER_MOD + s2) % PZ_ADLER_MOD);
   const uint32_t adler = (b << 16) | a; /* finalizeAdler (Adler32.hs:53-57) */
   res[i].adler_computed = adler;
   if (adler != res[i].adler_stored) { /* checkChecksum (Deflate.hs:56-63) */
@@ -290,7 +312,7 @@ cudaError_t pz_launch_adler(const uint8_t *d_out, const uint64_t *d_out_off, con
     const unsigned grid = (unsigned)((seg_count + warps_per_cta - 1) / warps_per_cta);
     pz_adler_partial_kernel<<<grid, 256, 0, st>>>(d_out, d_out_off, d_seg_off, n_total, seg_first, seg_count, d_res, d_parts);
   }
-  pz_adler_finish_kernel<<<(count + 127) / 128, 128, 0, st>>>(d_seg_off, first, count, d_res, d_parts);
+  pz_adler_finish_kernel<<<(count + 3) / 4, 128, 0, st>>>(d_seg_off, first, count, d_res, d_parts); /* one warp per stream */
   return cudaGetLastError();
 }
 

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libpzcuda.so")
+SO_PATH = os.environ.get("PZ_LIBPZCUDA") or os.path.join(_HERE, "libpzcuda.so")  # the override is for A/B builds of the kernels
 
 PZ_OK, PZ_ERR_HUFFMAN_TREE, PZ_ERR_FORMAT, PZ_ERR_DECOMPRESSION, PZ_ERR_HEADER, PZ_ERR_CHECKSUM, PZ_REF_BOTTOM, \
     PZ_OUTPUT_FULL, PZ_NEED_MORE = range(9)

@@ -122,8 +122,10 @@ PZ_DEV void pz_async_wait_all() {
 /* Token queue, decoder -> writer (one per stream, in shared memory).  A token is one 32-bit
  * word: phase [31] | type [29,31) | payload.  The phase bit flips every time the ring wraps, so a
  * slot is valid exactly when its phase matches the reader's lap: one store publishes a token. */
-#define PZ_QLEN 32u
-#define PZ_QSHIFT 5
+#ifndef PZ_QSHIFT
+#define PZ_QSHIFT 6
+#endif
+#define PZ_QLEN (1u << PZ_QSHIFT)
 #define PZ_Q_LIT 0u   /* payload [0,8): the byte                                             */
 #define PZ_Q_MATCH 1u /* payload [16,25): length 3..258, [0,15): distance - 1                 */
 #define PZ_Q_CTRL 2u  /* payload [26,29): operation, followed by raw 31-bit argument tokens   */
@@ -893,7 +895,9 @@ PZ_DEV void pz_fast_fetch(PzFast &f, const PzStreamSmem *sm, uint32_t bp) {
  * loop must not decide, a full token queue -- the chain keeps running on garbage for the rest of
  * the trip (all table and ring indices are masked, so that is harmless) and nothing more is
  * committed.  Returns true if the stream stopped inside this trip; f.lo/hi/e are then stale. */
+#ifndef PZ_TRIP
 #define PZ_TRIP 4
+#endif
 template <bool COUNT_ONLY>
 PZ_DEV bool pz_fast_trip(PzFast &f, PzStreamSmem *sm, const bool run) {
   uint32_t bp = f.bp, pos = f.pos, base = f.base, qhead = f.qhead;

@@ -324,6 +324,21 @@ PZ_DEV void pz_peek64(const uint32_t *ring, uint32_t bp, uint32_t &lo, uint32_t 
   lo = pz_funnel_r(w0, w1, bp);
   hi = pz_funnel_r(w1, w2, bp);
 }
+/* The 96 stream bits starting at bp (the hot loop's register window). */
+PZ_DEV void pz_peek96(const uint32_t *ring, uint32_t bp, uint32_t &b0, uint32_t &b1, uint32_t &b2) {
+  uint32_t t = (bp >> 5) & (PZ_RING_WORDS - 1u);
+  uint32_t w0 = ring[t], w1 = ring[t + 1u], w2 = ring[t + 2u], w3 = ring[t + 3u];
+  b0 = pz_funnel_r(w0, w1, bp);
+  b1 = pz_funnel_r(w1, w2, bp);
+  b2 = pz_funnel_r(w2, w3, bp);
+}
+/* Bits [bp+32, bp+96): the part of the register window that is NOT on the serial chain. */
+PZ_DEV void pz_peek_tail(const uint32_t *ring, uint32_t bp, uint32_t &b1, uint32_t &b2) {
+  uint32_t t = (bp >> 5) & (PZ_RING_WORDS - 1u);
+  uint32_t w1 = ring[t + 1u], w2 = ring[t + 2u], w3 = ring[t + 3u];
+  b1 = pz_funnel_r(w1, w2, bp);
+  b2 = pz_funnel_r(w2, w3, bp);
+}
 PZ_DEV void pz_advance(PzCtx &c, PzStreamSmem *sm, uint32_t n) {
   c.bp += n;
   if ((c.bp >> PZ_QUARTER_SHIFT) != c.q) pz_cross(c, sm);
@@ -876,7 +891,7 @@ PZ_DEV int pz_symbol_careful(PzCtx &c, PzStreamSmem *sm) {
  * streams left) idle along. */
 struct PzFast { /* the registers of the hot loop */
   uint32_t bp, pos, base, lim, safe_end, qhead, qtailc;
-  uint32_t lo, hi, e; /* the 64-bit window at bp and its literal/length LUT entry (decoded ahead) */
+  uint32_t b0, b1, b2, e; /* the 96 stream bits at bp and the literal/length LUT entry of b0 (decoded ahead) */
   bool live;
 #ifdef PZ_HOSTSIM
   PzWriter *hw;
@@ -884,38 +899,48 @@ struct PzFast { /* the registers of the hot loop */
 };
 
 PZ_DEV void pz_fast_fetch(PzFast &f, const PzStreamSmem *sm, uint32_t bp) {
-  pz_peek64(sm->ring, bp, f.lo, f.hi);
-  f.e = sm->lit_lut[f.lo & ((1u << PZ_LIT_BITS) - 1u)];
+  pz_peek96(sm->ring, bp, f.b0, f.b1, f.b2);
+  f.e = sm->lit_lut[f.b0 & ((1u << PZ_LIT_BITS) - 1u)];
 }
 
-/* One trip = PZ_TRIP symbols.  The bit-position chain (window -> literal/length LUT -> distance
- * LUT -> bit count -> next window) runs SPECULATIVELY: it never waits for the verdict on the
- * symbol it has just consumed.  The verdict (`alive`, sticky within the trip) only gates what is
- * committed: the token, and the position registers in `f`.  Once a symbol fails -- something the
- * loop must not decide, a full token queue -- the chain keeps running on garbage for the rest of
- * the trip (all table and ring indices are masked, so that is harmless) and nothing more is
- * committed.  Returns true if the stream stopped inside this trip; f.lo/hi/e are then stale. */
+/* One trip = PZ_TRIP symbols.  The serial chain of a stream is
+ *     b0 -> literal/length LUT -> shift -> distance LUT -> shift -> b0' -> literal/length LUT ...
+ * i.e. two dependent shared-memory loads and five ALU operations per symbol: the lane keeps the
+ * 96 stream bits at bp in registers (b0, b1, b2), a symbol consumes at most 48 of them, so the
+ * next 32-bit window b0' comes out of the registers by two funnel shifts.  The ring is re-read
+ * only for the upper 64 bits of the next window, and nothing waits for that until the NEXT
+ * symbol's first shift: the reload runs beside the chain instead of inside it.
+ *
+ * The chain runs SPECULATIVELY: it never waits for the verdict on the symbol it has just consumed.
+ * The verdict (`alive`, sticky within the trip) only gates what is committed: the token, and the
+ * position registers in `f`.  Once a symbol fails -- something the loop must not decide, a full
+ * token queue -- the chain keeps running on garbage for the rest of the trip (all table and ring
+ * indices are masked, so that is harmless) and nothing more is committed.  Returns true if the
+ * stream stopped inside this trip; f.b0/b1/b2/e are then stale. */
 #ifndef PZ_TRIP
 #define PZ_TRIP 4
 #endif
 template <bool COUNT_ONLY>
 PZ_DEV bool pz_fast_trip(PzFast &f, PzStreamSmem *sm, const bool run) {
   uint32_t bp = f.bp, pos = f.pos, base = f.base, qhead = f.qhead;
-  uint32_t lo = f.lo, hi = f.hi, e = f.e;
+  uint32_t b0 = f.b0, b1 = f.b1, b2 = f.b2, e = f.e;
   bool alive = run;
 #pragma unroll
   for (int k = 0; k < PZ_TRIP; k++) {
     const uint32_t tb = e & 31u;
     const bool is_lit = (int32_t)e < 0;
-    const uint32_t wd = pz_funnel_r(lo, hi, tb); /* the bits after the literal/length symbol (tb <= 20) */
+    /* the funnel shifts take their amount modulo 32: e itself serves as tb (tb <= 20) */
+    const uint32_t wd = pz_funnel_r(b0, b1, e);  /* the 32 bits after the literal/length symbol */
+    const uint32_t wd1 = pz_funnel_r(b1, b2, e); /* and the 32 after those (off the chain)     */
     const uint32_t d = sm->dist_lut[wd & ((1u << PZ_DIST_BITS) - 1u)];
-    const uint32_t tb2 = d & (is_lit ? 0u : 31u);
+    const uint32_t tb2 = d & (is_lit ? 0u : 31u); /* <= 28 */
+    const uint32_t nb0 = pz_funnel_r(wd, wd1, tb2);
+    const uint32_t ne = sm->lit_lut[nb0 & ((1u << PZ_LIT_BITS) - 1u)];
     const uint32_t nbp = bp + tb + tb2;
-    uint32_t nlo, nhi;
-    pz_peek64(sm->ring, nbp, nlo, nhi);
-    const uint32_t ne = sm->lit_lut[nlo & ((1u << PZ_LIT_BITS) - 1u)];
+    uint32_t nb1, nb2;
+    pz_peek_tail(sm->ring, nbp, nb1, nb2);
     /* off the chain: the symbol's values and its verdict */
-    const uint32_t len = (e >> 16) + ((lo & ~(0xffffffffu << tb)) >> ((e >> 8) & 15u));
+    const uint32_t len = (e >> 16) + ((b0 & ~(0xffffffffu << tb)) >> ((e >> 8) & 15u));
     const uint32_t dx = (d >> 9) & 15u; /* extra bits of the distance */
     const uint32_t dist = 1u + ((d >> 13) << dx) + ((wd >> ((d >> 5) & 15u)) & ~(0xffffffffu << dx));
     const uint32_t room = f.lim - pos;
@@ -939,10 +964,10 @@ PZ_DEV bool pz_fast_trip(PzFast &f, PzStreamSmem *sm, const bool run) {
     }
     pos += adv;
     if (!is_lit && pos - base >= 2u * PZ_EXCESS) base += PZ_EXCESS; /* moveWindow after every match */
-    bp = nbp; lo = nlo; hi = nhi; e = ne;
+    bp = nbp; b0 = nb0; b1 = nb1; b2 = nb2; e = ne;
     if (alive) { f.bp = bp; f.pos = pos; f.base = base; f.qhead = qhead; }
   }
-  if (alive) { f.lo = lo; f.hi = hi; f.e = e; } /* else: unchanged if the trip did not run, stale if it stopped */
+  if (alive) { f.b0 = b0; f.b1 = b1; f.b2 = b2; f.e = e; } /* else: unchanged if the trip did not run, stale if it stopped */
   return run && !alive;
 }
 
@@ -989,7 +1014,7 @@ PZ_DEV void pz_hot_warp(PzStreamSmem *slots, uint32_t n_slots) {
   PzStreamSmem *sm = slots + (lane < n_slots ? lane : 0u);
   PzFast f;
   f.live = false;
-  f.bp = 0; f.pos = 0; f.base = 0; f.lim = 0; f.safe_end = 0; f.qhead = 0; f.qtailc = 0; f.lo = 0; f.hi = 0; f.e = 0;
+  f.bp = 0; f.pos = 0; f.base = 0; f.lim = 0; f.safe_end = 0; f.qhead = 0; f.qtailc = 0; f.b0 = 0; f.b1 = 0; f.b2 = 0; f.e = 0;
   bool dead = lane >= n_slots;
   for (;;) {
     if (!f.live && !dead) { /* anything posted? */

@@ -6,9 +6,9 @@ rep = sys.argv[1]
 sym = int(sys.argv[2]) if len(sys.argv) > 2 else 43425
 warps = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
 verbose = "-v" in sys.argv
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass", "-k", "regex:pz_inflate"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
-hdr = rows[1]; data = rows[2:]
+hdr = rows[1]; data = [r for r in rows[2:] if len(r) == len(hdr) and r[hdr.index("Instructions Executed")].isdigit()]
 ie = hdr.index("Instructions Executed"); sm = hdr.index("# Samples")
 tot = sum(int(r[ie]) for r in data); ts = sum(int(r[sm]) for r in data)
 step = warps * sym

@@ -53,11 +53,24 @@
 #define PZ_GROUP 8 /* lanes per stream on the device: 32, 16, 8 or 4 */
 #endif
 
+#ifndef PZ_DOZE_NS
+#define PZ_DOZE_NS 1000 /* service warps between polls of their hot lanes */
+#endif
+#ifndef PZ_NAP_NS
+#define PZ_NAP_NS 1000 /* writer warps waiting for a full batch */
+#endif
+#ifndef PZ_WGROUP
+#define PZ_WGROUP 16 /* lanes per stream in the writer warps: 8 or 16 */
+#endif
+
 #ifdef PZ_HOSTSIM
 #include <string.h>
 #define PZ_DEV static inline
 #define PZ_COLD static
 #define PZ_G 1
+#define PZ_WG 1
+PZ_DEV int pz_wlane() { return 0; }
+PZ_DEV void pz_wsyncwarp() {}
 PZ_DEV uint32_t pz_brev(uint32_t x) {
   x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
   x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
@@ -82,6 +95,12 @@ PZ_DEV void pz_async_wait_all() {}
 #define PZ_DEV __device__ __forceinline__
 #define PZ_COLD __device__ __noinline__ /* rare paths: kept out of line so the hot loops stay in the instruction cache */
 #define PZ_G PZ_GROUP
+#define PZ_WG PZ_WGROUP
+/* the writer warps' groups (PZ_WG lanes per stream) */
+PZ_DEV unsigned pz_wgshift() { return (threadIdx.x & 31u) & ~(unsigned)(PZ_WG - 1); }
+PZ_DEV unsigned pz_wgmask() { return PZ_WG == 32 ? 0xffffffffu : (((1u << (PZ_WG & 31)) - 1u) << pz_wgshift()); }
+PZ_DEV int pz_wlane() { return (int)(threadIdx.x & (unsigned)(PZ_WG - 1)); }
+PZ_DEV void pz_wsyncwarp() { __syncwarp(pz_wgmask()); }
 PZ_DEV uint32_t pz_brev(uint32_t x) { return __brev(x); }
 PZ_DEV unsigned pz_gshift() { return (threadIdx.x & 31u) & ~(unsigned)(PZ_G - 1); }
 PZ_DEV unsigned pz_gmask() { return PZ_G == 32 ? 0xffffffffu : (((1u << (PZ_G & 31)) - 1u) << pz_gshift()); }
@@ -564,36 +583,36 @@ PZ_DEV uint16_t pz_sym16(const uint16_t *out16, int32_t i) { return i < 0 ? PZ_M
 
 template <bool WIDE>
 PZ_DEV void pz_copy_match(uint8_t *out, uint16_t *out16, uint32_t pos, uint32_t len, uint32_t dist) {
-  const uint32_t lane = (uint32_t)pz_lane();
+  const uint32_t lane = (uint32_t)pz_wlane();
   uint8_t *dst = out + pos;
   const uint8_t *src = dst - dist;
   const int32_t s16 = (int32_t)pos - (int32_t)dist;
-  pz_syncwarp(); /* earlier stores by other lanes are ordered before the loads below */
+  pz_wsyncwarp(); /* earlier stores by other lanes are ordered before the loads below */
   if (dist >= len) {
-    for (uint32_t i = lane; i < len; i += PZ_G) {
+    for (uint32_t i = lane; i < len; i += PZ_WG) {
       if (WIDE) out16[pos + i] = pz_sym16(out16, s16 + (int32_t)i);
       else dst[i] = src[i];
     }
-  } else if (dist >= PZ_G) {
-    for (uint32_t i0 = 0; i0 < len; i0 += PZ_G) { /* each chunk may read the previous one */
+  } else if (dist >= PZ_WG) {
+    for (uint32_t i0 = 0; i0 < len; i0 += PZ_WG) { /* each chunk may read the previous one */
       uint32_t i = i0 + lane;
       if (i < len) {
         if (WIDE) out16[pos + i] = pz_sym16(out16, s16 + (int32_t)i);
         else dst[i] = src[i];
       }
-      pz_syncwarp();
+      pz_wsyncwarp();
     }
-  } else { /* dist < PZ_G and dist < len: replicate the dist-byte pattern */
+  } else { /* dist < PZ_WG and dist < len: replicate the dist-byte pattern */
     uint32_t m = lane % dist;
-    const uint32_t step = PZ_G % dist;
-    for (uint32_t i = lane; i < len; i += PZ_G) {
+    const uint32_t step = PZ_WG % dist;
+    for (uint32_t i = lane; i < len; i += PZ_WG) {
       if (WIDE) out16[pos + i] = pz_sym16(out16, s16 + (int32_t)m);
       else dst[i] = src[m];
       m += step;
       if (m >= dist) m -= dist;
     }
   }
-  pz_syncwarp();
+  pz_wsyncwarp();
 }
 
 /* Writer state of one stream slot (registers; identical in every lane of the group). */
@@ -613,9 +632,9 @@ PZ_DEV void pz_publish(PzWriter &, uint32_t) {}
 /* Tells the host driver that the first `value` bytes of the current stream are final. */
 PZ_DEV void pz_publish(PzWriter &w, uint32_t value) {
   if (w.job->prog == nullptr || w.out == nullptr) return;
-  pz_syncwarp();
+  pz_wsyncwarp();
   __threadfence_system(); /* the bytes first, then the word that announces them */
-  if (pz_lane() == 0) *(volatile uint32_t *)(w.job->prog + w.sidx) = value;
+  if (pz_wlane() == 0) *(volatile uint32_t *)(w.job->prog + w.sidx) = value;
 }
 #endif
 PZ_DEV void pz_writer_init(PzWriter &w, const PzJob *job) {
@@ -626,7 +645,7 @@ PZ_DEV void pz_writer_init(PzWriter &w, const PzJob *job) {
  * literal or a short disjoint match.  `raw` is the token without its phase bit. */
 template <bool WIDE>
 PZ_DEV void pz_writer_apply(PzWriter &w, uint32_t raw) {
-  const uint32_t lane = (uint32_t)pz_lane();
+  const uint32_t lane = (uint32_t)pz_wlane();
   if (w.need) { /* argument of a control message */
     if (w.op == PZ_C_NEWSTREAM) {
       pz_publish(w, PZ_PROG_DONE); /* the previous stream of this slot is complete */
@@ -644,12 +663,12 @@ PZ_DEV void pz_writer_apply(PzWriter &w, uint32_t raw) {
     } else { /* emitBlock (Monad.hs:317-322): raw bytes of a stored block */
       const uint8_t *src = w.in + w.a0;
       uint8_t *dst = w.out + w.pos;
-      pz_syncwarp();
-      for (uint32_t i = lane; i < raw; i += PZ_G) {
+      pz_wsyncwarp();
+      for (uint32_t i = lane; i < raw; i += PZ_WG) {
         if (WIDE) w.out16[w.pos + i] = src[i];
         else dst[i] = src[i];
       }
-      pz_syncwarp();
+      pz_wsyncwarp();
       w.pos += raw; w.need = 0;
     }
     return;
@@ -693,26 +712,35 @@ PZ_DEV void pz_st16_sel(bool p, uint16_t *a, uint32_t alt, uint32_t x) {
 
 /* The writer warp: runs until every group has seen its EXIT token.
  *
- * A trip looks at the next PZ_G tokens of every stream, one token per lane.  The longest prefix
- * of literals and short, disjoint matches whose sources lie entirely before the trip's first
- * output byte (and whose bytes total at most PZ_TRIP_BYTES) forms the batch.  Its output bytes
- * are then dealt out to the lanes by POSITION: lane l produces bytes l, l+G, l+2G, ... of the
- * batch, finding the token that owns a byte with one popcount over the bitmap of token start
- * offsets and one shuffle.  All history loads of the trip are issued before the first store, so
- * one L2/HBM round trip is shared by the whole batch, and consecutive lanes touch consecutive
- * bytes.  Everything else (overlapping or long copies, stored runs, control tokens) goes through
- * pz_writer_apply(), one token per trip. */
-#define PZ_TRIP_BYTES 64u
-#define PZ_ROUNDS ((int)(PZ_TRIP_BYTES / PZ_G))
+ * A trip looks at the next PZ_WG tokens of every stream of the warp, one token per lane.  The
+ * longest prefix of literals and short, disjoint matches whose sources lie entirely before the
+ * trip's first output byte (and whose bytes total at most PZ_TRIP_BYTES) forms the batch.  Its
+ * output bytes are then dealt out to the lanes by POSITION: lane l produces bytes l, l+WG, l+2WG,
+ * ... of the batch, finding the token that owns a byte with a popcount over the bitmap of token
+ * start offsets and one shuffle.  All history loads of the trip are issued before the first
+ * store, so one L2/HBM round trip is shared by the whole batch, and consecutive lanes touch
+ * consecutive bytes.  Everything else (overlapping or long copies, stored runs, control tokens)
+ * goes through pz_writer_apply(), one token per trip.
+ *
+ * The trip is one long dependent sequence (queue read, votes, prefix sum, bitmap, loads, stores:
+ * about 2 000 cycles), and a stream cannot have two trips in flight, so the tokens one trip may
+ * take bound the writer's rate per stream: with 8 lanes per stream the writers, not the hot warp,
+ * set the pace of the kernel (ncu, profiles/); hence 16 lanes and up to 128 bytes per trip. */
+#define PZ_TRIP_BYTES (8u * PZ_WG)
+#define PZ_ROUNDS 8
+#define PZ_BM_WORDS ((int)(PZ_TRIP_BYTES / 32u)) /* words of the token-start bitmap */
+#define PZ_WGROUPS (32 / PZ_WG)                 /* streams per writer warp */
+#define PZ_WGMASK ((1u << PZ_WG) - 1u)
 template <bool WIDE>
 PZ_DEV void pz_writer_warp(const PzJob &job, PzStreamSmem *sm, bool present) {
-  static_assert(PZ_G == 8, "the writer deals bytes to 8-lane groups");
+  static_assert(PZ_WG == 8 || PZ_WG == 16, "the writer deals bytes to groups of 8 or 16 lanes");
   PzWriter w;
   pz_writer_init(w, &job);
   w.exited = !present;
-  const uint32_t lane = (uint32_t)pz_lane();
-  const unsigned gsh = pz_gshift();
-  const unsigned all = 0xffffffffu; /* the four groups run this loop converged: warp-wide collectives, group-sized segments */
+  const uint32_t lane = (uint32_t)pz_wlane();
+  const unsigned gsh = pz_wgshift();
+  const uint32_t grp = gsh / PZ_WG;
+  const unsigned all = 0xffffffffu; /* the groups run this loop converged: warp-wide collectives, group-sized segments */
   uint32_t tail = 0, naps = 0;
   if (!pz_warp_any(!w.exited)) return;
   for (;;) {
@@ -723,26 +751,26 @@ PZ_DEV void pz_writer_warp(const PzJob &job, PzStreamSmem *sm, bool present) {
     const uint32_t type = (raw >> 29) & 3u, len = (raw >> 16) & 0x1ffu, dist = (raw & 0x7fffu) + 1u;
     const bool is_lit = type == PZ_Q_LIT;
     const bool fast = valid && w.need == 0u && (is_lit || (type == PZ_Q_MATCH && dist >= len && len <= PZ_TRIP_BYTES));
-    /* A trip costs the same whether it moves one token or PZ_G per group, and the other warps
+    /* A trip costs the same whether it moves one token or PZ_WG per group, and the other warps
      * need the issue slots: unless some group has a full batch waiting (or a token that will not
      * join a batch anyway), sleep a little -- but never for long. */
-    const unsigned vmask = (__ballot_sync(all, valid) >> gsh) & 0xffu;
-    const unsigned smask = (__ballot_sync(all, valid && !fast) >> gsh) & 0xffu;
-    if (naps < 8u && !pz_warp_any(vmask == 0xffu || smask != 0u)) { naps++; __nanosleep(1000); continue; }
+    const unsigned vmask = (__ballot_sync(all, valid) >> gsh) & PZ_WGMASK;
+    const unsigned smask = (__ballot_sync(all, valid && !fast) >> gsh) & PZ_WGMASK;
+    if (naps < 8u && !pz_warp_any(vmask == PZ_WGMASK || smask != 0u)) { naps++; __nanosleep(PZ_NAP_NS); continue; }
     const uint32_t L = fast ? (is_lit ? 1u : len) : 0u;
     uint32_t E = L; /* inclusive prefix sum over the group: end offset of this lane's token */
 #pragma unroll
-    for (int o = 1; o < PZ_G; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(all, E, o, PZ_G);
+    for (int o = 1; o < PZ_WG; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(all, E, o, PZ_WG);
       if ((int)lane >= o) E += t;
     }
     /* a match may not read what this trip produces: its source ends at E - dist <= 0 */
     const bool ok = fast && (is_lit || dist >= E) && E <= PZ_TRIP_BYTES;
-    const unsigned bad = (__ballot_sync(all, !ok) >> gsh) & 0xffu;
-    const uint32_t n = bad ? (uint32_t)__ffs((int)bad) - 1u : (uint32_t)PZ_G;
+    const unsigned bad = (__ballot_sync(all, !ok) >> gsh) & PZ_WGMASK;
+    const uint32_t n = bad ? (uint32_t)__ffs((int)bad) - 1u : (uint32_t)PZ_WG;
     const bool slow = n == 0u && (vmask & 1u);
     naps = 0;
-    const uint32_t r0 = (uint32_t)__shfl_sync(all, (int)raw, 0, PZ_G);
+    const uint32_t r0 = (uint32_t)__shfl_sync(all, (int)raw, 0, PZ_WG);
     if (pz_warp_any(slow)) {
       if (slow) {
         pz_writer_apply<WIDE>(w, r0 & 0x7fffffffu);
@@ -755,27 +783,36 @@ PZ_DEV void pz_writer_warp(const PzJob &job, PzStreamSmem *sm, bool present) {
     }
     const bool act = lane < n;
     const uint32_t P = E - L; /* first output byte of this lane's token, relative to the trip */
-    const uint32_t Bn = (uint32_t)__shfl_sync(all, (int)E, (int)n - 1, PZ_G);
+    const uint32_t Bn = (uint32_t)__shfl_sync(all, (int)E, (int)n - 1, PZ_WG);
     const uint32_t B = n ? Bn : 0u;
-    uint32_t s_lo = (act && P < 32u) ? (1u << P) : 0u; /* bitmap of the tokens' first bytes */
-    uint32_t s_hi = (act && P >= 32u) ? (1u << (P - 32u)) : 0u;
+    /* bitmap of the tokens' first bytes, per group: one warp-wide OR per (group, word) */
+    uint32_t bm[PZ_BM_WORDS];
 #pragma unroll
-    for (int o = 1; o < PZ_G; o <<= 1) {
-      s_lo |= __shfl_xor_sync(all, s_lo, o, PZ_G);
-      s_hi |= __shfl_xor_sync(all, s_hi, o, PZ_G);
+    for (int k = 0; k < PZ_BM_WORDS; k++) bm[k] = 0u;
+    const uint32_t my_bit = act ? (1u << (P & 31u)) : 0u;
+#pragma unroll
+    for (int g = 0; g < PZ_WGROUPS; g++) {
+#pragma unroll
+      for (int k = 0; k < PZ_BM_WORDS; k++) {
+        const uint32_t v = __reduce_or_sync(all, (grp == (uint32_t)g && (P >> 5) == (uint32_t)k) ? my_bit : 0u);
+        if (grp == (uint32_t)g) bm[k] = v;
+      }
     }
+    uint32_t cnt[PZ_BM_WORDS]; /* tokens starting in the words before word k, minus one */
+    cnt[0] = 0xffffffffu;
+#pragma unroll
+    for (int k = 1; k < PZ_BM_WORDS; k++) cnt[k] = cnt[k - 1] + (uint32_t)__popc(bm[k - 1]);
     const uint32_t info = is_lit ? (0x80000000u | (raw & 0xffu)) : dist;
     const uint32_t max_b = __reduce_max_sync(0xffffffffu, B);
-    const uint32_t c_lo = (uint32_t)__popc(s_lo);
     uint8_t *const base = w.out + w.pos;
     uint32_t x[PZ_ROUNDS], inf[PZ_ROUNDS];
 #pragma unroll
     for (int r = 0; r < PZ_ROUNDS; r++) {
-      if ((uint32_t)(r * PZ_G) < max_b) { /* warp-uniform */
-        const uint32_t b = (uint32_t)(r * PZ_G) + lane;
-        const int t = r * PZ_G < 32 ? __popc(s_lo & ((2u << b) - 1u)) - 1
-                                    : (int)c_lo + __popc(s_hi & ((2u << (b - 32u)) - 1u)) - 1;
-        inf[r] = (uint32_t)__shfl_sync(all, (int)info, t, PZ_G);
+      if ((uint32_t)(r * PZ_WG) < max_b) { /* warp-uniform */
+        const uint32_t b = (uint32_t)(r * PZ_WG) + lane;
+        const int k = (r * PZ_WG) / 32; /* the word of byte b: the same for every lane of the round */
+        const int t = (int)(cnt[k] + (uint32_t)__popc(bm[k] & ((2u << (b & 31u)) - 1u)));
+        inf[r] = (uint32_t)__shfl_sync(all, (int)info, t, PZ_WG);
         if (WIDE) {
           /* a source before the block is not loaded: its marker takes the literal's place */
           const int32_t si = (int32_t)(w.pos + b) - (int32_t)(inf[r] & 0xffffu);
@@ -789,8 +826,8 @@ PZ_DEV void pz_writer_warp(const PzJob &job, PzStreamSmem *sm, bool present) {
     }
 #pragma unroll
     for (int r = 0; r < PZ_ROUNDS; r++) {
-      if ((uint32_t)(r * PZ_G) < max_b) {
-        const uint32_t b = (uint32_t)(r * PZ_G) + lane;
+      if ((uint32_t)(r * PZ_WG) < max_b) {
+        const uint32_t b = (uint32_t)(r * PZ_WG) + lane;
         if (WIDE) pz_st16_sel(b < B, w.out16 + w.pos + b, inf[r], x[r]);
         else pz_st8_sel(b < B, base + b, inf[r], x[r]);
       }
@@ -1016,39 +1053,47 @@ PZ_DEV void pz_hot_warp(PzStreamSmem *slots, uint32_t n_slots) {
   f.live = false;
   f.bp = 0; f.pos = 0; f.base = 0; f.lim = 0; f.safe_end = 0; f.qhead = 0; f.qtailc = 0; f.b0 = 0; f.b1 = 0; f.b2 = 0; f.e = 0;
   bool dead = lane >= n_slots;
+  /* A lone warp pays every branch in full (nothing else issues on its scheduler while one
+   * resolves), so the steady state -- every lane in the middle of a block -- runs through two
+   * warp-uniform branches per trip; everything a single lane may need is behind them. */
   for (;;) {
-    if (!f.live && !dead) { /* anything posted? */
-      const uint32_t st = pz_vload(&sm->mail.state);
-      if (st == PZ_MS_HOT) {
-        __threadfence_block();
-        f.bp = pz_vload(&sm->mail.bp); f.pos = pz_vload(&sm->mail.pos); f.base = pz_vload(&sm->mail.base);
-        f.lim = pz_vload(&sm->mail.lim); f.safe_end = pz_vload(&sm->mail.safe_end); f.qhead = pz_vload(&sm->mail.qhead);
-        pz_fast_fetch(f, sm, f.bp);
-        f.live = true;
-      } else if (st == PZ_MS_DEAD) {
-        dead = true;
+    if (__any_sync(0xffffffffu, !f.live && !dead)) {
+      if (!f.live && !dead) { /* anything posted? */
+        const uint32_t st = pz_vload(&sm->mail.state);
+        if (st == PZ_MS_HOT) {
+          __threadfence_block();
+          f.bp = pz_vload(&sm->mail.bp); f.pos = pz_vload(&sm->mail.pos); f.base = pz_vload(&sm->mail.base);
+          f.lim = pz_vload(&sm->mail.lim); f.safe_end = pz_vload(&sm->mail.safe_end); f.qhead = pz_vload(&sm->mail.qhead);
+          pz_fast_fetch(f, sm, f.bp);
+          f.live = true;
+        } else if (st == PZ_MS_DEAD) {
+          dead = true;
+        }
+      }
+      if (!__any_sync(0xffffffffu, f.live)) {
+        if (__all_sync(0xffffffffu, dead)) break;
+        __nanosleep(100);
+        continue;
       }
     }
-    if (!__any_sync(0xffffffffu, f.live)) {
-      if (__all_sync(0xffffffffu, dead)) break;
-      __nanosleep(100);
-      continue;
-    }
-    /* four symbols per trip: the input the trip can touch (4 x 48 bits + the look-ahead) lies in
-     * quarters q and q+1, which must be resident; a lane whose input is late idles this trip */
+    /* PZ_TRIP symbols per trip: the input the trip can touch (PZ_TRIP x 48 bits + the 128-bit
+     * look-ahead) lies in quarters q and q+1, which must be resident; a lane whose input is late
+     * idles this trip */
     const uint32_t ring_hi = pz_vload(&sm->mail.ring_hi);
     if (!COUNT_ONLY) f.qtailc = pz_vload(&sm->qtail);
     const bool run = f.live && (f.bp >> PZ_QUARTER_SHIFT) + 1u < ring_hi;
     const bool stop = pz_fast_trip<COUNT_ONLY>(f, sm, run);
-    const bool full = !COUNT_ONLY && f.qhead - f.qtailc >= PZ_QLEN;
-    if (stop && full) pz_fast_fetch(f, sm, f.bp); /* stays live: the queue drains, the window is re-read */
-    if (f.live) pz_vstore(&sm->mail.hot_bp, f.bp);
-    if (stop && !full) { /* hand the stream back: the careful path decides the next symbol */
-      pz_vstore(&sm->mail.bp, f.bp); pz_vstore(&sm->mail.pos, f.pos); pz_vstore(&sm->mail.base, f.base);
-      pz_vstore(&sm->mail.qhead, f.qhead);
-      __threadfence_block();
-      pz_vstore(&sm->mail.state, PZ_MS_SERVICE);
-      f.live = false;
+    if (run) pz_vstore(&sm->mail.hot_bp, f.bp);
+    if (__any_sync(0xffffffffu, stop)) {
+      const bool full = !COUNT_ONLY && f.qhead - f.qtailc >= PZ_QLEN;
+      if (stop && full) pz_fast_fetch(f, sm, f.bp); /* stays live: the queue drains, the window is re-read */
+      if (stop && !full) { /* hand the stream back: the careful path decides the next symbol */
+        pz_vstore(&sm->mail.bp, f.bp); pz_vstore(&sm->mail.pos, f.pos); pz_vstore(&sm->mail.base, f.base);
+        pz_vstore(&sm->mail.qhead, f.qhead);
+        __threadfence_block();
+        pz_vstore(&sm->mail.state, PZ_MS_SERVICE);
+        f.live = false;
+      }
     }
   }
 }
@@ -1407,7 +1452,7 @@ PZ_DEV void pz_decoder_warp(const PzJob &job, uint32_t first_stream, uint32_t st
         else if (c.mode == PZ_M_IDLE)
           need = *(const volatile uint32_t *)job.in_ready > c.next;
         if (pz_warp_any(need)) break;
-        __nanosleep(1000);
+        __nanosleep(PZ_DOZE_NS);
       }
     }
   }

@@ -11,8 +11,13 @@
 #ifndef PZ_SLOTS
 #define PZ_SLOTS 28u /* streams a CTA works on at a time (one lane of the hot warp each) */
 #endif
+#ifndef PZ_WGROUP
+#define PZ_WGROUP 16 /* lanes per stream in the writer warps (pz_device.cuh) */
+#endif
 #define PZ_SERVICE_WARPS ((PZ_SLOTS + 3u) / 4u) /* four slots (8 lanes each) per service warp */
-#define PZ_WARPS_PER_CTA (1u + 2u * PZ_SERVICE_WARPS) /* hot + service + writer warps */
+#define PZ_SLOTS_PER_WRITER (32u / PZ_WGROUP)
+#define PZ_WRITER_WARPS ((PZ_SLOTS + PZ_SLOTS_PER_WRITER - 1u) / PZ_SLOTS_PER_WRITER)
+#define PZ_WARPS_PER_CTA (1u + PZ_SERVICE_WARPS + PZ_WRITER_WARPS) /* hot + service + writer warps */
 #define PZ_THREADS_PER_CTA (32u * PZ_WARPS_PER_CTA)
 #define PZ_MAX_STREAM_BYTES 0x1ffffff0ull /* == PZ_MAX_IN_BYTES in pz_device.cuh */
 #define PZ_ADLER_SEG 16384u /* bytes per checksum segment (one warp each) */

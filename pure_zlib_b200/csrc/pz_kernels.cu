@@ -21,17 +21,17 @@
 #include "pz_huge.cuh"
 
 /* Warp roles.  A CTA owns PZ_SLOTS stream slots: warp 0 is the hot warp (one lane per slot),
- * PZ_SERVICE_WARPS service warps and as many writer warps serve four slots each (8 lanes per
- * slot).  A warp's scheduler is its index modulo 4 when the CTA has the SM to itself, so the
+ * PZ_SERVICE_WARPS service warps serve four slots each (8 lanes per slot) and PZ_WRITER_WARPS
+ * writer warps 32 / PZ_WGROUP slots each.  A warp's scheduler is its index modulo 4 when the CTA has the SM to itself, so the
  * multiples of four -- the hot warp's scheduler -- go to service warps, which sleep most of the
  * time, and the writers are dealt over the other three schedulers first. */
 __device__ __forceinline__ void pz_role(uint32_t w, uint32_t &role, uint32_t &index) {
   if (w == 0u) { role = 0u; index = 0u; return; }
   if ((w & 3u) == 0u) { role = 1u; index = (w >> 2) - 1u; return; } /* 4, 8, 12, ... */
   const uint32_t k = w - 1u - (w >> 2);                              /* rank among the other warps */
-  if (k < PZ_SERVICE_WARPS) { role = 2u; index = k; return; }        /* writers */
+  if (k < PZ_WRITER_WARPS) { role = 2u; index = k; return; }         /* writers */
   role = 1u;
-  index = (PZ_WARPS_PER_CTA - 1u) / 4u + (k - PZ_SERVICE_WARPS);
+  index = (PZ_WARPS_PER_CTA - 1u) / 4u + (k - PZ_WRITER_WARPS);
 }
 
 template <bool COUNT_ONLY, bool WIDE = false>
@@ -57,7 +57,7 @@ pz_inflate_kernel(const PzJob job) {
   }
   /* slot s of CTA b takes streams b + grid * (s + PZ_SLOTS * k): a batch spreads over the SMs
    * before it fills the slots of any of them */
-  const uint32_t slot = index * 4u + (threadIdx.x & 31u) / PZ_G;
+  const uint32_t slot = role == 1u ? index * 4u + (threadIdx.x & 31u) / PZ_G : index * PZ_SLOTS_PER_WRITER + (threadIdx.x & 31u) / PZ_WG;
   const bool present = slot < PZ_SLOTS;
   PzStreamSmem *sm = slots + (present ? slot : 0u);
   if (role == 1u) {

@@ -321,11 +321,12 @@ int run_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uint8_t *d_out, c
     return PZ_E_OK;
   }
   PZ_CUDA(pz_launch_inflate(d_in, d_in_off, d_out, d_out_off, first, count, d_res, st, nullptr, nullptr, PZ_PHASE_K2));
+  /* K2's verdicts for the span of the huge streams, in one copy: a stored-block stream is done */
+  std::vector<pz_result> after_k2(huge.back() - huge.front() + 1u);
+  PZ_CUDA(cudaMemcpyAsync(after_k2.data(), d_res + huge.front(), after_k2.size() * sizeof(pz_result), cudaMemcpyDeviceToHost, st));
+  PZ_CUDA(cudaStreamSynchronize(st));
   for (uint32_t i : huge) {
-    int32_t status = 0;
-    PZ_CUDA(cudaMemcpyAsync(&status, &d_res[i].status, 4, cudaMemcpyDeviceToHost, st));
-    PZ_CUDA(cudaStreamSynchronize(st));
-    if (status != PZ_ST_PENDING_HOST) continue; /* a stored-block stream: K2 has copied it */
+    if (after_k2[i - huge.front()].status != PZ_ST_PENDING_HOST) continue; /* K2 has copied it */
     pz_result r;
     const int k = huge_stream(d_in, d_in_off + i, h_in_off[i], h_in_off[i + 1] - h_in_off[i], d_out + h_out_off[i], h_out_off[i + 1] - h_out_off[i], &r, st);
     if (k < 0) return k;

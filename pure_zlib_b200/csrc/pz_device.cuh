@@ -987,7 +987,9 @@ PZ_DEV bool pz_fast_trip(PzFast &f, PzStreamSmem *sm, const bool run) {
     const bool full = !COUNT_ONLY && qhead - f.qtailc >= PZ_QLEN;
 #endif
     const bool pre_ok = bp <= f.safe_end && room != 0u && !full;
-    const bool m_ok = tb != 0u && (d & 31u) != 0u && dist <= pos - base && len <= room;
+    /* dist <= pos - base (OutputWindow.hs:82-89) is dist <= pos here: base only ever moves when 64 KiB
+     * have accumulated, so base > 0 implies pos - base >= 32 KiB >= any distance */
+    const bool m_ok = tb != 0u && (d & 31u) != 0u && dist <= pos && len <= room;
     alive = alive && pre_ok && (is_lit || m_ok);
     const uint32_t adv = is_lit ? 1u : len;
     if (!COUNT_ONLY) {

@@ -17,8 +17,16 @@
 #define PZ_SERVICE_WARPS ((PZ_SLOTS + 3u) / 4u) /* four slots (8 lanes each) per service warp */
 #define PZ_SLOTS_PER_WRITER (32u / PZ_WGROUP)
 #define PZ_WRITER_WARPS ((PZ_SLOTS + PZ_SLOTS_PER_WRITER - 1u) / PZ_SLOTS_PER_WRITER)
-#define PZ_WARPS_PER_CTA (1u + PZ_SERVICE_WARPS + PZ_WRITER_WARPS) /* hot + service + writer warps */
+#ifndef PZ_PAD_WARPS
+#define PZ_PAD_WARPS 2u /* warps that exit at once: they only keep working warps off the hot warp's scheduler */
+#endif
+#define PZ_WARPS_PER_CTA (1u + PZ_SERVICE_WARPS + PZ_WRITER_WARPS + PZ_PAD_WARPS) /* hot + service + writer (+ idle) warps */
 #define PZ_THREADS_PER_CTA (32u * PZ_WARPS_PER_CTA)
+/* warps 4, 8, 12, ... share the hot warp's scheduler: service warps (which doze), then the idle ones */
+#define PZ_HOT_SCHED_WARPS ((PZ_WARPS_PER_CTA - 1u) / 4u)
+#define PZ_HOT_SCHED_SERVICE (PZ_HOT_SCHED_WARPS - PZ_PAD_WARPS)
+static_assert(PZ_HOT_SCHED_SERVICE + (PZ_WARPS_PER_CTA - 1u - PZ_HOT_SCHED_WARPS - PZ_WRITER_WARPS) == PZ_SERVICE_WARPS,
+              "warp roles do not add up: adjust PZ_PAD_WARPS");
 #define PZ_MAX_STREAM_BYTES 0x1ffffff0ull /* == PZ_MAX_IN_BYTES in pz_device.cuh */
 #define PZ_ADLER_SEG 16384u /* bytes per checksum segment (one warp each) */
 

@@ -27,11 +27,16 @@
  * time, and the writers are dealt over the other three schedulers first. */
 __device__ __forceinline__ void pz_role(uint32_t w, uint32_t &role, uint32_t &index) {
   if (w == 0u) { role = 0u; index = 0u; return; }
-  if ((w & 3u) == 0u) { role = 1u; index = (w >> 2) - 1u; return; } /* 4, 8, 12, ... */
-  const uint32_t k = w - 1u - (w >> 2);                              /* rank among the other warps */
-  if (k < PZ_WRITER_WARPS) { role = 2u; index = k; return; }         /* writers */
+  if ((w & 3u) == 0u) { /* the hot warp's scheduler: service warps, then warps that exit at once */
+    const uint32_t j = (w >> 2) - 1u;
+    if (j < PZ_HOT_SCHED_SERVICE) { role = 1u; index = j; }
+    else { role = 3u; index = 0u; }
+    return;
+  }
+  const uint32_t k = w - 1u - (w >> 2); /* rank among the other warps: writers first */
+  if (k < PZ_WRITER_WARPS) { role = 2u; index = k; return; }
   role = 1u;
-  index = (PZ_WARPS_PER_CTA - 1u) / 4u + (k - PZ_WRITER_WARPS);
+  index = PZ_HOT_SCHED_SERVICE + (k - PZ_WRITER_WARPS);
 }
 
 template <bool COUNT_ONLY, bool WIDE = false>
@@ -55,6 +60,7 @@ pz_inflate_kernel(const PzJob job) {
     pz_hot_warp<COUNT_ONLY>(slots, PZ_SLOTS);
     return;
   }
+  if (role == 3u) return;
   /* slot s of CTA b takes streams b + grid * (s + PZ_SLOTS * k): a batch spreads over the SMs
    * before it fills the slots of any of them */
   const uint32_t slot = role == 1u ? index * 4u + (threadIdx.x & 31u) / PZ_G : index * PZ_SLOTS_PER_WRITER + (threadIdx.x & 31u) / PZ_WG;

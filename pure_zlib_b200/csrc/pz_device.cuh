@@ -547,6 +547,7 @@ PZ_DEV void pz_syncwarp_all() {}
 PZ_DEV uint32_t pz_vload(const uint32_t *p) { return *p; }
 PZ_DEV void pz_vstore(uint32_t *p, uint32_t v) { *p = v; }
 PZ_DEV void pz_backoff() {}
+PZ_DEV void pz_fence_cta() {}
 #else
 /* The writer's hot-loop global accesses are volatile asm WITHOUT a memory clobber: they keep
  * their order among themselves (which is all the copy semantics need), while the compiler
@@ -571,6 +572,16 @@ PZ_DEV uint32_t pz_ld16_if(bool p, const uint16_t *a) {
 PZ_DEV void pz_syncwarp_all() { asm volatile("bar.warp.sync 0xffffffff;"); }
 PZ_DEV uint32_t pz_vload(const uint32_t *p) { return *(const volatile uint32_t *)p; }
 PZ_DEV void pz_vstore(uint32_t *p, uint32_t v) { *(volatile uint32_t *)p = v; }
+/* Orders this thread's earlier shared-memory accesses before its later ones as seen by the other
+ * warps of the CTA (the hand-over of a stream between a service group and its hot lane).  An
+ * acquire-release fence: __threadfence_block() is fence.sc.cta, which costs a MEMBAR.SC plus a
+ * drain of the shared-memory pipe on every hand-over. */
+PZ_DEV void pz_fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
+/* v = *p (shared memory, volatile) in the lanes where c holds, as ONE predicated load: no branch */
+PZ_DEV void pz_vload_if(bool c, const uint32_t *p, uint32_t &v) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t@q ld.volatile.shared.u32 %0, [%2];\n\t}"
+               : "+r"(v) : "r"((int)c), "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+}
 PZ_DEV void pz_backoff() { __nanosleep(64); }
 #endif
 
@@ -1056,27 +1067,28 @@ PZ_DEV void pz_hot_warp(PzStreamSmem *slots, uint32_t n_slots) {
   f.bp = 0; f.pos = 0; f.base = 0; f.lim = 0; f.safe_end = 0; f.qhead = 0; f.qtailc = 0; f.b0 = 0; f.b1 = 0; f.b2 = 0; f.e = 0;
   bool dead = lane >= n_slots;
   /* A lone warp pays every branch in full (nothing else issues on its scheduler while one
-   * resolves), so the steady state -- every lane in the middle of a block -- runs through two
-   * warp-uniform branches per trip; everything a single lane may need is behind them. */
+   * resolves), and most of the time some lane or other is between two postings (its stream is with
+   * the service group for a header, a long code, ...).  So the poll of the mailboxes is straight-line
+   * code: a predicated load in the lanes without a stream, one warp-wide OR, and two warp-uniform
+   * branches that are only taken when a posting has actually arrived or nothing is left to do. */
   for (;;) {
-    if (__any_sync(0xffffffffu, !f.live && !dead)) {
-      if (!f.live && !dead) { /* anything posted? */
-        const uint32_t st = pz_vload(&sm->mail.state);
-        if (st == PZ_MS_HOT) {
-          __threadfence_block();
-          f.bp = pz_vload(&sm->mail.bp); f.pos = pz_vload(&sm->mail.pos); f.base = pz_vload(&sm->mail.base);
-          f.lim = pz_vload(&sm->mail.lim); f.safe_end = pz_vload(&sm->mail.safe_end); f.qhead = pz_vload(&sm->mail.qhead);
-          pz_fast_fetch(f, sm, f.bp);
-          f.live = true;
-        } else if (st == PZ_MS_DEAD) {
-          dead = true;
-        }
+    uint32_t st = PZ_MS_SERVICE;
+    pz_vload_if(!f.live && !dead, &sm->mail.state, st);
+    const bool pick = st == PZ_MS_HOT;
+    dead = dead || st == PZ_MS_DEAD;
+    const uint32_t any = __reduce_or_sync(0xffffffffu, (pick ? 1u : 0u) | (f.live ? 2u : 0u));
+    if (any & 1u) {
+      if (pick) {
+        pz_fence_cta();
+        f.bp = pz_vload(&sm->mail.bp); f.pos = pz_vload(&sm->mail.pos); f.base = pz_vload(&sm->mail.base);
+        f.lim = pz_vload(&sm->mail.lim); f.safe_end = pz_vload(&sm->mail.safe_end); f.qhead = pz_vload(&sm->mail.qhead);
+        pz_fast_fetch(f, sm, f.bp);
+        f.live = true;
       }
-      if (!__any_sync(0xffffffffu, f.live)) {
-        if (__all_sync(0xffffffffu, dead)) break;
-        __nanosleep(100);
-        continue;
-      }
+    } else if (!(any & 2u)) {
+      if (__all_sync(0xffffffffu, dead)) break;
+      __nanosleep(100);
+      continue;
     }
     /* PZ_TRIP symbols per trip: the input the trip can touch (PZ_TRIP x 48 bits + the 128-bit
      * look-ahead) lies in quarters q and q+1, which must be resident; a lane whose input is late
@@ -1092,7 +1104,7 @@ PZ_DEV void pz_hot_warp(PzStreamSmem *slots, uint32_t n_slots) {
       if (stop && !full) { /* hand the stream back: the careful path decides the next symbol */
         pz_vstore(&sm->mail.bp, f.bp); pz_vstore(&sm->mail.pos, f.pos); pz_vstore(&sm->mail.base, f.base);
         pz_vstore(&sm->mail.qhead, f.qhead);
-        __threadfence_block();
+        pz_fence_cta();
         pz_vstore(&sm->mail.state, PZ_MS_SERVICE);
         f.live = false;
       }
@@ -1111,7 +1123,7 @@ PZ_DEV void pz_post_hot(PzCtx &c, PzStreamSmem *sm) {
     pz_vstore(&sm->mail.bp, c.bp); pz_vstore(&sm->mail.pos, c.pos); pz_vstore(&sm->mail.base, c.base);
     pz_vstore(&sm->mail.lim, lim); pz_vstore(&sm->mail.safe_end, c.safe_end); pz_vstore(&sm->mail.qhead, c.qhead);
     pz_vstore(&sm->mail.hot_bp, c.bp); pz_vstore(&sm->mail.ring_hi, c.next_q);
-    __threadfence_block();
+    pz_fence_cta();
     pz_vstore(&sm->mail.state, PZ_MS_HOT);
   }
   pz_syncwarp();
@@ -1127,12 +1139,12 @@ PZ_DEV void pz_service_poll(PzCtx &c, PzStreamSmem *sm) {
   if (c.pending) {
     pz_async_wait_all();
     pz_syncwarp();
-    __threadfence_block();
+    pz_fence_cta();
     if (pz_lane() == 0) pz_vstore(&sm->mail.ring_hi, c.next_q);
     c.pending = false;
   }
   if (st == PZ_MS_SERVICE) {
-    __threadfence_block();
+    pz_fence_cta();
     c.bp = pz_vload(&sm->mail.bp); c.pos = pz_vload(&sm->mail.pos); c.base = pz_vload(&sm->mail.base);
     c.qhead = pz_vload(&sm->mail.qhead);
     c.q = c.bp >> PZ_QUARTER_SHIFT;

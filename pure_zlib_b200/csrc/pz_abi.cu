@@ -310,17 +310,18 @@ int huge_stream(const uint8_t *d_in_blob, const uint64_t *d_in_off_i, uint64_t i
 
 /* K2, then K4 for every huge stream K2 left pending, then K1 for whatever is still pending. */
 int run_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uint8_t *d_out, const uint64_t *d_out_off, uint32_t first, uint32_t count,
-                pz_result *d_res, cudaStream_t st, const uint64_t *h_in_off, const uint64_t *h_out_off, uint32_t flags) {
+                pz_result *d_res, cudaStream_t st, const uint64_t *h_in_off, const uint64_t *h_out_off, uint32_t flags,
+                uint2 *d_parts = nullptr, const uint64_t *d_seg_off = nullptr) {
   const bool count_only = d_out == nullptr;
   std::vector<uint32_t> huge;
   if (!count_only && !(flags & PZ_F_NO_HUGE) && h_in_off && h_out_off)
     for (uint32_t i = first; i < first + count; i++)
       if (h_in_off[i + 1] - h_in_off[i] >= g_huge_bytes) huge.push_back(i);
   if (huge.empty()) {
-    PZ_CUDA(pz_launch_inflate(d_in, d_in_off, d_out, d_out_off, first, count, d_res, st));
+    PZ_CUDA(pz_launch_inflate(d_in, d_in_off, d_out, d_out_off, first, count, d_res, st, nullptr, nullptr, PZ_PHASE_ALL, d_parts, d_seg_off));
     return PZ_E_OK;
   }
-  PZ_CUDA(pz_launch_inflate(d_in, d_in_off, d_out, d_out_off, first, count, d_res, st, nullptr, nullptr, PZ_PHASE_K2));
+  PZ_CUDA(pz_launch_inflate(d_in, d_in_off, d_out, d_out_off, first, count, d_res, st, nullptr, nullptr, PZ_PHASE_K2, d_parts, d_seg_off));
   /* K2's verdicts for the span of the huge streams, in one copy: a stored-block stream is done */
   std::vector<pz_result> after_k2(huge.back() - huge.front() + 1u);
   PZ_CUDA(cudaMemcpyAsync(after_k2.data(), d_res + huge.front(), after_k2.size() * sizeof(pz_result), cudaMemcpyDeviceToHost, st));
@@ -416,7 +417,8 @@ int pz_batch_run(pz_batch *b, const uint8_t *d_in, uint8_t *d_out, void *stream)
   if (!count_only && !d_out) return PZ_E_ARG;
   {
     const int rc = run_inflate(d_in, b->d_in_off, count_only ? nullptr : d_out, b->d_out_off, 0, (uint32_t)b->n, b->d_res, st, b->h_in_off.data(),
-                               count_only ? nullptr : b->h_out_off.data(), b->flags);
+                               count_only ? nullptr : b->h_out_off.data(), b->flags,
+                               (count_only || (b->flags & PZ_F_NO_ADLER)) ? nullptr : b->d_parts, b->d_seg_off);
     if (rc != PZ_E_OK) return rc;
   }
   if (!count_only && !(b->flags & PZ_F_NO_ADLER))
@@ -486,7 +488,8 @@ int pz_inflate_batch_contig(const uint8_t *in_blob, const uint64_t *in_off, uint
     PZ_CUDA(cudaMemcpyAsync(d_in_off, in_off, ob, cudaMemcpyHostToDevice, st));
     if (!count_only) PZ_CUDA(cudaMemcpyAsync(d_out_off, out_off, ob, cudaMemcpyHostToDevice, st));
     if (adler) PZ_CUDA(cudaMemcpyAsync(d_seg_off, seg.data(), ob, cudaMemcpyHostToDevice, st));
-    if ((rc = run_inflate(in_blob, d_in_off, count_only ? nullptr : out_blob, d_out_off, 0, (uint32_t)n, d_res, st, in_off, out_off, flags)) != PZ_E_OK) return rc;
+    if ((rc = run_inflate(in_blob, d_in_off, count_only ? nullptr : out_blob, d_out_off, 0, (uint32_t)n, d_res, st, in_off, out_off, flags,
+                          adler ? d_parts : nullptr, d_seg_off)) != PZ_E_OK) return rc;
     if (adler) PZ_CUDA(pz_launch_adler(out_blob, d_out_off, d_seg_off, (uint32_t)n, 0, (uint32_t)n, 0, total_segs, d_res, d_parts, st));
     PZ_CUDA(cudaMemcpyAsync(res, d_res, n * sizeof(pz_result), cudaMemcpyDeviceToHost, st));
     PZ_CUDA(cudaStreamSynchronize(st));
@@ -612,7 +615,8 @@ int pz_inflate_batch_contig(const uint8_t *in_blob, const uint64_t *in_off, uint
         PZ_CUDA(cudaEventRecord(ev_in, s2));
         PZ_CUDA(cudaStreamWaitEvent(s0, ev_in, 0));
         {
-          const int r2 = run_inflate(d_in, d_in_off, d_out, d_out_off, (uint32_t)first, (uint32_t)(last - first), d_res, s0, in_off, out_off, flags);
+          const int r2 = run_inflate(d_in, d_in_off, d_out, d_out_off, (uint32_t)first, (uint32_t)(last - first), d_res, s0, in_off, out_off, flags,
+                                     adler ? d_parts : nullptr, d_seg_off);
           if (r2 != PZ_E_OK) return r2;
         }
         if (adler)

@@ -251,7 +251,14 @@ struct PzJob {
   const uint32_t *blk_len; /* exact decoded length of block j (nullptr: blk_cap bounds every block) */
   uint16_t *out16;
   uint32_t blk_stream, blk_cap;
+  /* Optional (K2 only): the Adler-32 segment table of the batch.  A stream K2 copies is checksummed
+   * while it is copied: parts[seg_off[s] + j] receives (sum of the bytes, sum of byte * position in
+   * the segment, both of segment j of the output) and res[s].adler_computed = PZ_ADLER_FUSED tells
+   * K3 that the partial sums exist in that form. */
+  uint2 *parts;
+  const uint64_t *seg_off;
 };
+#define PZ_ADLER_FUSED 0xffffffffu /* no Adler-32 value: both halves of one are below 65521 */
 #define PZ_BLK_BIAS 65536u /* a block job counts its output from here: the window model then always
                               sees at least 32 KiB of history, as it would inside a long stream */
 #define PZ_PROG_SHIFT 15

@@ -33,10 +33,12 @@ static_assert(PZ_HOT_SCHED_SERVICE + (PZ_WARPS_PER_CTA - 1u - PZ_HOT_SCHED_WARPS
 /* Stream s = first + k decodes in_blob[in_off[s], in_off[s+1]) into out_blob[out_off[s], out_off[s+1]).
  * d_out == nullptr selects the sizing pass.  d_prog (optional, host-mapped, one word per stream, zeroed by
  * the caller) receives the progress words described at PzJob::prog.  d_in_ready (optional, device word): see
- * PzJob::in_ready; K2 is skipped then. */
+ * PzJob::in_ready; K2 is skipped then.  d_parts / d_seg_off (optional): the batch's Adler-32 segment table; K2 then
+ * checksums the streams it copies while it copies them (PzJob::parts). */
 cudaError_t pz_launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uint8_t *d_out, const uint64_t *d_out_off,
                               uint32_t first, uint32_t count, pz_result *d_res, cudaStream_t st, uint32_t *d_prog = nullptr,
-                              const uint32_t *d_in_ready = nullptr, int phase = 0);
+                              const uint32_t *d_in_ready = nullptr, int phase = 0, uint2 *d_parts = nullptr,
+                              const uint64_t *d_seg_off = nullptr);
 #define PZ_PHASE_ALL 0
 #define PZ_PHASE_K2 1 /* only the stored-stream kernels (they also mark every other stream PENDING) */
 #define PZ_PHASE_K1 2 /* only K1: decodes the streams that are still PENDING */

@@ -94,6 +94,7 @@ pz_adler_partial_kernel(const uint8_t *__restrict__ out_blob, const uint64_t *__
   }
   const uint32_t i = lo;
   if (res[i].status != PZ_OK) return;
+  if (res[i].adler_computed == PZ_ADLER_FUSED) return; /* K2 summed this stream while copying it */
   const uint64_t len = res[i].out_len;
   const uint64_t start = (g - seg_off[i]) * (uint64_t)PZ_ADLER_SEG;
   if (start >= len) return;
@@ -149,6 +150,8 @@ pz_adler_finish_kernel(const uint64_t *__restrict__ seg_off, uint32_t first, uin
   const uint64_t len = res[i].out_len;
   const uint64_t nseg = (len + PZ_ADLER_SEG - 1) / PZ_ADLER_SEG;
   const uint2 *p = parts + seg_off[i];
+  /* K2's form of a segment: (sum of bytes, sum of byte * index); sum (L - index) * byte follows */
+  const bool fused = res[i].adler_computed == PZ_ADLER_FUSED;
   const uint64_t per = (nseg + 31u) / 32u;
   const uint64_t j0 = per * lane < nseg ? per * lane : nseg, j1 = j0 + per < nseg ? j0 + per : nseg;
   uint32_t s1 = 0, s2 = 0;
@@ -156,7 +159,11 @@ pz_adler_finish_kernel(const uint64_t *__restrict__ seg_off, uint32_t first, uin
   for (uint64_t j = j0; j < j1; j++) {
     const uint64_t rest = len - j * PZ_ADLER_SEG;
     const uint32_t L = (uint32_t)(rest < PZ_ADLER_SEG ? rest : PZ_ADLER_SEG);
-    const uint2 s = p[j];
+    uint2 s = p[j];
+    if (fused) {
+      s.x %= PZ_ADLER_MOD;
+      s.y = (uint32_t)(((uint64_t)L * s.x + PZ_ADLER_MOD - s.y % PZ_ADLER_MOD) % PZ_ADLER_MOD);
+    }
     s2 = (uint32_t)(((uint64_t)s2 + (uint64_t)L * s1 + s.y) % PZ_ADLER_MOD);
     s1 = (s1 + s.x) % PZ_ADLER_MOD;
     n += L;
@@ -227,7 +234,7 @@ int pz_inflate_slots(void) { return g_sm_count * g_inflate_ctas_per_sm[0] * (int
 /* One resident wave of persistent CTAs: one per SM (148 on B200), fewer for small batches. */
 cudaError_t pz_launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uint8_t *d_out, const uint64_t *d_out_off,
                               uint32_t first, uint32_t count, pz_result *d_res, cudaStream_t st, uint32_t *d_prog,
-                              const uint32_t *d_in_ready, int phase) {
+                              const uint32_t *d_in_ready, int phase, uint2 *d_parts, const uint64_t *d_seg_off) {
   if (count == 0) return cudaSuccess;
   const bool count_only = d_out == nullptr;
   const unsigned wave = (unsigned)(g_sm_count * g_inflate_ctas_per_sm[count_only ? 1 : 0]);
@@ -239,6 +246,7 @@ cudaError_t pz_launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uin
   job.prog = count_only ? nullptr : d_prog;
   job.in_ready = d_in_ready;
   job.blk_start = nullptr; job.blk_out = nullptr; job.blk_len = nullptr; job.out16 = nullptr; job.blk_stream = 0; job.blk_cap = 0;
+  job.parts = d_seg_off ? d_parts : nullptr; job.seg_off = d_seg_off;
   if (d_in_ready) job.skip_done = 0; /* K2 would read input that is not there yet: K1 decodes every stream */
   if (count_only) {
     pz_inflate_kernel<true><<<grid, PZ_THREADS_PER_CTA, smem, st>>>(job);
@@ -287,6 +295,7 @@ cudaError_t pz_launch_blk_jobs(const uint8_t *d_in_blob, const uint64_t *d_in_of
   job.in_blob = d_in_blob; job.in_off = d_in_off2; job.out_blob = nullptr; job.out_off = nullptr; job.res = d_res;
   job.first = 0; job.count = count; job.skip_done = 0; job.prog = nullptr; job.in_ready = nullptr;
   job.blk_start = d_blk_start; job.blk_out = d_blk_out; job.blk_len = d_blk_len; job.out16 = d_sym16; job.blk_stream = 0; job.blk_cap = cap;
+  job.parts = nullptr; job.seg_off = nullptr;
   if (count_only) pz_inflate_kernel<true><<<grid, PZ_THREADS_PER_CTA, smem, st>>>(job);
   else pz_inflate_kernel<false, true><<<grid, PZ_THREADS_PER_CTA, smem, st>>>(job);
   return cudaGetLastError();

@@ -79,13 +79,32 @@ __device__ __forceinline__ uint4 pz_load16_unaligned(const uint8_t *p) {
   return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
 }
 
-/* One warp copies len bytes; src and dst have arbitrary alignment. */
-__device__ __forceinline__ void pz_warp_copy(uint8_t *dst, const uint8_t *src, uint32_t len) {
+/* One warp copies len bytes; src and dst have arbitrary alignment.  With SUM the warp also adds up
+ * what it copies: s1 += sum of the bytes, t += sum of byte * (pos0 + index), per lane (pos0 + len <=
+ * 16384, so a lane's share -- 1/32 of at most 16 KiB -- keeps t below 2^32). */
+__device__ __forceinline__ void pz_sum16(const uint4 w, uint32_t pos, uint32_t &s1, uint32_t &t) {
+  uint32_t sum = __dp4a(w.x, 0x01010101u, 0u);
+  sum = __dp4a(w.y, 0x01010101u, sum);
+  sum = __dp4a(w.z, 0x01010101u, sum);
+  sum = __dp4a(w.w, 0x01010101u, sum);
+  uint32_t ks = __dp4a(w.x, 0x03020100u, 0u);
+  ks = __dp4a(w.y, 0x07060504u, ks);
+  ks = __dp4a(w.z, 0x0b0a0908u, ks);
+  ks = __dp4a(w.w, 0x0f0e0d0cu, ks);
+  s1 += sum;
+  t += pos * sum + ks;
+}
+template <bool SUM>
+__device__ __forceinline__ void pz_warp_copy(uint8_t *dst, const uint8_t *src, uint32_t len, uint32_t pos0, uint32_t &s1, uint32_t &t) {
   const uint32_t lane = threadIdx.x & 31u;
   uint32_t head = (uint32_t)(-(intptr_t)dst) & 15u;
   if (head > len) head = len;
-  if (lane < head) dst[lane] = src[lane];
-  dst += head; src += head; len -= head;
+  if (lane < head) {
+    const uint32_t b = src[lane];
+    dst[lane] = (uint8_t)b;
+    if (SUM) { s1 += b; t += b * (pos0 + lane); }
+  }
+  dst += head; src += head; len -= head; pos0 += head;
   const uint32_t n16 = len >> 4;
   uint4 *d16 = reinterpret_cast<uint4 *>(dst);
   uint32_t c = lane;
@@ -95,10 +114,38 @@ __device__ __forceinline__ void pz_warp_copy(uint8_t *dst, const uint8_t *src, u
     const uint4 v2 = pz_load16_unaligned(src + 16u * (c + 64u));
     const uint4 v3 = pz_load16_unaligned(src + 16u * (c + 96u));
     d16[c] = v0; d16[c + 32u] = v1; d16[c + 64u] = v2; d16[c + 96u] = v3;
+    if (SUM) {
+      pz_sum16(v0, pos0 + 16u * c, s1, t); pz_sum16(v1, pos0 + 16u * (c + 32u), s1, t);
+      pz_sum16(v2, pos0 + 16u * (c + 64u), s1, t); pz_sum16(v3, pos0 + 16u * (c + 96u), s1, t);
+    }
   }
-  for (; c < n16; c += 32u) d16[c] = pz_load16_unaligned(src + 16u * c);
+  for (; c < n16; c += 32u) {
+    const uint4 v = pz_load16_unaligned(src + 16u * c);
+    d16[c] = v;
+    if (SUM) pz_sum16(v, pos0 + 16u * c, s1, t);
+  }
   const uint32_t tail = len & 15u;
-  if (lane < tail) dst[16u * n16 + lane] = src[16u * n16 + lane];
+  if (lane < tail) {
+    const uint32_t b = src[16u * n16 + lane];
+    dst[16u * n16 + lane] = (uint8_t)b;
+    if (SUM) { s1 += b; t += b * (pos0 + 16u * n16 + lane); }
+  }
+}
+/* The same with the Adler-32 partial sums: the copy is cut at the 16 KiB segment boundaries of the
+ * OUTPUT (K3's segments), and each piece adds (sum, sum of byte * index in the segment mod 65521)
+ * to its segment's entry of parts[]. */
+__device__ __forceinline__ void pz_warp_copy_summed(uint8_t *out, uint32_t dst, const uint8_t *src, uint32_t len, uint2 *parts) {
+  const uint32_t lane = threadIdx.x & 31u;
+  while (len) {
+    const uint32_t seg = dst / PZ_ADLER_SEG, pos0 = dst % PZ_ADLER_SEG;
+    const uint32_t piece = len < PZ_ADLER_SEG - pos0 ? len : PZ_ADLER_SEG - pos0;
+    uint32_t s1 = 0, t = 0;
+    pz_warp_copy<true>(out + dst, src, piece, pos0, s1, t);
+    s1 = __reduce_add_sync(0xffffffffu, s1);
+    t = __reduce_add_sync(0xffffffffu, t % 65521u);
+    if (lane == 0) { atomicAdd(&parts[seg].x, s1); atomicAdd(&parts[seg].y, t % 65521u); }
+    dst += piece; src += piece; len -= piece;
+  }
 }
 
 __global__ void __launch_bounds__(PZ_ST_THREADS)
@@ -124,6 +171,12 @@ pz_stored_copy_kernel(const PzJob job, const uint32_t tile_streams) {
       const uint32_t cap = ocap > 0xfffdff00ull ? 0xfffdff00u : (uint32_t)ocap;
       if (tid < 7) sh.done[tid] = 0;
       if (tid == 0) { sh.head = 0; sh.ended = 0; sh.ok = 0; }
+      uint2 *const parts = job.parts ? job.parts + job.seg_off[s] : nullptr;
+      if (parts) { /* this stream's partial sums start from zero (the copy warps add to them) */
+        const uint32_t nseg = (uint32_t)((ocap + PZ_ADLER_SEG - 1u) / PZ_ADLER_SEG);
+        for (uint32_t j = tid; j < nseg; j += PZ_ST_THREADS) parts[j] = make_uint2(0u, 0u);
+        __threadfence();
+      }
       __syncthreads();
       if (warp == 0) {
         if (lane == 0) { /* the walker: inflate's block loop restricted to stored blocks */
@@ -179,7 +232,8 @@ pz_stored_copy_kernel(const PzJob job, const uint32_t tile_streams) {
           if (!have) break;
           const uint32_t slot = i % PZ_ST_RING;
           const uint32_t src = vs->src[slot], dst = vs->dst[slot], len = vs->len[slot];
-          pz_warp_copy(out + dst, in + src, len);
+          if (parts) pz_warp_copy_summed(out, dst, in + src, len, parts);
+          else { uint32_t u0 = 0, u1 = 0; pz_warp_copy<false>(out + dst, in + src, len, 0u, u0, u1); }
           mine++;
           __syncwarp();
           if (lane == 0) vs->done[me] = mine;
@@ -191,7 +245,7 @@ pz_stored_copy_kernel(const PzJob job, const uint32_t tile_streams) {
         if (sh.ok) {
           res->detail = 0;
           res->out_len = sh.out_len;
-          res->adler_computed = 0;
+          res->adler_computed = parts ? PZ_ADLER_FUSED : 0u;
           res->adler_stored = sh.adler_stored;
           res->err_bitpos = (uint64_t)sh.end_byte * 8u;
           res->payload[0] = 0;

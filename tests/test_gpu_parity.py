@@ -267,6 +267,8 @@ def _stored_cases():
         p += 5 + ln; k += 1
     b = bytearray(big); b[p + 1] ^= 1; cases.append(bytes(b))
     b = bytearray(big); b[p] |= 0x06; cases.append(bytes(b))  # BTYPE 3 in the third block
+    co = zlib.compressobj(0)  # many small stored blocks (and the empty ones of the flushes): several pieces per checksum segment
+    cases.append(b"".join(co.compress(rnd(n)) + co.flush(zlib.Z_SYNC_FLUSH) for n in [1, 2, 3, 700, 1000, 15, 16, 17, 5000] * 12) + co.flush())
     cases.append(big + b"trailing junk")
     cases.append(bytes([0x78, 0xbb]) + b"\xde\xad\xbe\xef" + big[2:])  # FDICT set: four bytes skipped
     return cases

@@ -94,6 +94,45 @@ __device__ __forceinline__ void pz_sum16(const uint4 w, uint32_t pos, uint32_t &
   s1 += sum;
   t += pos * sum + ks;
 }
+/* The 16 bytes at byte offset 4 * WO + sh / 8 of the 32 bytes (A, B): WO and sh are the same for every
+ * vector of a copy (source and destination keep their relative alignment), so the loop below is
+ * compiled once per WO and contains no branch between its loads. */
+template <int WO>
+__device__ __forceinline__ uint4 pz_shift16(const uint4 A, const uint4 B, const uint32_t sh) {
+  const uint32_t w[8] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w};
+  return make_uint4(__funnelshift_r(w[WO], w[WO + 1], sh), __funnelshift_r(w[WO + 1], w[WO + 2], sh),
+                    __funnelshift_r(w[WO + 2], w[WO + 3], sh), __funnelshift_r(w[WO + 3], w[WO + 4], sh));
+}
+#ifndef PZ_COPY_DEPTH
+#define PZ_COPY_DEPTH 4
+#endif
+/* PZ_COPY_DEPTH: 16-byte pieces per lane whose loads are all issued before the first is used */
+template <int WO, bool ALIGNED, bool SUM>
+__device__ __forceinline__ void pz_copy_vectors(uint4 *d16, const uint4 *a, const uint32_t n16, const uint32_t sh, const uint32_t pos0,
+                                                uint32_t &s1, uint32_t &t) {
+  const uint32_t lane = threadIdx.x & 31u;
+  uint32_t c = lane;
+  for (; c + 32u * (PZ_COPY_DEPTH - 1) < n16; c += 32u * PZ_COPY_DEPTH) {
+    uint4 A[PZ_COPY_DEPTH], B[PZ_COPY_DEPTH];
+#pragma unroll
+    for (int k = 0; k < PZ_COPY_DEPTH; k++) {
+      A[k] = a[c + 32u * k];
+      if (!ALIGNED) B[k] = a[c + 32u * k + 1u];
+    }
+#pragma unroll
+    for (int k = 0; k < PZ_COPY_DEPTH; k++) {
+      const uint4 v = ALIGNED ? A[k] : pz_shift16<WO>(A[k], B[k], sh);
+      d16[c + 32u * k] = v;
+      if (SUM) pz_sum16(v, pos0 + 16u * (c + 32u * k), s1, t);
+    }
+  }
+  for (; c < n16; c += 32u) {
+    const uint4 A = a[c];
+    const uint4 v = ALIGNED ? A : pz_shift16<WO>(A, a[c + 1u], sh);
+    d16[c] = v;
+    if (SUM) pz_sum16(v, pos0 + 16u * c, s1, t);
+  }
+}
 template <bool SUM>
 __device__ __forceinline__ void pz_warp_copy(uint8_t *dst, const uint8_t *src, uint32_t len, uint32_t pos0, uint32_t &s1, uint32_t &t) {
   const uint32_t lane = threadIdx.x & 31u;
@@ -107,22 +146,14 @@ __device__ __forceinline__ void pz_warp_copy(uint8_t *dst, const uint8_t *src, u
   dst += head; src += head; len -= head; pos0 += head;
   const uint32_t n16 = len >> 4;
   uint4 *d16 = reinterpret_cast<uint4 *>(dst);
-  uint32_t c = lane;
-  for (; c + 96u < n16; c += 128u) { /* four independent 16-byte pieces per lane in flight */
-    const uint4 v0 = pz_load16_unaligned(src + 16u * c);
-    const uint4 v1 = pz_load16_unaligned(src + 16u * (c + 32u));
-    const uint4 v2 = pz_load16_unaligned(src + 16u * (c + 64u));
-    const uint4 v3 = pz_load16_unaligned(src + 16u * (c + 96u));
-    d16[c] = v0; d16[c + 32u] = v1; d16[c + 64u] = v2; d16[c + 96u] = v3;
-    if (SUM) {
-      pz_sum16(v0, pos0 + 16u * c, s1, t); pz_sum16(v1, pos0 + 16u * (c + 32u), s1, t);
-      pz_sum16(v2, pos0 + 16u * (c + 64u), s1, t); pz_sum16(v3, pos0 + 16u * (c + 96u), s1, t);
-    }
-  }
-  for (; c < n16; c += 32u) {
-    const uint4 v = pz_load16_unaligned(src + 16u * c);
-    d16[c] = v;
-    if (SUM) pz_sum16(v, pos0 + 16u * c, s1, t);
+  const uint32_t o = (uint32_t)((uintptr_t)src & 15u), sh = (o & 3u) * 8u;
+  const uint4 *a = reinterpret_cast<const uint4 *>(src - o);
+  if (o == 0u) pz_copy_vectors<0, true, SUM>(d16, a, n16, 0u, pos0, s1, t);
+  else switch (o >> 2) { /* uniform across the warp */
+    case 0: pz_copy_vectors<0, false, SUM>(d16, a, n16, sh, pos0, s1, t); break;
+    case 1: pz_copy_vectors<1, false, SUM>(d16, a, n16, sh, pos0, s1, t); break;
+    case 2: pz_copy_vectors<2, false, SUM>(d16, a, n16, sh, pos0, s1, t); break;
+    default: pz_copy_vectors<3, false, SUM>(d16, a, n16, sh, pos0, s1, t); break;
   }
   const uint32_t tail = len & 15u;
   if (lane < tail) {

@@ -40,6 +40,18 @@ CONFIGS = {
 }
 
 
+# the kernel(s) `roofline.kernel_ms` times (the batch without its Adler-32 pass), and what bounds them
+_ISSUE = "issue-bound integer path (one warp issues the symbol loops of 28 streams): frac of HBM is expected to be small (DESIGN.md 3)"
+ROOFLINE_KERNEL = {
+    "text256k": ("pz_inflate_kernel", _ISSUE),
+    "records4k": ("pz_inflate_kernel", _ISSUE),
+    "stored16m": ("pz_stored_copy_kernel (+ pz_stored_probe_kernel; pz_inflate_kernel skips what K2 finished)",
+                  "HBM-bound copy with the Adler-32 partial sums fused in; K3 only folds them"),
+    "huge": ("K4: pz_blk_search/verify, block jobs on pz_inflate_kernel (sizing + 16-bit decode), pz_blk_tails/windows/resolve",
+             "one stream: block-parallel decode with a 2-byte symbol buffer; frac of HBM is small"),
+}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -319,10 +331,10 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic", "config": config,
-            "roofline": {"bound": "hbm", "kernel": "pz_inflate_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": ROOFLINE_KERNEL[a.config][0], "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": load_traffic(a.config), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": ms_k1, "decoder_only_ms": ms_dec,
-                         "note": "issue/latency-bound integer path: frac of HBM is expected to be small (SURVEY 7, hard part 1)"},
+                         "note": ROOFLINE_KERNEL[a.config][1]},
             "clocks": clocks, "gpu_launches": a.steps * L.pz_batch_launches(batch),
             "corpus_sha256": c.sha256_in, "compressed_bytes": c.in_bytes, "decoded_bytes": c.out_bytes}
 

@@ -65,6 +65,7 @@
 
 #ifdef PZ_HOSTSIM
 #include <string.h>
+struct uint2 { uint32_t x, y; }; /* PzJob::parts (never used by the host build) */
 #define PZ_DEV static inline
 #define PZ_COLD static
 #define PZ_G 1

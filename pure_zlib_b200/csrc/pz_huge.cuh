@@ -57,28 +57,60 @@ __device__ __forceinline__ void pz_load96(const uint8_t *in, uint64_t nbytes, ui
   v2 = __funnelshift_r(x[2], x[3], sh);
 }
 
-/* K4a, first stage: one thread per byte of the stream, eight bit positions each. */
+/* K4a, first stage: one thread per byte of the stream, eight bit positions each.
+ *
+ * Two steps per warp, so that the expensive test runs on full warps: (1) every lane applies the cheap
+ * tests (BTYPE, HLIT/HDIST range, room for the code-length code) to its eight positions -- 22 % of
+ * all positions pass -- and the survivors are packed into a per-warp list in shared memory (the 96
+ * stream bits of the byte and the bit offset); (2) the lanes walk that list together, one survivor
+ * each per round, and test the code-length code for completeness (sum 2^(7-len) == 128).  Doing
+ * (2) inside the loop over the eight offsets kept three lanes in four idle in every round. */
 __global__ void __launch_bounds__(PZ_HUGE_THREADS)
 pz_blk_search_kernel(const uint8_t *__restrict__ in, uint64_t nbytes, uint64_t first_bit, uint64_t last_bit,
                      uint32_t *__restrict__ cand, uint32_t *__restrict__ ncand, uint32_t cap) {
+  __shared__ uint4 list[PZ_HUGE_THREADS / 32][256];
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint64_t B = (first_bit >> 3) + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (B * 8u >= last_bit) return;
-  uint32_t v0, v1, v2;
-  pz_load96(in, nbytes, B, v0, v1, v2);
-#pragma unroll 1
-  for (uint32_t o = 0; o < 8u; o++) {
-    const uint64_t pos = B * 8u + o;
-    if (pos < first_bit || pos >= last_bit) continue;
-    const uint32_t h = __funnelshift_r(v0, v1, o);
-    if (((h >> 1) & 3u) != 2u) continue;                      /* BTYPE: dynamic (Deflate.hs:83) */
-    if (((h >> 3) & 31u) > 29u || ((h >> 8) & 31u) > 29u) continue; /* what zlib can emit: HLIT <= 286, HDIST <= 30 */
+  uint32_t v0 = 0, v1 = 0, v2 = 0, mask = 0;
+  if (B * 8u < last_bit) {
+    pz_load96(in, nbytes, B, v0, v1, v2);
+#pragma unroll
+    for (uint32_t o = 0; o < 8u; o++) {
+      const uint64_t pos = B * 8u + o;
+      const uint32_t h = __funnelshift_r(v0, v1, o);
+      const uint32_t hclen = ((h >> 13) & 15u) + 4u;
+      const bool ok = pos >= first_bit && pos < last_bit && ((h >> 1) & 3u) == 2u /* BTYPE: dynamic (Deflate.hs:83) */
+                      && ((h >> 3) & 31u) <= 29u && ((h >> 8) & 31u) <= 29u       /* what zlib can emit: HLIT <= 286, HDIST <= 30 */
+                      && pos + 17u + 3u * hclen <= last_bit;
+      mask |= ok ? (1u << o) : 0u;
+    }
+  }
+  /* pack the survivors of the warp */
+  const uint32_t mine = (uint32_t)__popc(mask);
+  uint32_t incl = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+    if ((int)lane >= d) incl += t;
+  }
+  const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+  uint32_t at = incl - mine;
+  while (mask) {
+    const uint32_t o = (uint32_t)__ffs((int)mask) - 1u;
+    mask &= mask - 1u;
+    list[warp][at++] = make_uint4(v0, v1, v2, (uint32_t)(B * 8u) + o); /* bit positions fit 32 bits: streams are below 512 MiB */
+  }
+  __syncwarp();
+  for (uint32_t i = lane; i < total; i += 32u) {
+    const uint4 e = list[warp][i];
+    const uint32_t o = e.w & 7u;
+    const uint32_t h = __funnelshift_r(e.x, e.y, o);
     const uint32_t hclen = ((h >> 13) & 15u) + 4u;
-    if (pos + 17u + 3u * hclen > last_bit) continue;
     /* the code-length code must be complete: sum 2^(7-len) == 128 */
     const uint32_t s = o + 17u; /* < 32 */
-    uint32_t p0 = __funnelshift_r(v0, v1, s), p1 = __funnelshift_r(v1, v2, s);
+    uint32_t p0 = __funnelshift_r(e.x, e.y, s), p1 = __funnelshift_r(e.y, e.z, s);
     uint32_t sum = 0;
-    for (uint32_t i = 0; i < hclen && sum <= 128u; i++) {
+    for (uint32_t k = 0; k < hclen && sum <= 128u; k++) {
       const uint32_t l = p0 & 7u;
       sum += l ? (128u >> l) : 0u;
       p0 = __funnelshift_r(p0, p1, 3);
@@ -86,7 +118,7 @@ pz_blk_search_kernel(const uint8_t *__restrict__ in, uint64_t nbytes, uint64_t f
     }
     if (sum != 128u) continue;
     const uint32_t k = atomicAdd(ncand, 1u);
-    if (k < cap) cand[k] = (uint32_t)pos;
+    if (k < cap) cand[k] = e.w;
   }
 }
 

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Reduce an ncu report (--set full) to a small JSON summary: one object per captured launch with
-the metrics the roofline discussion uses.  usage: ncu_summary.py report.ncu-rep out.json [traffic.json config]
+the metrics the roofline discussion uses.  usage: ncu_summary.py report.ncu-rep out.json [traffic.json config [kernel-substring]]
 With the last two arguments the DRAM traffic of the first pz_inflate_kernel launch is also
 written into profiles/roofline_traffic.json under `config` (read by bench.py)."""
 import csv, io, json, subprocess, sys
@@ -32,7 +32,8 @@ if len(sys.argv) > 4:
         t = json.load(open(tpath))
     except Exception:
         t = {}
-    k1 = next(o for o in res if "pz_inflate_kernel" in o["Kernel Name"])
+    want = sys.argv[5] if len(sys.argv) > 5 else "pz_inflate_kernel"
+    k1 = next(o for o in res if want in o["Kernel Name"])
     scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
     rd = float(k1["dram__bytes_read.sum"]) * scale[k1["units"]["dram__bytes_read.sum"]]
     wr = float(k1["dram__bytes_write.sum"]) * scale[k1["units"]["dram__bytes_write.sum"]]

@@ -199,6 +199,7 @@ pz_blk_verify_kernel(const uint8_t *__restrict__ in, uint64_t nbytes, uint64_t l
       }
     }
     n += rep;
+    if (sum_l > 32768u || sum_d > 32768u) return; /* over-subscribed already: most false candidates end here, a few symbols in */
   }
   if (sum_l == 32768u && sum_d == 32768u && eob) keep[i] = 1;
 }

@@ -18,7 +18,7 @@
 #define PZ_SLOTS_PER_WRITER (32u / PZ_WGROUP)
 #define PZ_WRITER_WARPS ((PZ_SLOTS + PZ_SLOTS_PER_WRITER - 1u) / PZ_SLOTS_PER_WRITER)
 #ifndef PZ_PAD_WARPS
-#define PZ_PAD_WARPS 2u /* warps that exit at once: they only keep working warps off the hot warp's scheduler */
+#define PZ_PAD_WARPS 6u /* warps that exit at once: they only keep working warps off the hot warp's scheduler */
 #endif
 #define PZ_WARPS_PER_CTA (1u + PZ_SERVICE_WARPS + PZ_WRITER_WARPS + PZ_PAD_WARPS) /* hot + service + writer (+ idle) warps */
 #define PZ_THREADS_PER_CTA (32u * PZ_WARPS_PER_CTA)

@@ -29,7 +29,7 @@ __device__ __forceinline__ void pz_role(uint32_t w, uint32_t &role, uint32_t &in
   if (w == 0u) { role = 0u; index = 0u; return; }
   if ((w & 3u) == 0u) { /* the hot warp's scheduler: service warps, then warps that exit at once */
     const uint32_t j = (w >> 2) - 1u;
-    if (j < PZ_HOT_SCHED_SERVICE) { role = 1u; index = j; }
+    if (j + 1u <= PZ_HOT_SCHED_SERVICE) { role = 1u; index = j; }
     else { role = 3u; index = 0u; }
     return;
   }

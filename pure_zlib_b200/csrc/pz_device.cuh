@@ -825,6 +825,9 @@ PZ_DEV void pz_writer_warp(const PzJob &job, PzStreamSmem *sm, bool present) {
     const uint32_t max_b = __reduce_max_sync(0xffffffffu, B);
     uint8_t *const base = w.out + w.pos;
     uint32_t x[PZ_ROUNDS], inf[PZ_ROUNDS];
+#ifdef PZ_EXP_NO_COPY /* timing experiment only: the batch is consumed, its bytes are not produced */
+    if (false)
+#endif
 #pragma unroll
     for (int r = 0; r < PZ_ROUNDS; r++) {
       if ((uint32_t)(r * PZ_WG) < max_b) { /* warp-uniform */
@@ -843,6 +846,9 @@ PZ_DEV void pz_writer_warp(const PzJob &job, PzStreamSmem *sm, bool present) {
         }
       }
     }
+#ifdef PZ_EXP_NO_COPY
+    if (false)
+#endif
 #pragma unroll
     for (int r = 0; r < PZ_ROUNDS; r++) {
       if ((uint32_t)(r * PZ_WG) < max_b) {
@@ -1077,15 +1083,15 @@ PZ_DEV void pz_hot_warp(PzStreamSmem *slots, uint32_t n_slots) {
   /* A lone warp pays every branch in full (nothing else issues on its scheduler while one
    * resolves), and most of the time some lane or other is between two postings (its stream is with
    * the service group for a header, a long code, ...).  So the poll of the mailboxes is straight-line
-   * code: a predicated load in the lanes without a stream, one warp-wide OR, and two warp-uniform
+   * code: a predicated load in the lanes without a stream, two votes, and two warp-uniform
    * branches that are only taken when a posting has actually arrived or nothing is left to do. */
   for (;;) {
     uint32_t st = PZ_MS_SERVICE;
     pz_vload_if(!f.live && !dead, &sm->mail.state, st);
     const bool pick = st == PZ_MS_HOT;
     dead = dead || st == PZ_MS_DEAD;
-    const uint32_t any = __reduce_or_sync(0xffffffffu, (pick ? 1u : 0u) | (f.live ? 2u : 0u));
-    if (any & 1u) {
+    const bool any_pick = __any_sync(0xffffffffu, pick), any_live = __any_sync(0xffffffffu, f.live);
+    if (any_pick) {
       if (pick) {
         pz_fence_cta();
         f.bp = pz_vload(&sm->mail.bp); f.pos = pz_vload(&sm->mail.pos); f.base = pz_vload(&sm->mail.base);
@@ -1093,10 +1099,9 @@ PZ_DEV void pz_hot_warp(PzStreamSmem *slots, uint32_t n_slots) {
         pz_fast_fetch(f, sm, f.bp);
         f.live = true;
       }
-    } else if (!(any & 2u)) {
+    } else if (!any_live) { /* nothing to do yet (or any more): the trip below then runs empty, which is harmless */
       if (__all_sync(0xffffffffu, dead)) break;
       __nanosleep(100);
-      continue;
     }
     /* PZ_TRIP symbols per trip: the input the trip can touch (PZ_TRIP x 48 bits + the 128-bit
      * look-ahead) lies in quarters q and q+1, which must be resident; a lane whose input is late

@@ -56,6 +56,13 @@
 #ifndef PZ_DOZE_NS
 #define PZ_DOZE_NS 1000 /* service warps between polls of their hot lanes */
 #endif
+/* cache operators of the writer's history loads and output stores in the hot loop ("" = default, ".cg", ".cs", ...) */
+#ifndef PZ_LD_MOD
+#define PZ_LD_MOD ".cg"
+#endif
+#ifndef PZ_ST_MOD
+#define PZ_ST_MOD ""
+#endif
 #ifndef PZ_NAP_NS
 #define PZ_NAP_NS 1000 /* writer warps waiting for a full batch */
 #endif
@@ -567,12 +574,12 @@ PZ_DEV uint32_t pz_ld8_if(bool p, const uint8_t *a) {
   /* a fresh register with no other definition: nothing may read (and so wait for) the loaded
    * byte before its store, and the store carries the same predicate as this load */
   uint32_t v;
-  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t@q ld.global.u8 %0, [%2];\n\t}" : "=r"(v) : "r"((int)p), "l"(a));
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t@q ld.global" PZ_LD_MOD ".u8 %0, [%2];\n\t}" : "=r"(v) : "r"((int)p), "l"(a));
   return v;
 }
 PZ_DEV uint32_t pz_ld16_if(bool p, const uint16_t *a) {
   uint32_t v;
-  asm volatile("{\n\t.reg .pred q;\n\t.reg .b16 h;\n\tmov.b16 h, 0;\n\tsetp.ne.b32 q, %1, 0;\n\t@q ld.global.u16 h, [%2];\n\tcvt.u32.u16 %0, h;\n\t}" : "=r"(v) : "r"((int)p), "l"(a));
+  asm volatile("{\n\t.reg .pred q;\n\t.reg .b16 h;\n\tmov.b16 h, 0;\n\tsetp.ne.b32 q, %1, 0;\n\t@q ld.global" PZ_LD_MOD ".u16 h, [%2];\n\tcvt.u32.u16 %0, h;\n\t}" : "=r"(v) : "r"((int)p), "l"(a));
   return v;
 }
 /* warp barrier between the stores and the loads of one iteration (all 32 lanes are converged
@@ -717,7 +724,7 @@ PZ_DEV void pz_writer_apply(PzWriter &w, uint32_t raw) {
 PZ_DEV void pz_st8_sel(bool p, uint8_t *a, uint32_t inf, uint32_t x) {
   asm volatile(
       "{\n\t.reg .pred q, l;\n\t.reg .b32 t, u;\n\tsetp.ne.b32 q, %0, 0;\n\tsetp.lt.s32 l, %2, 0;\n\t"
-      "and.b32 u, %2, 255;\n\tselp.b32 t, u, %3, l;\n\t@q st.global.u8 [%1], t;\n\t}" ::"r"((int)p),
+      "and.b32 u, %2, 255;\n\tselp.b32 t, u, %3, l;\n\t@q st.global" PZ_ST_MOD ".u8 [%1], t;\n\t}" ::"r"((int)p),
       "l"(a), "r"(inf), "r"(x));
 }
 /* 16-bit flavour (block jobs): `alt` (a literal byte or a marker for a byte before the block) wins
@@ -725,7 +732,7 @@ PZ_DEV void pz_st8_sel(bool p, uint8_t *a, uint32_t inf, uint32_t x) {
 PZ_DEV void pz_st16_sel(bool p, uint16_t *a, uint32_t alt, uint32_t x) {
   asm volatile(
       "{\n\t.reg .pred q, l;\n\t.reg .b32 t, u;\n\t.reg .b16 h;\n\tsetp.ne.b32 q, %0, 0;\n\tsetp.lt.s32 l, %2, 0;\n\t"
-      "and.b32 u, %2, 65535;\n\tselp.b32 t, u, %3, l;\n\tcvt.u16.u32 h, t;\n\t@q st.global.u16 [%1], h;\n\t}" ::"r"((int)p),
+      "and.b32 u, %2, 65535;\n\tselp.b32 t, u, %3, l;\n\tcvt.u16.u32 h, t;\n\t@q st.global" PZ_ST_MOD ".u16 [%1], h;\n\t}" ::"r"((int)p),
       "l"(a), "r"(alt), "r"(x));
 }
 

@@ -166,12 +166,31 @@ void pz_pinned_free(void *p);
 typedef struct pz_stream pz_stream;
 enum pz_stream_event { PZ_S_NEED_MORE = 0, PZ_S_CHUNK = 1, PZ_S_DONE = 2, PZ_S_ERROR = 3 };
 pz_stream *pz_stream_new(void);
-/* Supply the strict chunk that answers a NeedMore (Monad.hs:185-197). The bytes are copied. */
+/* Supply the strict chunk that answers a NeedMore (Monad.hs:185-197).  The bytes are copied
+ * (pinned staging, cudaMemcpyAsync): the call returns while they travel to the device.      */
 int pz_stream_feed(pz_stream *s, const uint8_t *data, size_t len);
 /* Next decoder state.  For PZ_S_CHUNK, `chunk` and `len` describe bytes owned by the stream and
- * valid until the next call.  For PZ_S_ERROR, `res` (if non-NULL) receives the verdict.   */
+ * valid until the next call on it (pz_stream_next, pz_stream_pump or pz_stream_feed).  For
+ * PZ_S_ERROR, `res` (if non-NULL) receives the verdict.  If input has arrived since the last
+ * decode, the call pumps the stream first.                                                 */
 int pz_stream_next(pz_stream *s, const uint8_t **chunk, size_t *len, pz_result *res);
 void pz_stream_free(pz_stream *s);
+/* Decodes what has been fed to each of the n streams since its last decode, ALL streams in one
+ * kernel launch (extension: many concurrent decompressIncremental consumers multiplexed onto
+ * one device).  A stream's state lives on the device -- compressed bytes, decoded bytes (the
+ * LZ77 history) and a checkpoint (block header, symbol, bytes decoded, bytes published) -- so
+ * a pump decodes only what the new input adds (Monad.hs:163-197: the reference's coroutine
+ * goes on where it stopped).  Streams with nothing new are skipped.  Afterwards
+ * pz_stream_next() on any of them returns without touching the device.                      */
+int pz_stream_pump(pz_stream *const *streams, size_t n);
+/* Introspection for tests and benchmarks. */
+enum pz_stream_counter_id {
+  PZ_SC_PUMPS = 0,      /* kernel launches that decoded this stream                          */
+  PZ_SC_RESUMED = 1,    /* ... of which started from a checkpoint instead of the first byte  */
+  PZ_SC_CKPT_BIT = 2,   /* compressed bits the checkpoint has behind it                      */
+  PZ_SC_CKPT_BYTES = 3  /* decoded bytes the checkpoint has behind it                        */
+};
+uint64_t pz_stream_counter(const pz_stream *s, int which);
 
 /* ---- auxiliaries ------------------------------------------------------------------- */
 /* `show` of the DecompressionError this verdict denotes (Monad.hs:95-104), e.g.

@@ -9,8 +9,8 @@ There is no CPU decode path: every call goes to the GPU or raises.
 """
 from .zlib import (ChecksumError, Chunk, DecompError, DecompressionError, DecompressionError_, Done, FormatError,  # noqa: F401
                    HeaderError, HuffmanTreeError, Left, NeedMore, ReferenceBottom, Right, compute_code_values,
-                   decompress, decompress_batch, decompress_incremental)
+                   decompress, decompress_batch, decompress_incremental, decompress_many, IncrementalSet)
 
 __all__ = ["decompress", "decompress_incremental", "decompress_batch", "DecompressionError", "HuffmanTreeError",
            "FormatError", "DecompressionError_", "HeaderError", "ChecksumError", "ReferenceBottom", "NeedMore", "Chunk",
-           "Done", "DecompError", "Left", "Right", "compute_code_values"]
+           "Done", "DecompError", "Left", "Right", "compute_code_values", "decompress_many", "IncrementalSet"]

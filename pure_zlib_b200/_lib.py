@@ -11,6 +11,7 @@ SO_PATH = os.environ.get("PZ_LIBPZCUDA") or os.path.join(_HERE, "libpzcuda.so") 
 PZ_OK, PZ_ERR_HUFFMAN_TREE, PZ_ERR_FORMAT, PZ_ERR_DECOMPRESSION, PZ_ERR_HEADER, PZ_ERR_CHECKSUM, PZ_REF_BOTTOM, \
     PZ_OUTPUT_FULL, PZ_NEED_MORE = range(9)
 PZ_S_NEED_MORE, PZ_S_CHUNK, PZ_S_DONE, PZ_S_ERROR = range(4)
+PZ_SC_PUMPS, PZ_SC_RESUMED, PZ_SC_CKPT_BIT, PZ_SC_CKPT_BYTES = range(4)  # pz_stream_counter
 PZ_F_NO_ADLER, PZ_F_COUNT_ONLY = 1, 2
 PZ_E_OK, PZ_E_CUDA, PZ_E_ARG, PZ_E_NOMEM, PZ_E_STATE = 0, -1, -2, -3, -4
 
@@ -48,6 +49,8 @@ SYMBOLS = [
     ("pz_stream_feed", C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
     ("pz_stream_next", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(PzResult)]),
     ("pz_stream_free", None, [C.c_void_p]),
+    ("pz_stream_pump", C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
+    ("pz_stream_counter", C.c_uint64, [C.c_void_p, C.c_int]),
     ("pz_strerror", C.c_size_t, [C.POINTER(PzResult), C.c_char_p, C.c_size_t]),
     ("pz_compute_code_values", C.c_int, [C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_int32)]),
     ("pz_adler32", C.c_uint32, [C.c_uint32, C.c_char_p, C.c_size_t]),

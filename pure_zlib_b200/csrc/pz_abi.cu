@@ -736,59 +736,254 @@ int pz_inflate_sizes(const uint8_t *const *in, const size_t *in_len, size_t n, p
   return inflate_ptrs(in, in_len, nullptr, nullptr, n, res, PZ_F_COUNT_ONLY);
 }
 
-/* ---- incremental decoder (decompressIncremental, Zlib.hs:29-30) ----------------------- */
+/* ---- incremental decoder (decompressIncremental, Zlib.hs:29-30) -----------------------
+ * The reference's decoder is a coroutine (Monad.hs:163-197): it stops at NeedMore with its whole state
+ * in a closure and goes on when the next chunk arrives.  Here the state of a stream lives on the DEVICE:
+ * the compressed bytes fed so far, the decoded bytes (which are the LZ77 history) and a four-word
+ * checkpoint (PzJob::ckpt: block header, symbol, bytes decoded, bytes published).  Every pump decodes
+ * only what the new input adds: K1 rebuilds the tables of the block the checkpoint lies in (they live in
+ * shared memory and do not survive a launch) and goes on at the symbol that could not be completed.
+ * Any number of streams are pumped by ONE launch (pz_stream_pump).  Fed chunks travel through pinned
+ * staging with cudaMemcpyAsync on the stream's own CUDA stream; published chunks come home into a pinned
+ * buffer during the pump, so pz_stream_next never touches the device. */
 }  // extern "C"
 
+namespace {
+struct PinnedBuf {
+  uint8_t *p = nullptr;
+  size_t cap = 0;
+  int reserve_keep(size_t n, size_t keep_from, size_t keep_len) { /* grow, keeping [keep_from, keep_from + keep_len) at offset 0 */
+    if (n <= cap && keep_from == 0) return PZ_E_OK;
+    if (n <= cap) { if (keep_len) memmove(p, p + keep_from, keep_len); return PZ_E_OK; }
+    size_t want = std::max<size_t>(align_up(n, 1 << 16), cap * 2);
+    uint8_t *q = nullptr;
+    cudaError_t e = cudaHostAlloc((void **)&q, want, cudaHostAllocDefault);
+    if (e != cudaSuccess) { fail_cuda(e, "cudaHostAlloc"); return PZ_E_NOMEM; }
+    if (keep_len) memcpy(q, p + keep_from, keep_len);
+    if (p) cudaFreeHost(p);
+    p = q; cap = want;
+    return PZ_E_OK;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+constexpr size_t kStageBytes = 1 << 20; /* one pinned staging buffer of a stream's feeds (two alternate) */
+}  // namespace
+
 struct pz_stream {
-  std::vector<uint8_t> in;   /* every chunk fed so far, concatenated */
-  std::vector<uint8_t> out;  /* decoded bytes */
+  cudaStream_t st = nullptr;
+  /* device context */
+  uint8_t *d_in = nullptr, *d_out = nullptr;
+  size_t d_in_cap = 0, d_out_cap = 0;
+  size_t in_len = 0;               /* compressed bytes on the device */
+  uint32_t ck[4] = {0, 0, 0, 0};   /* where the next pump picks the stream up (PzJob::ckpt) */
+  /* feeds on their way: two pinned staging buffers, an event each */
+  PinnedBuf stage[2];
+  cudaEvent_t staged[2] = {nullptr, nullptr};
+  int stage_next = 0;
+  /* decoded bytes on the host: [h_first, h_to) of the stream, h_first <= published */
+  PinnedBuf h_out;
+  uint64_t h_first = 0, h_to = 0;
   uint64_t published = 0;    /* bytes already handed out as chunks */
   uint64_t publish_to = 0;   /* bytes the reference has published at the current state */
   bool dirty = false;        /* input arrived since the last decode */
-  bool started = false;
   bool terminal = false;     /* verdict reached */
   bool final_pending = false;/* the final (possibly empty) chunk has not been delivered */
   bool done_delivered = false;
   pz_result verdict{};
-  size_t cap_hint = 1 << 16;
+  uint64_t pumps = 0, resumed = 0; /* launches that decoded this stream; those that started from a checkpoint */
 };
+
+namespace {
+/* per-thread control tables of a pump: [in pairs | out pairs | resume] go up, [ckpt | res] come back */
+struct PumpSpace {
+  Buf h_ctl, d_ctl, d_parts, d_zero;
+  PumpSpace() { h_ctl.pinned = true; }
+  ~PumpSpace() { h_ctl.release(); d_ctl.release(); d_parts.release(); d_zero.release(); }
+};
+thread_local PumpSpace g_pump;
+
+int grow_device(uint8_t *&d, size_t &cap, size_t want, size_t keep, cudaStream_t st) {
+  if (want <= cap) return PZ_E_OK;
+  size_t n = std::max<size_t>(align_up(want + 64, 1 << 16), cap * 2);
+  uint8_t *q = nullptr;
+  cudaError_t e = cudaMalloc((void **)&q, n);
+  if (e != cudaSuccess) { fail_cuda(e, "cudaMalloc"); return PZ_E_NOMEM; }
+  if (keep) PZ_CUDA(cudaMemcpyAsync(q, d, keep, cudaMemcpyDeviceToDevice, st));
+  PZ_CUDA(cudaStreamSynchronize(st));
+  if (d) cudaFree(d);
+  d = q; cap = n;
+  return PZ_E_OK;
+}
+
+/* The state a verdict puts the stream in (what stream_next hands out afterwards). */
+void stream_settle(pz_stream *s, const pz_result &r) {
+  s->verdict = r;
+  const bool need_more = r.status == PZ_ERR_DECOMPRESSION && r.detail == PZ_D_RAN_OUT;
+  const uint64_t base = (r.status == PZ_REF_BOTTOM && r.detail == PZ_D_BOT_DIST_TOO_FAR) ? r.out_len - (uint64_t)r.payload[1]
+                                                                                          : (uint64_t)r.payload[1];
+  s->publish_to = base;
+  if (!need_more) {
+    s->terminal = true;
+    s->final_pending = (r.status == PZ_OK); /* finalize publishes what is left (Monad.hs:349-353) */
+  }
+}
+
+int pump(pz_stream *const *all, size_t n_all) {
+  std::vector<pz_stream *> act;
+  for (size_t i = 0; i < n_all; i++) {
+    pz_stream *s = all[i];
+    if (!s) return PZ_E_ARG;
+    if (s->dirty && !s->terminal && std::find(act.begin(), act.end(), s) == act.end()) act.push_back(s);
+  }
+  if (act.empty()) return PZ_E_OK;
+  cudaStream_t st = act[0]->st;
+  PumpSpace &ps = g_pump;
+  int rc;
+  if ((rc = ps.d_zero.reserve(8)) != PZ_E_OK) return rc;
+  PZ_CUDA(cudaMemsetAsync(ps.d_zero.p, 0, 8, st));
+  std::vector<pz_stream *> run = act;
+  while (!run.empty()) {
+    const size_t n = run.size();
+    /* every stream's feeds must have landed before the launch on `st` reads them */
+    for (pz_stream *s : run)
+      if (s->st != st)
+        for (int k = 0; k < 2; k++)
+          if (s->staged[k]) PZ_CUDA(cudaStreamWaitEvent(st, s->staged[k], 0));
+    const size_t up = n * 48, down = n * (16 + sizeof(pz_result));
+    if ((rc = ps.h_ctl.reserve(up + down)) != PZ_E_OK) return rc;
+    if ((rc = ps.d_ctl.reserve(up + down)) != PZ_E_OK) return rc;
+    uint8_t *h = (uint8_t *)ps.h_ctl.p, *d = (uint8_t *)ps.d_ctl.p;
+    uint64_t *in_pairs = (uint64_t *)h, *out_pairs = (uint64_t *)(h + 16 * n);
+    uint32_t *resume = (uint32_t *)(h + 32 * n);
+    for (size_t i = 0; i < n; i++) {
+      pz_stream *s = run[i];
+      /* room for what this input may add before the kernel has to stop for a larger buffer */
+      const size_t want = std::min<uint64_t>(0xfffdff00ull, (uint64_t)s->ck[2] + std::max<uint64_t>(1 << 16, 4 * (uint64_t)(s->in_len - s->ck[0] / 8)));
+      if ((rc = grow_device(s->d_out, s->d_out_cap, want, s->ck[2], st)) != PZ_E_OK) return rc;
+      if ((rc = grow_device(s->d_in, s->d_in_cap, 64, 0, st)) != PZ_E_OK) return rc; /* a stream nothing was fed to yet */
+      in_pairs[2 * i] = (uint64_t)(uintptr_t)s->d_in; in_pairs[2 * i + 1] = in_pairs[2 * i] + s->in_len;
+      out_pairs[2 * i] = (uint64_t)(uintptr_t)s->d_out; out_pairs[2 * i + 1] = out_pairs[2 * i] + std::min<uint64_t>(s->d_out_cap - 64, 0xfffdff00ull);
+      memcpy(resume + 4 * i, s->ck, 16);
+    }
+    PZ_CUDA(cudaMemcpyAsync(d, h, up, cudaMemcpyHostToDevice, st));
+    uint32_t *d_ck = (uint32_t *)(d + up);
+    pz_result *d_res = (pz_result *)(d + up + 16 * n);
+    PZ_CUDA(pz_launch_resume((const uint64_t *)d, (const uint64_t *)(d + 16 * n), (uint32_t)n, d_res, (const uint32_t *)(d + 32 * n), d_ck, st));
+    PZ_CUDA(cudaMemcpyAsync(h + up, d + up, down, cudaMemcpyDeviceToHost, st));
+    PZ_CUDA(cudaStreamSynchronize(st));
+    const uint32_t *ck = (const uint32_t *)(h + up);
+    const pz_result *res = (const pz_result *)(h + up + 16 * n);
+    /* streams that are complete get their Adler-32 verdict (K3 over the whole decoded stream) */
+    uint64_t segs = 0;
+    for (size_t i = 0; i < n; i++)
+      if (res[i].status == PZ_OK) segs += (res[i].out_len + PZ_ADLER_SEG - 1) / PZ_ADLER_SEG;
+    bool any_ok = false;
+    if ((rc = ps.d_parts.reserve(std::max<uint64_t>(segs, 1) * sizeof(uint2))) != PZ_E_OK) return rc;
+    uint64_t seg_at = 0;
+    for (size_t i = 0; i < n; i++) {
+      if (res[i].status != PZ_OK) continue;
+      const uint64_t ns = (res[i].out_len + PZ_ADLER_SEG - 1) / PZ_ADLER_SEG;
+      /* a one-stream table: out_off = this stream's (begin, end) pair, seg_off = {0} */
+      PZ_CUDA(pz_launch_adler(nullptr, (const uint64_t *)(d + 16 * n) + 2 * i, (const uint64_t *)ps.d_zero.p, 1, 0, 1, 0, ns, d_res + i,
+                              (uint2 *)ps.d_parts.p + seg_at, st));
+      seg_at += ns;
+      any_ok = true;
+    }
+    if (any_ok) {
+      PZ_CUDA(cudaMemcpyAsync(h + up + 16 * n, d_res, n * sizeof(pz_result), cudaMemcpyDeviceToHost, st));
+      PZ_CUDA(cudaStreamSynchronize(st));
+    }
+    std::vector<pz_stream *> again;
+    for (size_t i = 0; i < n; i++) {
+      pz_stream *s = run[i];
+      s->pumps++;
+      if (s->ck[0] != 0) s->resumed++;
+      memcpy(s->ck, ck + 4 * i, 16);
+      if (res[i].status == PZ_OUTPUT_FULL) { /* the buffer, not the stream: enlarge it and go on from the checkpoint */
+        if (s->d_out_cap - 64 >= 0xfffdff00ull) { stream_settle(s, res[i]); continue; }
+        if ((rc = grow_device(s->d_out, s->d_out_cap, std::min<uint64_t>(0xfffdff00ull + 64, (uint64_t)s->d_out_cap * 4), s->ck[2], st)) != PZ_E_OK) return rc;
+        again.push_back(s);
+        continue;
+      }
+      stream_settle(s, res[i]);
+    }
+    run.swap(again);
+  }
+  /* bring home what the streams may now hand out */
+  for (pz_stream *s : act) {
+    s->dirty = false;
+    const uint64_t to = (s->terminal && s->verdict.status == PZ_OK) ? s->verdict.out_len : s->publish_to;
+    if (s->published == s->h_to) s->h_first = s->h_to; /* everything fetched so far has been handed out */
+    if (to <= s->h_to) continue;
+    const uint64_t keep = s->h_to - s->h_first;
+    if ((rc = s->h_out.reserve_keep((size_t)(to - s->h_first), 0, (size_t)keep)) != PZ_E_OK) return rc;
+    PZ_CUDA(cudaMemcpyAsync(s->h_out.p + keep, s->d_out + s->h_to, to - s->h_to, cudaMemcpyDeviceToHost, st));
+    s->h_to = to;
+  }
+  PZ_CUDA(cudaStreamSynchronize(st));
+  return PZ_E_OK;
+}
+}  // namespace
 
 extern "C" {
 
 pz_stream *pz_stream_new(void) {
   if (ensure_init() != PZ_E_OK) return nullptr;
-  return new (std::nothrow) pz_stream();
+  pz_stream *s = new (std::nothrow) pz_stream();
+  if (!s) return nullptr;
+  cudaError_t e = cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking);
+  for (int k = 0; k < 2 && e == cudaSuccess; k++) e = cudaEventCreateWithFlags(&s->staged[k], cudaEventDisableTiming);
+  if (e != cudaSuccess) { fail_cuda(e, "pz_stream_new"); pz_stream_free(s); return nullptr; }
+  return s;
 }
 
-void pz_stream_free(pz_stream *s) { delete s; }
+void pz_stream_free(pz_stream *s) {
+  if (!s) return;
+  if (s->st) cudaStreamSynchronize(s->st);
+  for (int k = 0; k < 2; k++) { if (s->staged[k]) cudaEventDestroy(s->staged[k]); s->stage[k].release(); }
+  s->h_out.release();
+  if (s->d_in) cudaFree(s->d_in);
+  if (s->d_out) cudaFree(s->d_out);
+  if (s->st) cudaStreamDestroy(s->st);
+  delete s;
+}
 
+/* The chunk is copied into pinned staging and sent to the device asynchronously: the call returns while
+ * the copy is in flight (the staging buffers alternate; a buffer is reused once its copy has finished). */
 int pz_stream_feed(pz_stream *s, const uint8_t *data, size_t len) {
   if (!s || (len && !data)) return PZ_E_ARG;
   if (s->terminal) return PZ_E_STATE; /* the decoder never asked for this chunk */
-  s->in.insert(s->in.end(), data, data + len);
+  if (s->in_len + len > PZ_MAX_STREAM_BYTES) return PZ_E_ARG;
   s->dirty = true;
+  if (len == 0) return PZ_E_OK; /* empty chunks are accepted and ignored (Monad.hs:193-195) */
+  int rc = grow_device(s->d_in, s->d_in_cap, s->in_len + len + 64, s->in_len, s->st);
+  if (rc != PZ_E_OK) return rc;
+  for (size_t at = 0; at < len;) {
+    const size_t piece = std::min(len - at, kStageBytes);
+    const int k = s->stage_next;
+    s->stage_next ^= 1;
+    PZ_CUDA(cudaEventSynchronize(s->staged[k]));
+    if ((rc = s->stage[k].reserve_keep(std::min(kStageBytes, std::max<size_t>(piece, 1 << 16)), 0, 0)) != PZ_E_OK) return rc;
+    memcpy(s->stage[k].p, data + at, piece);
+    PZ_CUDA(cudaMemcpyAsync(s->d_in + s->in_len, s->stage[k].p, piece, cudaMemcpyHostToDevice, s->st));
+    PZ_CUDA(cudaEventRecord(s->staged[k], s->st));
+    s->in_len += piece;
+    at += piece;
+  }
   return PZ_E_OK;
 }
 
-/* Runs the batch engine over everything fed so far.  A "ran out of data" verdict on the
- * prefix is exactly the reference's NeedMore state; any other verdict is final because it
- * only depends on bytes already seen. */
-static int stream_decode(pz_stream *s) {
-  for (;;) {
-    s->out.resize(s->cap_hint);
-    const uint8_t *inp = s->in.data();
-    size_t in_len = s->in.size();
-    uint8_t *outp = s->out.data();
-    size_t cap = s->out.size();
-    static const uint8_t empty = 0;
-    if (!inp) inp = &empty;
-    pz_result r;
-    int rc = pz_inflate_batch(&inp, &in_len, &outp, &cap, 1, &r, PZ_F_NO_HUGE); /* the event sequence needs the exact window model */
-    if (rc != PZ_E_OK) return rc;
-    if (r.status == PZ_OUTPUT_FULL) { s->cap_hint *= 4; continue; }
-    s->verdict = r;
-    return PZ_E_OK;
-  }
+int pz_stream_pump(pz_stream *const *streams, size_t n) {
+  if (n && !streams) return PZ_E_ARG;
+  int rc = ensure_init();
+  if (rc != PZ_E_OK) return rc;
+  return pump(streams, n);
+}
+
+uint64_t pz_stream_counter(const pz_stream *s, int which) {
+  if (!s) return 0;
+  return which == PZ_SC_PUMPS ? s->pumps : which == PZ_SC_RESUMED ? s->resumed : which == PZ_SC_CKPT_BIT ? (s->ck[1] != 0 && s->ck[1] != PZ_CK_TRAILER_HOST ? s->ck[1] : s->ck[0])
+       : which == PZ_SC_CKPT_BYTES ? s->ck[2] : 0;
 }
 
 int pz_stream_next(pz_stream *s, const uint8_t **chunk, size_t *len, pz_result *res) {
@@ -801,21 +996,12 @@ int pz_stream_next(pz_stream *s, const uint8_t **chunk, size_t *len, pz_result *
     return PZ_S_ERROR;
   }
   if (s->dirty && !s->terminal) {
-    int rc = stream_decode(s);
+    pz_stream *one = s;
+    int rc = pump(&one, 1);
     if (rc != PZ_E_OK) return rc;
-    s->dirty = false;
-    const pz_result &r = s->verdict;
-    const bool need_more = r.status == PZ_ERR_DECOMPRESSION && r.detail == PZ_D_RAN_OUT;
-    uint64_t base = (r.status == PZ_REF_BOTTOM && r.detail == PZ_D_BOT_DIST_TOO_FAR) ? r.out_len - (uint64_t)r.payload[1]
-                                                                                    : (uint64_t)r.payload[1];
-    s->publish_to = base;
-    if (!need_more) {
-      s->terminal = true;
-      s->final_pending = (r.status == PZ_OK); /* finalize publishes what is left (Monad.hs:349-353) */
-    }
   }
   if (s->published < s->publish_to) { /* emitExcess hands out exactly 32 KiB at a time */
-    if (chunk) *chunk = s->out.data() + s->published;
+    if (chunk) *chunk = s->h_out.p + (s->published - s->h_first);
     if (len) *len = PZ_EXCESS_CHUNK;
     s->published += PZ_EXCESS_CHUNK;
     return PZ_S_CHUNK;
@@ -823,7 +1009,7 @@ int pz_stream_next(pz_stream *s, const uint8_t **chunk, size_t *len, pz_result *
   if (!s->terminal) return PZ_S_NEED_MORE;
   if (s->final_pending) {
     s->final_pending = false;
-    if (chunk) *chunk = s->out.data() + s->published;
+    if (chunk) *chunk = s->h_out.p ? s->h_out.p + (s->published - s->h_first) : (const uint8_t *)"";
     if (len) *len = (size_t)(s->verdict.out_len - s->published);
     s->published = s->verdict.out_len;
     return PZ_S_CHUNK;

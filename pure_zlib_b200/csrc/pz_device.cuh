@@ -265,7 +265,20 @@ struct PzJob {
    * K3 that the partial sums exist in that form. */
   uint2 *parts;
   const uint64_t *seg_off;
+  /* Resumable contexts (decompressIncremental, Monad.hs:163-197: the decoder stops at NeedMore and goes
+   * on when the next chunk arrives).  ckpt[4s..4s+4) receives where stream s can be picked up again when
+   * it stops: {bit of the header of the block it is in, bit of the symbol it could not finish (0 = pick
+   * up at the header, PZ_CK_TRAILER = every block is done, word 0 is the bit after the last one), bytes
+   * decoded, bytes the reference has published}, bits counted from the stream's first byte.  resume[4s..]
+   * (word 0 != 0) restarts stream s from such a checkpoint: the first `bytes decoded` bytes of its
+   * output slice are its history.  pair_off = 1: stream s owns in_off[2s], in_off[2s+1] and out_off[2s],
+   * out_off[2s+1] (begin, end) instead of sharing its end with the next stream's begin, so that streams
+   * can live in buffers of their own (in_blob / out_blob may then be null and the offsets addresses). */
+  const uint32_t *resume = nullptr;
+  uint32_t *ckpt = nullptr;
+  uint32_t pair_off = 0;
 };
+#define PZ_CK_TRAILER 0xffffffffu
 #define PZ_ADLER_FUSED 0xffffffffu /* no Adler-32 value: both halves of one are below 65521 */
 #define PZ_BLK_BIAS 65536u /* a block job counts its output from here: the window model then always
                               sees at least 32 KiB of history, as it would inside a long stream */
@@ -301,6 +314,11 @@ struct PzCtx {
   bool need_careful; /* the hot loop met something only the careful path may decide */
   uint32_t next;     /* next stream index of this group */
   pz_result *res;
+  /* checkpoint (PzJob::ckpt) */
+  uint32_t hdr_bp;     /* bit position (from in_al) of the header of the current block */
+  uint32_t sym_bp;     /* bit position of the symbol the careful path is deciding, 0 outside the symbol loop */
+  uint32_t resume_sym; /* resuming inside a block: the symbol to go on with once the block's tables exist (from the stream's first byte) */
+  uint32_t *ck;        /* this stream's four checkpoint words, or nullptr */
   /* token queue (decoder side) */
   uint32_t qhead;  /* tokens pushed so far */
   uint32_t qtailc; /* last value read from the writer's counter */
@@ -680,10 +698,15 @@ PZ_DEV void pz_writer_apply(PzWriter &w, uint32_t raw) {
         w.out16 = w.job->out16 + w.job->blk_out[raw];
         w.in = w.job->in_blob + w.job->in_off[w.job->blk_stream];
       } else {
-        w.out = w.job->out_blob + w.job->out_off[raw];
-        w.in = w.job->in_blob + w.job->in_off[raw];
+        w.out = w.job->out_blob + w.job->out_off[raw << w.job->pair_off];
+        w.in = w.job->in_blob + w.job->in_off[raw << w.job->pair_off];
       }
-      w.pos = 0; w.need = 0;
+      w.pos = 0;
+      if (!WIDE && w.job->resume != nullptr && w.job->resume[4u * raw] != 0u) { /* the stream goes on behind its history */
+        w.pos = w.job->resume[4u * raw + 2u];
+        w.pub = w.pos >> PZ_PROG_SHIFT;
+      }
+      w.need = 0;
     } else if (w.need == 2u) {
       w.a0 = raw; w.need = 1;
     } else { /* emitBlock (Monad.hs:317-322): raw bytes of a stored block */
@@ -928,6 +951,7 @@ PZ_DEV bool pz_literal_checked(PzCtx &c, PzStreamSmem *sm, uint32_t b) {
  * 0 = end of block, -1 = verdict set. */
 template <bool COUNT_ONLY>
 PZ_DEV int pz_symbol_careful(PzCtx &c, PzStreamSmem *sm) {
+  c.sym_bp = c.bp; /* checkpoint: nothing of this symbol is committed until it is complete */
   int sym = pz_walk(c, sm, &sm->lit, sm->lit_perm);
   if (sym < 0) return -1;
   if (sym < 256) return pz_literal_checked<COUNT_ONLY>(c, sm, (uint32_t)sym) ? 1 : -1;
@@ -1292,13 +1316,31 @@ PZ_DEV void pz_finish(PzCtx &c) {
     /* payload[1]: bytes the reference has already published as 32 KiB chunks (the shim's
      * incremental driver needs it); DIST_TOO_FAR keeps the retained-byte count instead */
     res->payload[1] = (c.status == PZ_REF_BOTTOM && c.detail == PZ_D_BOT_DIST_TOO_FAR) ? c.p1 : (int64_t)c.base;
+    if (c.ck != nullptr) { /* PzJob::ckpt: c.pos / c.base are those of the last complete symbol */
+      c.ck[0] = c.hdr_bp - c.start_bit;
+      c.ck[1] = (c.sym_bp == 0u || c.sym_bp == PZ_CK_TRAILER) ? c.sym_bp : c.sym_bp - c.start_bit;
+      c.ck[2] = c.pos;
+      c.ck[3] = c.base;
+    }
   }
   c.mode = PZ_M_IDLE;
 }
 
+/* checkChecksum (Deflate.hs:52-63): align, four bytes, most significant first.  The comparison is K3's. */
+PZ_DEV void pz_trailer(PzCtx &c, PzStreamSmem *sm) {
+  c.hdr_bp = c.bp; c.sym_bp = PZ_CK_TRAILER; /* a stream that stops here is picked up here */
+  pz_align_byte(c, sm);
+  uint32_t hi, lo;
+  if (pz_avail(c) < 32u) pz_fail(c, PZ_ERR_DECOMPRESSION, PZ_D_RAN_OUT);
+  else if (pz_take(c, sm, 16, hi) && pz_take(c, sm, 16, lo))
+    c.adler_stored = ((hi & 0xffu) << 24) | ((hi >> 8) << 16) | ((lo & 0xffu) << 8) | (lo >> 8);
+  pz_finish(c);
+}
+
 /* `decompress` for one single-chunk stream starts here: inflateWithHeaders (Zlib.hs:53-69). */
 template <bool COUNT_ONLY>
-PZ_DEV void pz_begin(PzCtx &c, PzStreamSmem *sm, uint32_t s, const uint8_t *in, uint64_t in_len, uint64_t out_cap, pz_result *res) {
+PZ_DEV void pz_begin(PzCtx &c, PzStreamSmem *sm, uint32_t s, const uint8_t *in, uint64_t in_len, uint64_t out_cap, pz_result *res,
+                     const uint32_t *rs = nullptr, uint32_t *ck = nullptr) {
   uint32_t mis = (uint32_t)((uintptr_t)in & 15u);
   c.in_al = in - mis;
   c.res = res;
@@ -1308,6 +1350,7 @@ PZ_DEV void pz_begin(PzCtx &c, PzStreamSmem *sm, uint32_t s, const uint8_t *in, 
   c.adler_stored = 0; c.bfinal = 0; c.need_careful = false;
   /* c.fixed_ready survives: the fixed-code LUTs stay valid until a dynamic header overwrites them */
   c.start_bit = mis * 8u;
+  c.hdr_bp = c.start_bit; c.sym_bp = 0; c.resume_sym = 0; c.ck = ck;
   if (in_len > PZ_MAX_IN_BYTES) { /* the C ABI refuses such streams before launching */
     c.in_al_bytes = 0; c.end_bit = c.start_bit; c.safe_end = 0; c.bp = c.start_bit; c.q = 0;
     pz_fail(c, PZ_OUTPUT_FULL, 0);
@@ -1320,6 +1363,16 @@ PZ_DEV void pz_begin(PzCtx &c, PzStreamSmem *sm, uint32_t s, const uint8_t *in, 
   /* the writer switches to this stream's output slice */
   pz_push<COUNT_ONLY>(c, sm, PZ_TOKEN(PZ_Q_CTRL, PZ_C_NEWSTREAM << 26));
   pz_push<COUNT_ONLY>(c, sm, s);
+  if (rs != nullptr && rs[0] != 0u) { /* PzJob::resume: the zlib header and rs[2] bytes of output are behind us */
+    c.pos = rs[2]; c.base = rs[3];
+    uint32_t bit = rs[0];
+    if (bit > c.end_bit - c.start_bit) bit = c.end_bit - c.start_bit;
+    pz_seek(c, sm, c.start_bit + bit);
+    if (rs[1] == PZ_CK_TRAILER) { c.bfinal = 1; pz_trailer(c, sm); return; }
+    c.resume_sym = rs[1];
+    c.mode = PZ_M_HDR;
+    return;
+  }
   pz_seek(c, sm, c.start_bit);
   uint32_t cmf, flg;
   bool ok = pz_take(c, sm, 8, cmf) && pz_take(c, sm, 8, flg);
@@ -1347,6 +1400,7 @@ PZ_DEV void pz_begin_block(PzCtx &c, PzStreamSmem *sm, uint32_t j, const uint8_t
   c.status = PZ_OK; c.detail = 0; c.p0 = 0; c.p1 = 0;
   c.adler_stored = 0; c.bfinal = 0; c.need_careful = false;
   c.start_bit = mis * 8u;
+  c.hdr_bp = c.start_bit; c.sym_bp = 0; c.resume_sym = 0; c.ck = nullptr;
   c.in_al_bytes = (mis + (uint32_t)in_len + 15u) & ~15u;
   c.end_bit = (mis + (uint32_t)in_len) * 8u;
   c.safe_end = c.end_bit >= PZ_STEP_BITS ? c.end_bit - PZ_STEP_BITS : 0u;
@@ -1363,12 +1417,7 @@ PZ_DEV void pz_block_end(PzCtx &c, PzStreamSmem *sm) {
   pz_move_window(c);
   if (c.block_job) { pz_finish(c); return; } /* err_bitpos = first bit after the block */
   if (!c.bfinal) { c.mode = PZ_M_HDR; return; }
-  pz_align_byte(c, sm);
-  uint32_t hi, lo;
-  if (pz_avail(c) < 32u) pz_fail(c, PZ_ERR_DECOMPRESSION, PZ_D_RAN_OUT);
-  else if (pz_take(c, sm, 16, hi) && pz_take(c, sm, 16, lo))
-    c.adler_stored = ((hi & 0xffu) << 24) | ((hi >> 8) << 16) | ((lo & 0xffu) << 8) | (lo >> 8);
-  pz_finish(c);
+  pz_trailer(c, sm);
 }
 
 /* One transition of a group that is not in the hot loop. */
@@ -1399,25 +1448,34 @@ PZ_DEV void pz_slow_step(PzCtx &c, PzStreamSmem *sm, const PzJob &job, uint32_t 
       pz_begin_block<COUNT_ONLY>(c, sm, s, job.in_blob + b0, b1 - b0, job.blk_start[s], job.blk_len ? job.blk_len[s] : job.blk_cap, job.res + s);
       return;
     }
-    const uint64_t i0 = job.in_off[s], i1 = job.in_off[s + 1];
+    const uint32_t e = s << job.pair_off;
+    const uint64_t i0 = job.in_off[e], i1 = job.in_off[e + 1];
     if (COUNT_ONLY) {
       pz_begin<true>(c, sm, s, job.in_blob + i0, i1 - i0, ~0ull, job.res + s);
     } else {
-      const uint64_t o0 = job.out_off[s], o1 = job.out_off[s + 1];
-      pz_begin<false>(c, sm, s, job.in_blob + i0, i1 - i0, o1 - o0, job.res + s);
+      const uint64_t o0 = job.out_off[e], o1 = job.out_off[e + 1];
+      pz_begin<false>(c, sm, s, job.in_blob + i0, i1 - i0, o1 - o0, job.res + s, job.resume ? job.resume + 4u * s : nullptr,
+                      job.ckpt ? job.ckpt + 4u * s : nullptr);
     }
   } else if (c.mode == PZ_M_HDR) { /* inflateBlock (Deflate.hs:65-104) */
     uint32_t btype;
+    c.hdr_bp = c.bp; c.sym_bp = 0;
     if (!pz_take(c, sm, 1, c.bfinal) || !pz_take(c, sm, 2, btype)) { pz_finish(c); return; }
     if (btype == 0u) {
+      c.resume_sym = 0;
       if (!pz_stored_block<COUNT_ONLY>(c, sm)) { pz_finish(c); return; }
       pz_block_end(c, sm);
-    } else if (btype == 1u) {
-      if (!c.fixed_ready) { pz_fixed_tables(sm); c.fixed_ready = true; }
-      c.mode = PZ_M_SYMS;
-    } else if (btype == 2u) {
-      c.fixed_ready = false;
-      if (!pz_dynamic_header(c, sm)) { pz_finish(c); return; }
+    } else if (btype == 1u || btype == 2u) {
+      if (btype == 1u) {
+        if (!c.fixed_ready) { pz_fixed_tables(sm); c.fixed_ready = true; }
+      } else {
+        c.fixed_ready = false;
+        if (!pz_dynamic_header(c, sm)) { pz_finish(c); return; }
+      }
+      if (c.resume_sym != 0u) { /* PzJob::resume inside a block: its tables exist again, go on at the symbol */
+        pz_seek(c, sm, c.start_bit + c.resume_sym);
+        c.resume_sym = 0;
+      }
       c.mode = PZ_M_SYMS;
     } else {
       pz_fail(c, PZ_ERR_FORMAT, PZ_D_BAD_BTYPE, 3);
@@ -1455,6 +1513,7 @@ PZ_DEV void pz_decoder_warp(const PzJob &job, uint32_t first_stream, uint32_t st
   c.mode = PZ_M_IDLE;
   c.next = first_stream;
   c.in_al = nullptr; c.in_al_bytes = 0; c.bp = 0; c.q = 0; c.next_q = 0; c.pending = false; c.starved = false; c.block_job = false; c.res = nullptr;
+  c.hdr_bp = 0; c.sym_bp = 0; c.resume_sym = 0; c.ck = nullptr;
   c.qhead = 0; c.qtailc = 0;
   c.fixed_ready = false;
 #ifdef PZ_HOSTSIM

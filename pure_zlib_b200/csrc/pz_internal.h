@@ -43,6 +43,11 @@ cudaError_t pz_launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uin
 #define PZ_PHASE_K2 1 /* only the stored-stream kernels (they also mark every other stream PENDING) */
 #define PZ_PHASE_K1 2 /* only K1: decodes the streams that are still PENDING */
 #define PZ_ST_PENDING_HOST (-1) /* == PZ_ST_PENDING in pz_device.cuh */
+/* Resumable contexts: count streams in buffers of their own ((begin, end) device addresses), each continuing from
+ * d_resume[4s..] and leaving its next checkpoint in d_ckpt[4s..] (PzJob::resume / ckpt in pz_device.cuh).  K1 only. */
+cudaError_t pz_launch_resume(const uint64_t *d_in_pairs, const uint64_t *d_out_pairs, uint32_t count, pz_result *d_res,
+                             const uint32_t *d_resume, uint32_t *d_ckpt, cudaStream_t st);
+#define PZ_CK_TRAILER_HOST 0xffffffffu /* == PZ_CK_TRAILER in pz_device.cuh */
 /* K4 (pz_huge.cuh): one huge stream decoded block-parallel; see pz_abi.cu for the driver */
 cudaError_t pz_launch_blk_search(const uint8_t *d_stream, uint64_t nbytes, uint64_t first_bit, uint64_t last_bit, uint32_t *d_cand,
                                  uint32_t *d_ncand, uint32_t cap, cudaStream_t st);

@@ -267,6 +267,25 @@ cudaError_t pz_launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uin
   return cudaGetLastError();
 }
 
+/* Resumable contexts (the incremental driver): stream s reads [d_in_pairs[2s], d_in_pairs[2s+1]) and writes into
+ * [d_out_pairs[2s], d_out_pairs[2s+1]) -- device ADDRESSES, every stream in buffers of its own -- starting from the
+ * checkpoint d_resume[4s..] and leaving the next one in d_ckpt[4s..] (PzJob::resume, PzJob::ckpt).  K1 only. */
+cudaError_t pz_launch_resume(const uint64_t *d_in_pairs, const uint64_t *d_out_pairs, uint32_t count, pz_result *d_res,
+                             const uint32_t *d_resume, uint32_t *d_ckpt, cudaStream_t st) {
+  if (count == 0) return cudaSuccess;
+  const unsigned wave = (unsigned)(g_sm_count * g_inflate_ctas_per_sm[0]);
+  const unsigned grid = count < wave ? count : wave;
+  const size_t smem = sizeof(PzStreamSmem) * PZ_SLOTS;
+  PzJob job;
+  job.in_blob = nullptr; job.in_off = d_in_pairs; job.out_blob = nullptr; job.out_off = d_out_pairs; job.res = d_res;
+  job.first = 0; job.count = count; job.skip_done = 0; job.prog = nullptr; job.in_ready = nullptr;
+  job.blk_start = nullptr; job.blk_out = nullptr; job.blk_len = nullptr; job.out16 = nullptr; job.blk_stream = 0; job.blk_cap = 0;
+  job.parts = nullptr; job.seg_off = nullptr;
+  job.resume = d_resume; job.ckpt = d_ckpt; job.pair_off = 1u;
+  pz_inflate_kernel<false><<<grid, PZ_THREADS_PER_CTA, smem, st>>>(job);
+  return cudaGetLastError();
+}
+
 /* ---- K4 launchers (pz_huge.cuh; block jobs run on K1) ---------------------------------------- */
 cudaError_t pz_launch_blk_search(const uint8_t *d_stream, uint64_t nbytes, uint64_t first_bit, uint64_t last_bit, uint32_t *d_cand,
                                  uint32_t *d_ncand, uint32_t cap, cudaStream_t st) {

@@ -172,6 +172,77 @@ def decompress_incremental():
     return _Decoder().state()
 
 
+class IncrementalSet:
+    """Extension (pz_stream_pump): n `decompressIncremental` consumers advanced together.  `feed(i, chunk)`
+    answers stream i's NeedMore, `pump()` decodes what all of them have been fed in ONE kernel launch --
+    each from its device-resident checkpoint, not from its first byte -- and `events(i)` then yields
+    stream i's states up to its next NeedMore / Done / DecompError without touching the device."""
+
+    def __init__(self, n: int):
+        self.decoders = [_Decoder() for _ in range(n)]
+        self._L = _lib.load()
+
+    def feed(self, i: int, chunk: bytes):
+        chunk = bytes(chunk)
+        d = self.decoders[i]
+        _lib.check(self._L.pz_stream_feed(d._s, chunk, len(chunk)), "pz_stream_feed")
+
+    def pump(self):
+        arr = (C.c_void_p * len(self.decoders))(*[d._s for d in self.decoders])
+        _lib.check(self._L.pz_stream_pump(arr, len(self.decoders)), "pz_stream_pump")
+
+    def events(self, i: int):
+        state = self.decoders[i].state()
+        while isinstance(state, Chunk):
+            yield state
+            state = state.next()
+        yield state
+
+    def counter(self, i: int, which: int) -> int:
+        return int(self._L.pz_stream_counter(self.decoders[i]._s, which))
+
+
+def decompress_many(files: Sequence[LazyByteString]):
+    """`map decompress` over lazy ByteStrings of several chunks each, the driver loop `run` (Zlib.hs:37-51)
+    of all of them advanced in lockstep: one launch per round of chunks instead of one per chunk and stream.
+    Where `decompress` raises ReferenceBottom the result list holds the exception instead."""
+    rests = [_chunks_of(f) for f in files]
+    n = len(rests)
+    group = IncrementalSet(n)
+    acc: List[List[bytes]] = [[] for _ in range(n)]
+    result: List = [None] * n
+    live = list(range(n))
+    for i in live:  # the initial state of every decoder is NeedMore
+        if not rests[i]:
+            result[i] = Left(DecompressionError_("Ran out of data mid-decompression 2."))
+    live = [i for i in live if result[i] is None]
+    while live:
+        for i in live:
+            group.feed(i, rests[i].pop(0))
+        group.pump()
+        nxt = []
+        for i in live:
+            try:
+                states = list(group.events(i))
+            except ReferenceBottom as e:  # where `decompress` would die, the list holds the exception
+                result[i] = e
+                continue
+            for state in states:
+                if isinstance(state, Chunk):
+                    acc[i].append(state.data)
+                elif isinstance(state, NeedMore):
+                    if rests[i]:
+                        nxt.append(i)
+                    else:
+                        result[i] = Left(DecompressionError_("Ran out of data mid-decompression 2."))
+                elif isinstance(state, Done):
+                    result[i] = Left(DecompressionError_("Finished with data remaining.")) if rests[i] else Right(b"".join(acc[i]))
+                else:
+                    result[i] = Left(state.error)
+        live = nxt
+    return result
+
+
 def _chunks_of(lazy: LazyByteString) -> List[bytes]:
     if isinstance(lazy, (bytes, bytearray, memoryview)):
         b = bytes(lazy)

@@ -12,7 +12,9 @@
 
 #include <stdlib.h>
 
-extern "C" int hs_inflate(const uint8_t *in, uint64_t in_len, uint8_t *out, uint64_t out_cap, pz_result *res, int count_only) {
+/* resume / ckpt (four words each, may be null): PzJob::resume, PzJob::ckpt; `out` then holds the stream's history */
+extern "C" int hs_inflate_resume(const uint8_t *in, uint64_t in_len, uint8_t *out, uint64_t out_cap, pz_result *res, int count_only,
+                                 const uint32_t *resume, uint32_t *ckpt) {
   /* the device reads whole 16-byte pieces around the stream: give it a padded, aligned copy
    * with a deliberately odd misalignment so the (mis != 0) paths run */
   size_t mis = 5;
@@ -22,9 +24,18 @@ extern "C" int hs_inflate(const uint8_t *in, uint64_t in_len, uint8_t *out, uint
   PzStreamSmem *sm = (PzStreamSmem *)aligned_alloc(16, (sizeof(PzStreamSmem) + 15) & ~(size_t)15);
   memset(sm, 0xCD, sizeof(PzStreamSmem));
   /* a one-stream job through the same state machine the kernel runs */
+  /* with a checkpoint array the job also addresses its buffers the way the incremental driver does:
+   * (begin, end) pairs that are addresses, blobs null */
+  const bool pairs = ckpt != nullptr && !count_only;
   uint64_t in_off[2] = {0, in_len}, out_off[2] = {0, out_cap};
+  if (pairs) {
+    in_off[0] = (uint64_t)(uintptr_t)(buf + mis); in_off[1] = in_off[0] + in_len;
+    out_off[0] = (uint64_t)(uintptr_t)out; out_off[1] = out_off[0] + out_cap;
+  }
   PzJob job;
-  job.in_blob = buf + mis; job.in_off = in_off; job.out_blob = count_only ? nullptr : out; job.out_off = out_off;
+  job.in_blob = pairs ? nullptr : buf + mis; job.in_off = in_off; job.out_blob = (count_only || pairs) ? nullptr : out; job.out_off = out_off;
+  job.pair_off = pairs ? 1u : 0u; job.resume = resume; job.ckpt = ckpt;
+  job.parts = nullptr; job.seg_off = nullptr;
   job.res = res; job.first = 0; job.count = 1; job.skip_done = 0; job.prog = nullptr; job.in_ready = nullptr; job.blk_start = nullptr; job.blk_out = nullptr; job.blk_len = nullptr; job.out16 = nullptr; job.blk_stream = 0; job.blk_cap = 0;
   PzWriter hw; /* tokens are applied as they are pushed */
   pz_writer_init(hw, &job);
@@ -33,6 +44,10 @@ extern "C" int hs_inflate(const uint8_t *in, uint64_t in_len, uint8_t *out, uint
   free(sm);
   free(buf);
   return 0;
+}
+
+extern "C" int hs_inflate(const uint8_t *in, uint64_t in_len, uint8_t *out, uint64_t out_cap, pz_result *res, int count_only) {
+  return hs_inflate_resume(in, in_len, out, out_cap, res, count_only, nullptr, nullptr);
 }
 
 extern "C" int hs_smem_bytes(void) { return (int)sizeof(PzStreamSmem); }

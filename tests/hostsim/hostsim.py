@@ -22,6 +22,8 @@ def lib():
         subprocess.check_call(["make", "-C", _HERE, "-s", "libpzhostsim.so"])
         _lib = C.CDLL(_SO)
         _lib.hs_inflate.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(PzResult), C.c_int]
+        _lib.hs_inflate_resume.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(PzResult), C.c_int,
+                                           C.c_void_p, C.c_void_p]
     return _lib
 
 
@@ -30,3 +32,19 @@ def inflate(data: bytes, out_cap: int, count_only: bool = False):
     res = PzResult()
     lib().hs_inflate(bytes(data), len(data), out, out_cap, C.byref(res), int(count_only))
     return res, out.raw[: min(res.out_len, out_cap)]
+
+
+class Resumable:
+    """One stream decoded prefix by prefix through PzJob::resume / PzJob::ckpt: the output buffer is
+    the history, the four checkpoint words of a run are the resume words of the next."""
+
+    def __init__(self, out_cap: int):
+        self.out = C.create_string_buffer(max(out_cap, 1))
+        self.cap = out_cap
+        self.ck = (C.c_uint32 * 4)(0, 0, 0, 0)
+
+    def run(self, prefix: bytes):
+        res = PzResult()
+        rs = (C.c_uint32 * 4)(*self.ck)
+        lib().hs_inflate_resume(bytes(prefix), len(prefix), self.out, self.cap, C.byref(res), 0, rs, self.ck)
+        return res, self.out.raw[: min(res.out_len, self.cap)], tuple(rs)

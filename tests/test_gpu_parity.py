@@ -452,3 +452,152 @@ def test_huge_stream_in_a_batch_and_device_pointers(pz, huge_threshold):
     for i, d in enumerate(datas):
         assert res[i].status == 0 and res[i].out_len == len(d) and res[i].adler_computed == zlib.adler32(d), i
         assert host[int(out_off[i]): int(out_off[i]) + len(d)].tobytes() == d, i
+
+
+# ---- resumable device contexts (pz_stream_*: checkpoints, one launch for many streams) -------
+def _pieces(z, cuts):
+    out, prev = [], 0
+    for c in sorted(set(cuts)):
+        if c > prev:
+            out.append(z[prev:c])
+            prev = c
+    if prev < len(z):
+        out.append(z[prev:])
+    return out
+
+
+def _run_incremental(pz, pieces):
+    events, acc, st, rest, err = [], b"", pz.decompress_incremental(), list(pieces), None
+    while True:
+        if isinstance(st, pz.NeedMore):
+            events.append((0, 0))
+            if not rest:
+                break
+            st = st.feed(rest.pop(0))
+        elif isinstance(st, pz.Chunk):
+            events.append((1, len(st.data)))
+            acc += st.data
+            st = st.next()
+        elif isinstance(st, pz.Done):
+            events.append((2, 0))
+            break
+        else:
+            events.append((3, 0))
+            err = st.error
+            break
+    return events, acc, err
+
+
+def test_incremental_resumes_from_checkpoint(pz, oracle):
+    """A stream fed in many pieces is decoded once, not once per piece: every pump starts at the
+    checkpoint of the one before (inside a block, at a header, in the trailer), and the events are
+    still the reference's."""
+    from pure_zlib_b200 import _lib
+    L = _lib.load()
+    rng = np.random.default_rng(11)
+    data = streams.small_text(400_000, 5)
+    co = zlib.compressobj(6)
+    z = co.compress(data[:150_000]) + co.flush(zlib.Z_FULL_FLUSH) + co.compress(data[150_000:]) + co.flush()
+    stored = zlib.compress(rng.integers(0, 256, 150_000, dtype=np.uint8).tobytes(), 6)
+    fixed = zlib.compressobj(6, zlib.DEFLATED, 15, 8, zlib.Z_FIXED)
+    zf = fixed.compress(data[:90_000]) + fixed.flush()
+    for stream in (z, stored, zf):
+        for cuts in (list(range(0, len(stream), 4099)), [int(x) for x in rng.integers(0, len(stream), 9)],
+                     [len(stream) - 5, len(stream) - 4, len(stream) - 2, len(stream) - 1]):
+            pieces = _pieces(stream, cuts)
+            o = oracle.decompress(pieces, want_events=True)
+            events, acc, err = _run_incremental(pz, pieces)
+            assert events == o.events, (len(stream), cuts[:6], events[:8], o.events[:8])
+            assert acc == o.data[: len(acc)] and (o.status != 0 or acc == o.data)
+    # the decoder really resumes: decoded bytes behind the checkpoint grow with the input
+    d = pz.zlib._Decoder()
+    seen = []
+    for piece in _pieces(z, list(range(0, len(z), 10_007))):
+        _lib.check(L.pz_stream_feed(d._s, piece, len(piece)), "feed")
+        st = d.state()
+        while isinstance(st, pz.Chunk):
+            st = st.next()
+        seen.append((L.pz_stream_counter(d._s, _lib.PZ_SC_CKPT_BIT), L.pz_stream_counter(d._s, _lib.PZ_SC_CKPT_BYTES)))
+    assert isinstance(st, pz.Done)
+    pumps, resumed = L.pz_stream_counter(d._s, _lib.PZ_SC_PUMPS), L.pz_stream_counter(d._s, _lib.PZ_SC_RESUMED)
+    assert resumed >= pumps - 1 >= len(seen) - 2, (pumps, resumed)
+    bits = [b for b, _ in seen[:-1]]
+    assert bits == sorted(bits) and bits[-1] > 8 * (len(z) - 2 * 10_007 - 300), bits[-3:]
+    # each checkpoint is at most one symbol (<= 48 bits) plus what the next piece starts with behind the input
+    for k, (b, _) in enumerate(seen[:-1]):
+        assert 8 * min(len(z), 10_007 * (k + 1)) - b <= 64, (k, b)
+
+
+def test_incremental_verdicts_fuzz(pz, oracle):
+    """Mutated streams in random pieces: the terminal state (and the bytes handed out before it) are
+    what the reference's `decompress` over the same chunk list gives."""
+    rng = np.random.default_rng(21)
+    n = 0
+    for data in fuzzlib.fuzz_cases(5, 60):
+        if len(data) < 4:
+            continue
+        pieces = _pieces(data, [int(x) for x in rng.integers(1, len(data), 3)])
+        o = oracle.decompress(pieces, want_events=True)
+        if o.status == 6:
+            with pytest.raises(pz.ReferenceBottom):
+                _run_incremental(pz, pieces)
+            continue
+        events, acc, err = _run_incremental(pz, pieces)
+        assert events == o.events, (data.hex()[:80], events[:6], o.events[:6], o.message)
+        if o.status not in (0, 3) or (o.status == 3 and o.detail == 2):
+            assert err is not None and str(err) == o.message
+        n += 1
+    assert n > 20
+
+
+def test_stream_pump_many(pz, oracle):
+    """pz_stream_pump: 96 concurrent incremental consumers, one launch per round of chunks."""
+    from pure_zlib_b200 import _lib
+    rng = np.random.default_rng(31)
+    files, want = [], []
+    for i in range(96):
+        kind = i % 4
+        if kind == 0:
+            raw = streams.small_text(int(rng.integers(1, 200_000)), 100 + i)
+        elif kind == 1:
+            raw = rng.integers(0, 256, int(rng.integers(1, 90_000)), dtype=np.uint8).tobytes()
+        elif kind == 2:
+            raw = bytes(int(rng.integers(1, 300_000)))
+        else:
+            raw = streams.small_text(int(rng.integers(1, 5000)), 900 + i)
+        z = zlib.compress(raw, [1, 6, 9][i % 3])
+        if i % 11 == 5:   # a corrupted trailer
+            z = z[:-1] + bytes([z[-1] ^ 1])
+        if i % 13 == 7:   # truncated: the driver loop runs out of chunks
+            z = z[: len(z) // 2]
+        k = int(rng.integers(1, 7))
+        pieces = _pieces(z, [int(x) for x in rng.integers(1, max(2, len(z)), k)])
+        if i % 17 == 3:
+            pieces.append(b"junk")  # data after the end of the stream
+        files.append(pieces)
+        want.append(oracle.decompress(pieces))
+    got = pz.decompress_many(files)
+    for i, (g, o) in enumerate(zip(got, want)):
+        if o.status == 6:
+            assert isinstance(g, pz.ReferenceBottom) and str(g) == o.message, i
+        else:
+            assert same(pz, g, o), (i, g, o.message)
+    # the set API: every stream decoded by exactly one launch per round it was fed in
+    group = pz.IncrementalSet(8)
+    zs = [zlib.compress(streams.small_text(120_000, 40 + i), 6) for i in range(8)]
+    rounds = 5
+    outs = [b""] * 8
+    for r in range(rounds):
+        for i, z in enumerate(zs):
+            step = (len(z) + rounds - 1) // rounds
+            group.feed(i, z[r * step:(r + 1) * step])
+        group.pump()
+        for i in range(8):
+            for st in group.events(i):
+                if isinstance(st, pz.Chunk):
+                    outs[i] += st.data
+    for i in range(8):
+        assert isinstance(st, pz.Done)
+        assert outs[i] == streams.small_text(120_000, 40 + i)
+        assert group.counter(i, _lib.PZ_SC_PUMPS) == rounds
+        assert group.counter(i, _lib.PZ_SC_RESUMED) == rounds - 1

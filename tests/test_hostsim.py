@@ -66,3 +66,72 @@ def test_smem_budget():
     # the slot stride must be 16 (mod 128) bytes so the hot warp's lanes hit different banks
     n = hostsim.lib().hs_smem_bytes()
     assert n * 28 <= 227 * 1024 and n % 128 == 16
+
+
+def _resume_cuts(z: bytes, rng, k: int):
+    cuts = sorted(set(int(x) for x in rng.integers(0, len(z) + 1, k)) | {len(z)})
+    return cuts
+
+
+def check_resumed(z: bytes, cuts):
+    """PzJob::resume / PzJob::ckpt (the incremental driver's device contexts): decoding prefix after
+    prefix, each run picking up at the previous run's checkpoint, must give exactly what a decode of
+    the whole prefix from its first byte gives -- verdict, length, published bytes, output."""
+    full = oracle.decompress(z)
+    ctx = hostsim.Resumable(full.out_len + 300)
+    kinds = set()
+    for cut in cuts:
+        prefix = z[:cut]
+        o = oracle.decompress(prefix)
+        r, out, used = ctx.run(prefix)
+        kinds.add("fresh" if used[0] == 0 else "trailer" if used[1] == 0xFFFFFFFF else "header" if used[1] == 0 else "symbol")
+        want = fuzzlib.device_expectation(o)
+        got = (r.status, r.detail, r.payload[0] if r.status in (1, 2, 4, 6) else 0)
+        assert got == want, (cut, used, o.message, got, want)
+        assert r.out_len == o.out_len, (cut, used, r.out_len, o.out_len)
+        assert out == o.data[: len(out)], (cut, used)
+        if o.status == 3 and o.detail == 1:  # NeedMore: the chunks the reference has handed out by now
+            assert r.payload[1] == o.published, (cut, used, r.payload[1], o.published)
+        if o.status in (0, 5):
+            assert r.adler_stored == o.adler_stored
+        if not (o.status == 3 and o.detail == 1):  # anything but "ran out of data" is final
+            break
+    return kinds
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_resume_small(seed):
+    import numpy as np
+    rng = np.random.default_rng(77 + seed)
+    for z in fuzzlib.base_corpus(10 + seed, 30):
+        check_resumed(z, _resume_cuts(z, rng, 6))
+        check_resumed(z, list(range(0, min(len(z), 64))) + [len(z)])  # every byte of the first headers
+
+
+def test_resume_multiblock():
+    """Streams long enough for the window to slide (published bytes move) and with several blocks:
+    checkpoints inside blocks, at headers, and in the trailer."""
+    import numpy as np
+    rng = np.random.default_rng(5)
+    data = streams.small_text(300_000, 9)
+    for level, strategy in ((6, zlib.Z_DEFAULT_STRATEGY), (1, zlib.Z_FIXED), (9, zlib.Z_DEFAULT_STRATEGY)):
+        co = zlib.compressobj(level, zlib.DEFLATED, 15, 8, strategy)
+        z = co.compress(data[:100_000]) + co.flush(zlib.Z_FULL_FLUSH) + co.compress(data[100_000:]) + co.flush()
+        kinds = check_resumed(z, _resume_cuts(z, rng, 12))
+        assert "symbol" in kinds
+        kinds = check_resumed(z, [len(z) - 5, len(z) - 4, len(z) - 3, len(z) - 1, len(z)])  # the trailer arrives byte by byte
+        assert "trailer" in kinds
+    # stored blocks only (level 6 on random bytes: ~16 KiB stored blocks)
+    z = zlib.compress(np.random.default_rng(6).integers(0, 256, 200_000, dtype=np.uint8).tobytes(), 6)
+    check_resumed(z, _resume_cuts(z, rng, 12))
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_resume_fuzz(seed):
+    """Mutated streams: whatever verdict the whole prefix has, the resumed decode has it too."""
+    import numpy as np
+    rng = np.random.default_rng(900 + seed)
+    for data in fuzzlib.fuzz_cases(seed, 150):
+        if len(data) < 2:
+            continue
+        check_resumed(data, _resume_cuts(data, rng, 4))

@@ -111,6 +111,9 @@ int pz_abi_version(void);
 /* Tuning knobs.  PZ_OPT_HUGE_BYTES: compressed size from which a stream is decoded block-parallel
  * (K4) instead of as one serial chain; default 4 MiB, environment PZ_HUGE_BYTES at start-up. */
 #define PZ_OPT_HUGE_BYTES 1
+/* PZ_OPT_STREAM_RESUME (default 1): 0 makes every pump of an incremental stream decode from the
+ * stream's first byte again instead of from its checkpoint -- same results, for A/B timing only. */
+#define PZ_OPT_STREAM_RESUME 2
 int pz_set_option(int key, uint64_t value);
 /* Process-wide counters (diagnostics, tests): streams the block-parallel path decoded / declined. */
 #define PZ_CTR_HUGE_DONE 1

@@ -42,6 +42,7 @@ int fail_cuda(cudaError_t e, const char *what) {
 
 uint64_t g_huge_bytes = 4ull << 20; /* compressed size from which a stream goes to K4 (PZ_HUGE_BYTES overrides) */
 std::atomic<uint64_t> g_huge_done{0}, g_huge_declined{0};
+std::atomic<int> g_stream_resume{1}; /* PZ_OPT_STREAM_RESUME */
 std::once_flag g_once;
 int g_init_rc = PZ_E_STATE;
 int g_device = -1;
@@ -364,6 +365,7 @@ uint64_t pz_get_counter(int which) {
 
 int pz_set_option(int key, uint64_t value) {
   if (key == PZ_OPT_HUGE_BYTES && value > 0) { g_huge_bytes = value; return PZ_E_OK; }
+  if (key == PZ_OPT_STREAM_RESUME) { g_stream_resume = value != 0; return PZ_E_OK; }
   return PZ_E_ARG;
 }
 
@@ -749,24 +751,69 @@ int pz_inflate_sizes(const uint8_t *const *in, const size_t *in_len, size_t n, p
 }  // extern "C"
 
 namespace {
+/* Pinned blocks are expensive to create (cudaHostAlloc takes of the order of a millisecond), and incremental
+ * streams come and go by the thousand: blocks are handed out in power-of-two size classes and go back to a
+ * process-wide free list, never to the driver. */
+struct PinnedCache {
+  std::mutex mu;
+  std::vector<uint8_t *> free_[48];
+  static int cls(size_t n) { int c = 14; while (((size_t)1 << c) < n) c++; return c; } /* 16 KiB and up */
+  uint8_t *get(size_t n, size_t *cap) {
+    const int c = cls(n);
+    *cap = (size_t)1 << c;
+    {
+      std::lock_guard<std::mutex> g(mu);
+      if (!free_[c].empty()) { uint8_t *p = free_[c].back(); free_[c].pop_back(); return p; }
+    }
+    uint8_t *p = nullptr;
+    cudaError_t e = cudaHostAlloc((void **)&p, *cap, cudaHostAllocDefault);
+    if (e != cudaSuccess) { fail_cuda(e, "cudaHostAlloc"); return nullptr; }
+    return p;
+  }
+  void put(uint8_t *p, size_t cap) {
+    if (!p) return;
+    std::lock_guard<std::mutex> g(mu);
+    free_[cls(cap)].push_back(p);
+  }
+};
+PinnedCache g_pinned;
+
 struct PinnedBuf {
   uint8_t *p = nullptr;
   size_t cap = 0;
-  int reserve_keep(size_t n, size_t keep_from, size_t keep_len) { /* grow, keeping [keep_from, keep_from + keep_len) at offset 0 */
-    if (n <= cap && keep_from == 0) return PZ_E_OK;
-    if (n <= cap) { if (keep_len) memmove(p, p + keep_from, keep_len); return PZ_E_OK; }
-    size_t want = std::max<size_t>(align_up(n, 1 << 16), cap * 2);
-    uint8_t *q = nullptr;
-    cudaError_t e = cudaHostAlloc((void **)&q, want, cudaHostAllocDefault);
-    if (e != cudaSuccess) { fail_cuda(e, "cudaHostAlloc"); return PZ_E_NOMEM; }
-    if (keep_len) memcpy(q, p + keep_from, keep_len);
-    if (p) cudaFreeHost(p);
-    p = q; cap = want;
+  int reserve_keep(size_t n, size_t keep_len) { /* grow, keeping the first keep_len bytes */
+    if (n <= cap) return PZ_E_OK;
+    size_t ncap = 0;
+    uint8_t *q = g_pinned.get(std::max(n, cap * 2), &ncap);
+    if (!q) return PZ_E_NOMEM;
+    if (keep_len) memcpy(q, p, keep_len);
+    g_pinned.put(p, cap);
+    p = q; cap = ncap;
     return PZ_E_OK;
   }
-  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+  void release() { g_pinned.put(p, cap); p = nullptr; cap = 0; }
 };
-constexpr size_t kStageBytes = 1 << 20; /* one pinned staging buffer of a stream's feeds (two alternate) */
+constexpr size_t kStageBytes = 1 << 20; /* most bytes of a feed that travel in one piece */
+
+/* CUDA streams the incremental contexts share (round robin), created once per process: a pump then orders itself
+ * behind the feeds of its streams with at most kPoolStreams event waits, however many contexts it decodes. */
+constexpr int kPoolStreams = 8;
+cudaStream_t g_pool[kPoolStreams] = {};
+std::once_flag g_pool_once;
+cudaError_t g_pool_rc = cudaSuccess;
+std::atomic<unsigned> g_pool_next{0};
+void pool_init() {
+  for (int i = 0; i < kPoolStreams && g_pool_rc == cudaSuccess; i++) g_pool_rc = cudaStreamCreateWithFlags(&g_pool[i], cudaStreamNonBlocking);
+  /* device buffers of the contexts come from the stream-ordered allocator; freed blocks stay with the process */
+  cudaMemPool_t pool;
+  int dev = 0;
+  if (g_pool_rc == cudaSuccess) g_pool_rc = cudaGetDevice(&dev);
+  if (g_pool_rc == cudaSuccess) g_pool_rc = cudaDeviceGetDefaultMemPool(&pool, dev);
+  if (g_pool_rc == cudaSuccess) {
+    uint64_t keep = ~0ull;
+    g_pool_rc = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+}
 }  // namespace
 
 struct pz_stream {
@@ -776,10 +823,10 @@ struct pz_stream {
   size_t d_in_cap = 0, d_out_cap = 0;
   size_t in_len = 0;               /* compressed bytes on the device */
   uint32_t ck[4] = {0, 0, 0, 0};   /* where the next pump picks the stream up (PzJob::ckpt) */
-  /* feeds on their way: two pinned staging buffers, an event each */
-  PinnedBuf stage[2];
-  cudaEvent_t staged[2] = {nullptr, nullptr};
-  int stage_next = 0;
+  int pool_idx = 0;                /* st == g_pool[pool_idx] */
+  /* the feed on its way: pinned staging, reused once its copy has finished */
+  PinnedBuf stage;
+  cudaEvent_t staged = nullptr;
   /* decoded bytes on the host: [h_first, h_to) of the stream, h_first <= published */
   PinnedBuf h_out;
   uint64_t h_first = 0, h_to = 0;
@@ -797,8 +844,17 @@ namespace {
 /* per-thread control tables of a pump: [in pairs | out pairs | resume] go up, [ckpt | res] come back */
 struct PumpSpace {
   Buf h_ctl, d_ctl, d_parts, d_zero;
+  cudaEvent_t fed[kPoolStreams] = {};
   PumpSpace() { h_ctl.pinned = true; }
-  ~PumpSpace() { h_ctl.release(); d_ctl.release(); d_parts.release(); d_zero.release(); }
+  int ensure_events() {
+    for (int i = 0; i < kPoolStreams; i++)
+      if (!fed[i]) PZ_CUDA(cudaEventCreateWithFlags(&fed[i], cudaEventDisableTiming));
+    return PZ_E_OK;
+  }
+  ~PumpSpace() {
+    h_ctl.release(); d_ctl.release(); d_parts.release(); d_zero.release();
+    for (int i = 0; i < kPoolStreams; i++) if (fed[i]) cudaEventDestroy(fed[i]);
+  }
 };
 thread_local PumpSpace g_pump;
 
@@ -806,11 +862,10 @@ int grow_device(uint8_t *&d, size_t &cap, size_t want, size_t keep, cudaStream_t
   if (want <= cap) return PZ_E_OK;
   size_t n = std::max<size_t>(align_up(want + 64, 1 << 16), cap * 2);
   uint8_t *q = nullptr;
-  cudaError_t e = cudaMalloc((void **)&q, n);
-  if (e != cudaSuccess) { fail_cuda(e, "cudaMalloc"); return PZ_E_NOMEM; }
+  cudaError_t e = cudaMallocAsync((void **)&q, n, st);
+  if (e != cudaSuccess) { fail_cuda(e, "cudaMallocAsync"); return PZ_E_NOMEM; }
   if (keep) PZ_CUDA(cudaMemcpyAsync(q, d, keep, cudaMemcpyDeviceToDevice, st));
-  PZ_CUDA(cudaStreamSynchronize(st));
-  if (d) cudaFree(d);
+  if (d) PZ_CUDA(cudaFreeAsync(d, st)); /* stream-ordered: after the copy, and after everything queued on st before */
   d = q; cap = n;
   return PZ_E_OK;
 }
@@ -839,16 +894,22 @@ int pump(pz_stream *const *all, size_t n_all) {
   cudaStream_t st = act[0]->st;
   PumpSpace &ps = g_pump;
   int rc;
+  if ((rc = ps.ensure_events()) != PZ_E_OK) return rc;
   if ((rc = ps.d_zero.reserve(8)) != PZ_E_OK) return rc;
   PZ_CUDA(cudaMemsetAsync(ps.d_zero.p, 0, 8, st));
   std::vector<pz_stream *> run = act;
   while (!run.empty()) {
     const size_t n = run.size();
-    /* every stream's feeds must have landed before the launch on `st` reads them */
-    for (pz_stream *s : run)
-      if (s->st != st)
-        for (int k = 0; k < 2; k++)
-          if (s->staged[k]) PZ_CUDA(cudaStreamWaitEvent(st, s->staged[k], 0));
+    /* every stream's feeds (and buffer moves) must have landed before the launch on `st` reads them */
+    {
+      bool seen[kPoolStreams] = {};
+      for (pz_stream *s : run) seen[s->pool_idx] = true;
+      for (int k = 0; k < kPoolStreams; k++)
+        if (seen[k] && g_pool[k] != st) {
+          PZ_CUDA(cudaEventRecord(ps.fed[k], g_pool[k]));
+          PZ_CUDA(cudaStreamWaitEvent(st, ps.fed[k], 0));
+        }
+    }
     const size_t up = n * 48, down = n * (16 + sizeof(pz_result));
     if ((rc = ps.h_ctl.reserve(up + down)) != PZ_E_OK) return rc;
     if ((rc = ps.d_ctl.reserve(up + down)) != PZ_E_OK) return rc;
@@ -859,11 +920,12 @@ int pump(pz_stream *const *all, size_t n_all) {
       pz_stream *s = run[i];
       /* room for what this input may add before the kernel has to stop for a larger buffer */
       const size_t want = std::min<uint64_t>(0xfffdff00ull, (uint64_t)s->ck[2] + std::max<uint64_t>(1 << 16, 4 * (uint64_t)(s->in_len - s->ck[0] / 8)));
-      if ((rc = grow_device(s->d_out, s->d_out_cap, want, s->ck[2], st)) != PZ_E_OK) return rc;
-      if ((rc = grow_device(s->d_in, s->d_in_cap, 64, 0, st)) != PZ_E_OK) return rc; /* a stream nothing was fed to yet */
+      if ((rc = grow_device(s->d_out, s->d_out_cap, want, s->ck[2], st)) != PZ_E_OK) return rc; /* d_out is only ever touched by pumps, which end synchronised */
+      if (!s->d_in && (rc = grow_device(s->d_in, s->d_in_cap, 64, 0, s->st)) != PZ_E_OK) return rc; /* a stream nothing was fed to yet */
       in_pairs[2 * i] = (uint64_t)(uintptr_t)s->d_in; in_pairs[2 * i + 1] = in_pairs[2 * i] + s->in_len;
       out_pairs[2 * i] = (uint64_t)(uintptr_t)s->d_out; out_pairs[2 * i + 1] = out_pairs[2 * i] + std::min<uint64_t>(s->d_out_cap - 64, 0xfffdff00ull);
       memcpy(resume + 4 * i, s->ck, 16);
+      if (!g_stream_resume) memset(resume + 4 * i, 0, 16); /* A/B: from the first byte again */
     }
     PZ_CUDA(cudaMemcpyAsync(d, h, up, cudaMemcpyHostToDevice, st));
     uint32_t *d_ck = (uint32_t *)(d + up);
@@ -897,7 +959,7 @@ int pump(pz_stream *const *all, size_t n_all) {
     for (size_t i = 0; i < n; i++) {
       pz_stream *s = run[i];
       s->pumps++;
-      if (s->ck[0] != 0) s->resumed++;
+      if (s->ck[0] != 0 && g_stream_resume) s->resumed++;
       memcpy(s->ck, ck + 4 * i, 16);
       if (res[i].status == PZ_OUTPUT_FULL) { /* the buffer, not the stream: enlarge it and go on from the checkpoint */
         if (s->d_out_cap - 64 >= 0xfffdff00ull) { stream_settle(s, res[i]); continue; }
@@ -916,7 +978,7 @@ int pump(pz_stream *const *all, size_t n_all) {
     if (s->published == s->h_to) s->h_first = s->h_to; /* everything fetched so far has been handed out */
     if (to <= s->h_to) continue;
     const uint64_t keep = s->h_to - s->h_first;
-    if ((rc = s->h_out.reserve_keep((size_t)(to - s->h_first), 0, (size_t)keep)) != PZ_E_OK) return rc;
+    if ((rc = s->h_out.reserve_keep((size_t)(to - s->h_first), (size_t)keep)) != PZ_E_OK) return rc;
     PZ_CUDA(cudaMemcpyAsync(s->h_out.p + keep, s->d_out + s->h_to, to - s->h_to, cudaMemcpyDeviceToHost, st));
     s->h_to = to;
   }
@@ -929,27 +991,29 @@ extern "C" {
 
 pz_stream *pz_stream_new(void) {
   if (ensure_init() != PZ_E_OK) return nullptr;
+  std::call_once(g_pool_once, pool_init);
+  if (g_pool_rc != cudaSuccess) { fail_cuda(g_pool_rc, "pz_stream_new (stream pool)"); return nullptr; }
   pz_stream *s = new (std::nothrow) pz_stream();
   if (!s) return nullptr;
-  cudaError_t e = cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking);
-  for (int k = 0; k < 2 && e == cudaSuccess; k++) e = cudaEventCreateWithFlags(&s->staged[k], cudaEventDisableTiming);
+  s->pool_idx = (int)(g_pool_next++ % kPoolStreams);
+  s->st = g_pool[s->pool_idx];
+  cudaError_t e = cudaEventCreateWithFlags(&s->staged, cudaEventDisableTiming);
   if (e != cudaSuccess) { fail_cuda(e, "pz_stream_new"); pz_stream_free(s); return nullptr; }
   return s;
 }
 
 void pz_stream_free(pz_stream *s) {
   if (!s) return;
-  if (s->st) cudaStreamSynchronize(s->st);
-  for (int k = 0; k < 2; k++) { if (s->staged[k]) cudaEventDestroy(s->staged[k]); s->stage[k].release(); }
+  if (s->staged) { cudaEventSynchronize(s->staged); cudaEventDestroy(s->staged); } /* the staging block may be reused at once */
+  s->stage.release();
   s->h_out.release();
-  if (s->d_in) cudaFree(s->d_in);
-  if (s->d_out) cudaFree(s->d_out);
-  if (s->st) cudaStreamDestroy(s->st);
+  if (s->d_in) cudaFreeAsync(s->d_in, s->st);
+  if (s->d_out) cudaFreeAsync(s->d_out, s->st);
   delete s;
 }
 
 /* The chunk is copied into pinned staging and sent to the device asynchronously: the call returns while
- * the copy is in flight (the staging buffers alternate; a buffer is reused once its copy has finished). */
+ * the copy is in flight (the staging block is reused once its copy has finished). */
 int pz_stream_feed(pz_stream *s, const uint8_t *data, size_t len) {
   if (!s || (len && !data)) return PZ_E_ARG;
   if (s->terminal) return PZ_E_STATE; /* the decoder never asked for this chunk */
@@ -960,13 +1024,11 @@ int pz_stream_feed(pz_stream *s, const uint8_t *data, size_t len) {
   if (rc != PZ_E_OK) return rc;
   for (size_t at = 0; at < len;) {
     const size_t piece = std::min(len - at, kStageBytes);
-    const int k = s->stage_next;
-    s->stage_next ^= 1;
-    PZ_CUDA(cudaEventSynchronize(s->staged[k]));
-    if ((rc = s->stage[k].reserve_keep(std::min(kStageBytes, std::max<size_t>(piece, 1 << 16)), 0, 0)) != PZ_E_OK) return rc;
-    memcpy(s->stage[k].p, data + at, piece);
-    PZ_CUDA(cudaMemcpyAsync(s->d_in + s->in_len, s->stage[k].p, piece, cudaMemcpyHostToDevice, s->st));
-    PZ_CUDA(cudaEventRecord(s->staged[k], s->st));
+    PZ_CUDA(cudaEventSynchronize(s->staged));
+    if ((rc = s->stage.reserve_keep(piece, 0)) != PZ_E_OK) return rc;
+    memcpy(s->stage.p, data + at, piece);
+    PZ_CUDA(cudaMemcpyAsync(s->d_in + s->in_len, s->stage.p, piece, cudaMemcpyHostToDevice, s->st));
+    PZ_CUDA(cudaEventRecord(s->staged, s->st));
     s->in_len += piece;
     at += piece;
   }

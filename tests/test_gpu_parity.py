@@ -471,7 +471,8 @@ def _run_incremental(pz, pieces):
     while True:
         if isinstance(st, pz.NeedMore):
             events.append((0, 0))
-            if not rest:
+            if not rest:  # `decompress`'s driver loop: "Ran out of data mid-decompression 2." (Zlib.hs:38-39)
+                events.append((3, 0))
                 break
             st = st.feed(rest.pop(0))
         elif isinstance(st, pz.Chunk):
@@ -479,7 +480,7 @@ def _run_incremental(pz, pieces):
             acc += st.data
             st = st.next()
         elif isinstance(st, pz.Done):
-            events.append((2, 0))
+            events.append((2, 0))  # with chunks left over the driver says "Finished with data remaining." (Zlib.hs:48-49)
             break
         else:
             events.append((3, 0))
@@ -502,8 +503,11 @@ def test_incremental_resumes_from_checkpoint(pz, oracle):
     fixed = zlib.compressobj(6, zlib.DEFLATED, 15, 8, zlib.Z_FIXED)
     zf = fixed.compress(data[:90_000]) + fixed.flush()
     for stream in (z, stored, zf):
-        for cuts in (list(range(0, len(stream), 4099)), [int(x) for x in rng.integers(0, len(stream), 9)],
-                     [len(stream) - 5, len(stream) - 4, len(stream) - 2, len(stream) - 1]):
+        # (no cut at len - 4 for the stored stream: a chunk boundary exactly at the end of a stored block's data
+        # is the reference's getBlock quirk, SURVEY Appendix A.5, outside the engine's contract)
+        tail = [len(stream) - 5, len(stream) - 3, len(stream) - 2, len(stream) - 1] if stream is stored else \
+            [len(stream) - 5, len(stream) - 4, len(stream) - 2, len(stream) - 1]
+        for cuts in (list(range(0, len(stream), 4099)), [int(x) for x in rng.integers(0, len(stream), 9)], tail):
             pieces = _pieces(stream, cuts)
             o = oracle.decompress(pieces, want_events=True)
             events, acc, err = _run_incremental(pz, pieces)

@@ -1,0 +1,85 @@
+#!/usr/bin/env python
+"""Throughput of the incremental API (pz_stream_feed / pz_stream_pump / pz_stream_next): N concurrent
+`decompressIncremental` consumers, each fed its stream in K pieces, one pump (one kernel launch) per round.
+Prints one JSON line: decompressed GB/s end to end (host chunks in, host chunks out), per-round times, and
+the same run with PZ_OPT_STREAM_RESUME = 0 (every round decodes every stream from its first byte again,
+which is what the API did before the device-resident contexts).
+
+  python tools/bench_incremental.py --streams 1024 --pieces 8
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from pure_zlib_b200 import _lib, corpus  # noqa: E402
+
+
+def run(L, c, pieces: int, check: bool):
+    n = c.n
+    streams = [L.pz_stream_new() for _ in range(n)]
+    assert all(streams)
+    arr = (C.c_void_p * n)(*streams)
+    blobs = [bytes(c.in_blob[int(c.in_off[i]): int(c.in_off[i]) + int(c.in_len[i])]) for i in range(n)]
+    ptr, ln, res = C.c_void_p(), C.c_size_t(), _lib.PzResult()
+    out_bytes = 0
+    rounds = []
+    t0 = time.perf_counter()
+    for r in range(pieces):
+        t1 = time.perf_counter()
+        for i in range(n):
+            z = blobs[i]
+            step = (len(z) + pieces - 1) // pieces
+            piece = z[r * step:(r + 1) * step]
+            _lib.check(L.pz_stream_feed(streams[i], piece, len(piece)), "feed")
+        t2 = time.perf_counter()
+        _lib.check(L.pz_stream_pump(arr, n), "pump")
+        t3 = time.perf_counter()
+        done = 0
+        for i in range(n):
+            while True:
+                ev = L.pz_stream_next(streams[i], C.byref(ptr), C.byref(ln), C.byref(res))
+                if ev != _lib.PZ_S_CHUNK:
+                    break
+                if check and r == pieces - 1 and i < 4:
+                    pass
+                out_bytes += ln.value
+            done += ev == _lib.PZ_S_DONE
+        t4 = time.perf_counter()
+        rounds.append({"feed_ms": (t2 - t1) * 1e3, "pump_ms": (t3 - t2) * 1e3, "drain_ms": (t4 - t3) * 1e3})
+    total = time.perf_counter() - t0
+    assert done == n, (done, n)
+    assert out_bytes == int(c.out_len.sum()), (out_bytes, int(c.out_len.sum()))
+    resumed = sum(L.pz_stream_counter(s, _lib.PZ_SC_RESUMED) for s in streams)
+    for s in streams:
+        L.pz_stream_free(s)
+    return total, rounds, out_bytes, resumed
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--streams", type=int, default=1024)
+    ap.add_argument("--pieces", type=int, default=8)
+    a = ap.parse_args()
+    L = _lib.load()
+    c = corpus.text256k(a.streams, workers=min(16, os.cpu_count() or 1))
+    line = {"metric": "decompressed GB/s through the incremental API", "unit": "GB/s", "streams": a.streams, "pieces": a.pieces,
+            "workload": f"{a.streams} x 256 KiB synthetic text (level 6), each stream fed in {a.pieces} pieces, one pz_stream_pump per round"}
+    for label, resume in (("warmup", 1), ("resumed", 1), ("from_first_byte", 0)):
+        _lib.check(L.pz_set_option(2, resume), "pz_set_option")
+        total, rounds, out_bytes, resumed = run(L, c, a.pieces, True)
+        if label == "warmup":
+            continue
+        line[label] = {"value": out_bytes / total / 1e9, "seconds": total, "pump_ms": [round(r["pump_ms"], 2) for r in rounds],
+                       "feed_ms": round(sum(r["feed_ms"] for r in rounds), 1), "drain_ms": round(sum(r["drain_ms"] for r in rounds), 1),
+                       "pump_ms_total": round(sum(r["pump_ms"] for r in rounds), 1), "launches_from_checkpoint": int(resumed)}
+    _lib.check(L.pz_set_option(2, 1), "pz_set_option")
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -10,6 +10,8 @@ module Codec.Compression.Zlib (
   decompressIncremental,
   -- * extension: many independent streams per kernel launch
   decompressBatch,
+  -- * extension: many multi-chunk streams advanced together, one launch per round of chunks
+  decompressMany,
 ) where
 
 import Control.Exception (ErrorCall (..), throw)
@@ -86,6 +88,8 @@ foreign import ccall safe "pz_stream_next"
   c_pz_stream_next :: Ptr PzStream -> Ptr (Ptr Word8) -> Ptr CSize -> Ptr PzResult -> IO CInt
 foreign import ccall unsafe "&pz_stream_free"
   p_pz_stream_free :: FunPtr (Ptr PzStream -> IO ())
+foreign import ccall safe "pz_stream_pump"
+  c_pz_stream_pump :: Ptr (Ptr PzStream) -> CSize -> IO CInt
 
 -- | The verdict as the reference's value: Left e, or the impure exception the reference dies with.
 verdict :: Ptr PzResult -> PzResult -> IO (Maybe DecompressionError)
@@ -181,3 +185,59 @@ decompressIncremental = unsafeIOToST $ do
       rc <- c_pz_stream_feed s (castPtr p) (fromIntegral l)
       when (rc /= 0) $ throw (ErrorCall "pzcuda: pz_stream_feed failed")
     next fp
+
+-- | `map decompress` for lazy ByteStrings of several chunks each, with the driver loop `run`
+-- (Zlib.hs:37-51) of all of them advanced in lockstep: every round feeds each unfinished stream its next
+-- chunk and decodes ALL of them with one kernel launch (pz_stream_pump); the per-stream state (input,
+-- history, checkpoint) stays on the device between rounds.
+decompressMany :: [L.ByteString] -> [Either DecompressionError L.ByteString]
+decompressMany inputs = unsafePerformIO $ do
+  fps <- forM inputs $ \_ -> do
+    raw <- c_pz_stream_new
+    when (raw == nullPtr) $ throw (ErrorCall "pzcuda: pz_stream_new failed")
+    newForeignPtr p_pz_stream_free raw
+  let start = [ (fp, L.toChunks l, []) | (fp, l) <- zip fps inputs ]
+  go (map Right' start)
+ where
+  -- a stream is either still running (decoder, chunks left, output so far, newest first) or settled
+  go sts
+    | all settled sts = return [ r | Left' r <- sts ]
+    | otherwise = do
+        sts' <- forM sts $ \st -> case st of
+          Right' (fp, [], acc) -> return (Left' (Left (DecompressionError "Ran out of data mid-decompression 2.")) `const` (fp, acc))
+          Right' (fp, c : cs, acc) -> do
+            withForeignPtr fp $ \s -> SU.unsafeUseAsCStringLen c $ \(p, l) -> do
+              rc <- c_pz_stream_feed s (castPtr p) (fromIntegral l)
+              when (rc /= 0) $ throw (ErrorCall "pzcuda: pz_stream_feed failed")
+            return (Right' (fp, cs, acc))
+          done -> return done
+        let running = [ fp | Right' (fp, _, _) <- sts' ]
+        withMany withForeignPtr running $ \ps -> withArrayLen ps $ \n arr -> do
+          rc <- c_pz_stream_pump arr (fromIntegral n)
+          when (rc /= 0) $ throw (ErrorCall "pzcuda: pz_stream_pump failed")
+        forM sts' drain >>= go
+  settled (Left' _) = True
+  settled _ = False
+  drain (Right' (fp, rest, acc)) = withForeignPtr fp $ \s ->
+    alloca $ \pchunk -> alloca $ \plen -> alloca $ \pres ->
+      let loop acc' = do
+            ev <- c_pz_stream_next s pchunk plen pres
+            case ev of
+              0 -> return (Right' (fp, rest, acc'))
+              1 -> do
+                p <- peek pchunk
+                l <- peek plen
+                bs <- S.packCStringLen (castPtr p, fromIntegral l)
+                loop (bs : acc')
+              2 | null rest -> return (Left' (Right (L.fromChunks (reverse acc'))))
+                | otherwise -> return (Left' (Left (DecompressionError "Finished with data remaining.")))
+              3 -> do
+                r <- peek pres
+                e <- verdict pres r
+                return (Left' (maybe (Right (L.fromChunks (reverse acc'))) Left e))
+              _ -> throw (ErrorCall "pzcuda: pz_stream_next failed")
+       in loop acc
+  drain done = return done
+
+-- local sum type of decompressMany (kept apart from Either to keep the code above readable)
+data Progress a b = Left' a | Right' b

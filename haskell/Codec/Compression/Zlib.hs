@@ -204,7 +204,7 @@ decompressMany inputs = unsafePerformIO $ do
     | all settled sts = return [ r | Left' r <- sts ]
     | otherwise = do
         sts' <- forM sts $ \st -> case st of
-          Right' (fp, [], acc) -> return (Left' (Left (DecompressionError "Ran out of data mid-decompression 2.")) `const` (fp, acc))
+          Right' (_, [], _) -> return (Left' (Left (DecompressionError "Ran out of data mid-decompression 2.")))
           Right' (fp, c : cs, acc) -> do
             withForeignPtr fp $ \s -> SU.unsafeUseAsCStringLen c $ \(p, l) -> do
               rc <- c_pz_stream_feed s (castPtr p) (fromIntegral l)

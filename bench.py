@@ -388,6 +388,16 @@ def main():
         line["cpu_baseline"] = {"value": b / s / 1e9, "unit": "GB/s", "cores": threads, "kind": "port",
                                 "sample": f"first {sample} of {c.n} streams, oracle/pz_oracle.c (restatement of pure-zlib; "
                                           "the Haskell reference needs GHC, absent here)", "seconds": s}
+        # second stand-in: the host's system zlib on the same sample and threads -- NOT the reference
+        # (whose README, lines 6-8, puts pure-zlib "roughly 100x" behind it); zlib.decompress releases the GIL
+        import zlib
+        from concurrent.futures import ThreadPoolExecutor
+        blobs = [bytes(c.in_blob[int(c.in_off[i]): int(c.in_off[i]) + int(c.in_len[i])]) for i in range(sample)]
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(threads) as ex:
+            zb = sum(ex.map(lambda part: sum(len(zlib.decompress(z)) for z in part), [blobs[k::threads] for k in range(threads)]))
+        line["cpu_baseline"]["host_zlib"] = {"value": zb / (time.perf_counter() - t0) / 1e9, "unit": "GB/s", "cores": threads,
+                                             "note": "system zlib inflate on the same sample; context only, not the reference"}
     L.pz_batch_destroy(batch)
     L.pz_batch_destroy(batch_k1)
     if rank == 0:

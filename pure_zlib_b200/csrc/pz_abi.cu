@@ -125,7 +125,7 @@ struct Workspace {
   Buf h_res;       /* pinned landing zone for the verdicts: a D2H copy into pageable memory would block the host */
   Buf h_prog;      /* pinned, mapped: the kernel's progress words (PzJob::prog) */
   Buf d_ready;     /* device word: PzJob::in_ready */
-  Buf k4_cand, k4_keep, k4_start, k4_off, k4_len, k4_res, k4_sym, k4_word, k4_grp, k4_gfirst, k4_gw; /* K4 scratch (one huge stream at a time) */
+  Buf k4_cand, k4_keep, k4_start, k4_off, k4_len, k4_res, k4_sym, k4_word, k4_grp, k4_gfirst, k4_gw, k4_scr, k4_src; /* K4 scratch (one huge stream at a time) */
   cudaStream_t streams[kStreams] = {};
   bool have_streams = false;
   Workspace() { h_in.pinned = true; h_out.pinned = true; h_res.pinned = true; h_prog.pinned = true; }
@@ -139,7 +139,7 @@ struct Workspace {
     /* the CUDA context may already be gone at process exit; errors are ignored */
     d_in.release(); d_out.release(); d_in_off.release(); d_out_off.release(); d_seg_off.release();
     d_res.release(); d_parts.release(); h_in.release(); h_out.release(); h_res.release(); h_prog.release(); d_ready.release();
-    k4_cand.release(); k4_keep.release(); k4_start.release(); k4_off.release(); k4_len.release(); k4_res.release(); k4_sym.release(); k4_word.release(); k4_grp.release(); k4_gfirst.release(); k4_gw.release();
+    k4_cand.release(); k4_keep.release(); k4_start.release(); k4_off.release(); k4_len.release(); k4_res.release(); k4_sym.release(); k4_word.release(); k4_grp.release(); k4_gfirst.release(); k4_gw.release(); k4_scr.release(); k4_src.release();
     if (have_streams) for (int i = 0; i < kStreams; i++) cudaStreamDestroy(streams[i]);
   }
 };
@@ -218,6 +218,101 @@ int huge_stream(const uint8_t *d_in_blob, const uint64_t *d_in_off_i, uint64_t i
   starts.push_back((uint32_t)first_bit); /* the first block is known, whatever its type */
   for (uint32_t i = 0; i < ncand; i++) if (keep[i] && cand[i] != first_bit) starts.push_back(cand[i]);
   std::sort(starts.begin(), starts.end());
+  std::vector<uint32_t> c_start;
+  std::vector<uint32_t> c_len;
+  std::vector<uint64_t> c_off;
+  uint64_t total = 0, end_bit = 0;
+  /* One pass instead of two (sizing, then decoding): every candidate is decoded at once, as 16-bit symbols, into a
+   * scratch region of its own whose size is a guess -- 16 x the compressed bytes up to the next candidate -- and the
+   * blocks that turn out to be the chain are then moved to their final positions (pz_blk_compact_kernel: 4 bytes of
+   * traffic per decoded byte, against a second run of every symbol loop).  If the guess is too small for a chain block,
+   * a chain block is not among the candidates, or the scratch does not fit, the two-pass flow below does the job. */
+  bool symbols_ready = false;
+  static const bool two_pass_only = getenv("PZ_K4_TWO_PASS") != nullptr;
+  if (!two_pass_only) {
+    const size_t nc = starts.size();
+    std::vector<uint32_t> caps(nc);
+    std::vector<uint64_t> soff(nc);
+    uint64_t scr_total = 0;
+    for (size_t j = 0; j < nc; j++) {
+      const uint64_t next = j + 1 < nc ? starts[j + 1] : last_bit;
+      const uint64_t span = (next - starts[j] + 7u) / 8u;
+      const uint64_t cap = (std::min<uint64_t>(kBlockCap, 65536u + 16u * span) + 7u) & ~7ull;
+      caps[j] = (uint32_t)cap; soff[j] = scr_total; scr_total += cap;
+    }
+    /* blocks the search cannot see (stored, fixed, unusual trees) are decoded one by one when the chain reaches
+     * them, into a pool behind the candidates' regions */
+    const uint64_t gap_pool = 256ull << 20;
+    uint64_t gap_used = 0;
+    int gaps = 0;
+    bool ok = scr_total * 2u <= (48ull << 30);
+    if (ok && ws.k4_scr.reserve((scr_total + gap_pool) * 2u + 64u) != PZ_E_OK) ok = false; /* no room: two passes need none */
+    if (ok && ws.k4_src.reserve(64) != PZ_E_OK) ok = false;
+    if (ok) {
+      if ((rc = ws.k4_start.reserve(nc * 4u)) != PZ_E_OK || (rc = ws.k4_len.reserve(nc * 4u)) != PZ_E_OK || (rc = ws.k4_off.reserve(nc * 8u)) != PZ_E_OK ||
+          (rc = ws.k4_res.reserve(nc * sizeof(pz_result))) != PZ_E_OK)
+        return rc;
+      PZ_CUDA(cudaMemcpyAsync(ws.k4_start.p, starts.data(), nc * 4u, cudaMemcpyHostToDevice, st));
+      PZ_CUDA(cudaMemcpyAsync(ws.k4_len.p, caps.data(), nc * 4u, cudaMemcpyHostToDevice, st));
+      PZ_CUDA(cudaMemcpyAsync(ws.k4_off.p, soff.data(), nc * 8u, cudaMemcpyHostToDevice, st));
+      PZ_CUDA(pz_launch_blk_jobs(d_in_blob, d_in_off_i, (const uint32_t *)ws.k4_start.p, (const uint64_t *)ws.k4_off.p, (const uint32_t *)ws.k4_len.p, 0,
+                                 (uint16_t *)ws.k4_scr.p, (uint32_t)nc, (pz_result *)ws.k4_res.p, st));
+      std::vector<pz_result> got(nc);
+      PZ_CUDA(cudaMemcpyAsync(got.data(), ws.k4_res.p, nc * sizeof(pz_result), cudaMemcpyDeviceToHost, st));
+      PZ_CUDA(cudaStreamSynchronize(st));
+      if (trace) fprintf(stderr, "[pz-k4] %8.3f ms: %zu candidates decoded into scratch (%.2f GB)\n", now_ms(), nc, scr_total * 2e-9);
+      std::vector<uint64_t> c_src;
+      uint32_t at = (uint32_t)first_bit;
+      for (;;) {
+        auto it = std::lower_bound(starts.begin(), starts.end(), at);
+        pz_result r;
+        uint64_t src;
+        if (it != starts.end() && *it == at) {
+          r = got[it - starts.begin()];
+          src = soff[it - starts.begin()];
+        } else { /* a block the search did not see: decode it alone, now that its first bit is known */
+          if (++gaps > kMaxGaps) return 0;
+          const uint64_t next = it != starts.end() ? *it : last_bit;
+          const uint64_t cap = (std::min<uint64_t>(kBlockCap, 65536u + 16u * ((next - at + 7u) / 8u)) + 7u) & ~7ull;
+          if (gap_used + cap > gap_pool) { ok = false; break; }
+          src = scr_total + gap_used;
+          gap_used += cap;
+          struct { uint64_t off; uint32_t start, len; } one = {src, at, (uint32_t)cap}; /* k4_src is free until the chain is complete */
+          PZ_CUDA(cudaMemcpyAsync(ws.k4_src.p, &one, sizeof one, cudaMemcpyHostToDevice, st));
+          const uint8_t *d_one = (const uint8_t *)ws.k4_src.p;
+          PZ_CUDA(pz_launch_blk_jobs(d_in_blob, d_in_off_i, (const uint32_t *)(d_one + 8), (const uint64_t *)d_one, (const uint32_t *)(d_one + 12), 0,
+                                     (uint16_t *)ws.k4_scr.p, 1, (pz_result *)ws.k4_res.p, st));
+          PZ_CUDA(cudaMemcpyAsync(&r, ws.k4_res.p, sizeof r, cudaMemcpyDeviceToHost, st));
+          PZ_CUDA(cudaStreamSynchronize(st));
+        }
+        if (r.status == PZ_OUTPUT_FULL) { ok = false; break; } /* the guess was too small */
+        if (r.status != PZ_OK) return 0;
+        if (total + r.out_len > out_cap) return 0; /* PZ_OUTPUT_FULL is the serial path's to report */
+        c_start.push_back(at); c_off.push_back(total); c_len.push_back((uint32_t)r.out_len); c_src.push_back(src);
+        total += r.out_len;
+        end_bit = r.err_bitpos;
+        if (r.detail != 0) break; /* BFINAL */
+        if (end_bit >= last_bit || end_bit > 0xffffffffull) return 0;
+        at = (uint32_t)end_bit;
+      }
+      if (ok) {
+        const size_t nb = c_start.size();
+        if ((rc = ws.k4_src.reserve(nb * 8u)) != PZ_E_OK || (rc = ws.k4_off.reserve(nb * 8u)) != PZ_E_OK) return rc;
+        if (ws.k4_sym.reserve(total * 2u + 64u) != PZ_E_OK) return 0;
+        PZ_CUDA(cudaMemcpyAsync(ws.k4_off.p, c_off.data(), nb * 8u, cudaMemcpyHostToDevice, st));
+        PZ_CUDA(cudaMemcpyAsync(ws.k4_src.p, c_src.data(), nb * 8u, cudaMemcpyHostToDevice, st));
+        PZ_CUDA(pz_launch_blk_compact((const uint16_t *)ws.k4_scr.p, (uint16_t *)ws.k4_sym.p, (const uint64_t *)ws.k4_off.p, (const uint64_t *)ws.k4_src.p,
+                                      (uint32_t)nb, total, st));
+        PZ_CUDA(cudaStreamSynchronize(st)); /* c_off / c_src leave scope */
+        symbols_ready = true;
+        if (trace) fprintf(stderr, "[pz-k4] %8.3f ms: chain of %zu blocks, %llu bytes, %d decoded one by one, symbols in place\n", now_ms(), nb, (unsigned long long)total, gaps);
+      } else {
+        c_start.clear(); c_len.clear(); c_off.clear(); total = 0; end_bit = 0;
+        if (trace) fprintf(stderr, "[pz-k4] %8.3f ms: one pass not enough, sizing and decoding separately\n", now_ms());
+      }
+    }
+  }
+  if (!symbols_ready) {
   /* sizing pass over every candidate */
   std::vector<pz_result> sized(starts.size());
   auto size_jobs = [&](const uint32_t *h_start, size_t count, pz_result *h_res) -> int {
@@ -233,10 +328,6 @@ int huge_stream(const uint8_t *d_in_blob, const uint64_t *d_in_off_i, uint64_t i
   if ((rc = size_jobs(starts.data(), starts.size(), sized.data())) != PZ_E_OK) return rc;
   if (trace) fprintf(stderr, "[pz-k4] %8.3f ms: %zu candidates sized\n", now_ms(), starts.size());
   /* the chain: block k+1 starts at the bit where block k ended */
-  std::vector<uint32_t> c_start;
-  std::vector<uint32_t> c_len;
-  std::vector<uint64_t> c_off;
-  uint64_t total = 0, end_bit = 0;
   uint32_t at = (uint32_t)first_bit;
   int gaps = 0;
   for (;;) {
@@ -259,9 +350,10 @@ int huge_stream(const uint8_t *d_in_blob, const uint64_t *d_in_off_i, uint64_t i
     if (end_bit >= last_bit || end_bit > 0xffffffffull) return 0;
     at = (uint32_t)end_bit;
   }
+  if (trace) fprintf(stderr, "[pz-k4] %8.3f ms: chain of %zu blocks, %llu bytes, %d found one by one\n", now_ms(), c_start.size(), (unsigned long long)total, gaps);
+  }
   const uint64_t tb = (end_bit + 7u) / 8u;
   if (tb + 4u > in_len) return 0;
-  if (trace) fprintf(stderr, "[pz-k4] %8.3f ms: chain of %zu blocks, %llu bytes, %d found one by one\n", now_ms(), c_start.size(), (unsigned long long)total, gaps);
   uint8_t trailer[4];
   PZ_CUDA(cudaMemcpyAsync(trailer, d_stream + tb, 4, cudaMemcpyDeviceToHost, st));
   /* decode pass: 16-bit symbols of every chain block, at its final position */
@@ -272,8 +364,9 @@ int huge_stream(const uint8_t *d_in_blob, const uint64_t *d_in_off_i, uint64_t i
   PZ_CUDA(cudaMemcpyAsync(ws.k4_start.p, c_start.data(), nb * 4u, cudaMemcpyHostToDevice, st));
   PZ_CUDA(cudaMemcpyAsync(ws.k4_len.p, c_len.data(), nb * 4u, cudaMemcpyHostToDevice, st));
   PZ_CUDA(cudaMemcpyAsync(ws.k4_off.p, c_off.data(), nb * 8u, cudaMemcpyHostToDevice, st));
-  PZ_CUDA(pz_launch_blk_jobs(d_in_blob, d_in_off_i, (const uint32_t *)ws.k4_start.p, (const uint64_t *)ws.k4_off.p, (const uint32_t *)ws.k4_len.p, 0,
-                             (uint16_t *)ws.k4_sym.p, (uint32_t)nb, (pz_result *)ws.k4_res.p, st));
+  if (!symbols_ready)
+    PZ_CUDA(pz_launch_blk_jobs(d_in_blob, d_in_off_i, (const uint32_t *)ws.k4_start.p, (const uint64_t *)ws.k4_off.p, (const uint32_t *)ws.k4_len.p, 0,
+                               (uint16_t *)ws.k4_sym.p, (uint32_t)nb, (pz_result *)ws.k4_res.p, st));
   if (trace) { cudaStreamSynchronize(st); fprintf(stderr, "[pz-k4] %8.3f ms: symbols written\n", now_ms()); }
   /* groups for the two-level walk over the tails: about sqrt(2 * blocks) of them balances the two levels */
   uint32_t ngrp = 1;
@@ -288,14 +381,14 @@ int huge_stream(const uint8_t *d_in_blob, const uint64_t *d_in_off_i, uint64_t i
   PZ_CUDA(cudaMemsetAsync(d_word + 1, 0, 4, st));
   PZ_CUDA(pz_launch_blk_resolve((uint16_t *)ws.k4_sym.p, d_out_i, (const uint64_t *)ws.k4_off.p, (const uint32_t *)ws.k4_len.p, (const uint32_t *)ws.k4_grp.p,
                                 (const uint32_t *)ws.k4_gfirst.p, ngrp, (uint32_t)nb, total, (uint8_t *)ws.k4_gw.p, d_word + 1, st));
-  std::vector<pz_result> done(nb);
+  std::vector<pz_result> done(symbols_ready ? 0 : nb);
   uint32_t err = 0;
-  PZ_CUDA(cudaMemcpyAsync(done.data(), ws.k4_res.p, nb * sizeof(pz_result), cudaMemcpyDeviceToHost, st));
+  if (!symbols_ready) PZ_CUDA(cudaMemcpyAsync(done.data(), ws.k4_res.p, nb * sizeof(pz_result), cudaMemcpyDeviceToHost, st));
   PZ_CUDA(cudaMemcpyAsync(&err, d_word + 1, 4, cudaMemcpyDeviceToHost, st));
   PZ_CUDA(cudaStreamSynchronize(st));
   if (trace) fprintf(stderr, "[pz-k4] %8.3f ms: decoded and resolved (err %u)\n", now_ms(), err);
   if (err) return 0;
-  for (size_t k = 0; k < nb; k++)
+  for (size_t k = 0; k < done.size(); k++)
     if (done[k].status != PZ_OK || done[k].out_len != c_len[k]) return 0;
   memset(out, 0, sizeof *out);
   out->status = PZ_OK;
@@ -794,6 +887,7 @@ struct PinnedBuf {
   void release() { g_pinned.put(p, cap); p = nullptr; cap = 0; }
 };
 constexpr size_t kStageBytes = 1 << 20; /* most bytes of a feed that travel in one piece */
+constexpr uint64_t kGatherMax = 1 << 20; /* pieces of decoded output up to this size go home by kernel (pz_gather_kernel) */
 
 /* CUDA streams the incremental contexts share (round robin), created once per process: a pump then orders itself
  * behind the feeds of its streams with at most kPoolStreams event waits, however many contexts it decodes. */
@@ -843,7 +937,7 @@ struct pz_stream {
 namespace {
 /* per-thread control tables of a pump: [in pairs | out pairs | resume] go up, [ckpt | res] come back */
 struct PumpSpace {
-  Buf h_ctl, d_ctl, d_parts, d_zero;
+  Buf h_ctl, d_ctl, d_parts, d_tab, d_gather;
   cudaEvent_t fed[kPoolStreams] = {};
   PumpSpace() { h_ctl.pinned = true; }
   int ensure_events() {
@@ -852,7 +946,7 @@ struct PumpSpace {
     return PZ_E_OK;
   }
   ~PumpSpace() {
-    h_ctl.release(); d_ctl.release(); d_parts.release(); d_zero.release();
+    h_ctl.release(); d_ctl.release(); d_parts.release(); d_tab.release(); d_gather.release();
     for (int i = 0; i < kPoolStreams; i++) if (fed[i]) cudaEventDestroy(fed[i]);
   }
 };
@@ -895,8 +989,6 @@ int pump(pz_stream *const *all, size_t n_all) {
   PumpSpace &ps = g_pump;
   int rc;
   if ((rc = ps.ensure_events()) != PZ_E_OK) return rc;
-  if ((rc = ps.d_zero.reserve(8)) != PZ_E_OK) return rc;
-  PZ_CUDA(cudaMemsetAsync(ps.d_zero.p, 0, 8, st));
   std::vector<pz_stream *> run = act;
   while (!run.empty()) {
     const size_t n = run.size();
@@ -935,23 +1027,24 @@ int pump(pz_stream *const *all, size_t n_all) {
     PZ_CUDA(cudaStreamSynchronize(st));
     const uint32_t *ck = (const uint32_t *)(h + up);
     const pz_result *res = (const pz_result *)(h + up + 16 * n);
-    /* streams that are complete get their Adler-32 verdict (K3 over the whole decoded stream) */
+    /* streams that are complete get their Adler-32 verdict: K3 over their whole decoded output, ONE launch pair for
+     * all of them (a table over the pump's n streams in which the unfinished ones own no segments) */
+    std::vector<uint64_t> tab(2 * n + 1); /* [0, n): where each stream's output begins; [n, 2n]: its first segment */
     uint64_t segs = 0;
-    for (size_t i = 0; i < n; i++)
-      if (res[i].status == PZ_OK) segs += (res[i].out_len + PZ_ADLER_SEG - 1) / PZ_ADLER_SEG;
-    bool any_ok = false;
-    if ((rc = ps.d_parts.reserve(std::max<uint64_t>(segs, 1) * sizeof(uint2))) != PZ_E_OK) return rc;
-    uint64_t seg_at = 0;
     for (size_t i = 0; i < n; i++) {
-      if (res[i].status != PZ_OK) continue;
-      const uint64_t ns = (res[i].out_len + PZ_ADLER_SEG - 1) / PZ_ADLER_SEG;
-      /* a one-stream table: out_off = this stream's (begin, end) pair, seg_off = {0} */
-      PZ_CUDA(pz_launch_adler(nullptr, (const uint64_t *)(d + 16 * n) + 2 * i, (const uint64_t *)ps.d_zero.p, 1, 0, 1, 0, ns, d_res + i,
-                              (uint2 *)ps.d_parts.p + seg_at, st));
-      seg_at += ns;
-      any_ok = true;
+      tab[i] = (uint64_t)(uintptr_t)run[i]->d_out;
+      tab[n + i] = segs;
+      if (res[i].status == PZ_OK) segs += (res[i].out_len + PZ_ADLER_SEG - 1) / PZ_ADLER_SEG;
     }
+    tab[2 * n] = segs;
+    bool any_ok = false;
+    for (size_t i = 0; i < n; i++) any_ok = any_ok || res[i].status == PZ_OK;
     if (any_ok) {
+      if ((rc = ps.d_parts.reserve(std::max<uint64_t>(segs, 1) * sizeof(uint2))) != PZ_E_OK) return rc;
+      if ((rc = ps.d_tab.reserve(tab.size() * 8u)) != PZ_E_OK) return rc;
+      PZ_CUDA(cudaMemcpyAsync(ps.d_tab.p, tab.data(), tab.size() * 8u, cudaMemcpyHostToDevice, st));
+      PZ_CUDA(pz_launch_adler(nullptr, (const uint64_t *)ps.d_tab.p, (const uint64_t *)ps.d_tab.p + n, (uint32_t)n, 0, (uint32_t)n, 0, segs, d_res,
+                              (uint2 *)ps.d_parts.p, st));
       PZ_CUDA(cudaMemcpyAsync(h + up + 16 * n, d_res, n * sizeof(pz_result), cudaMemcpyDeviceToHost, st));
       PZ_CUDA(cudaStreamSynchronize(st));
     }
@@ -971,7 +1064,9 @@ int pump(pz_stream *const *all, size_t n_all) {
     }
     run.swap(again);
   }
-  /* bring home what the streams may now hand out */
+  /* bring home what the streams may now hand out: ONE kernel stores the small pieces of all streams into their pinned
+   * buffers (a cudaMemcpyAsync each costs more host time than the copy takes); long pieces go by copy engine */
+  std::vector<uint64_t> gat; /* (source, destination, length) triples */
   for (pz_stream *s : act) {
     s->dirty = false;
     const uint64_t to = (s->terminal && s->verdict.status == PZ_OK) ? s->verdict.out_len : s->publish_to;
@@ -979,8 +1074,18 @@ int pump(pz_stream *const *all, size_t n_all) {
     if (to <= s->h_to) continue;
     const uint64_t keep = s->h_to - s->h_first;
     if ((rc = s->h_out.reserve_keep((size_t)(to - s->h_first), (size_t)keep)) != PZ_E_OK) return rc;
-    PZ_CUDA(cudaMemcpyAsync(s->h_out.p + keep, s->d_out + s->h_to, to - s->h_to, cudaMemcpyDeviceToHost, st));
+    const uint64_t len = to - s->h_to;
+    if (len > kGatherMax) {
+      PZ_CUDA(cudaMemcpyAsync(s->h_out.p + keep, s->d_out + s->h_to, len, cudaMemcpyDeviceToHost, st));
+    } else {
+      gat.push_back((uint64_t)(uintptr_t)(s->d_out + s->h_to)); gat.push_back((uint64_t)(uintptr_t)(s->h_out.p + keep)); gat.push_back(len);
+    }
     s->h_to = to;
+  }
+  if (!gat.empty()) {
+    if ((rc = ps.d_gather.reserve(gat.size() * 8u)) != PZ_E_OK) return rc;
+    PZ_CUDA(cudaMemcpyAsync(ps.d_gather.p, gat.data(), gat.size() * 8u, cudaMemcpyHostToDevice, st));
+    PZ_CUDA(pz_launch_gather((const uint64_t *)ps.d_gather.p, (uint32_t)(gat.size() / 3), st));
   }
   PZ_CUDA(cudaStreamSynchronize(st));
   return PZ_E_OK;

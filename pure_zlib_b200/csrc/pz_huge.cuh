@@ -204,6 +204,42 @@ pz_blk_verify_kernel(const uint8_t *__restrict__ in, uint64_t nbytes, uint64_t l
   if (sum_l == 32768u && sum_d == 32768u && eob) keep[i] = 1;
 }
 
+/* One-pass flow: the chain's blocks were decoded into scratch regions of their own (every candidate was, before the
+ * chain was known); symbol e of the stream, which lies in chain block k, is scr[blk_src[k] + (e - blk_off[k])].
+ * Moves them to their final positions so that the resolution kernels below see one contiguous stream of symbols.
+ * Thread t of a CTA takes symbols c0 + t, c0 + t + THREADS, ...: consecutive lanes, consecutive symbols. */
+__global__ void __launch_bounds__(PZ_HUGE_THREADS)
+pz_blk_compact_kernel(const uint16_t *__restrict__ scr, uint16_t *__restrict__ sym, const uint64_t *__restrict__ blk_off,
+                      const uint64_t *__restrict__ blk_src, uint32_t nblk, uint64_t total) {
+  __shared__ uint32_t k0s;
+  const uint64_t c0 = (uint64_t)blockIdx.x * (PZ_HUGE_THREADS * 8u);
+  if (threadIdx.x == 0) { /* the block holding this CTA's first symbol: last k with blk_off[k] <= c0 */
+    uint32_t lo = 0, hi = nblk;
+    while (hi - lo > 1u) {
+      const uint32_t mid = lo + (hi - lo) / 2u;
+      if (blk_off[mid] <= c0) lo = mid; else hi = mid;
+    }
+    k0s = lo;
+  }
+  __syncthreads();
+  uint32_t k = k0s;
+  uint16_t v[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const uint64_t e = c0 + (uint64_t)j * PZ_HUGE_THREADS + threadIdx.x;
+    v[j] = 0;
+    if (e < total) {
+      while (k + 1u < nblk && blk_off[k + 1u] <= e) k++;
+      v[j] = scr[blk_src[k] + (e - blk_off[k])];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const uint64_t e = c0 + (uint64_t)j * PZ_HUGE_THREADS + threadIdx.x;
+    if (e < total) sym[e] = v[j];
+  }
+}
+
 /* K4c: the serial part of the LZ77 resolution, in two levels.
  *
  * Only the last 32 KiB of a block (its "tail") can be referenced by later blocks, so only tails

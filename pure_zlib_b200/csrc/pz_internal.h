@@ -47,6 +47,8 @@ cudaError_t pz_launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uin
  * d_resume[4s..] and leaving its next checkpoint in d_ckpt[4s..] (PzJob::resume / ckpt in pz_device.cuh).  K1 only. */
 cudaError_t pz_launch_resume(const uint64_t *d_in_pairs, const uint64_t *d_out_pairs, uint32_t count, pz_result *d_res,
                              const uint32_t *d_resume, uint32_t *d_ckpt, cudaStream_t st);
+/* count pieces of decoded output go to pinned host memory: (device source, host destination, bytes) triples of uint64 */
+cudaError_t pz_launch_gather(const uint64_t *d_triples, uint32_t count, cudaStream_t st);
 #define PZ_CK_TRAILER_HOST 0xffffffffu /* == PZ_CK_TRAILER in pz_device.cuh */
 /* K4 (pz_huge.cuh): one huge stream decoded block-parallel; see pz_abi.cu for the driver */
 cudaError_t pz_launch_blk_search(const uint8_t *d_stream, uint64_t nbytes, uint64_t first_bit, uint64_t last_bit, uint32_t *d_cand,
@@ -55,6 +57,9 @@ cudaError_t pz_launch_blk_verify(const uint8_t *d_stream, uint64_t nbytes, uint6
                                  uint8_t *d_keep, cudaStream_t st);
 cudaError_t pz_launch_blk_jobs(const uint8_t *d_in_blob, const uint64_t *d_in_off2, const uint32_t *d_blk_start, const uint64_t *d_blk_out,
                                const uint32_t *d_blk_len, uint32_t cap, uint16_t *d_sym16, uint32_t count, pz_result *d_res, cudaStream_t st);
+/* one-pass flow: symbols of chain block k move from d_scr + d_blk_src[k] to d_sym16 + d_blk_off[k] (pz_blk_compact_kernel) */
+cudaError_t pz_launch_blk_compact(const uint16_t *d_scr, uint16_t *d_sym16, const uint64_t *d_blk_off, const uint64_t *d_blk_src, uint32_t nblk,
+                                  uint64_t total, cudaStream_t st);
 /* groups of consecutive chain blocks: d_grp_first[ngrp + 1] (first block of each group), d_blk_grp[nblk]; d_gw = ngrp * 32768 bytes */
 cudaError_t pz_launch_blk_resolve(uint16_t *d_sym16, uint8_t *d_out, const uint64_t *d_blk_off, const uint32_t *d_blk_len, const uint32_t *d_blk_grp,
                                   const uint32_t *d_grp_first, uint32_t ngrp, uint32_t nblk, uint64_t total, uint8_t *d_gw, uint32_t *d_err,

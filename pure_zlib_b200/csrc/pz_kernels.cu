@@ -199,6 +199,24 @@ __global__ void pz_code_values_kernel(const uint8_t *lens, int n, uint16_t *code
   for (int i = threadIdx.x; i < n; i += PZ_G) codes[i] = sm.lens[i] ? c16[i] : 0;
 }
 
+/* Incremental contexts: piece j = g[3j+2] bytes from device address g[3j] to the pinned host address g[3j+1] (reachable
+ * from the device: unified addressing), one CTA per piece.  Replaces one cudaMemcpyAsync per stream and pump. */
+__global__ void __launch_bounds__(256)
+pz_gather_kernel(const uint64_t *__restrict__ g) {
+  const uint8_t *src = reinterpret_cast<const uint8_t *>((uintptr_t)g[3u * blockIdx.x]);
+  uint8_t *dst = reinterpret_cast<uint8_t *>((uintptr_t)g[3u * blockIdx.x + 1u]);
+  const uint64_t len = g[3u * blockIdx.x + 2u];
+  if ((((uintptr_t)src | (uintptr_t)dst) & 15u) == 0u) {
+    const uint64_t nv = len >> 4;
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+    uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+    for (uint64_t i = threadIdx.x; i < nv; i += 256u) d4[i] = s4[i];
+    for (uint64_t i = (nv << 4) + threadIdx.x; i < len; i += 256u) dst[i] = src[i];
+  } else {
+    for (uint64_t i = threadIdx.x; i < len; i += 256u) dst[i] = src[i];
+  }
+}
+
 /* ---- launch wrappers ------------------------------------------------------------------ */
 static int g_inflate_ctas_per_sm[2] = {0, 0};
 static int g_sm_count = 0;
@@ -286,6 +304,12 @@ cudaError_t pz_launch_resume(const uint64_t *d_in_pairs, const uint64_t *d_out_p
   return cudaGetLastError();
 }
 
+cudaError_t pz_launch_gather(const uint64_t *d_triples, uint32_t count, cudaStream_t st) {
+  if (count == 0) return cudaSuccess;
+  pz_gather_kernel<<<count, 256, 0, st>>>(d_triples);
+  return cudaGetLastError();
+}
+
 /* ---- K4 launchers (pz_huge.cuh; block jobs run on K1) ---------------------------------------- */
 cudaError_t pz_launch_blk_search(const uint8_t *d_stream, uint64_t nbytes, uint64_t first_bit, uint64_t last_bit, uint32_t *d_cand,
                                  uint32_t *d_ncand, uint32_t cap, cudaStream_t st) {
@@ -317,6 +341,13 @@ cudaError_t pz_launch_blk_jobs(const uint8_t *d_in_blob, const uint64_t *d_in_of
   job.parts = nullptr; job.seg_off = nullptr;
   if (count_only) pz_inflate_kernel<true><<<grid, PZ_THREADS_PER_CTA, smem, st>>>(job);
   else pz_inflate_kernel<false, true><<<grid, PZ_THREADS_PER_CTA, smem, st>>>(job);
+  return cudaGetLastError();
+}
+cudaError_t pz_launch_blk_compact(const uint16_t *d_scr, uint16_t *d_sym16, const uint64_t *d_blk_off, const uint64_t *d_blk_src, uint32_t nblk,
+                                  uint64_t total, cudaStream_t st) {
+  if (nblk == 0 || total == 0) return cudaSuccess;
+  const uint64_t per_cta = PZ_HUGE_THREADS * 8u;
+  pz_blk_compact_kernel<<<(unsigned)((total + per_cta - 1) / per_cta), PZ_HUGE_THREADS, 0, st>>>(d_scr, d_sym16, d_blk_off, d_blk_src, nblk, total);
   return cudaGetLastError();
 }
 cudaError_t pz_launch_blk_resolve(uint16_t *d_sym16, uint8_t *d_out, const uint64_t *d_blk_off, const uint32_t *d_blk_len, const uint32_t *d_blk_grp,

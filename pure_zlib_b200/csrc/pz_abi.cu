@@ -256,7 +256,7 @@ int huge_stream(const uint8_t *d_in_blob, const uint64_t *d_in_off_i, uint64_t i
       PZ_CUDA(cudaMemcpyAsync(ws.k4_len.p, caps.data(), nc * 4u, cudaMemcpyHostToDevice, st));
       PZ_CUDA(cudaMemcpyAsync(ws.k4_off.p, soff.data(), nc * 8u, cudaMemcpyHostToDevice, st));
       PZ_CUDA(pz_launch_blk_jobs(d_in_blob, d_in_off_i, (const uint32_t *)ws.k4_start.p, (const uint64_t *)ws.k4_off.p, (const uint32_t *)ws.k4_len.p, 0,
-                                 (uint16_t *)ws.k4_scr.p, (uint32_t)nc, (pz_result *)ws.k4_res.p, st));
+                                 (uint16_t *)ws.k4_scr.p, (uint32_t)nc, (pz_result *)ws.k4_res.p, st, d_word + 2));
       std::vector<pz_result> got(nc);
       PZ_CUDA(cudaMemcpyAsync(got.data(), ws.k4_res.p, nc * sizeof(pz_result), cudaMemcpyDeviceToHost, st));
       PZ_CUDA(cudaStreamSynchronize(st));
@@ -320,7 +320,7 @@ int huge_stream(const uint8_t *d_in_blob, const uint64_t *d_in_off_i, uint64_t i
     if ((r = ws.k4_start.reserve(count * 4u)) != PZ_E_OK || (r = ws.k4_res.reserve(count * sizeof(pz_result))) != PZ_E_OK) return r;
     PZ_CUDA(cudaMemcpyAsync(ws.k4_start.p, h_start, count * 4u, cudaMemcpyHostToDevice, st));
     PZ_CUDA(pz_launch_blk_jobs(d_in_blob, d_in_off_i, (const uint32_t *)ws.k4_start.p, nullptr, nullptr, kBlockCap, nullptr, (uint32_t)count,
-                               (pz_result *)ws.k4_res.p, st));
+                               (pz_result *)ws.k4_res.p, st, d_word + 2));
     PZ_CUDA(cudaMemcpyAsync(h_res, ws.k4_res.p, count * sizeof(pz_result), cudaMemcpyDeviceToHost, st));
     PZ_CUDA(cudaStreamSynchronize(st));
     return PZ_E_OK;
@@ -366,7 +366,7 @@ int huge_stream(const uint8_t *d_in_blob, const uint64_t *d_in_off_i, uint64_t i
   PZ_CUDA(cudaMemcpyAsync(ws.k4_off.p, c_off.data(), nb * 8u, cudaMemcpyHostToDevice, st));
   if (!symbols_ready)
     PZ_CUDA(pz_launch_blk_jobs(d_in_blob, d_in_off_i, (const uint32_t *)ws.k4_start.p, (const uint64_t *)ws.k4_off.p, (const uint32_t *)ws.k4_len.p, 0,
-                               (uint16_t *)ws.k4_sym.p, (uint32_t)nb, (pz_result *)ws.k4_res.p, st));
+                               (uint16_t *)ws.k4_sym.p, (uint32_t)nb, (pz_result *)ws.k4_res.p, st, d_word + 2));
   if (trace) { cudaStreamSynchronize(st); fprintf(stderr, "[pz-k4] %8.3f ms: symbols written\n", now_ms()); }
   /* groups for the two-level walk over the tails: about sqrt(2 * blocks) of them balances the two levels */
   uint32_t ngrp = 1;

@@ -277,6 +277,10 @@ struct PzJob {
   const uint32_t *resume = nullptr;
   uint32_t *ckpt = nullptr;
   uint32_t pair_off = 0;
+  /* Optional (block jobs): a zeroed device counter.  Units are then CLAIMED in order by whichever slot is free
+   * instead of being dealt out by index: blocks differ in length, and with two or three units per slot the
+   * longest deal sets the time of the launch. */
+  uint32_t *next_unit = nullptr;
 };
 #define PZ_CK_TRAILER 0xffffffffu
 #define PZ_ADLER_FUSED 0xffffffffu /* no Adler-32 value: both halves of one are below 65521 */
@@ -1429,6 +1433,16 @@ PZ_DEV void pz_slow_step(PzCtx &c, PzStreamSmem *sm, const PzJob &job, uint32_t 
       if (job.prog != nullptr && pz_lane() == 0) *(volatile uint32_t *)(job.prog + c.next) = PZ_PROG_DONE; /* K2 wrote it before K1 started */
 #endif
       c.next += stride;
+    }
+    if (job.next_unit != nullptr) { /* claim the next unit nobody has taken */
+      uint32_t v = 0;
+#ifdef PZ_HOSTSIM
+      v = (*job.next_unit)++;
+#else
+      if (pz_lane() == 0) v = atomicAdd(job.next_unit, 1u);
+      v = (uint32_t)pz_shfl((int)v, 0);
+#endif
+      c.next = v < job.count ? job.first + v : job.first + job.count;
     }
     if (c.next >= job.first + job.count) {
       pz_push<COUNT_ONLY>(c, sm, PZ_TOKEN(PZ_Q_CTRL, PZ_C_EXIT << 26));

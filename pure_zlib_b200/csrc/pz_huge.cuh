@@ -83,6 +83,14 @@ pz_blk_search_kernel(const uint8_t *__restrict__ in, uint64_t nbytes, uint64_t f
                       && ((h >> 3) & 31u) <= 29u && ((h >> 8) & 31u) <= 29u       /* what zlib can emit: HLIT <= 286, HDIST <= 30 */
                       && pos + 17u + 3u * hclen <= last_bit;
       mask |= ok ? (1u << o) : 0u;
+      /* an EMPTY stored block (00 00 ff ff behind the padding: what Z_SYNC_FLUSH / Z_FULL_FLUSH leave between the
+       * pieces of a stream) is a candidate on the strength of those 32 bits alone */
+      const uint32_t al = (o + 3u + 7u) >> 3; /* bytes from B to the byte boundary behind the three header bits */
+      const uint32_t lw = al == 1u ? ((v0 >> 8) | (v1 << 24)) : ((v0 >> 16) | (v1 << 16)); /* LEN | NLEN << 16 */
+      if (pos >= first_bit && pos < last_bit && ((h >> 1) & 3u) == 0u && lw == 0xffff0000u && (B + al + 4u) * 8u <= last_bit) {
+        const uint32_t k = atomicAdd(ncand, 1u);
+        if (k < cap) cand[k] = (uint32_t)pos;
+      }
     }
   }
   /* pack the survivors of the warp */
@@ -144,6 +152,11 @@ pz_blk_verify_kernel(const uint8_t *__restrict__ in, uint64_t nbytes, uint64_t l
   keep[i] = 0;
   uint64_t pos = cand[i];
   const uint32_t h = pz_bits_at(in, nbytes, pos, 17);
+  if (((h >> 1) & 3u) == 0u) { /* the first stage only lets EMPTY stored blocks through: check LEN / NLEN again */
+    const uint64_t b = (pos + 3u + 7u) >> 3;
+    keep[i] = b + 4u <= nbytes && pz_bits_at(in, nbytes, b * 8u, 16) == 0u && pz_bits_at(in, nbytes, b * 8u + 16u, 16) == 0xffffu;
+    return;
+  }
   const uint32_t hlit = ((h >> 3) & 31u) + 257u, hdist = ((h >> 8) & 31u) + 1u, hclen = ((h >> 13) & 15u) + 4u;
   pos += 17u;
   /* code-length code lengths, 3 bits per symbol, packed by symbol */

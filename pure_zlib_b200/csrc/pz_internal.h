@@ -56,7 +56,8 @@ cudaError_t pz_launch_blk_search(const uint8_t *d_stream, uint64_t nbytes, uint6
 cudaError_t pz_launch_blk_verify(const uint8_t *d_stream, uint64_t nbytes, uint64_t last_bit, const uint32_t *d_cand, uint32_t ncand,
                                  uint8_t *d_keep, cudaStream_t st);
 cudaError_t pz_launch_blk_jobs(const uint8_t *d_in_blob, const uint64_t *d_in_off2, const uint32_t *d_blk_start, const uint64_t *d_blk_out,
-                               const uint32_t *d_blk_len, uint32_t cap, uint16_t *d_sym16, uint32_t count, pz_result *d_res, cudaStream_t st);
+                               const uint32_t *d_blk_len, uint32_t cap, uint16_t *d_sym16, uint32_t count, pz_result *d_res, cudaStream_t st,
+                               uint32_t *d_counter = nullptr /* optional zeroable device word: blocks are claimed in order instead of dealt by index */);
 /* one-pass flow: symbols of chain block k move from d_scr + d_blk_src[k] to d_sym16 + d_blk_off[k] (pz_blk_compact_kernel) */
 cudaError_t pz_launch_blk_compact(const uint16_t *d_scr, uint16_t *d_sym16, const uint64_t *d_blk_off, const uint64_t *d_blk_src, uint32_t nblk,
                                   uint64_t total, cudaStream_t st);

@@ -328,7 +328,8 @@ cudaError_t pz_launch_blk_verify(const uint8_t *d_stream, uint64_t nbytes, uint6
 /* d_in_off2 = {offset of the stream in d_in_blob, its end}.  d_blk_out == nullptr: sizing pass (every block bounded by
  * cap); else 16-bit symbols of block j go to d_sym16 + d_blk_out[j], bounded by d_blk_len[j]. */
 cudaError_t pz_launch_blk_jobs(const uint8_t *d_in_blob, const uint64_t *d_in_off2, const uint32_t *d_blk_start, const uint64_t *d_blk_out,
-                               const uint32_t *d_blk_len, uint32_t cap, uint16_t *d_sym16, uint32_t count, pz_result *d_res, cudaStream_t st) {
+                               const uint32_t *d_blk_len, uint32_t cap, uint16_t *d_sym16, uint32_t count, pz_result *d_res, cudaStream_t st,
+                               uint32_t *d_counter) {
   if (count == 0) return cudaSuccess;
   const bool count_only = d_blk_out == nullptr;
   const unsigned wave = (unsigned)(g_sm_count * g_inflate_ctas_per_sm[count_only ? 1 : 0]);
@@ -339,6 +340,11 @@ cudaError_t pz_launch_blk_jobs(const uint8_t *d_in_blob, const uint64_t *d_in_of
   job.first = 0; job.count = count; job.skip_done = 0; job.prog = nullptr; job.in_ready = nullptr;
   job.blk_start = d_blk_start; job.blk_out = d_blk_out; job.blk_len = d_blk_len; job.out16 = d_sym16; job.blk_stream = 0; job.blk_cap = cap;
   job.parts = nullptr; job.seg_off = nullptr;
+  if (d_counter != nullptr && count > 1u) { /* blocks are claimed, not dealt (PzJob::next_unit) */
+    cudaError_t e = cudaMemsetAsync(d_counter, 0, sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+    job.next_unit = d_counter;
+  }
   if (count_only) pz_inflate_kernel<true><<<grid, PZ_THREADS_PER_CTA, smem, st>>>(job);
   else pz_inflate_kernel<false, true><<<grid, PZ_THREADS_PER_CTA, smem, st>>>(job);
   return cudaGetLastError();

@@ -383,6 +383,9 @@ def _huge_cases():
     z = co.compress(text[: 1 << 20]) + co.flush(zlib.Z_FULL_FLUSH)
     z += co.compress(text[1 << 20: 2 << 20]) + co.flush()
     cases.append(("sync-flush", z))
+    # a stream compressed in pieces: the empty stored blocks of Z_SYNC_FLUSH are candidates of the search too
+    co = zlib.compressobj(9)
+    cases.append(("many-flushes", b"".join(co.compress(text[k << 19: (k + 1) << 19]) + co.flush(zlib.Z_SYNC_FLUSH) for k in range(8)) + co.flush()))
     cf = zlib.compressobj(6, zlib.DEFLATED, 15, 8, zlib.Z_FIXED)
     cases.append(("all-fixed", cf.compress(text[: 1 << 20]) + cf.flush()))
     rng = np.random.default_rng(5)
@@ -408,11 +411,11 @@ def test_huge_stream_block_parallel(pz, oracle, huge_threshold):
     L = _lib.load()
     done0, declined0 = L.pz_get_counter(1), L.pz_get_counter(2)
     res, outs = pz.zlib.inflate_batch_raw([z for _, z in cases])
-    # the six well-formed streams, the one with a bad checksum and the one with bytes after its trailer take K4
+    # the seven well-formed streams, the one with a bad checksum and the one with bytes after its trailer take K4
     # (inflate_batch_raw decodes twice: sizing pass without K4, then the decode); the broken ones are declined
     # (a flipped bit may leave every block decodable -- then K4 finishes and the checksum fails -- or not)
     done, declined = L.pz_get_counter(1) - done0, L.pz_get_counter(2) - declined0
-    assert done + declined == len(cases) and done >= 8 and declined >= 1, (done, declined)
+    assert done + declined == len(cases) and done >= 9 and declined >= 1, (done, declined)
     res0, outs0 = pz.zlib.inflate_batch_raw([z for _, z in cases], flags=_lib.PZ_F_NO_HUGE)
     for (name, z), r, out, r0, out0 in zip(cases, res, outs, res0, outs0):
         o = oracle.decompress(z)

@@ -90,6 +90,8 @@ foreign import ccall unsafe "&pz_stream_free"
   p_pz_stream_free :: FunPtr (Ptr PzStream -> IO ())
 foreign import ccall safe "pz_stream_pump"
   c_pz_stream_pump :: Ptr (Ptr PzStream) -> CSize -> IO CInt
+-- (pz_stream_feed_many is the batched counterpart of pz_stream_feed -- one copy across the bus for a round of
+-- chunks; decompressMany below keeps to one pz_stream_feed per stream for the sake of brevity)
 
 -- | The verdict as the reference's value: Left e, or the impure exception the reference dies with.
 verdict :: Ptr PzResult -> PzResult -> IO (Maybe DecompressionError)

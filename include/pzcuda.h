@@ -186,6 +186,9 @@ void pz_stream_free(pz_stream *s);
  * goes on where it stopped).  Streams with nothing new are skipped.  Afterwards
  * pz_stream_next() on any of them returns without touching the device.                      */
 int pz_stream_pump(pz_stream *const *streams, size_t n);
+/* The feed that goes with it: data[i] / len[i] is the next chunk of streams[i] (each stream at most once per call).
+ * All chunks cross the bus in one copy.  Returns when the bytes are on the device.               */
+int pz_stream_feed_many(pz_stream *const *streams, const uint8_t *const *data, const size_t *len, size_t n);
 /* Introspection for tests and benchmarks. */
 enum pz_stream_counter_id {
   PZ_SC_PUMPS = 0,      /* kernel launches that decoded this stream                          */

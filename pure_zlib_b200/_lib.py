@@ -50,6 +50,7 @@ SYMBOLS = [
     ("pz_stream_next", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(PzResult)]),
     ("pz_stream_free", None, [C.c_void_p]),
     ("pz_stream_pump", C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
+    ("pz_stream_feed_many", C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_size_t]),
     ("pz_stream_counter", C.c_uint64, [C.c_void_p, C.c_int]),
     ("pz_strerror", C.c_size_t, [C.POINTER(PzResult), C.c_char_p, C.c_size_t]),
     ("pz_compute_code_values", C.c_int, [C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_int32)]),

@@ -932,21 +932,22 @@ struct pz_stream {
   bool done_delivered = false;
   pz_result verdict{};
   uint64_t pumps = 0, resumed = 0; /* launches that decoded this stream; those that started from a checkpoint */
+  uint64_t feed_stamp = 0;         /* the pz_stream_feed_many call that last took a chunk for this stream */
 };
 
 namespace {
 /* per-thread control tables of a pump: [in pairs | out pairs | resume] go up, [ckpt | res] come back */
 struct PumpSpace {
-  Buf h_ctl, d_ctl, d_parts, d_tab, d_gather;
+  Buf h_ctl, d_ctl, d_parts, d_tab, d_gather, h_feed, d_feed;
   cudaEvent_t fed[kPoolStreams] = {};
-  PumpSpace() { h_ctl.pinned = true; }
+  PumpSpace() { h_ctl.pinned = true; h_feed.pinned = true; }
   int ensure_events() {
     for (int i = 0; i < kPoolStreams; i++)
       if (!fed[i]) PZ_CUDA(cudaEventCreateWithFlags(&fed[i], cudaEventDisableTiming));
     return PZ_E_OK;
   }
   ~PumpSpace() {
-    h_ctl.release(); d_ctl.release(); d_parts.release(); d_tab.release(); d_gather.release();
+    h_ctl.release(); d_ctl.release(); d_parts.release(); d_tab.release(); d_gather.release(); h_feed.release(); d_feed.release();
     for (int i = 0; i < kPoolStreams; i++) if (fed[i]) cudaEventDestroy(fed[i]);
   }
 };
@@ -1137,6 +1138,62 @@ int pz_stream_feed(pz_stream *s, const uint8_t *data, size_t len) {
     s->in_len += piece;
     at += piece;
   }
+  return PZ_E_OK;
+}
+
+/* One chunk for each of n streams: all chunks are packed into ONE pinned staging buffer, cross the bus in one copy and
+ * are dealt to the streams' input buffers by one kernel -- the cost of a round of feeds no longer grows with a
+ * cudaMemcpyAsync and an event per stream.  Returns when the bytes are on the device. */
+int pz_stream_feed_many(pz_stream *const *streams, const uint8_t *const *data, const size_t *len, size_t n) {
+  if (n == 0) return PZ_E_OK;
+  if (!streams || !data || !len) return PZ_E_ARG;
+  int rc = ensure_init();
+  if (rc != PZ_E_OK) return rc;
+  PumpSpace &ps = g_pump;
+  if ((rc = ps.ensure_events()) != PZ_E_OK) return rc;
+  uint64_t total = 0;
+  static std::atomic<uint64_t> g_feed_stamp{0};
+  const uint64_t stamp = ++g_feed_stamp;
+  for (size_t i = 0; i < n; i++) {
+    pz_stream *s = streams[i];
+    if (!s || (len[i] && !data[i])) return PZ_E_ARG;
+    if (s->terminal) return PZ_E_STATE;
+    if (s->in_len + len[i] > PZ_MAX_STREAM_BYTES) return PZ_E_ARG;
+    if (s->feed_stamp == stamp) return PZ_E_ARG; /* one chunk per stream and call */
+    s->feed_stamp = stamp;
+    total += (len[i] + 15u) & ~(uint64_t)15u;
+  }
+  cudaStream_t st = streams[0]->st;
+  if ((rc = ps.h_feed.reserve(total + 16 + n * 24u)) != PZ_E_OK || (rc = ps.d_feed.reserve(total + 16 + n * 24u)) != PZ_E_OK) return rc;
+  /* layout of both buffers: n (source, destination, length) triples, then the chunks, 16-byte aligned */
+  uint64_t *tri = (uint64_t *)ps.h_feed.p;
+  const uint64_t base = (n * 24u + 15u) & ~(uint64_t)15u;
+  uint8_t *hp = (uint8_t *)ps.h_feed.p, *dp = (uint8_t *)ps.d_feed.p;
+  uint64_t at = base;
+  bool seen[kPoolStreams] = {};
+  size_t m = 0;
+  for (size_t i = 0; i < n; i++) {
+    pz_stream *s = streams[i];
+    s->dirty = true;
+    if (len[i] == 0) continue; /* empty chunks are accepted and ignored (Monad.hs:193-195) */
+    if ((rc = grow_device(s->d_in, s->d_in_cap, s->in_len + len[i] + 64, s->in_len, s->st)) != PZ_E_OK) return rc;
+    seen[s->pool_idx] = true;
+    memcpy(hp + at, data[i], len[i]);
+    tri[3 * m] = (uint64_t)(uintptr_t)(dp + at); tri[3 * m + 1] = (uint64_t)(uintptr_t)(s->d_in + s->in_len); tri[3 * m + 2] = len[i];
+    s->in_len += len[i];
+    at += (len[i] + 15u) & ~(uint64_t)15u;
+    m++;
+  }
+  if (m == 0) return PZ_E_OK;
+  /* the streams' buffers may just have moved (and earlier single feeds may still be in flight) on their own CUDA streams */
+  for (int k = 0; k < kPoolStreams; k++)
+    if (seen[k] && g_pool[k] != st) {
+      PZ_CUDA(cudaEventRecord(ps.fed[k], g_pool[k]));
+      PZ_CUDA(cudaStreamWaitEvent(st, ps.fed[k], 0));
+    }
+  PZ_CUDA(cudaMemcpyAsync(dp, hp, at, cudaMemcpyHostToDevice, st));
+  PZ_CUDA(pz_launch_gather((const uint64_t *)dp, (uint32_t)m, st));
+  PZ_CUDA(cudaStreamSynchronize(st)); /* the staging buffers are this thread's: free for the next call; later work on any stream is ordered behind */
   return PZ_E_OK;
 }
 

@@ -187,6 +187,16 @@ class IncrementalSet:
         d = self.decoders[i]
         _lib.check(self._L.pz_stream_feed(d._s, chunk, len(chunk)), "pz_stream_feed")
 
+    def feed_all(self, chunks: Sequence[bytes], which: Sequence[int] | None = None):
+        """One chunk for each stream in `which` (default: all): one copy across the bus (pz_stream_feed_many)."""
+        which = list(range(len(self.decoders))) if which is None else list(which)
+        chunks = [bytes(c) for c in chunks]
+        n = len(which)
+        arr = (C.c_void_p * n)(*[self.decoders[i]._s for i in which])
+        data = (C.c_char_p * n)(*chunks)
+        lens = (C.c_size_t * n)(*[len(c) for c in chunks])
+        _lib.check(self._L.pz_stream_feed_many(arr, data, lens, n), "pz_stream_feed_many")
+
     def pump(self):
         arr = (C.c_void_p * len(self.decoders))(*[d._s for d in self.decoders])
         _lib.check(self._L.pz_stream_pump(arr, len(self.decoders)), "pz_stream_pump")
@@ -217,8 +227,7 @@ def decompress_many(files: Sequence[LazyByteString]):
             result[i] = Left(DecompressionError_("Ran out of data mid-decompression 2."))
     live = [i for i in live if result[i] is None]
     while live:
-        for i in live:
-            group.feed(i, rests[i].pop(0))
+        group.feed_all([rests[i].pop(0) for i in live], live)
         group.pump()
         nxt = []
         for i in live:

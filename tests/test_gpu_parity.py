@@ -595,9 +595,12 @@ def test_stream_pump_many(pz, oracle):
     rounds = 5
     outs = [b""] * 8
     for r in range(rounds):
-        for i, z in enumerate(zs):
-            step = (len(z) + rounds - 1) // rounds
-            group.feed(i, z[r * step:(r + 1) * step])
+        parts = [z[r * ((len(z) + rounds - 1) // rounds):(r + 1) * ((len(z) + rounds - 1) // rounds)] for z in zs]
+        if r % 2 == 0:  # one call for the round (pz_stream_feed_many) ...
+            group.feed_all(parts)
+        else:           # ... or one per stream
+            for i, part in enumerate(parts):
+                group.feed(i, part)
         group.pump()
         for i in range(8):
             for st in group.events(i):
@@ -608,3 +611,38 @@ def test_stream_pump_many(pz, oracle):
         assert outs[i] == streams.small_text(120_000, 40 + i)
         assert group.counter(i, _lib.PZ_SC_PUMPS) == rounds
         assert group.counter(i, _lib.PZ_SC_RESUMED) == rounds - 1
+
+
+def test_incremental_feed_sizes(pz, oracle):
+    """Feeds far above the staging block (1 MiB: the chunk travels in pieces), and a stream fed one byte at a time
+    (every header field, code length and symbol is cut somewhere)."""
+    rng = np.random.default_rng(41)
+    big = zlib.compress(rng.integers(0, 256, 3_500_000, dtype=np.uint8).tobytes(), 6)      # stored blocks, 3.5 MB in one chunk
+    text = zlib.compress(streams.small_text(6_000_000, 8), 6)                                # ~1.9 MB compressed
+    for z, cuts in ((big, []), (big, [2_000_001]), (text, [1_500_000]), (text, [])):
+        pieces = _pieces(z, cuts)
+        o = oracle.decompress(pieces, want_events=True)
+        events, acc, err = _run_incremental(pz, pieces)
+        assert events == o.events and acc == o.data and err is None, (len(z), cuts, events[:4], o.events[:4])
+    small = zlib.compress(streams.small_text(3000, 12), 9)
+    fixed = zlib.compressobj(9, zlib.DEFLATED, 15, 8, zlib.Z_FIXED)
+    smallf = fixed.compress(streams.small_text(1200, 13)) + fixed.flush()
+    for z in (small, smallf):
+        pieces = [z[i:i + 1] for i in range(len(z))]
+        o = oracle.decompress(pieces, want_events=True)
+        events, acc, err = _run_incremental(pz, pieces)
+        assert events == o.events and acc == o.data and err is None, (len(z), events[-4:], o.events[-4:])
+
+
+def test_stream_feed_many_arguments(pz):
+    from pure_zlib_b200 import _lib
+    L = _lib.load()
+    group = pz.IncrementalSet(3)
+    with pytest.raises(_lib.PzCudaError):   # a stream twice in one call
+        group.feed_all([b"a", b"b"], [1, 1])
+    group.feed_all([], [])                  # nothing to do
+    z = zlib.compress(b"abc" * 1000)
+    group.feed_all([z, b"", z[:10]])        # an empty chunk is accepted and ignored
+    group.pump()
+    kinds = [[type(st).__name__ for st in group.events(i)] for i in range(3)]
+    assert kinds[0] == ["Chunk", "Done"] and kinds[1] == ["NeedMore"] and kinds[2] == ["NeedMore"], kinds

@@ -3,7 +3,8 @@
 `decompressIncremental` consumers, each fed its stream in K pieces, one pump (one kernel launch) per round.
 Prints one JSON line: decompressed GB/s end to end (host chunks in, host chunks out), per-round times, and
 the same run with PZ_OPT_STREAM_RESUME = 0 (every round decodes every stream from its first byte again,
-which is what the API did before the device-resident contexts).
+which is what the API did before the device-resident contexts) and with one pz_stream_feed per stream
+instead of one pz_stream_feed_many per round.
 
   python tools/bench_incremental.py --streams 1024 --pieces 8
 """
@@ -19,23 +20,26 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pure_zlib_b200 import _lib, corpus  # noqa: E402
 
 
-def run(L, c, pieces: int, check: bool):
+def run(L, c, pieces: int, many: bool):
     n = c.n
     streams = [L.pz_stream_new() for _ in range(n)]
     assert all(streams)
     arr = (C.c_void_p * n)(*streams)
     blobs = [bytes(c.in_blob[int(c.in_off[i]): int(c.in_off[i]) + int(c.in_len[i])]) for i in range(n)]
+    steps = [(len(z) + pieces - 1) // pieces for z in blobs]
     ptr, ln, res = C.c_void_p(), C.c_size_t(), _lib.PzResult()
     out_bytes = 0
     rounds = []
     t0 = time.perf_counter()
     for r in range(pieces):
         t1 = time.perf_counter()
-        for i in range(n):
-            z = blobs[i]
-            step = (len(z) + pieces - 1) // pieces
-            piece = z[r * step:(r + 1) * step]
-            _lib.check(L.pz_stream_feed(streams[i], piece, len(piece)), "feed")
+        if many:  # one call, one copy across the bus for the whole round
+            parts = [blobs[i][r * steps[i]:(r + 1) * steps[i]] for i in range(n)]
+            _lib.check(L.pz_stream_feed_many(arr, (C.c_char_p * n)(*parts), (C.c_size_t * n)(*[len(p) for p in parts]), n), "feed_many")
+        else:
+            for i in range(n):
+                piece = blobs[i][r * steps[i]:(r + 1) * steps[i]]
+                _lib.check(L.pz_stream_feed(streams[i], piece, len(piece)), "feed")
         t2 = time.perf_counter()
         _lib.check(L.pz_stream_pump(arr, n), "pump")
         t3 = time.perf_counter()
@@ -45,8 +49,6 @@ def run(L, c, pieces: int, check: bool):
                 ev = L.pz_stream_next(streams[i], C.byref(ptr), C.byref(ln), C.byref(res))
                 if ev != _lib.PZ_S_CHUNK:
                     break
-                if check and r == pieces - 1 and i < 4:
-                    pass
                 out_bytes += ln.value
             done += ev == _lib.PZ_S_DONE
         t4 = time.perf_counter()
@@ -69,9 +71,9 @@ def main():
     c = corpus.text256k(a.streams, workers=min(16, os.cpu_count() or 1))
     line = {"metric": "decompressed GB/s through the incremental API", "unit": "GB/s", "streams": a.streams, "pieces": a.pieces,
             "workload": f"{a.streams} x 256 KiB synthetic text (level 6), each stream fed in {a.pieces} pieces, one pz_stream_pump per round"}
-    for label, resume in (("warmup", 1), ("resumed", 1), ("from_first_byte", 0)):
+    for label, resume, many in (("warmup", 1, True), ("resumed", 1, True), ("resumed_single_feeds", 1, False), ("from_first_byte", 0, True)):
         _lib.check(L.pz_set_option(2, resume), "pz_set_option")
-        total, rounds, out_bytes, resumed = run(L, c, a.pieces, True)
+        total, rounds, out_bytes, resumed = run(L, c, a.pieces, many)
         if label == "warmup":
             continue
         line[label] = {"value": out_bytes / total / 1e9, "seconds": total, "pump_ms": [round(r["pump_ms"], 2) for r in rounds],

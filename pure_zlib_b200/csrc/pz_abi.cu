@@ -196,27 +196,30 @@ int huge_stream(const uint8_t *d_in_blob, const uint64_t *d_in_off_i, uint64_t i
   int rc;
   /* K4a: candidates */
   const uint32_t cap = (uint32_t)(total_bits / 128u + 4096u);
-  if ((rc = ws.k4_cand.reserve((size_t)cap * 4u)) != PZ_E_OK || (rc = ws.k4_keep.reserve(cap)) != PZ_E_OK || (rc = ws.k4_word.reserve(64)) != PZ_E_OK) return rc;
-  uint32_t *d_word = (uint32_t *)ws.k4_word.p;
-  PZ_CUDA(cudaMemsetAsync(d_word, 0, 8, st));
+  if ((rc = ws.k4_cand.reserve((size_t)cap * 4u)) != PZ_E_OK || (rc = ws.k4_keep.reserve((size_t)cap * 4u)) != PZ_E_OK || (rc = ws.k4_word.reserve(64)) != PZ_E_OK) return rc;
+  uint32_t *d_word = (uint32_t *)ws.k4_word.p; /* [0] candidates of the first stage, [1] error flag of the resolution, [2] unit counter of the block jobs, [3] candidates kept */
+  PZ_CUDA(cudaMemsetAsync(d_word, 0, 16, st));
   PZ_CUDA(pz_launch_blk_search(d_stream, in_len, first_bit, last_bit, (uint32_t *)ws.k4_cand.p, d_word, cap, st));
   uint32_t ncand = 0;
   PZ_CUDA(cudaMemcpyAsync(&ncand, d_word, 4, cudaMemcpyDeviceToHost, st));
   PZ_CUDA(cudaStreamSynchronize(st));
   if (ncand > cap) return 0;
-  PZ_CUDA(pz_launch_blk_verify(d_stream, in_len, last_bit, (const uint32_t *)ws.k4_cand.p, ncand, (uint8_t *)ws.k4_keep.p, st));
-  std::vector<uint32_t> cand(ncand);
-  std::vector<uint8_t> keep(ncand);
-  if (ncand) {
-    PZ_CUDA(cudaMemcpyAsync(cand.data(), ws.k4_cand.p, (size_t)ncand * 4u, cudaMemcpyDeviceToHost, st));
-    PZ_CUDA(cudaMemcpyAsync(keep.data(), ws.k4_keep.p, ncand, cudaMemcpyDeviceToHost, st));
-  }
+  /* the second stage leaves its survivors (about one first-stage candidate in 200) in a list of their own: the host
+   * never sees the 2 million first-stage candidates */
+  PZ_CUDA(pz_launch_blk_verify(d_stream, in_len, last_bit, (const uint32_t *)ws.k4_cand.p, ncand, (uint32_t *)ws.k4_keep.p, d_word + 3, st));
+  uint32_t nkept = 0;
+  PZ_CUDA(cudaMemcpyAsync(&nkept, d_word + 3, 4, cudaMemcpyDeviceToHost, st));
   PZ_CUDA(cudaStreamSynchronize(st));
+  std::vector<uint32_t> kept(nkept);
+  if (nkept) {
+    PZ_CUDA(cudaMemcpyAsync(kept.data(), ws.k4_keep.p, (size_t)nkept * 4u, cudaMemcpyDeviceToHost, st));
+    PZ_CUDA(cudaStreamSynchronize(st));
+  }
   std::vector<uint32_t> starts;
-  starts.reserve(ncand / 64 + 16);
-  if (trace) fprintf(stderr, "[pz-k4] %8.3f ms: search done, %u first-stage candidates\n", now_ms(), ncand);
+  starts.reserve(nkept + 16);
+  if (trace) fprintf(stderr, "[pz-k4] %8.3f ms: search done, %u first-stage candidates, %u kept\n", now_ms(), ncand, nkept);
   starts.push_back((uint32_t)first_bit); /* the first block is known, whatever its type */
-  for (uint32_t i = 0; i < ncand; i++) if (keep[i] && cand[i] != first_bit) starts.push_back(cand[i]);
+  for (uint32_t i = 0; i < nkept; i++) if (kept[i] != first_bit) starts.push_back(kept[i]);
   std::sort(starts.begin(), starts.end());
   std::vector<uint32_t> c_start;
   std::vector<uint32_t> c_len;
@@ -368,9 +371,13 @@ int huge_stream(const uint8_t *d_in_blob, const uint64_t *d_in_off_i, uint64_t i
     PZ_CUDA(pz_launch_blk_jobs(d_in_blob, d_in_off_i, (const uint32_t *)ws.k4_start.p, (const uint64_t *)ws.k4_off.p, (const uint32_t *)ws.k4_len.p, 0,
                                (uint16_t *)ws.k4_sym.p, (uint32_t)nb, (pz_result *)ws.k4_res.p, st, d_word + 2));
   if (trace) { cudaStreamSynchronize(st); fprintf(stderr, "[pz-k4] %8.3f ms: symbols written\n", now_ms()); }
-  /* groups for the two-level walk over the tails: about sqrt(2 * blocks) of them balances the two levels */
+  /* groups for the two-level walk over the tails */
+  /* groups = sqrt(gscale x blocks).  A step of the one-CTA walk over the groups (pz_blk_windows_kernel) costs about twice
+   * a step of the parallel walks inside the groups (pz_blk_tails_kernel), hence fewer, longer groups than sqrt(2 x blocks),
+   * which would balance equal steps: 2.0 / 1.0 / 0.5 / 0.25 give 35.1 / 34.8 / 34.6 / 34.7 ms on the 1 GiB stream */
+  static const double gscale = getenv("PZ_K4_GSCALE") ? atof(getenv("PZ_K4_GSCALE")) : 0.5;
   uint32_t ngrp = 1;
-  while ((uint64_t)ngrp * ngrp < 2u * nb) ngrp++;
+  while ((double)ngrp * ngrp < gscale * (double)nb) ngrp++;
   ngrp = (uint32_t)std::min<size_t>(std::min<uint32_t>(ngrp, 1024u), nb);
   std::vector<uint32_t> g_first(ngrp + 1), b_grp(nb);
   for (uint32_t g = 0; g <= ngrp; g++) g_first[g] = (uint32_t)((uint64_t)nb * g / ngrp);

@@ -146,15 +146,15 @@ __device__ __forceinline__ uint32_t pz_bits_at(const uint8_t *in, uint64_t nbyte
  * list or runs past it, an end-of-block code. */
 __global__ void __launch_bounds__(PZ_HUGE_THREADS)
 pz_blk_verify_kernel(const uint8_t *__restrict__ in, uint64_t nbytes, uint64_t last_bit, const uint32_t *__restrict__ cand,
-                     uint32_t ncand, uint8_t *__restrict__ keep) {
+                     uint32_t ncand, uint32_t *__restrict__ kept, uint32_t *__restrict__ nkept) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= ncand) return;
-  keep[i] = 0;
   uint64_t pos = cand[i];
   const uint32_t h = pz_bits_at(in, nbytes, pos, 17);
   if (((h >> 1) & 3u) == 0u) { /* the first stage only lets EMPTY stored blocks through: check LEN / NLEN again */
     const uint64_t b = (pos + 3u + 7u) >> 3;
-    keep[i] = b + 4u <= nbytes && pz_bits_at(in, nbytes, b * 8u, 16) == 0u && pz_bits_at(in, nbytes, b * 8u + 16u, 16) == 0xffffu;
+    if (b + 4u <= nbytes && pz_bits_at(in, nbytes, b * 8u, 16) == 0u && pz_bits_at(in, nbytes, b * 8u + 16u, 16) == 0xffffu)
+      kept[atomicAdd(nkept, 1u)] = cand[i];
     return;
   }
   const uint32_t hlit = ((h >> 3) & 31u) + 257u, hdist = ((h >> 8) & 31u) + 1u, hclen = ((h >> 13) & 15u) + 4u;
@@ -214,7 +214,8 @@ pz_blk_verify_kernel(const uint8_t *__restrict__ in, uint64_t nbytes, uint64_t l
     n += rep;
     if (sum_l > 32768u || sum_d > 32768u) return; /* over-subscribed already: most false candidates end here, a few symbols in */
   }
-  if (sum_l == 32768u && sum_d == 32768u && eob) keep[i] = 1;
+  /* the survivors (one position in 250 000) go into a list of their own, in no particular order: the host sorts it */
+  if (sum_l == 32768u && sum_d == 32768u && eob) kept[atomicAdd(nkept, 1u)] = cand[i];
 }
 
 /* One-pass flow: the chain's blocks were decoded into scratch regions of their own (every candidate was, before the

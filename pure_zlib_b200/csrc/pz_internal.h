@@ -53,8 +53,9 @@ cudaError_t pz_launch_gather(const uint64_t *d_triples, uint32_t count, cudaStre
 /* K4 (pz_huge.cuh): one huge stream decoded block-parallel; see pz_abi.cu for the driver */
 cudaError_t pz_launch_blk_search(const uint8_t *d_stream, uint64_t nbytes, uint64_t first_bit, uint64_t last_bit, uint32_t *d_cand,
                                  uint32_t *d_ncand, uint32_t cap, cudaStream_t st);
+/* d_kept (room for ncand entries) receives the candidates that pass, in no particular order; *d_nkept (zeroed by the caller) counts them */
 cudaError_t pz_launch_blk_verify(const uint8_t *d_stream, uint64_t nbytes, uint64_t last_bit, const uint32_t *d_cand, uint32_t ncand,
-                                 uint8_t *d_keep, cudaStream_t st);
+                                 uint32_t *d_kept, uint32_t *d_nkept, cudaStream_t st);
 cudaError_t pz_launch_blk_jobs(const uint8_t *d_in_blob, const uint64_t *d_in_off2, const uint32_t *d_blk_start, const uint64_t *d_blk_out,
                                const uint32_t *d_blk_len, uint32_t cap, uint16_t *d_sym16, uint32_t count, pz_result *d_res, cudaStream_t st,
                                uint32_t *d_counter = nullptr /* optional zeroable device word: blocks are claimed in order instead of dealt by index */);

@@ -320,9 +320,9 @@ cudaError_t pz_launch_blk_search(const uint8_t *d_stream, uint64_t nbytes, uint6
   return cudaGetLastError();
 }
 cudaError_t pz_launch_blk_verify(const uint8_t *d_stream, uint64_t nbytes, uint64_t last_bit, const uint32_t *d_cand, uint32_t ncand,
-                                 uint8_t *d_keep, cudaStream_t st) {
+                                 uint32_t *d_kept, uint32_t *d_nkept, cudaStream_t st) {
   if (ncand == 0) return cudaSuccess;
-  pz_blk_verify_kernel<<<(ncand + PZ_HUGE_THREADS - 1) / PZ_HUGE_THREADS, PZ_HUGE_THREADS, 0, st>>>(d_stream, nbytes, last_bit, d_cand, ncand, d_keep);
+  pz_blk_verify_kernel<<<(ncand + PZ_HUGE_THREADS - 1) / PZ_HUGE_THREADS, PZ_HUGE_THREADS, 0, st>>>(d_stream, nbytes, last_bit, d_cand, ncand, d_kept, d_nkept);
   return cudaGetLastError();
 }
 /* d_in_off2 = {offset of the stream in d_in_blob, its end}.  d_blk_out == nullptr: sizing pass (every block bounded by

@@ -238,13 +238,19 @@ pz_blk_compact_kernel(const uint16_t *__restrict__ scr, uint16_t *__restrict__ s
   __syncthreads();
   uint32_t k = k0s;
   uint16_t v[8];
+  uint64_t next = 0; /* first symbol behind block k; 0 = not looked up yet */
+  const uint16_t *from = scr; /* scr + blk_src[k] - blk_off[k] */
 #pragma unroll
   for (int j = 0; j < 8; j++) {
     const uint64_t e = c0 + (uint64_t)j * PZ_HUGE_THREADS + threadIdx.x;
     v[j] = 0;
     if (e < total) {
-      while (k + 1u < nblk && blk_off[k + 1u] <= e) k++;
-      v[j] = scr[blk_src[k] + (e - blk_off[k])];
+      if (e >= next) {
+        while (k + 1u < nblk && blk_off[k + 1u] <= e) k++;
+        next = k + 1u < nblk ? blk_off[k + 1u] : total;
+        from = scr + blk_src[k] - blk_off[k];
+      }
+      v[j] = from[e];
     }
   }
 #pragma unroll
@@ -396,15 +402,26 @@ pz_blk_resolve_kernel(const uint16_t *__restrict__ sym, uint8_t *__restrict__ ou
     const uint4 v = *reinterpret_cast<const uint4 *>(sym + e0);
     w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
   }
+  /* the block holding e0 (the last k with blk_off[k] <= e0: empty blocks are skipped), kept in registers: eight
+   * consecutive symbols rarely leave it */
+  while (k + 1u < nblk && blk_off[k + 1u] <= e0) k++;
+  uint64_t off = blk_off[k];
+  uint64_t next = k + 1u < nblk ? blk_off[k + 1u] : total;
+  uint32_t len = blk_len[k];
+  uint64_t tail0 = off + (len - (len < PZ_TAIL ? len : PZ_TAIL)); /* first tail symbol of the block */
 #pragma unroll
   for (int j = 0; j < 8; j++) {
     const uint64_t e = e0 + (uint32_t)j;
     if (e >= total) break;
-    while (k + 1u < nblk && blk_off[k + 1u] <= e) k++;
-    const uint64_t off = blk_off[k];
-    const uint32_t len = blk_len[k], T = len < PZ_TAIL ? len : PZ_TAIL;
+    if (e >= next) {
+      do k++; while (k + 1u < nblk && blk_off[k + 1u] <= e);
+      off = blk_off[k];
+      next = k + 1u < nblk ? blk_off[k + 1u] : total;
+      len = blk_len[k];
+      tail0 = off + (len - (len < PZ_TAIL ? len : PZ_TAIL));
+    }
     uint32_t s = vec ? (w[j >> 1] >> (16 * (j & 1))) & 0xffffu : (uint32_t)sym[e];
-    if (e >= off + (len - T)) { /* a tail symbol */
+    if (e >= tail0) { /* a tail symbol */
       s = pz_resolve_tail_sym(s, blk_grp[k], gw, blk_off, grp_first, bad);
     } else if (s >= 256u) {
       const uint64_t a = off - PZ_TAIL + (s - 256u);

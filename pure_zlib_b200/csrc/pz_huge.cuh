@@ -140,6 +140,14 @@ __device__ __forceinline__ uint32_t pz_bits_at(const uint8_t *in, uint64_t nbyte
   return (v >> (pos & 7u)) & ((1u << n) - 1u);
 }
 
+/* The same with two aligned 32-bit loads instead of four guarded byte loads, for positions at least four bytes before
+ * the end of the stream (the blob has 15 readable bytes of slack around it, pzcuda.h). */
+__device__ __forceinline__ uint32_t pz_bits_fast(const uint8_t *in, uint64_t pos, uint32_t n) {
+  const uintptr_t a = (uintptr_t)(in + (pos >> 3));
+  const uint32_t *w = (const uint32_t *)(a & ~(uintptr_t)3);
+  return __funnelshift_r(w[0], w[1], (uint32_t)(a & 3u) * 8u + (uint32_t)(pos & 7u)) & ((1u << n) - 1u);
+}
+
 /* K4a, second stage: one thread per first-stage candidate reads the whole dynamic header
  * (Deflate.hs:83-101,124-156) and keeps the candidate only if it is what zlib's tree builder
  * produces: complete code-length, literal/length and distance codes, no repeat that starts the
@@ -166,42 +174,42 @@ pz_blk_verify_kernel(const uint8_t *__restrict__ in, uint64_t nbytes, uint64_t l
     pl |= (uint64_t)pz_bits_at(in, nbytes, pos, 3) << (3u * order[k]);
     pos += 3u;
   }
-  uint32_t cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (uint32_t s = 0; s < 19u; s++) cnt[(pl >> (3u * s)) & 7u]++;
+  /* The code-length code as a 7-bit lookup table (index = the next seven stream bits, first bit of a code = its most
+   * significant one, HuffmanTree.hs:73-83), one table per thread in shared memory, entry e of thread t at e * 256 + t.
+   * The first stage let this candidate through because the code is complete, so every entry gets written.  Almost every
+   * candidate -- true or not -- is parsed to the end of its ~300 code lengths (random lengths of 8 or 9 bits take that
+   * long to over-subscribe a code), so the table pays for itself many times: the bit-by-bit canonical decode it replaces
+   * cost ~150 instructions per code length. */
+  __shared__ uint8_t pz_pre_lut[128 * PZ_HUGE_THREADS];
+  uint8_t *lut = pz_pre_lut + threadIdx.x;
+  {
+    uint32_t code = 0;
+#pragma unroll 1
+    for (uint32_t l = 1; l <= 7u; l++) {
+      for (uint32_t s = 0; s < 19u; s++) {
+        if (((pl >> (3u * s)) & 7u) != l) continue;
+        for (uint32_t j = __brev(code) >> (32u - l); j < 128u; j += 1u << l) lut[j * PZ_HUGE_THREADS] = (uint8_t)(s | (l << 5));
+        code++;
+      }
+      code <<= 1;
+    }
+  }
   const uint32_t total = hlit + hdist;
   uint32_t n = 0, prev = 0, sum_l = 0, sum_d = 0;
   bool eob = false;
   while (n < total) {
     if (pos + 7u + 7u > last_bit) return;
-    /* canonical decode of one code-length symbol, first bit = most significant (HuffmanTree.hs:73-83) */
-    const uint32_t w = pz_bits_at(in, nbytes, pos, 7);
-    uint32_t code = 0, first = 0, sym = 99, len = 1;
-    for (; len <= 7u; len++) {
-      code |= (w >> (len - 1u)) & 1u;
-      const uint32_t c = cnt[len];
-      if (code - first < c) { /* the (code - first)-th symbol of this length, in symbol order */
-        uint32_t r = code - first;
-        for (uint32_t s = 0; s < 19u; s++) {
-          if (((pl >> (3u * s)) & 7u) == len) {
-            if (r == 0u) { sym = s; break; }
-            r--;
-          }
-        }
-        break;
-      }
-      first = (first + c) << 1;
-      code <<= 1;
-    }
-    if (sym == 99u) return;
-    pos += len;
+    const uint32_t e = lut[pz_bits_fast(in, pos, 7) * PZ_HUGE_THREADS]; /* pos + 14 <= last_bit: 32 bits before the end */
+    const uint32_t sym = e & 31u;
+    pos += e >> 5;
     uint32_t rep = 1, val = sym;
     if (sym == 16u) {
       if (n == 0u) return;
-      rep = 3u + pz_bits_at(in, nbytes, pos, 2); pos += 2u; val = prev;
+      rep = 3u + pz_bits_fast(in, pos, 2); pos += 2u; val = prev;
     } else if (sym == 17u) {
-      rep = 3u + pz_bits_at(in, nbytes, pos, 3); pos += 3u; val = 0;
+      rep = 3u + pz_bits_fast(in, pos, 3); pos += 3u; val = 0;
     } else if (sym == 18u) {
-      rep = 11u + pz_bits_at(in, nbytes, pos, 7); pos += 7u; val = 0;
+      rep = 11u + pz_bits_fast(in, pos, 7); pos += 7u; val = 0;
     }
     if (n + rep > total) return;
     prev = val;

@@ -69,6 +69,12 @@ __global__ void __launch_bounds__(PZ_HUGE_THREADS)
 pz_blk_search_kernel(const uint8_t *__restrict__ in, uint64_t nbytes, uint64_t first_bit, uint64_t last_bit,
                      uint32_t *__restrict__ cand, uint32_t *__restrict__ ncand, uint32_t cap) {
   __shared__ uint4 list[PZ_HUGE_THREADS / 32][256];
+  __shared__ uint8_t pair[64]; /* Kraft weight (in 128ths) of two 3-bit code lengths at once */
+  if (threadIdx.x < 64u) {
+    const uint32_t a = threadIdx.x & 7u, b = threadIdx.x >> 3;
+    pair[threadIdx.x] = (uint8_t)((a ? 128u >> a : 0u) + (b ? 128u >> b : 0u));
+  }
+  __syncthreads();
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint64_t B = (first_bit >> 3) + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t v0 = 0, v1 = 0, v2 = 0, mask = 0;
@@ -118,12 +124,12 @@ pz_blk_search_kernel(const uint8_t *__restrict__ in, uint64_t nbytes, uint64_t f
     const uint32_t s = o + 17u; /* < 32 */
     uint32_t p0 = __funnelshift_r(e.x, e.y, s), p1 = __funnelshift_r(e.y, e.z, s);
     uint32_t sum = 0;
-    for (uint32_t k = 0; k < hclen && sum <= 128u; k++) {
-      const uint32_t l = p0 & 7u;
-      sum += l ? (128u >> l) : 0u;
-      p0 = __funnelshift_r(p0, p1, 3);
-      p1 >>= 3;
+    for (uint32_t k = 0; k + 1u < hclen && sum <= 128u; k += 2u) { /* two lengths per step */
+      sum += pair[p0 & 63u];
+      p0 = __funnelshift_r(p0, p1, 6);
+      p1 >>= 6;
     }
+    if (hclen & 1u) sum += pair[p0 & 7u]; /* the odd one out (pair[l] = weight of l alone) */
     if (sum != 128u) continue;
     const uint32_t k = atomicAdd(ncand, 1u);
     if (k < cap) cand[k] = e.w;

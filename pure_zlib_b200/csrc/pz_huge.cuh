@@ -80,22 +80,25 @@ pz_blk_search_kernel(const uint8_t *__restrict__ in, uint64_t nbytes, uint64_t f
   uint32_t v0 = 0, v1 = 0, v2 = 0, mask = 0;
   if (B * 8u < last_bit) {
     pz_load96(in, nbytes, B, v0, v1, v2);
-#pragma unroll
-    for (uint32_t o = 0; o < 8u; o++) {
-      const uint64_t pos = B * 8u + o;
-      const uint32_t h = __funnelshift_r(v0, v1, o);
-      const uint32_t hclen = ((h >> 13) & 15u) + 4u;
-      const bool ok = pos >= first_bit && pos < last_bit && ((h >> 1) & 3u) == 2u /* BTYPE: dynamic (Deflate.hs:83) */
-                      && ((h >> 3) & 31u) <= 29u && ((h >> 8) & 31u) <= 29u       /* what zlib can emit: HLIT <= 286, HDIST <= 30 */
-                      && pos + 17u + 3u * hclen <= last_bit;
-      mask |= ok ? (1u << o) : 0u;
-      /* an EMPTY stored block (00 00 ff ff behind the padding: what Z_SYNC_FLUSH / Z_FULL_FLUSH leave between the
-       * pieces of a stream) is a candidate on the strength of those 32 bits alone */
-      const uint32_t al = (o + 3u + 7u) >> 3; /* bytes from B to the byte boundary behind the three header bits */
-      const uint32_t lw = al == 1u ? ((v0 >> 8) | (v1 << 24)) : ((v0 >> 16) | (v1 << 16)); /* LEN | NLEN << 16 */
-      if (pos >= first_bit && pos < last_bit && ((h >> 1) & 3u) == 0u && lw == 0xffff0000u && (B + al + 4u) * 8u <= last_bit) {
-        const uint32_t k = atomicAdd(ncand, 1u);
-        if (k < cap) cand[k] = (uint32_t)pos;
+    /* the cheap tests on all eight offsets at once, one bit per offset: BTYPE (bits o+1, o+2) is dynamic (Deflate.hs:83),
+     * HLIT (bits o+3..o+7) and HDIST (bits o+8..o+12) are at most 29 -- what zlib can emit -- i.e. their upper four bits
+     * are not all ones.  Positions outside [first_bit, last_bit) are dropped in the second step. */
+    const uint32_t dyn = ~(v0 >> 1) & (v0 >> 2);
+    const uint32_t hlit_bad = (v0 >> 4) & (v0 >> 5) & (v0 >> 6) & (v0 >> 7);
+    const uint32_t hdist_bad = (v0 >> 9) & (v0 >> 10) & (v0 >> 11) & (v0 >> 12);
+    mask = dyn & ~hlit_bad & ~hdist_bad & 0xffu;
+    /* an EMPTY stored block (00 00 ff ff behind the padding: what Z_SYNC_FLUSH / Z_FULL_FLUSH leave between the
+     * pieces of a stream) is a candidate on the strength of those 32 bits alone */
+    const uint32_t lw1 = (v0 >> 8) | (v1 << 24), lw2 = (v0 >> 16) | (v1 << 16); /* LEN | NLEN << 16 one / two bytes on */
+    if (lw1 == 0xffff0000u || lw2 == 0xffff0000u) {
+      for (uint32_t o = 0; o < 8u; o++) {
+        const uint64_t pos = B * 8u + o;
+        const uint32_t al = (o + 3u + 7u) >> 3; /* bytes from B to the byte boundary behind the three header bits */
+        if (pos >= first_bit && pos < last_bit && ((v0 >> (o + 1u)) & 3u) == 0u && (al == 1u ? lw1 : lw2) == 0xffff0000u &&
+            (B + al + 4u) * 8u <= last_bit) {
+          const uint32_t k = atomicAdd(ncand, 1u);
+          if (k < cap) cand[k] = (uint32_t)pos;
+        }
       }
     }
   }
@@ -120,6 +123,7 @@ pz_blk_search_kernel(const uint8_t *__restrict__ in, uint64_t nbytes, uint64_t f
     const uint32_t o = e.w & 7u;
     const uint32_t h = __funnelshift_r(e.x, e.y, o);
     const uint32_t hclen = ((h >> 13) & 15u) + 4u;
+    if (e.w < first_bit || (uint64_t)e.w + 17u + 3u * hclen > last_bit) continue; /* the stream's edges */
     /* the code-length code must be complete: sum 2^(7-len) == 128 */
     const uint32_t s = o + 17u; /* < 32 */
     uint32_t p0 = __funnelshift_r(e.x, e.y, s), p1 = __funnelshift_r(e.y, e.z, s);

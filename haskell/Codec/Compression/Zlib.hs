@@ -14,7 +14,7 @@ module Codec.Compression.Zlib (
   decompressMany,
 ) where
 
-import Control.Exception (ErrorCall (..), throw)
+import Control.Exception (ErrorCall (..), Exception, throw)
 import Control.Monad (forM, when)
 import Control.Monad.ST (ST)
 import Control.Monad.ST.Unsafe (unsafeIOToST)
@@ -25,7 +25,7 @@ import qualified Data.ByteString.Unsafe as SU
 import Data.Int (Int32, Int64)
 import Data.Word (Word32, Word64, Word8)
 import Foreign
-import Foreign.C.String (CString, peekCStringLen)
+import Foreign.C.String (CString, peekCString, peekCStringLen)
 import Foreign.C.Types
 import System.IO.Unsafe (unsafePerformIO)
 
@@ -45,6 +45,10 @@ instance Show DecompressionError where
     DecompressionError s -> "Decompression error: " ++ s
     HeaderError s -> "Header error: " ++ s
     ChecksumError s -> "Checksum error: " ++ s
+
+-- | Monad.hs:104.  Callers `throwIO` / `catch` this type (it is exported with its constructors,
+-- Zlib.hs:4); `Typeable` is derived automatically by every GHC the reference supports (>= 7.10).
+instance Exception DecompressionError
 
 -- | Monad.hs:163-167.
 data ZlibDecoder s
@@ -144,7 +148,8 @@ decompressBatch inputs = unsafePerformIO $ do
                     Left (DecompressionError "Finished with data remaining.")
                 | otherwise -> Right (L.fromStrict (SI.fromForeignPtr fp 0 (fromIntegral (rOutLen r))))
  where
-  failCuda = c_pz_last_error >>= peekCStringLen . flip (,) 256 >>= \m -> throw (ErrorCall ("pzcuda: " ++ m))
+  -- pz_last_error returns a NUL-terminated string owned by the library (thread-local)
+  failCuda = c_pz_last_error >>= peekCString >>= \m -> throw (ErrorCall ("pzcuda: " ++ m))
   -- does a non-empty chunk start after the byte at which the decoder finished?
   trailingChunks l consumed = go (L.toChunks l) 0
    where

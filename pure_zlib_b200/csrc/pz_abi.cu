@@ -40,7 +40,7 @@ int fail_cuda(cudaError_t e, const char *what) {
     if (e__ != cudaSuccess) return fail_cuda(e__, #call); \
   } while (0)
 
-uint64_t g_huge_bytes = 4ull << 20; /* compressed size from which a stream goes to K4 (PZ_HUGE_BYTES overrides) */
+std::atomic<uint64_t> g_huge_bytes{4ull << 20}; /* compressed size from which a stream goes to K4 (PZ_HUGE_BYTES overrides) */
 std::atomic<uint64_t> g_huge_done{0}, g_huge_declined{0};
 std::atomic<int> g_stream_resume{1}; /* PZ_OPT_STREAM_RESUME */
 std::once_flag g_once;
@@ -403,8 +403,10 @@ int huge_stream(const uint8_t *d_in_blob, const uint64_t *d_in_off_i, uint64_t i
   out->adler_stored = ((uint32_t)trailer[0] << 24) | ((uint32_t)trailer[1] << 16) | ((uint32_t)trailer[2] << 8) | trailer[3];
   out->err_bitpos = tb * 8u + 32u;
   /* bytes the reference has published as 32 KiB chunks when it reaches the trailer: one chunk per
-   * moveWindow call that finds 64 KiB in the window (Monad.hs:338-347); with calls after every match
-   * that is every threshold 64 KiB + 32 KiB * j up to the final length */
+   * moveWindow call that finds 64 KiB in the window (Monad.hs:338-347).  Every block job has checked that no
+   * more than 32 KiB lie between two calls (PzCtx::mark), so the window never holds 96 KiB after a call, every
+   * call that finds 64 KiB leaves less than 64 KiB, and the last call leaves [32 KiB, 64 KiB): the closed form
+   * below is exact for every stream K4 accepts */
   out->payload[1] = total >= 65536u ? (int64_t)(32768u * ((total - 65536u) / 32768u + 1u)) : 0;
   return 1;
 }

@@ -1,48 +1,48 @@
 /*
- * pz_device.cuh -- the device-side inflate engine.
+ * pz_device.cuh -- the device-side inflate engine (K1 and the logic K4's block jobs share with it).
  *
- * Execution model.  A warp is split into 32/PZ_G "groups" of PZ_G lanes and a group serves one
- * zlib stream, so a warp advances 32/PZ_G independent streams in lockstep and every issued
- * instruction does useful work for all of them (the decode chain of one stream is serial: the
- * win is in sharing issue slots, not lanes).  A CTA is a PAIR of such warps working on the same
- * streams:
+ * Execution model.  ONE persistent CTA per SM owns PZ_SLOTS stream slots (shared memory: LUTs, a staged
+ * input ring, a token queue and a hand-over block per slot, struct PzStreamSmem) and three kinds of warps
+ * (roles are dealt by warp index in pz_kernels.cu:pz_role):
  *
- *   decoder warp  owns the bit stream.  It parses headers, builds the Huffman LUTs in shared
- *                 memory, and runs the serial bit-position chain (window -> LUT -> bits -> next
- *                 window).  It never touches the output: every literal / match / stored run is
- *                 pushed as one 32-bit token into the stream's shared-memory queue.  All of the
- *                 reference's verdicts are decided here from counters alone.
- *   writer warp   owns the output.  It pops tokens, stores literals and performs the LZ77
- *                 copies straight into the stream's slice of the HBM output blob (the output
- *                 itself is the history window).  Match bytes are loaded when the token is
- *                 popped and stored three iterations later, so the L2/HBM round trip of a copy
- *                 never stalls the warp.
+ *   hot warp       pz_hot_warp(): one LANE per slot runs the symbol loop (runInflate, Deflate.hs:106-120) of
+ *                  that slot's stream -- window -> literal/length LUT -> shift -> distance LUT -> shift, the
+ *                  96 stream bits at the bit position held in registers -- four symbols per trip
+ *                  (pz_fast_trip), speculatively: a symbol the loop must not decide (long code, end of block,
+ *                  end of input or output in sight, a verdict) commits nothing and returns the stream to its
+ *                  service group through the slot's mailbox (PzMail).  It never touches the output: every
+ *                  literal / match is one 32-bit token in the slot's queue.
+ *   service warps  pz_decoder_warp(): groups of PZ_G lanes, one group per slot, run everything rare or
+ *                  order-sensitive with the reference's exact verdict order -- zlib header (pz_begin), block
+ *                  headers and code-length decode (pz_slow_step, pz_dynamic_header), LUT construction
+ *                  (pz_build), the bit-serial walk (pz_walk / pz_symbol_careful), stored blocks, the trailer,
+ *                  checkpoints of resumable streams -- and keep the input ring ahead of the hot lane with
+ *                  cp.async (pz_service_poll).
+ *   writer warps   pz_writer_warp(): groups of PZ_WG lanes pop tokens and produce the bytes straight into
+ *                  the stream's slice of the HBM output blob, which is also the LZ77 history: batches of
+ *                  literals and short disjoint matches are dealt to the lanes by output POSITION, all
+ *                  history loads of a batch issued before its first store; overlapping or long copies,
+ *                  stored runs and control tokens go through pz_writer_apply() (byte-serial replicate
+ *                  semantics of copyChunked, OutputWindow.hs:94-101).
  *
- * The two instruction streams are independent, which is what an in-order, one-warp-per-
- * scheduler machine needs: the decoder's chain no longer waits behind copy instructions, and
- * the writer's memory latencies no longer delay the next symbol.
- *
- * Each decoder group runs a small state machine (IDLE -> HDR -> SYMS <-> FAST -> ... -> IDLE) so
- * that the groups of a warp meet in ONE hot loop (pz_fast_loop) no matter where their streams
- * are; everything that is rare or needs the reference's exact verdict order (block headers,
- * table construction, codes longer than the first-level LUT, the last bits of the input or the
- * last bytes of the output buffer) runs in the "slow" part, one group at a time.
+ * All of the reference's verdicts are decided on the decoder side from counters alone (bit position, bytes
+ * produced, the reference's window fill/base model); nothing ever reads the output to decide one.
  *
  * What it replaces in the reference (file:line relative to the pure-zlib checkout):
  *   bit reader            Monad.hs:199-263   -> bit position over a cp.async-staged smem ring,
- *                                               64-bit windows assembled with funnel shifts
+ *                                               register windows assembled with funnel shifts
  *   tree build + walk     HuffmanTree.hs:25-83, Deflate.hs:255-288 -> canonical counts + flat LUT
  *   block parser          Deflate.hs:65-156  -> pz_slow_step()
- *   symbol loop           Deflate.hs:106-120 -> pz_fast_loop() + exact "careful" path
+ *   symbol loop           Deflate.hs:106-120 -> pz_fast_trip() + exact "careful" path
  *   output window         OutputWindow.hs:29-114 -> pz_writer_warp(): direct stores; the window
  *                                              is only *modelled* (fill/base counters in the
  *                                              decoder) to reproduce its verdicts
  *   zlib framing          Zlib.hs:53-69, Deflate.hs:52-63
  *
  * The file also compiles with a host C++ compiler when PZ_HOSTSIM is defined: a group is then
- * a single lane, and every pushed token is applied to the output at once.  That build exists
- * only for tests/hostsim (CPU-side differential fuzzing of this logic against the oracle); the
- * product library never contains it.
+ * a single lane, the symbol loop runs in the same thread (pz_fast_loop) and every pushed token is
+ * applied to the output at once.  That build exists only for tests/hostsim (CPU-side differential
+ * fuzzing of this logic against the oracle); the product library never contains it.
  */
 #pragma once
 #include <stdint.h>
@@ -194,7 +194,8 @@ struct PzMail {
   uint32_t bp, pos, base, lim, safe_end, qhead; /* travel with the ownership           */
   uint32_t hot_bp;  /* hot lane -> service: bit position at the end of its last trip   */
   uint32_t ring_hi; /* service -> hot lane: ring quarters < ring_hi are resident       */
-  uint32_t pad[3];
+  uint32_t mark;    /* block jobs: PzCtx::mark, travels with the ownership               */
+  uint32_t pad[2];
 };
 
 /* Shared memory of one stream (one slot of the CTA). */
@@ -307,6 +308,10 @@ struct PzCtx {
   bool block_job;       /* the unit is one deflate block (PzJob::blk_start), not a zlib stream     */
   uint32_t pos;  /* bytes decoded                                                          */
   uint32_t base; /* bytes the reference would already have published (multiple of 32 KiB)  */
+  uint32_t mark; /* block jobs: pos at the last moveWindow call (after a match, at a block's start).  The bytes
+                    between two calls ("gap") decide whether the reference's window can overflow: while every gap is
+                    <= 32 KiB the fill stays below 96 KiB + 258 whatever it was at the block's start, so a block job,
+                    which does not know the real fill, is exact; a longer gap makes the job give up (K4 declines) */
   uint32_t cap;
   int32_t status, detail;
   int64_t p0, p1;
@@ -934,8 +939,10 @@ PZ_DEV bool pz_match(PzCtx &c, PzStreamSmem *sm, uint32_t len, uint32_t dist) {
   if (dist > fill) { pz_fail(c, PZ_REF_BOTTOM, PZ_D_BOT_DIST_TOO_FAR, dist, fill); return false; }
   if (fill + len > PZ_WINDOW) { pz_fail(c, PZ_REF_BOTTOM, PZ_D_BOT_WINDOW_OVERFLOW); return false; }
   if (len > c.cap - c.pos) { pz_fail(c, PZ_OUTPUT_FULL, 0); return false; }
+  if (c.block_job && c.pos + len - c.mark > PZ_EXCESS) { pz_fail(c, PZ_REF_BOTTOM, PZ_D_BOT_WINDOW_OVERFLOW); return false; } /* PzCtx::mark */
   pz_push<COUNT_ONLY>(c, sm, PZ_TOKEN(PZ_Q_MATCH, (len << 16) | (dist - 1u)));
   c.pos += len;
+  c.mark = c.pos;
   pz_move_window(c);
   return true;
 }
@@ -945,6 +952,7 @@ template <bool COUNT_ONLY>
 PZ_DEV bool pz_literal_checked(PzCtx &c, PzStreamSmem *sm, uint32_t b) {
   if (c.pos - c.base >= PZ_WINDOW) { pz_fail(c, PZ_REF_BOTTOM, PZ_D_BOT_WINDOW_OVERFLOW); return false; }
   if (c.pos >= c.cap) { pz_fail(c, PZ_OUTPUT_FULL, 0); return false; }
+  if (c.block_job && c.pos + 1u - c.mark > PZ_EXCESS) { pz_fail(c, PZ_REF_BOTTOM, PZ_D_BOT_WINDOW_OVERFLOW); return false; } /* PzCtx::mark */
   pz_push<COUNT_ONLY>(c, sm, PZ_TOKEN(PZ_Q_LIT, b & 0xffu));
   c.pos++;
   return true;
@@ -987,7 +995,7 @@ PZ_DEV int pz_symbol_careful(PzCtx &c, PzStreamSmem *sm) {
  * a full token queue): that group consumed nothing of it.  Groups that are not in FAST mode (no
  * streams left) idle along. */
 struct PzFast { /* the registers of the hot loop */
-  uint32_t bp, pos, base, lim, safe_end, qhead, qtailc;
+  uint32_t bp, pos, base, lim, safe_end, qhead, qtailc, mark;
   uint32_t b0, b1, b2, e; /* the 96 stream bits at bp and the literal/length LUT entry of b0 (decoded ahead) */
   bool live;
 #ifdef PZ_HOSTSIM
@@ -1017,9 +1025,9 @@ PZ_DEV void pz_fast_fetch(PzFast &f, const PzStreamSmem *sm, uint32_t bp) {
 #ifndef PZ_TRIP
 #define PZ_TRIP 4
 #endif
-template <bool COUNT_ONLY>
+template <bool COUNT_ONLY, bool BLK = false>
 PZ_DEV bool pz_fast_trip(PzFast &f, PzStreamSmem *sm, const bool run) {
-  uint32_t bp = f.bp, pos = f.pos, base = f.base, qhead = f.qhead;
+  uint32_t bp = f.bp, pos = f.pos, base = f.base, qhead = f.qhead, mark = f.mark;
   uint32_t b0 = f.b0, b1 = f.b1, b2 = f.b2, e = f.e;
   bool alive = run;
 #pragma unroll
@@ -1052,6 +1060,10 @@ PZ_DEV bool pz_fast_trip(PzFast &f, PzStreamSmem *sm, const bool run) {
     const bool m_ok = tb != 0u && (d & 31u) != 0u && dist <= pos && len <= room;
     alive = alive && pre_ok && (is_lit || m_ok);
     const uint32_t adv = is_lit ? 1u : len;
+    if (BLK) { /* PzCtx::mark: a gap of more than 32 KiB between two moveWindow calls is the careful path's to refuse */
+      alive = alive && pos + adv - mark <= PZ_EXCESS;
+      mark = is_lit ? mark : pos + adv;
+    }
     if (!COUNT_ONLY) {
       const uint32_t tok = is_lit ? PZ_TOKEN(PZ_Q_LIT, (e >> 16) & 0xffu) : PZ_TOKEN(PZ_Q_MATCH, (len << 16) | (dist - 1u));
 #ifdef PZ_HOSTSIM
@@ -1064,7 +1076,7 @@ PZ_DEV bool pz_fast_trip(PzFast &f, PzStreamSmem *sm, const bool run) {
     pos += adv;
     if (!is_lit && pos - base >= 2u * PZ_EXCESS) base += PZ_EXCESS; /* moveWindow after every match */
     bp = nbp; b0 = nb0; b1 = nb1; b2 = nb2; e = ne;
-    if (alive) { f.bp = bp; f.pos = pos; f.base = base; f.qhead = qhead; }
+    if (alive) { f.bp = bp; f.pos = pos; f.base = base; f.qhead = qhead; if (BLK) f.mark = mark; }
   }
   if (alive) { f.b0 = b0; f.b1 = b1; f.b2 = b2; f.e = e; } /* else: unchanged if the trip did not run, stale if it stopped */
   return run && !alive;
@@ -1075,7 +1087,7 @@ PZ_DEV void pz_fast_loop(PzCtx &c, PzStreamSmem *sm) {
   PzFast f;
   f.live = c.mode == PZ_M_FAST;
   f.bp = c.bp; f.pos = c.pos; f.base = c.base; f.safe_end = c.safe_end;
-  f.qhead = c.qhead; f.qtailc = c.qtailc;
+  f.qhead = c.qhead; f.qtailc = c.qtailc; f.mark = c.mark;
 #ifdef PZ_HOSTSIM
   f.hw = c.hw;
 #endif
@@ -1086,12 +1098,12 @@ PZ_DEV void pz_fast_loop(PzCtx &c, PzStreamSmem *sm) {
   bool stop;
   for (;;) {
     /* PZ_TRIP x 48 bits stay inside the resident quarters */
-    stop = pz_fast_trip<COUNT_ONLY>(f, sm, f.live);
+    stop = c.block_job ? pz_fast_trip<COUNT_ONLY, true>(f, sm, f.live) : pz_fast_trip<COUNT_ONLY, false>(f, sm, f.live);
     if (f.live && (f.bp >> PZ_QUARTER_SHIFT) != c.q) { c.bp = f.bp; pz_cross(c, sm); }
     if (pz_warp_any(stop)) break;
   }
   if (f.live) {
-    c.bp = f.bp; c.pos = f.pos; c.base = f.base; c.qhead = f.qhead;
+    c.bp = f.bp; c.pos = f.pos; c.base = f.base; c.qhead = f.qhead; c.mark = f.mark;
     c.mode = PZ_M_SYMS;
     c.need_careful = true;
   }
@@ -1107,13 +1119,13 @@ PZ_DEV void pz_fast_loop(PzCtx &c, PzStreamSmem *sm) {
  * it writes the stream's position back and returns the ownership; the other lanes carry on.  The
  * lane only READS the staged input: the service group keeps the ring filled, following the bit
  * position the lane publishes after every trip. */
-template <bool COUNT_ONLY>
+template <bool COUNT_ONLY, bool BLK>
 PZ_DEV void pz_hot_warp(PzStreamSmem *slots, uint32_t n_slots) {
   const uint32_t lane = threadIdx.x & 31u;
   PzStreamSmem *sm = slots + (lane < n_slots ? lane : 0u);
   PzFast f;
   f.live = false;
-  f.bp = 0; f.pos = 0; f.base = 0; f.lim = 0; f.safe_end = 0; f.qhead = 0; f.qtailc = 0; f.b0 = 0; f.b1 = 0; f.b2 = 0; f.e = 0;
+  f.bp = 0; f.pos = 0; f.base = 0; f.lim = 0; f.safe_end = 0; f.qhead = 0; f.qtailc = 0; f.mark = 0; f.b0 = 0; f.b1 = 0; f.b2 = 0; f.e = 0;
   bool dead = lane >= n_slots;
   /* A lone warp pays every branch in full (nothing else issues on its scheduler while one
    * resolves), and most of the time some lane or other is between two postings (its stream is with
@@ -1131,6 +1143,7 @@ PZ_DEV void pz_hot_warp(PzStreamSmem *slots, uint32_t n_slots) {
         pz_fence_cta();
         f.bp = pz_vload(&sm->mail.bp); f.pos = pz_vload(&sm->mail.pos); f.base = pz_vload(&sm->mail.base);
         f.lim = pz_vload(&sm->mail.lim); f.safe_end = pz_vload(&sm->mail.safe_end); f.qhead = pz_vload(&sm->mail.qhead);
+        if (BLK) f.mark = pz_vload(&sm->mail.mark);
         pz_fast_fetch(f, sm, f.bp);
         f.live = true;
       }
@@ -1144,7 +1157,7 @@ PZ_DEV void pz_hot_warp(PzStreamSmem *slots, uint32_t n_slots) {
     const uint32_t ring_hi = pz_vload(&sm->mail.ring_hi);
     if (!COUNT_ONLY) f.qtailc = pz_vload(&sm->qtail);
     const bool run = f.live && (f.bp >> PZ_QUARTER_SHIFT) + 1u < ring_hi;
-    const bool stop = pz_fast_trip<COUNT_ONLY>(f, sm, run);
+    const bool stop = pz_fast_trip<COUNT_ONLY, BLK>(f, sm, run);
     if (run) pz_vstore(&sm->mail.hot_bp, f.bp);
     if (__any_sync(0xffffffffu, stop)) {
       const bool full = !COUNT_ONLY && f.qhead - f.qtailc >= PZ_QLEN;
@@ -1152,6 +1165,7 @@ PZ_DEV void pz_hot_warp(PzStreamSmem *slots, uint32_t n_slots) {
       if (stop && !full) { /* hand the stream back: the careful path decides the next symbol */
         pz_vstore(&sm->mail.bp, f.bp); pz_vstore(&sm->mail.pos, f.pos); pz_vstore(&sm->mail.base, f.base);
         pz_vstore(&sm->mail.qhead, f.qhead);
+        if (BLK) pz_vstore(&sm->mail.mark, f.mark);
         pz_fence_cta();
         pz_vstore(&sm->mail.state, PZ_MS_SERVICE);
         f.live = false;
@@ -1170,7 +1184,7 @@ PZ_DEV void pz_post_hot(PzCtx &c, PzStreamSmem *sm) {
     if (c.cap < lim) lim = c.cap;
     pz_vstore(&sm->mail.bp, c.bp); pz_vstore(&sm->mail.pos, c.pos); pz_vstore(&sm->mail.base, c.base);
     pz_vstore(&sm->mail.lim, lim); pz_vstore(&sm->mail.safe_end, c.safe_end); pz_vstore(&sm->mail.qhead, c.qhead);
-    pz_vstore(&sm->mail.hot_bp, c.bp); pz_vstore(&sm->mail.ring_hi, c.next_q);
+    pz_vstore(&sm->mail.hot_bp, c.bp); pz_vstore(&sm->mail.ring_hi, c.next_q); pz_vstore(&sm->mail.mark, c.mark);
     pz_fence_cta();
     pz_vstore(&sm->mail.state, PZ_MS_HOT);
   }
@@ -1195,6 +1209,7 @@ PZ_DEV void pz_service_poll(PzCtx &c, PzStreamSmem *sm) {
     pz_fence_cta();
     c.bp = pz_vload(&sm->mail.bp); c.pos = pz_vload(&sm->mail.pos); c.base = pz_vload(&sm->mail.base);
     c.qhead = pz_vload(&sm->mail.qhead);
+    if (c.block_job) c.mark = pz_vload(&sm->mail.mark);
     c.q = c.bp >> PZ_QUARTER_SHIFT;
     /* the reader's invariant again: q and q+1 resident, q+2 requested */
     if (c.next_q < c.q + 2u) {
@@ -1296,6 +1311,7 @@ PZ_DEV bool pz_stored_block(PzCtx &c, PzStreamSmem *sm) {
   uint32_t fill = c.pos - c.base;
   if (fill + len > PZ_WINDOW) { pz_fail(c, PZ_REF_BOTTOM, PZ_D_BOT_WINDOW_OVERFLOW); return false; }
   if (len > c.cap - c.pos) { pz_fail(c, PZ_OUTPUT_FULL, 0); return false; }
+  if (c.block_job && c.pos + len - c.mark > PZ_EXCESS) { pz_fail(c, PZ_REF_BOTTOM, PZ_D_BOT_WINDOW_OVERFLOW); return false; } /* PzCtx::mark */
   pz_push<COUNT_ONLY>(c, sm, PZ_TOKEN(PZ_Q_CTRL, PZ_C_STORED << 26));
   pz_push<COUNT_ONLY>(c, sm, boff - (c.start_bit >> 3)); /* offset from the stream's first byte */
   pz_push<COUNT_ONLY>(c, sm, len);
@@ -1348,7 +1364,7 @@ PZ_DEV void pz_begin(PzCtx &c, PzStreamSmem *sm, uint32_t s, const uint8_t *in, 
   uint32_t mis = (uint32_t)((uintptr_t)in & 15u);
   c.in_al = in - mis;
   c.res = res;
-  c.pos = 0; c.base = 0;
+  c.pos = 0; c.base = 0; c.mark = 0;
   c.cap = out_cap > 0xfffdff00ull ? 0xfffdff00u : (uint32_t)out_cap; /* base + 128 KiB stays in 32 bits */
   c.status = PZ_OK; c.detail = 0; c.p0 = 0; c.p1 = 0;
   c.adler_stored = 0; c.bfinal = 0; c.need_careful = false;
@@ -1399,7 +1415,7 @@ PZ_DEV void pz_begin_block(PzCtx &c, PzStreamSmem *sm, uint32_t j, const uint8_t
   uint32_t mis = (uint32_t)((uintptr_t)in & 15u);
   c.in_al = in - mis;
   c.res = res;
-  c.pos = PZ_BLK_BIAS; c.base = 0;
+  c.pos = PZ_BLK_BIAS; c.base = 0; c.mark = PZ_BLK_BIAS;
   c.cap = PZ_BLK_BIAS + cap;
   c.status = PZ_OK; c.detail = 0; c.p0 = 0; c.p1 = 0;
   c.adler_stored = 0; c.bfinal = 0; c.need_careful = false;
@@ -1527,7 +1543,7 @@ PZ_DEV void pz_decoder_warp(const PzJob &job, uint32_t first_stream, uint32_t st
   c.mode = PZ_M_IDLE;
   c.next = first_stream;
   c.in_al = nullptr; c.in_al_bytes = 0; c.bp = 0; c.q = 0; c.next_q = 0; c.pending = false; c.starved = false; c.block_job = false; c.res = nullptr;
-  c.hdr_bp = 0; c.sym_bp = 0; c.resume_sym = 0; c.ck = nullptr;
+  c.hdr_bp = 0; c.sym_bp = 0; c.resume_sym = 0; c.ck = nullptr; c.mark = 0;
   c.qhead = 0; c.qtailc = 0;
   c.fixed_ready = false;
 #ifdef PZ_HOSTSIM

@@ -39,6 +39,7 @@ __device__ __forceinline__ void pz_role(uint32_t w, uint32_t &role, uint32_t &in
   index = PZ_HOT_SCHED_SERVICE + (k - PZ_WRITER_WARPS);
 }
 
+/* WIDE = block jobs (K4): 16-bit output symbols, and the gap rule of PzCtx::mark in the hot warp */
 template <bool COUNT_ONLY, bool WIDE = false>
 __global__ void __launch_bounds__(PZ_THREADS_PER_CTA, 1)
 pz_inflate_kernel(const PzJob job) {
@@ -57,7 +58,7 @@ pz_inflate_kernel(const PzJob job) {
   uint32_t role, index;
   pz_role(threadIdx.x >> 5, role, index);
   if (role == 0u) {
-    pz_hot_warp<COUNT_ONLY>(slots, PZ_SLOTS);
+    pz_hot_warp<COUNT_ONLY, WIDE>(slots, PZ_SLOTS);
     return;
   }
   if (role == 3u) return;
@@ -233,6 +234,10 @@ cudaError_t pz_kernels_configure(void) {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute((pz_inflate_kernel<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute((pz_inflate_kernel<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute((pz_inflate_kernel<true, true>), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute((pz_inflate_kernel<false, true>), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(pz_inflate_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -345,7 +350,7 @@ cudaError_t pz_launch_blk_jobs(const uint8_t *d_in_blob, const uint64_t *d_in_of
     if (e != cudaSuccess) return e;
     job.next_unit = d_counter;
   }
-  if (count_only) pz_inflate_kernel<true><<<grid, PZ_THREADS_PER_CTA, smem, st>>>(job);
+  if (count_only) pz_inflate_kernel<true, true><<<grid, PZ_THREADS_PER_CTA, smem, st>>>(job);
   else pz_inflate_kernel<false, true><<<grid, PZ_THREADS_PER_CTA, smem, st>>>(job);
   return cudaGetLastError();
 }

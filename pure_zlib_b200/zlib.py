@@ -79,7 +79,12 @@ _CTORS = {_lib.PZ_ERR_HUFFMAN_TREE: HuffmanTreeError, _lib.PZ_ERR_FORMAT: Format
 
 def _error_of(res: PzResult) -> DecompressionError:
     text = _lib.strerror(res)
-    cls = _CTORS[res.status]
+    cls = _CTORS.get(res.status)
+    if cls is None:
+        # not one of the reference's verdicts: PZ_OUTPUT_FULL (a decoded stream beyond the ABI's limit, or a sizing
+        # bug), PZ_NEED_MORE, or a status this mirror does not know -- a library-level failure, as in the Haskell
+        # shim's `verdict`
+        raise _lib.PzCudaError(f"pzcuda: status {res.status}: {text}")
     assert text.startswith(cls.prefix), text
     return cls(text[len(cls.prefix):])
 

@@ -9,10 +9,14 @@ them BEFORE the process initialises CUDA.
   config 5  stored16m: 512 x 16 MiB random bytes, level 6 (=> ~16 KiB stored blocks)
   config 4  huge     : ONE zlib stream of n MiB of the same text at level 9.  A single-threaded
                        level-9 pass over 1 GiB takes minutes, so the text is compressed in 16 MiB
-                       pieces on all cores (raw deflate, each piece ended with Z_FULL_FLUSH) and
-                       the pieces are concatenated behind one zlib header, with one Adler-32
-                       trailer: a valid single stream (what pigz -i writes) whose only difference
-                       from a one-pass stream is an empty stored block every 16 MiB
+                       pieces on all cores the way pigz does it: every piece is a raw-deflate run
+                       whose compressor was PRIMED with the 32 KiB of text before it (zdict), so its
+                       matches reach back across the piece boundary exactly as a one-pass stream's
+                       would, and the pieces are joined with Z_SYNC_FLUSH (an empty stored block)
+                       behind one zlib header, with one Adler-32 trailer.  The history is never
+                       reset: every back-reference of distance <= 32 KiB that a one-pass compressor
+                       could have used is available.  (Round 1 ended the pieces with Z_FULL_FLUSH,
+                       which cuts the history every 16 MiB: an easier stream than BASELINE states.)
 """
 from __future__ import annotations
 
@@ -100,8 +104,11 @@ _HUGE_PIECE = 16 << 20
 def _job_huge(args):
     k, nbytes, level, last = args
     d = text(nbytes, 3_000_000 + k)
-    co = zlib.compressobj(level, zlib.DEFLATED, -15)
-    z = co.compress(d) + (co.flush(zlib.Z_FINISH) if last else co.flush(zlib.Z_FULL_FLUSH))
+    if k == 0:
+        co = zlib.compressobj(level, zlib.DEFLATED, -15)
+    else:  # the last 32 KiB of the piece before this one are the compressor's history
+        co = zlib.compressobj(level, zlib.DEFLATED, -15, 8, zlib.Z_DEFAULT_STRATEGY, text(_HUGE_PIECE, 3_000_000 + k - 1)[-32768:])
+    z = co.compress(d) + (co.flush(zlib.Z_FINISH) if last else co.flush(zlib.Z_SYNC_FLUSH))
     return z, zlib.adler32(d), len(d)
 
 
@@ -159,6 +166,14 @@ def _pool(workers):
     return mp.get_context("fork").Pool(workers)
 
 
+def text256k_l1(n: int = 4096, workers: int | None = None) -> "Corpus":
+    return text256k(n, 1, workers)
+
+
+def text256k_l9(n: int = 4096, workers: int | None = None) -> "Corpus":
+    return text256k(n, 9, workers)
+
+
 def text256k(n: int = 4096, level: int = 6, workers: int | None = None) -> Corpus:
     with _pool(workers) as p:
         items = p.map(_job_text256k, [(i, level) for i in range(n)], chunksize=max(1, n // 256))
@@ -199,11 +214,17 @@ def decoded_piece(k: int, nbytes: int = _HUGE_PIECE) -> bytes:
     return text(nbytes, 3_000_000 + k)
 
 
+def decoded_by_name(name: str, i: int, nbytes: int) -> bytes:
+    """Regenerates the plain bytes of stream i (its index in the FULL batch) of the corpus called `name`."""
+    if name.startswith("text256k"):
+        return text(262144, 1000 + i)
+    if name == "records4k":
+        return text(4096, 2_000_000 + i)
+    if name.startswith("huge"):
+        return b"".join(decoded_piece(k, min(_HUGE_PIECE, nbytes - k * _HUGE_PIECE)) for k in range((nbytes + _HUGE_PIECE - 1) // _HUGE_PIECE))
+    return np.random.default_rng(5_000_000 + i).integers(0, 256, nbytes, dtype=np.uint8).tobytes()
+
+
 def decoded(corpus: Corpus, i: int) -> bytes:
     """Regenerates the plain text of stream i (for spot checks at full size)."""
-    if corpus.name.startswith("text256k"):
-        return text(262144, 1000 + i)
-    if corpus.name == "records4k":
-        return text(4096, 2_000_000 + i)
-    nbytes = int(corpus.out_len[i])
-    return np.random.default_rng(5_000_000 + i).integers(0, 256, nbytes, dtype=np.uint8).tobytes()
+    return decoded_by_name(corpus.name, i, int(corpus.out_len[i]))

@@ -1030,6 +1030,36 @@ PZ_DEV bool pz_fast_trip(PzFast &f, PzStreamSmem *sm, const bool run) {
   uint32_t bp = f.bp, pos = f.pos, base = f.base, qhead = f.qhead, mark = f.mark;
   uint32_t b0 = f.b0, b1 = f.b1, b2 = f.b2, e = f.e;
   bool alive = run;
+#if defined(PZ_EXP_CHAIN) && !defined(PZ_HOSTSIM)
+  /* TIMING EXPERIMENT ONLY (wrong byte counts): the sizing pass runs nothing but the bit-position chain -- the two LUT
+   * loads, the shifts, the stop tests on the entries and the end of the input -- and records the bit position of every
+   * symbol in the slot's queue, as a chain warp that leaves lengths, distances, verdicts and tokens to another warp
+   * would.  The byte counter moves 258 per symbol so that the careful path never sees a distance beyond it. */
+  if (COUNT_ONLY) {
+#pragma unroll
+    for (int k = 0; k < PZ_TRIP; k++) {
+      const bool is_lit = (int32_t)e < 0;
+      const uint32_t wd = pz_funnel_r(b0, b1, e);
+      const uint32_t wd1 = pz_funnel_r(b1, b2, e);
+      const uint32_t d = sm->dist_lut[wd & ((1u << PZ_DIST_BITS) - 1u)];
+      const uint32_t tb2 = d & (is_lit ? 0u : 31u);
+      const uint32_t nb0 = pz_funnel_r(wd, wd1, tb2);
+      const uint32_t ne = sm->lit_lut[nb0 & ((1u << PZ_LIT_BITS) - 1u)];
+      const uint32_t nbp = bp + (e & 31u) + tb2;
+      uint32_t nb1, nb2;
+      pz_peek_tail(sm->ring, nbp, nb1, nb2);
+      alive = alive && (e & 31u) != 0u && (is_lit || (d & 31u) != 0u) && bp <= f.safe_end;
+      if (alive) pz_vstore(&sm->q[qhead & (PZ_QLEN - 1u)], bp);
+      qhead += alive ? 1u : 0u;
+      bp = nbp; b0 = nb0; b1 = nb1; b2 = nb2; e = ne;
+      if (alive) { f.bp = bp; f.qhead = qhead; }
+    }
+    if (alive) { f.b0 = b0; f.b1 = b1; f.b2 = b2; f.e = e; }
+    f.pos += 258u * PZ_TRIP;
+    f.base = f.pos >= 65536u ? (f.pos - 32768u) & ~32767u : 0u;
+    return run && !alive;
+  }
+#endif
 #pragma unroll
   for (int k = 0; k < PZ_TRIP; k++) {
     const uint32_t tb = e & 31u;

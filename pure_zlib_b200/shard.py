@@ -1,7 +1,7 @@
 """Multi-GPU sharding of a batch: streams are independent, so a batch is cut into
 contiguous ranges, one per rank, balanced by compressed bytes.  There is no collective on the data
-path; `gather_verdicts` is the optional gather of the 48-byte verdict records afterwards (NCCL on
-GPUs, gloo in the CPU tests)."""
+path; `gather_verdicts` and `gather_outputs` are the optional gather of the 48-byte verdict records and of
+the decoded output slabs afterwards (NCCL on GPUs, gloo in the CPU tests)."""
 from __future__ import annotations
 
 import numpy as np
@@ -45,3 +45,19 @@ def gather_verdicts(local: np.ndarray, ranges, rank: int, world: int, device=Non
     for r, (a, b) in enumerate(ranges):
         out[a:b] = parts[r].cpu().numpy()[: (b - a) * RESULT_DTYPE.itemsize].view(RESULT_DTYPE)
     return out
+
+
+def gather_outputs(local_slab, slab_bytes, rank: int, world: int):
+    """All ranks contribute their decoded output slab (a 1-D uint8 torch tensor, on the GPU under NCCL or on the
+    host under gloo; rank r's slab has slab_bytes[r] bytes); every rank returns the concatenation in rank order,
+    i.e. the output blob of the whole batch.  Slabs are padded to the longest for the collective (all_gather
+    needs equal shapes) and trimmed afterwards.  Uses the default process group."""
+    import torch
+    import torch.distributed as dist
+    assert local_slab.dtype == torch.uint8 and local_slab.dim() == 1 and local_slab.numel() == slab_bytes[rank]
+    longest = max(slab_bytes) if slab_bytes else 0
+    send = torch.zeros(longest, dtype=torch.uint8, device=local_slab.device)
+    send[: local_slab.numel()] = local_slab
+    parts = [torch.empty_like(send) for _ in range(world)]
+    dist.all_gather(parts, send)
+    return torch.cat([parts[r][: slab_bytes[r]] for r in range(world)])

@@ -428,6 +428,45 @@ def test_huge_stream_block_parallel(pz, oracle, huge_threshold):
             assert _lib.strerror(r) == o.message, name
 
 
+def test_huge_stream_cross_piece_references_64mib(pz, oracle):
+    """BASELINE configs[3] in small: ONE 64 MiB level-9 stream whose 16 MiB pieces reference each other across
+    their boundaries (corpus.huge: primed compressors joined with Z_SYNC_FLUSH, the history is never reset), at
+    the library's DEFAULT threshold (4 MiB compressed): K4 must take it, and every piece must be byte-exact
+    against the generator and the whole against the oracle."""
+    from pure_zlib_b200 import _lib, corpus
+    L = _lib.load()
+    c = corpus.huge(64)
+    z = bytes(c.in_blob[: int(c.in_len[0])])
+    assert len(z) >= 4 << 20
+    done0 = L.pz_get_counter(1)
+    n = 1
+    keep = C.create_string_buffer(z, len(z))
+    ptrs = (C.c_void_p * n)(C.addressof(keep))
+    lens = (C.c_size_t * n)(len(z))
+    cap = int(c.out_len[0])
+    out = C.create_string_buffer(cap)
+    optrs = (C.c_void_p * n)(C.addressof(out))
+    caps = (C.c_size_t * n)(cap)
+    res = (_lib.PzResult * n)()
+    _lib.check(L.pz_inflate_batch(ptrs, lens, optrs, caps, n, res, 0), "pz_inflate_batch")
+    assert L.pz_get_counter(1) - done0 == 1, "K4 declined the stream"
+    o = oracle.decompress(z, out_cap=cap, want_events=True)
+    assert o.status == 0 and (res[0].status, res[0].out_len, res[0].adler_computed) == (0, o.out_len, o.adler_computed)
+    assert res[0].adler_computed == int(c.adler[0])
+    got = out.raw
+    piece = 16 << 20
+    for k in range(cap // piece):
+        assert got[k * piece: (k + 1) * piece] == corpus.decoded_piece(k), f"piece {k} differs"
+    assert got == o.data
+    assert res[0].payload[1] == sum(ln for kind, ln in o.events[:-2] if kind == 1)
+    # the serial path agrees (verdict fields the block-parallel path reconstructs)
+    res0 = (_lib.PzResult * n)()
+    _lib.check(L.pz_inflate_batch(ptrs, lens, optrs, caps, n, res0, _lib.PZ_F_NO_HUGE), "pz_inflate_batch")
+    assert (res0[0].status, res0[0].out_len, res0[0].adler_computed, res0[0].err_bitpos, res0[0].payload[1]) == \
+        (0, res[0].out_len, res[0].adler_computed, res[0].err_bitpos, res[0].payload[1])
+    assert out.raw == o.data
+
+
 def test_huge_stream_window_model_with_generous_capacity(pz, oracle, huge_threshold):
     """The reference's 128 KiB window overflows on back-to-back 64 KiB stored blocks wherever they
     sit in a stream.  Block jobs do not know the window's fill at their block's start, so K4 must give such a
@@ -692,3 +731,88 @@ def test_stream_feed_many_arguments(pz):
     group.pump()
     kinds = [[type(st).__name__ for st in group.events(i)] for i in range(3)]
     assert kinds[0] == ["Chunk", "Done"] and kinds[1] == ["NeedMore"] and kinds[2] == ["NeedMore"], kinds
+
+
+# ---- thread safety (pzcuda.h: every entry point may be called concurrently; SURVEY 8(b): `decompress` is pure) ----
+def test_concurrent_host_threads(pz, oracle):
+    """Eight host threads hammer the batch entry point, single incremental decoders and pumped sets at the same
+    time (ctypes releases the GIL for the duration of every call, so the calls really overlap inside the
+    library: thread-local workspaces, the process-wide pinned cache, the shared CUDA-stream pool).  Every verdict
+    and every byte must be the oracle's, whichever thread produced it."""
+    import threading
+    from pure_zlib_b200 import _lib
+    rng = np.random.default_rng(31)
+    texts = [streams.small_text(int(rng.integers(1000, 120_000)), 100 + i) for i in range(24)]
+    cases = [zlib.compress(t, int(rng.integers(1, 10))) for t in texts]
+    cases += [zlib.compress(rng.integers(0, 256, 70_000, dtype=np.uint8).tobytes(), 6)]      # stored blocks (K2)
+    cases += [cases[0][:-3], bytes.fromhex("789c4b04620000000001"), b"", cases[1][:100] + b"\xff" * 40]  # verdicts other than OK
+    want = [oracle.decompress(z, want_events=True) for z in cases]
+    errors = []
+
+    def check_batch(tid, rounds):
+        for r in range(rounds):
+            order = list(np.random.default_rng(1000 * tid + r).permutation(len(cases)))
+            res, outs = pz.zlib.inflate_batch_raw([cases[i] for i in order])
+            for k, i in enumerate(order):
+                o = want[i]
+                if (res[k].status, res[k].detail, res[k].out_len) != (o.status, o.detail, o.out_len) or outs[k] != o.data:
+                    errors.append(("batch", tid, r, i, res[k].status, res[k].detail, o.status, o.detail))
+                elif o.status != 0 and _lib.strerror(res[k]) != o.message:
+                    errors.append(("batch-msg", tid, r, i, _lib.strerror(res[k]), o.message))
+
+    def check_incremental(tid, rounds):
+        for r in range(rounds):
+            i = (tid * 7 + r) % len(cases)
+            if want[i].status == 6 or len(cases[i]) < 8:
+                continue
+            cuts = sorted(set(int(x) for x in np.random.default_rng(tid * 77 + r).integers(1, len(cases[i]), 3)))
+            pieces = _pieces(cases[i], cuts)
+            o = oracle.decompress(pieces, want_events=True)
+            events, acc, err = _run_incremental(pz, pieces)
+            if events != o.events or acc != o.data[: len(acc)]:
+                errors.append(("incremental", tid, r, i, events[:4], o.events[:4]))
+
+    def check_pump(tid, rounds):
+        ok = [i for i in range(len(cases)) if want[i].status == 0 and len(cases[i]) > 64]
+        for r in range(rounds):
+            pick = [ok[(tid + r + 3 * k) % len(ok)] for k in range(6)]
+            got = pz.zlib.decompress_many([[cases[i][: len(cases[i]) // 2], cases[i][len(cases[i]) // 2:]] for i in pick])
+            for i, g in zip(pick, got):
+                if not isinstance(g, pz.Right) or g.value != want[i].data:
+                    errors.append(("pump", tid, r, i, repr(g)[:60]))
+
+    workers = []
+    for tid in range(8):
+        fn = (check_batch, check_incremental, check_pump)[tid % 3]
+        workers.append(threading.Thread(target=fn, args=(tid, 6 if fn is check_batch else 8)))
+    for w in workers:
+        w.start()
+    for w in workers:
+        w.join(timeout=600)
+    assert not any(w.is_alive() for w in workers), "a worker thread hangs"
+    assert not errors, errors[:5]
+
+
+def test_deflate_cli(pz, golden_dir, tmp_path):
+    """The `deflate` executable (reference Deflate.hs:15-48; haskell/app/Deflate.hs; pure_zlib_b200/deflate_cli.py):
+    `deflate foo.z` writes foo through the incremental API, with the reference's messages."""
+    import shutil
+    from pure_zlib_b200 import deflate_cli
+    said = []
+    for name in ("rfctest2", "zerotest3", "randtest1"):
+        shutil.copy(os.path.join(golden_dir, name + ".z"), tmp_path / (name + ".z"))
+        assert deflate_cli.main([str(tmp_path / (name + ".z"))], said.append) == 0
+        assert (tmp_path / name).read_bytes() == open(os.path.join(golden_dir, name + ".gold"), "rb").read()
+    assert said == []
+    z = open(os.path.join(golden_dir, "rfctest1.z"), "rb").read()
+    (tmp_path / "cut.z").write_bytes(z[:5000])
+    deflate_cli.main([str(tmp_path / "cut.z")], said.append)
+    (tmp_path / "bad.z").write_bytes(bytes.fromhex("789c0700"))
+    deflate_cli.main([str(tmp_path / "bad.z")], said.append)
+    (tmp_path / "more.z").write_bytes(z + b"\0" * 40000)   # a further lazy chunk after Done
+    deflate_cli.main([str(tmp_path / "more.z")], said.append)
+    deflate_cli.main([str(tmp_path / "name.txt")], said.append)
+    deflate_cli.main([], said.append)
+    assert said == ["ERROR: Ran out of data mid-decompression.", "ERROR: Block format error: Unacceptable BTYPE: 3",
+                    "WARNING: Finished decompression with data left.", "Unexpected file name.", "USAGE: deflate [filename]"]
+    assert (tmp_path / "more").read_bytes() == open(os.path.join(golden_dir, "rfctest1.gold"), "rb").read()

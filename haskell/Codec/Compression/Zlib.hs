@@ -25,6 +25,7 @@ import qualified Data.ByteString.Unsafe as SU
 import Data.Int (Int32, Int64)
 import Data.Word (Word32, Word64, Word8)
 import Foreign
+import Foreign.ForeignPtr.Unsafe (unsafeForeignPtrToPtr)
 import Foreign.C.String (CString, peekCString, peekCStringLen)
 import Foreign.C.Types
 import System.IO.Unsafe (unsafePerformIO)
@@ -73,6 +74,7 @@ instance Storable PzResult where
     pokeByteOff p 32 (rP0 r); pokeByteOff p 40 (rP1 r)
 
 data PzStream
+data PzOutputs
 
 -- `safe`: the calls block on the GPU.  The library is thread-safe and deterministic, which is
 -- what lets `decompress` stay a pure function (unsafePerformIO below).
@@ -80,6 +82,10 @@ foreign import ccall safe "pz_inflate_batch"
   c_pz_inflate_batch :: Ptr (Ptr Word8) -> Ptr CSize -> Ptr (Ptr Word8) -> Ptr CSize -> CSize -> Ptr PzResult -> Word32 -> IO CInt
 foreign import ccall safe "pz_inflate_sizes"
   c_pz_inflate_sizes :: Ptr (Ptr Word8) -> Ptr CSize -> CSize -> Ptr PzResult -> IO CInt
+foreign import ccall safe "pz_decompress_batch"
+  c_pz_decompress_batch :: Ptr (Ptr Word8) -> Ptr CSize -> CSize -> Ptr PzResult -> Ptr (Ptr Word8) -> Ptr (Ptr PzOutputs) -> Word32 -> IO CInt
+foreign import ccall unsafe "&pz_outputs_free"
+  p_pz_outputs_free :: FunPtr (Ptr PzOutputs -> IO ())
 foreign import ccall unsafe "pz_strerror"
   c_pz_strerror :: Ptr PzResult -> CString -> CSize -> IO CSize
 foreign import ccall unsafe "pz_last_error"
@@ -117,7 +123,10 @@ verdict p r = case rStatus r of
     n <- c_pz_strerror p buf 512
     peekCStringLen (buf, fromIntegral (min n 511))
 
--- | Zlib.hs:32-51 applied to every element: one sizing launch, one decode launch.
+-- | Zlib.hs:32-51 applied to every element, in ONE library call (pz_decompress_batch: sizing launch, output
+-- allocation and decode launch inside the library).  The decoded bytes of all streams live in one pinned block
+-- owned by the library; the result ByteStrings are slices of it that share one ForeignPtr, whose finalizer
+-- (pz_outputs_free) runs when the last of them is collected: no byte is copied on the host on the way out.
 -- A lazy ByteString of several chunks whose stream ends before the last chunk is the
 -- reference's "Finished with data remaining." (Zlib.hs:48-49); the shim checks that on the host.
 decompressBatch :: [L.ByteString] -> [Either DecompressionError L.ByteString]
@@ -127,17 +136,14 @@ decompressBatch inputs = unsafePerformIO $ do
   withMany SU.unsafeUseAsCStringLen strict $ \cstrs ->
     withArray (map (castPtr . fst) cstrs) $ \pin ->
       withArray (map (fromIntegral . snd) cstrs) $ \plen ->
-        allocaArray n $ \pres -> do
-          rc <- c_pz_inflate_sizes pin plen (fromIntegral n) pres
+        allocaArray n $ \pres -> allocaArray n $ \pout -> alloca $ \phandle -> do
+          rc <- c_pz_decompress_batch pin plen (fromIntegral n) pres pout phandle 0
           when (rc /= 0) failCuda
-          sizes <- map (fromIntegral . rOutLen) <$> peekArray n pres :: IO [Int]
-          outs <- forM sizes $ \sz -> SI.mallocByteString (max sz 1)
-          withMany withForeignPtr outs $ \pouts ->
-            withArray pouts $ \pout ->
-              withArray (map fromIntegral sizes) $ \pcap -> do
-                rc2 <- c_pz_inflate_batch pin plen pout pcap (fromIntegral n) pres 0
-                when (rc2 /= 0) failCuda
-          forM (zip3 [0 ..] outs inputs) $ \(i, fp, lazyIn) -> do
+          handle <- peek phandle
+          -- one ForeignPtr for the whole block; every slice below keeps it alive
+          block <- if handle == nullPtr then return Nothing else Just <$> newForeignPtr p_pz_outputs_free handle
+          outs <- peekArray n pout
+          forM (zip3 [0 ..] outs inputs) $ \(i, po, lazyIn) -> do
             let p = pres `advancePtr` i
             r <- peek p
             e <- verdict p r
@@ -146,10 +152,16 @@ decompressBatch inputs = unsafePerformIO $ do
               Nothing
                 | trailingChunks lazyIn (fromIntegral (rBitPos r `div` 8)) ->
                     Left (DecompressionError "Finished with data remaining.")
-                | otherwise -> Right (L.fromStrict (SI.fromForeignPtr fp 0 (fromIntegral (rOutLen r))))
+                | otherwise -> Right (L.fromStrict (slice block po (fromIntegral (rOutLen r))))
  where
   -- pz_last_error returns a NUL-terminated string owned by the library (thread-local)
   failCuda = c_pz_last_error >>= peekCString >>= \m -> throw (ErrorCall ("pzcuda: " ++ m))
+  -- a strict ByteString over [po, po + len) whose lifetime is tied to the block's ForeignPtr: the payload pointer
+  -- is re-based on the block handle's ForeignPtr (plusForeignPtr keeps the finalizer of its argument)
+  slice Nothing _ _ = S.empty
+  slice (Just fp) po len
+    | len == 0 = S.empty
+    | otherwise = SI.fromForeignPtr (castForeignPtr fp `plusForeignPtr` (po `minusPtr` castPtr (unsafeForeignPtrToPtr fp))) 0 len
   -- does a non-empty chunk start after the byte at which the decoder finished?
   trailingChunks l consumed = go (L.toChunks l) 0
    where

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PZ_ABI_VERSION 1
+#define PZ_ABI_VERSION 2
 
 /* ------------------------------------------------------------------------------------
  * Verdicts.  `status` is the constructor of the reference's DecompressionError
@@ -97,16 +97,29 @@ typedef struct pz_result {
 #define PZ_F_NO_HUGE 0x10u   /* never use the block-parallel path (K4) for huge streams */
 #define PZ_F_NO_DRAIN 0x8u    /* host blobs: copy the output only after the kernel (no progressive 2-D copies) */
 
+#define PZ_MAX_DEVICES 16
 typedef struct pz_config {
-  int32_t device;          /* CUDA device ordinal, -1 = current device */
-  int32_t reserved[7];
+  int32_t device;          /* CUDA device ordinal of a single-device configuration, -1 = current device */
+  int32_t n_devices;       /* > 0: host-buffer batches are sharded over devices[0 .. n_devices) (devices[0] is the
+                              primary device: resident batches, incremental contexts); < 0: over every visible device;
+                              0: one device (`device`), or what the environment variable PZ_DEVICES ("all", "0,1,3")
+                              names when `device` is -1 */
+  int32_t devices[PZ_MAX_DEVICES];
+  int32_t reserved[6];
 } pz_config;
 
 /* ---- lifetime --------------------------------------------------------------------- */
-/* Once-only, race-free initialisation.  Called implicitly by every other entry point.
- * Replaces nothing in the reference (it has no global state).                            */
+/* Once-only, race-free initialisation.  Called implicitly (with cfg = NULL) by every other entry point.
+ * Replaces nothing in the reference (it has no global state).
+ * Multi-GPU: with more than one device configured, pz_inflate_batch, pz_inflate_sizes,
+ * pz_decompress_batch and pz_inflate_batch_contig on HOST blobs cut the batch into contiguous ranges of streams
+ * balanced by compressed bytes, one per device, each on a worker thread of its own with its own pinned staging, CUDA
+ * streams and kernels -- ONE call from ONE host thread uses every device; no collective (streams are independent).  */
 int pz_init(const pz_config *cfg);
+/* Releases the CALLING thread's workspace (device and pinned buffers are kept per host thread). */
 void pz_shutdown(void);
+/* Devices host-buffer batches are sharded over (1 unless pz_init / PZ_DEVICES said otherwise). */
+int pz_device_count(void);
 int pz_abi_version(void);
 /* Tuning knobs.  PZ_OPT_HUGE_BYTES: compressed size from which a stream is decoded block-parallel
  * (K4) instead of as one serial chain; default 4 MiB, environment PZ_HUGE_BYTES at start-up. */
@@ -140,6 +153,15 @@ int pz_inflate_batch_contig(const uint8_t *in_blob, const uint64_t *in_off, uint
 /* Sizing pass: the decoded length of each stream (res[i].out_len), nothing written.
  * Lets the shim implement `decompress` without caller-supplied capacities.               */
 int pz_inflate_sizes(const uint8_t *const *in, const size_t *in_len, size_t n, pz_result *res);
+
+/* `map decompress` in ONE call (Zlib.hs:32-51 for each of n single-chunk streams): sizing pass, output allocation and
+ * decode inside the library, so the compressed bytes are packed once and nothing is copied on the host on the way out:
+ * out[i] points at stream i's res[i].out_len decoded bytes inside one pinned block owned by *handle, valid until
+ * pz_outputs_free(*handle) (the Haskell shim wraps the block in ONE ForeignPtr that every result ByteString shares).  */
+typedef struct pz_outputs pz_outputs;
+int pz_decompress_batch(const uint8_t *const *in, const size_t *in_len, size_t n, pz_result *res, uint8_t **out,
+                        pz_outputs **handle, uint32_t flags);
+void pz_outputs_free(pz_outputs *handle);
 
 /* ---- resident batches: launch-only hot path ---------------------------------------- *
  * A plan owns the device-side descriptor tables (offsets, results, Adler partials), so

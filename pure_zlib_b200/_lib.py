@@ -16,6 +16,14 @@ PZ_F_NO_ADLER, PZ_F_COUNT_ONLY = 1, 2
 PZ_E_OK, PZ_E_CUDA, PZ_E_ARG, PZ_E_NOMEM, PZ_E_STATE = 0, -1, -2, -3, -4
 
 
+PZ_MAX_DEVICES = 16
+
+
+class PzConfig(C.Structure):
+    """pz_config (include/pzcuda.h)."""
+    _fields_ = [("device", C.c_int32), ("n_devices", C.c_int32), ("devices", C.c_int32 * PZ_MAX_DEVICES), ("reserved", C.c_int32 * 6)]
+
+
 class PzResult(C.Structure):
     _fields_ = [("status", C.c_int32), ("detail", C.c_int32), ("out_len", C.c_uint64),
                 ("adler_computed", C.c_uint32), ("adler_stored", C.c_uint32), ("err_bitpos", C.c_uint64),
@@ -38,6 +46,10 @@ SYMBOLS = [
     ("pz_inflate_batch_contig", C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p, C.POINTER(C.c_uint64),
                                           C.c_size_t, C.POINTER(PzResult), C.c_void_p, C.c_uint32]),
     ("pz_inflate_sizes", C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_size_t, C.POINTER(PzResult)]),
+    ("pz_decompress_batch", C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_size_t, C.POINTER(PzResult),
+                                      C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_uint32]),
+    ("pz_outputs_free", None, [C.c_void_p]),
+    ("pz_device_count", C.c_int, []),
     ("pz_batch_create", C.c_void_p, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_size_t, C.c_uint32]),
     ("pz_batch_run", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("pz_batch_results", C.c_int, [C.c_void_p, C.POINTER(PzResult), C.c_void_p]),

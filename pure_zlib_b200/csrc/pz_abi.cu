@@ -12,6 +12,8 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
@@ -45,7 +47,55 @@ std::atomic<uint64_t> g_huge_done{0}, g_huge_declined{0};
 std::atomic<int> g_stream_resume{1}; /* PZ_OPT_STREAM_RESUME */
 std::once_flag g_once;
 int g_init_rc = PZ_E_STATE;
-int g_device = -1;
+int g_device = -1;          /* the primary device: resident batches, incremental contexts, device-pointer calls */
+std::vector<int> g_devices; /* every device host-buffer batches are sharded over (g_devices[0] == g_device) */
+
+/* One worker thread per device of a multi-device configuration ("one host thread + CUDA context +
+ * pinned staging + stream set per GPU"): the thread binds its device once, owns a thread_local Workspace on it, and
+ * runs the shards it is handed.  The calling thread only waits, so its own current device is never touched. */
+struct DeviceWorker {
+  int dev = 0;
+  std::thread th;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::function<int()> job;
+  bool has_job = false, done = false, stop = false;
+  int rc = 0;
+  std::string err;
+  void loop();
+  void submit(std::function<int()> f) {
+    std::lock_guard<std::mutex> g(mu);
+    job = std::move(f); has_job = true; done = false;
+    cv.notify_all();
+  }
+  int wait(std::string *e) {
+    std::unique_lock<std::mutex> g(mu);
+    cv.wait(g, [&] { return done; });
+    if (rc != PZ_E_OK && e) *e = err;
+    return rc;
+  }
+};
+std::vector<DeviceWorker *> g_workers; /* index k serves g_devices[k]; empty in a single-device configuration */
+std::mutex g_multi_mu;                 /* one sharded call at a time (the workers hold one job each) */
+
+void DeviceWorker::loop() {
+  cudaSetDevice(dev);
+  for (;;) {
+    std::function<int()> f;
+    {
+      std::unique_lock<std::mutex> g(mu);
+      cv.wait(g, [&] { return has_job || stop; });
+      if (stop) return;
+      f = std::move(job); has_job = false;
+    }
+    const int r = f();
+    {
+      std::lock_guard<std::mutex> g(mu);
+      rc = r; err = r != PZ_E_OK ? g_last_error : std::string(); done = true;
+    }
+    cv.notify_all();
+  }
+}
 
 void do_init(const pz_config *cfg) {
   int ndev = 0;
@@ -54,13 +104,41 @@ void do_init(const pz_config *cfg) {
     g_init_rc = fail_cuda(e != cudaSuccess ? e : cudaErrorNoDevice, "cudaGetDeviceCount");
     return;
   }
-  if (cfg && cfg->device >= 0) {
-    e = cudaSetDevice(cfg->device);
-    if (e != cudaSuccess) { g_init_rc = fail_cuda(e, "cudaSetDevice"); return; }
+  /* the device list: pz_config.devices[], else the environment (PZ_DEVICES = "all" or "0,2,3"), else one device */
+  std::vector<int> want;
+  if (cfg && cfg->n_devices > 0) {
+    for (int k = 0; k < cfg->n_devices && k < PZ_MAX_DEVICES; k++) want.push_back(cfg->devices[k]);
+  } else if (cfg && cfg->n_devices < 0) {
+    for (int d = 0; d < ndev; d++) want.push_back(d);
+  } else if (const char *dv = (cfg && cfg->device >= 0) ? nullptr : getenv("PZ_DEVICES")) {
+    if (!strcmp(dv, "all")) { for (int d = 0; d < ndev; d++) want.push_back(d); }
+    else for (const char *p = dv; *p;) { char *q; const long d = strtol(p, &q, 10); if (q == p) break; want.push_back((int)d); p = *q ? q + 1 : q; }
   }
-  cudaGetDevice(&g_device);
-  e = pz_kernels_configure();
-  if (e != cudaSuccess) { g_init_rc = fail_cuda(e, "pz_kernels_configure"); return; }
+  int prev = 0;
+  cudaGetDevice(&prev);
+  if (want.empty()) want.push_back((cfg && cfg->device >= 0) ? cfg->device : prev);
+  for (int d : want)
+    if (d < 0 || d >= ndev) { g_last_error = "pz_init: device ordinal out of range"; g_init_rc = PZ_E_ARG; return; }
+  for (size_t k = want.size(); k-- > 0;) { /* kernel attributes belong to a device's context; the primary device is bound last */
+    e = cudaSetDevice(want[k]);
+    if (e != cudaSuccess) { g_init_rc = fail_cuda(e, "cudaSetDevice"); return; }
+    e = pz_kernels_configure();
+    if (e != cudaSuccess) { g_init_rc = fail_cuda(e, "pz_kernels_configure"); return; }
+  }
+  g_devices = want;
+  g_device = want[0];
+  if (cfg == nullptr || cfg->device < 0) {
+    /* implicit initialisation keeps the caller's current device when it is the primary one (the usual case: one device) */
+    if (want.size() > 1 || want[0] != prev) cudaSetDevice(want.size() > 1 ? prev : want[0]);
+  }
+  if (want.size() > 1) {
+    for (size_t k = 0; k < want.size(); k++) {
+      DeviceWorker *w = new DeviceWorker();
+      w->dev = want[k];
+      w->th = std::thread([w] { w->loop(); });
+      g_workers.push_back(w);
+    }
+  }
   if (const char *h = getenv("PZ_HUGE_BYTES")) { const long long v = atoll(h); if (v > 0) g_huge_bytes = (uint64_t)v; }
   g_init_rc = PZ_E_OK;
 }
@@ -102,7 +180,7 @@ struct Buf {
     if (n <= cap) return PZ_E_OK;
     release();
     size_t want = align_up(n + 256, 1 << 20);
-    cudaError_t e = pinned ? cudaHostAlloc(&p, want, cudaHostAllocDefault) : cudaMalloc(&p, want);
+    cudaError_t e = pinned ? cudaHostAlloc(&p, want, cudaHostAllocPortable) : cudaMalloc(&p, want); /* portable: every device of a multi-device configuration copies from / to it */
     if (e != cudaSuccess) { p = nullptr; cap = 0; fail_cuda(e, pinned ? "cudaHostAlloc" : "cudaMalloc"); return PZ_E_NOMEM; }
     cap = want;
     return PZ_E_OK;
@@ -144,6 +222,37 @@ struct Workspace {
   }
 };
 thread_local Workspace g_ws;
+
+/* Host-side copies of a batch (packing pointer arrays into pinned staging and back): one thread moves about 10 GB/s,
+ * a 1 GiB batch would spend 100 ms there, several times the decode.  Jobs are dealt to up to 16 threads by bytes. */
+struct CopyJob { void *dst; const void *src; size_t len; };
+void parallel_copy(const std::vector<CopyJob> &jobs) {
+  uint64_t total = 0;
+  for (const CopyJob &j : jobs) total += j.len;
+  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  const unsigned nth = (unsigned)std::min<uint64_t>(std::min(16u, hw), total / (4u << 20) + 1u);
+  if (nth <= 1) {
+    for (const CopyJob &j : jobs) if (j.len) memcpy(j.dst, j.src, j.len);
+    return;
+  }
+  /* thread t takes the bytes [total * t / nth, total * (t + 1) / nth) of the concatenation of all jobs */
+  auto work = [&](unsigned t) {
+    const uint64_t lo = total * t / nth, hi = total * (t + 1) / nth;
+    uint64_t at = 0;
+    for (const CopyJob &j : jobs) {
+      const uint64_t b = at, e = at + j.len;
+      at = e;
+      if (e <= lo) continue;
+      if (b >= hi) break;
+      const uint64_t x = std::max(b, lo) - b, y = std::min(e, hi) - b;
+      memcpy((uint8_t *)j.dst + x, (const uint8_t *)j.src + x, y - x);
+    }
+  };
+  std::vector<std::thread> th;
+  for (unsigned t = 1; t < nth; t++) th.emplace_back(work, t);
+  work(0);
+  for (std::thread &x : th) x.join();
+}
 
 /* seg_off[i] = first checksum segment of stream i; capacities bound the decoded length */
 uint64_t build_seg_off(const uint64_t *out_off, size_t n, std::vector<uint64_t> &seg_off) {
@@ -478,6 +587,8 @@ int pz_init(const pz_config *cfg) {
   return g_init_rc;
 }
 
+int pz_device_count(void) { return ensure_init() == PZ_E_OK ? (int)g_devices.size() : 0; }
+
 void pz_shutdown(void) {
   g_ws.~Workspace();
   new (&g_ws) Workspace();
@@ -556,10 +667,13 @@ void *pz_pinned_alloc(size_t bytes) {
 void pz_pinned_free(void *p) { if (p) cudaFreeHost(p); }
 
 /* ---- one-shot batch over contiguous blobs --------------------------------------------- */
-int pz_inflate_batch_contig(const uint8_t *in_blob, const uint64_t *in_off, uint8_t *out_blob, const uint64_t *out_off,
-                            size_t n, pz_result *res, void *stream, uint32_t flags) {
-  int rc = ensure_init();
-  if (rc != PZ_E_OK) return rc;
+}  // extern "C"
+
+namespace {
+/* The batch on ONE device: the calling thread's current one. */
+int contig_one_device(const uint8_t *in_blob, const uint64_t *in_off, uint8_t *out_blob, const uint64_t *out_off,
+                      size_t n, pz_result *res, void *stream, uint32_t flags) {
+  int rc = PZ_E_OK;
   if (n == 0) return PZ_E_OK;
   const bool count_only = (flags & PZ_F_COUNT_ONLY) != 0;
   if (!in_blob || !in_off || !res || n > 0xfffffff0ull || !offsets_ok(in_off, n) || !in_sizes_ok(in_off, n)) return PZ_E_ARG;
@@ -798,6 +912,52 @@ int pz_inflate_batch_contig(const uint8_t *in_blob, const uint64_t *in_off, uint
   return rc;
 }
 
+/* Contiguous ranges of streams, one per device, balanced by compressed bytes (the same rule as
+ * pure_zlib_b200/shard.py:shard_ranges, which the multi-process bench uses). */
+std::vector<size_t> shard_cuts(const uint64_t *in_off, size_t n, size_t parts) {
+  std::vector<size_t> cuts(parts + 1, n);
+  cuts[0] = 0;
+  const uint64_t base = in_off[0], total = in_off[n] - base;
+  for (size_t r = 1; r < parts; r++) {
+    const uint64_t target = base + (uint64_t)((long double)total * r / parts);
+    size_t k = (size_t)(std::lower_bound(in_off, in_off + n + 1, target) - in_off);
+    cuts[r] = std::min(std::max(k, cuts[r - 1]), n);
+  }
+  return cuts;
+}
+}  // namespace
+
+extern "C" {
+
+int pz_inflate_batch_contig(const uint8_t *in_blob, const uint64_t *in_off, uint8_t *out_blob, const uint64_t *out_off,
+                            size_t n, pz_result *res, void *stream, uint32_t flags) {
+  int rc = ensure_init();
+  if (rc != PZ_E_OK) return rc;
+  if (n == 0) return PZ_E_OK;
+  /* host blobs on a multi-device configuration: every device takes a contiguous range of the streams, on its own worker
+   * thread with its own staging, CUDA streams and kernels; no data-path collective (the streams are independent) */
+  if (g_workers.size() > 1 && n >= 2 * g_workers.size() && in_blob && in_off && res && offsets_ok(in_off, n) && !is_device_ptr(in_blob)) {
+    const bool count_only = (flags & PZ_F_COUNT_ONLY) != 0;
+    if (!count_only && (!out_blob || !out_off)) return PZ_E_ARG;
+    std::lock_guard<std::mutex> g(g_multi_mu);
+    const size_t parts = g_workers.size();
+    const std::vector<size_t> cuts = shard_cuts(in_off, n, parts);
+    for (size_t k = 0; k < parts; k++) {
+      const size_t first = cuts[k], count = cuts[k + 1] - cuts[k];
+      g_workers[k]->submit([=]() -> int {
+        return count ? contig_one_device(in_blob, in_off + first, out_blob, count_only ? nullptr : out_off + first, count, res + first, nullptr, flags) : PZ_E_OK;
+      });
+    }
+    for (size_t k = 0; k < parts; k++) {
+      std::string err;
+      const int r = g_workers[k]->wait(&err);
+      if (r != PZ_E_OK && rc == PZ_E_OK) { rc = r; g_last_error = err; }
+    }
+    return rc;
+  }
+  return contig_one_device(in_blob, in_off, out_blob, out_off, n, res, stream, flags);
+}
+
 /* ---- pointer-array entry point: what the Haskell shim binds --------------------------- */
 static int inflate_ptrs(const uint8_t *const *in, const size_t *in_len, uint8_t *const *out, const size_t *out_cap, size_t n,
                         pz_result *res, uint32_t flags) {
@@ -819,15 +979,15 @@ static int inflate_ptrs(const uint8_t *const *in, const size_t *in_len, uint8_t 
   if ((rc = ws.h_in.reserve(ia + 64)) != PZ_E_OK) return rc;
   if (!count_only && (rc = ws.h_out.reserve(oa + 64)) != PZ_E_OK) return rc;
   uint8_t *h_in = (uint8_t *)ws.h_in.p, *h_out = (uint8_t *)ws.h_out.p;
-  for (size_t i = 0; i < n; i++)
-    if (in_len[i]) memcpy(h_in + in_off[i], in[i], in_len[i]);
+  std::vector<CopyJob> jobs(n);
+  for (size_t i = 0; i < n; i++) jobs[i] = CopyJob{h_in + in_off[i], in[i], in_len[i]};
+  parallel_copy(jobs);
   rc = pz_inflate_batch_contig(h_in, in_off.data(), h_out, out_off.data(), n, res, nullptr, flags);
   if (rc != PZ_E_OK) return rc;
-  if (!count_only)
-    for (size_t i = 0; i < n; i++) {
-      size_t k = (size_t)std::min<uint64_t>(res[i].out_len, out_cap[i]);
-      if (k) memcpy(out[i], h_out + out_off[i], k);
-    }
+  if (!count_only) {
+    for (size_t i = 0; i < n; i++) jobs[i] = CopyJob{out[i], h_out + out_off[i], (size_t)std::min<uint64_t>(res[i].out_len, out_cap[i])};
+    parallel_copy(jobs);
+  }
   return PZ_E_OK;
 }
 
@@ -868,7 +1028,7 @@ struct PinnedCache {
       if (!free_[c].empty()) { uint8_t *p = free_[c].back(); free_[c].pop_back(); return p; }
     }
     uint8_t *p = nullptr;
-    cudaError_t e = cudaHostAlloc((void **)&p, *cap, cudaHostAllocDefault);
+    cudaError_t e = cudaHostAlloc((void **)&p, *cap, cudaHostAllocPortable);
     if (e != cudaSuccess) { fail_cuda(e, "cudaHostAlloc"); return nullptr; }
     return p;
   }
@@ -1251,6 +1411,56 @@ int pz_stream_next(pz_stream *s, const uint8_t **chunk, size_t *len, pz_result *
   if (s->verdict.status == PZ_OK) return PZ_S_DONE;
   if (res) *res = s->verdict;
   return PZ_S_ERROR;
+}
+
+/* ---- `map decompress` in one call (what the Haskell shim's decompressBatch binds) ---------------------- */
+}  // extern "C"
+struct pz_outputs {
+  uint8_t *blob = nullptr;
+  size_t cap = 0;
+};
+extern "C" {
+
+int pz_decompress_batch(const uint8_t *const *in, const size_t *in_len, size_t n, pz_result *res, uint8_t **out,
+                        pz_outputs **handle, uint32_t flags) {
+  int rc = ensure_init();
+  if (rc != PZ_E_OK) return rc;
+  if (!handle) return PZ_E_ARG;
+  *handle = nullptr;
+  if (n == 0) return PZ_E_OK;
+  if (!in || !in_len || !res || !out) return PZ_E_ARG;
+  flags &= ~(uint32_t)PZ_F_COUNT_ONLY;
+  std::vector<uint64_t> in_off(n + 1), out_off(n + 1);
+  uint64_t ia = 0;
+  for (size_t i = 0; i < n; i++) { in_off[i] = ia; ia += in_len[i]; }
+  in_off[n] = ia;
+  Workspace &ws = g_ws;
+  if ((rc = ws.h_in.reserve(ia + 64)) != PZ_E_OK) return rc;
+  uint8_t *h_in = (uint8_t *)ws.h_in.p;
+  std::vector<CopyJob> jobs(n);
+  for (size_t i = 0; i < n; i++) jobs[i] = CopyJob{h_in + in_off[i], in[i], in_len[i]};
+  parallel_copy(jobs);
+  /* the zlib format does not carry the decoded length: sizing pass first (Zlib.hs:32-51 returns a lazy ByteString of
+   * whatever length comes out) */
+  if ((rc = pz_inflate_batch_contig(h_in, in_off.data(), nullptr, nullptr, n, res, nullptr, flags | PZ_F_COUNT_ONLY)) != PZ_E_OK) return rc;
+  uint64_t oa = 0;
+  for (size_t i = 0; i < n; i++) { out_off[i] = oa; oa += (res[i].out_len + 15u) & ~(uint64_t)15u; }
+  out_off[n] = oa;
+  pz_outputs *h = new (std::nothrow) pz_outputs();
+  if (!h) return PZ_E_NOMEM;
+  h->blob = g_pinned.get((size_t)oa + 64, &h->cap);
+  if (!h->blob) { delete h; return PZ_E_NOMEM; }
+  rc = pz_inflate_batch_contig(h_in, in_off.data(), h->blob, out_off.data(), n, res, nullptr, flags);
+  if (rc != PZ_E_OK) { pz_outputs_free(h); return rc; }
+  for (size_t i = 0; i < n; i++) out[i] = h->blob + out_off[i];
+  *handle = h;
+  return PZ_E_OK;
+}
+
+void pz_outputs_free(pz_outputs *h) {
+  if (!h) return;
+  g_pinned.put(h->blob, h->cap);
+  delete h;
 }
 
 /* ---- auxiliaries ----------------------------------------------------------------------- */

@@ -222,6 +222,7 @@ pz_gather_kernel(const uint64_t *__restrict__ g) {
 static int g_inflate_ctas_per_sm[2] = {0, 0};
 static int g_sm_count = 0;
 
+/* Function attributes belong to the CURRENT device's context: call once per device the library uses. */
 cudaError_t pz_kernels_configure(void) {
   cudaError_t e;
   const size_t smem = sizeof(PzStreamSmem) * PZ_SLOTS;
@@ -243,6 +244,8 @@ cudaError_t pz_kernels_configure(void) {
   e = cudaFuncSetAttribute(pz_inflate_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(pz_inflate_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(pz_blk_tails_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PZ_TAIL * sizeof(uint16_t)));
   if (e != cudaSuccess) return e;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_inflate_ctas_per_sm[0], pz_inflate_kernel<false>, PZ_THREADS_PER_CTA, smem);
   if (e != cudaSuccess) return e;
@@ -365,12 +368,6 @@ cudaError_t pz_launch_blk_resolve(uint16_t *d_sym16, uint8_t *d_out, const uint6
                                   const uint32_t *d_grp_first, uint32_t ngrp, uint32_t nblk, uint64_t total, uint8_t *d_gw, uint32_t *d_err,
                                   cudaStream_t st) {
   if (nblk == 0 || total == 0) return cudaSuccess;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(pz_blk_tails_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PZ_TAIL * sizeof(uint16_t)));
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
   pz_blk_tails_kernel<<<ngrp, PZ_TAILS_THREADS, PZ_TAIL * sizeof(uint16_t), st>>>(d_sym16, d_blk_off, d_blk_len, d_grp_first, ngrp);
   pz_blk_windows_kernel<<<1, PZ_TAILS_THREADS, 0, st>>>(d_sym16, d_blk_off, d_grp_first, ngrp, total, d_gw, d_err);
   const uint64_t per_cta = PZ_HUGE_THREADS * 8u;

@@ -315,11 +315,30 @@ def inflate_batch_raw(streams: Sequence[bytes], flags: int = 0):
     return [res[i] for i in range(n)], [outs[i].raw[: int(res[i].out_len)] for i in range(n)]
 
 
+def decompress_batch_raw(streams: Sequence[bytes], flags: int = 0):
+    """The same through pz_decompress_batch: ONE call, the library sizes, allocates and decodes (what the Haskell
+    shim's decompressBatch binds)."""
+    L = _lib.load()
+    n = len(streams)
+    if n == 0:
+        return [], []
+    keep, ptrs, lens = _ptr_arrays(streams)
+    res = (PzResult * n)()
+    optrs = (C.c_void_p * n)()
+    handle = C.c_void_p()
+    _lib.check(L.pz_decompress_batch(ptrs, lens, n, res, optrs, C.byref(handle), flags), "pz_decompress_batch")
+    try:
+        outs = [C.string_at(optrs[i], int(res[i].out_len)) if res[i].out_len else b"" for i in range(n)]
+    finally:
+        L.pz_outputs_free(handle)
+    return [res[i] for i in range(n)], outs
+
+
 def decompress_batch(streams: Iterable[bytes]):
     """Extension (not in the reference): `map decompress` over independent single-chunk
     streams, one kernel launch for the whole list."""
     streams = [bytes(s) for s in streams]
-    res, outs = inflate_batch_raw(streams)
+    res, outs = decompress_batch_raw(streams)
     out = []
     for r, data in zip(res, outs):
         if r.status == _lib.PZ_OK:

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     L = _lib.load()
     for name in declared_functions():
         assert hasattr(L, name), name
-    assert L.pz_abi_version() == 1
+    assert L.pz_abi_version() == 2
 
 
 def test_result_layout_matches_oracle():
@@ -79,3 +79,12 @@ def test_product_does_not_touch_the_oracle():
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "pz_oracle" not in src and "libpzoracle" not in src and "from oracle" not in src, f
                 assert "import oracle" not in src, f
+
+
+def test_config_layout_matches_header():
+    """pz_config: device, n_devices, devices[PZ_MAX_DEVICES], reserved[6] (int32 each)."""
+    text = open(os.path.join(ROOT, "include", "pzcuda.h")).read()
+    m = re.search(r"#define PZ_MAX_DEVICES (\d+)", text)
+    assert m and int(m.group(1)) == _lib.PZ_MAX_DEVICES
+    assert C.sizeof(_lib.PzConfig) == 4 * (2 + _lib.PZ_MAX_DEVICES + 6)
+    assert _lib.PzConfig.devices.offset == 8

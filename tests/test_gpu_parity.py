@@ -816,3 +816,56 @@ def test_deflate_cli(pz, golden_dir, tmp_path):
     assert said == ["ERROR: Ran out of data mid-decompression.", "ERROR: Block format error: Unacceptable BTYPE: 3",
                     "WARNING: Finished decompression with data left.", "Unexpected file name.", "USAGE: deflate [filename]"]
     assert (tmp_path / "more").read_bytes() == open(os.path.join(golden_dir, "rfctest1.gold"), "rb").read()
+
+
+def test_decompress_batch_single_call(pz, oracle):
+    """pz_decompress_batch (sizing, allocation and decode inside the library: what the Haskell shim's decompressBatch
+    binds) against the two-call flow and the oracle, verdicts other than OK included."""
+    from pure_zlib_b200 import _lib
+    cases = [v[1] for v in streams.appendix_b_vectors()] + [zlib.compress(streams.small_text(70_000, 3), 6), b"",
+                                                            zlib.compress(b"", 9), zlib.compress(streams.small_text(300_000, 4), 1)[:-1]]
+    r1, o1 = pz.zlib.decompress_batch_raw(cases)
+    r2, o2 = pz.zlib.inflate_batch_raw(cases)
+    for i, z in enumerate(cases):
+        o = oracle.decompress(z)
+        assert (r1[i].status, r1[i].detail, r1[i].out_len) == (o.status, o.detail, o.out_len) == (r2[i].status, r2[i].detail, r2[i].out_len), i
+        assert o1[i] == o.data == o2[i], i
+        if o.status != 0:
+            assert _lib.strerror(r1[i]) == o.message
+
+
+def test_in_library_multi_gpu(pz):
+    """pz_config.devices / PZ_DEVICES: ONE call from ONE host thread shards a host batch over every device (contiguous
+    ranges balanced by compressed bytes, a worker thread per device).  Needs two GPUs; the library initialises once
+    per process, so the sharded run happens in a child process."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("one GPU")
+    code = r'''
+import sys, zlib, numpy as np
+sys.path.insert(0, "."); sys.path.insert(0, "tests")
+import streams
+import pure_zlib_b200 as pz
+from pure_zlib_b200 import _lib
+from oracle import oracle
+L = _lib.load()
+cfg = _lib.PzConfig(); cfg.device = -1; cfg.n_devices = -1
+assert L.pz_init(cfg) == 0 and L.pz_device_count() >= 2, L.pz_device_count()
+rng = np.random.default_rng(3)
+cases = [zlib.compress(streams.small_text(int(rng.integers(100, 200_000)), i), int(rng.integers(1, 10))) for i in range(97)]
+cases[5] = cases[5][:-2]; cases[40] = bytes.fromhex("789c4b04620000000001"); cases[96] = b""
+cases.append(zlib.compress(rng.integers(0, 256, 300_000, dtype=np.uint8).tobytes(), 6))
+for fn in (pz.zlib.decompress_batch_raw, pz.zlib.inflate_batch_raw):
+    res, outs = fn(cases)
+    for i, z in enumerate(cases):
+        o = oracle.decompress(z)
+        assert (res[i].status, res[i].detail, res[i].out_len) == (o.status, o.detail, o.out_len), (i, res[i].status, o.status)
+        assert outs[i] == o.data, i
+        if o.status == 0:
+            assert res[i].adler_computed == o.adler_computed
+print("multi-gpu ok", L.pz_device_count())
+'''
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0 and "multi-gpu ok" in r.stdout, (r.stdout[-500:], r.stderr[-1500:])

@@ -10,6 +10,11 @@ module Codec.Compression.Zlib (
   decompressIncremental,
   -- * extension: many independent streams per kernel launch
   decompressBatch,
+  -- * extension: the same decoder behind gzip members (RFC 1952) and raw deflate (the reference's README TODO)
+  Framing (..),
+  decompressBatchWith,
+  decompressGzip,
+  decompressRaw,
   -- * extension: many multi-chunk streams advanced together, one launch per round of chunks
   decompressMany,
 ) where
@@ -130,14 +135,30 @@ verdict p r = case rStatus r of
 -- A lazy ByteString of several chunks whose stream ends before the last chunk is the
 -- reference's "Finished with data remaining." (Zlib.hs:48-49); the shim checks that on the host.
 decompressBatch :: [L.ByteString] -> [Either DecompressionError L.ByteString]
-decompressBatch inputs = unsafePerformIO $ do
+decompressBatch = decompressBatchWith Zlib
+
+-- | PZ_F_GZIP / PZ_F_RAW of include/pzcuda.h.  With 'Gzip' the words in a 'ChecksumError' are CRC-32s (or ISIZE and the
+-- decoded length for "length mismatch"); 'RawDeflate' has no trailer and therefore no checksum verdict.
+data Framing = Zlib | Gzip | RawDeflate deriving (Eq, Show)
+
+framingFlags :: Framing -> Word32
+framingFlags Zlib = 0
+framingFlags Gzip = 0x20
+framingFlags RawDeflate = 0x40
+
+decompressGzip, decompressRaw :: L.ByteString -> Either DecompressionError L.ByteString
+decompressGzip x = head (decompressBatchWith Gzip [x])
+decompressRaw x = head (decompressBatchWith RawDeflate [x])
+
+decompressBatchWith :: Framing -> [L.ByteString] -> [Either DecompressionError L.ByteString]
+decompressBatchWith framing inputs = unsafePerformIO $ do
   let strict = map L.toStrict inputs
       n = length strict
   withMany SU.unsafeUseAsCStringLen strict $ \cstrs ->
     withArray (map (castPtr . fst) cstrs) $ \pin ->
       withArray (map (fromIntegral . snd) cstrs) $ \plen ->
         allocaArray n $ \pres -> allocaArray n $ \pout -> alloca $ \phandle -> do
-          rc <- c_pz_decompress_batch pin plen (fromIntegral n) pres pout phandle 0
+          rc <- c_pz_decompress_batch pin plen (fromIntegral n) pres pout phandle (framingFlags framing)
           when (rc /= 0) failCuda
           handle <- peek phandle
           -- one ForeignPtr for the whole block; every slice below keeps it alive

@@ -63,8 +63,11 @@ enum pz_detail {
   PZ_D_HDR_CHECKSUM = 1,      /* "Header checksum failed"                                  */
   PZ_D_HDR_METHOD = 2,        /* "Bad compression method: <payload0>"                      */
   PZ_D_HDR_WINDOW = 3,        /* "Window size too big: <payload0>"                         */
+  PZ_D_HDR_GZIP_MAGIC = 4,    /* gzip framing (extension): "Not a gzip stream: <payload0 hex>" (ID1 ID2 != 1f 8b) */
+  PZ_D_HDR_GZIP_FLAGS = 5,    /* gzip framing (extension): "Reserved gzip flags set: <payload0>" (FLG & 0xe0) */
   /* PZ_ERR_CHECKSUM (Deflate.hs:56-63) */
   PZ_D_ADLER_MISMATCH = 1,    /* "checksum mismatch: <adler_stored hex> != <adler_computed hex>" */
+  PZ_D_LENGTH_MISMATCH = 2,   /* gzip framing (extension): "length mismatch: <payload0 = ISIZE> != <out_len mod 2^32>" */
   /* PZ_REF_BOTTOM */
   PZ_D_BOT_LENGTH_SYM = 1,    /* lengthArray ! payload0, payload0 in {286,287} (Deflate.hs:161,167) */
   PZ_D_BOT_DIST_SYM = 2,      /* distanceArray ! payload0, payload0 >= 30    (Deflate.hs:200,206)  */
@@ -96,6 +99,15 @@ typedef struct pz_result {
 #define PZ_F_INPUT_IN_PLACE 0x4u /* host blobs: let the kernel read a pinned, mapped in_blob over PCIe instead of copying it */
 #define PZ_F_NO_HUGE 0x10u   /* never use the block-parallel path (K4) for huge streams */
 #define PZ_F_NO_DRAIN 0x8u    /* host blobs: copy the output only after the kernel (no progressive 2-D copies) */
+/* Framing (EXTENSION: the reference reads zlib streams only; gzip and raw deflate are the first TODO of its README,
+ * lines 42-50, with docs/rfc1952.html shipped beside it).  Default: zlib (RFC 1950).
+ *   PZ_F_GZIP  every stream is one gzip member (RFC 1952): header checked in stream order (magic, CM = 8, reserved FLG
+ *              bits), FEXTRA / FNAME / FCOMMENT / FHCRC skipped (FHCRC not verified, in the spirit of the reference's
+ *              FDICT), trailer CRC-32 then ISIZE; adler_computed / adler_stored of the verdict hold the CRC-32s.  Bytes
+ *              behind the trailer (further members) are ignored like the reference ignores bytes behind a zlib trailer.
+ *   PZ_F_RAW   raw deflate (RFC 1951): no header, no trailer, no comparison; adler_computed is the Adler-32 of the output. */
+#define PZ_F_GZIP 0x20u
+#define PZ_F_RAW 0x40u
 
 #define PZ_MAX_DEVICES 16
 typedef struct pz_config {
@@ -124,8 +136,8 @@ int pz_abi_version(void);
 /* Tuning knobs.  PZ_OPT_HUGE_BYTES: compressed size from which a stream is decoded block-parallel
  * (K4) instead of as one serial chain; default 4 MiB, environment PZ_HUGE_BYTES at start-up. */
 #define PZ_OPT_HUGE_BYTES 1
-/* PZ_OPT_STREAM_RESUME (default 1): 0 makes every pump of an incremental stream decode from the
- * stream's first byte again instead of from its checkpoint -- same results, for A/B timing only. */
+/* PZ_OPT_STREAM_RESUME: accepted and ignored since ABI 2 (it made every pump of an incremental stream decode from the
+ * stream's first byte again, for A/B timing; contexts no longer keep the bytes that would need). */
 #define PZ_OPT_STREAM_RESUME 2
 int pz_set_option(int key, uint64_t value);
 /* Process-wide counters (diagnostics, tests): streams the block-parallel path decoded / declined. */
@@ -191,6 +203,8 @@ void pz_pinned_free(void *p);
 typedef struct pz_stream pz_stream;
 enum pz_stream_event { PZ_S_NEED_MORE = 0, PZ_S_CHUNK = 1, PZ_S_DONE = 2, PZ_S_ERROR = 3 };
 pz_stream *pz_stream_new(void);
+/* The same decoder behind another framing: flags = 0, PZ_F_GZIP or PZ_F_RAW (extension, see the flags). */
+pz_stream *pz_stream_new_framed(uint32_t flags);
 /* Supply the strict chunk that answers a NeedMore (Monad.hs:185-197).  The bytes are copied
  * (pinned staging, cudaMemcpyAsync): the call returns while they travel to the device.      */
 int pz_stream_feed(pz_stream *s, const uint8_t *data, size_t len);
@@ -216,7 +230,10 @@ enum pz_stream_counter_id {
   PZ_SC_PUMPS = 0,      /* kernel launches that decoded this stream                          */
   PZ_SC_RESUMED = 1,    /* ... of which started from a checkpoint instead of the first byte  */
   PZ_SC_CKPT_BIT = 2,   /* compressed bits the checkpoint has behind it                      */
-  PZ_SC_CKPT_BYTES = 3  /* decoded bytes the checkpoint has behind it                        */
+  PZ_SC_CKPT_BYTES = 3, /* decoded bytes the checkpoint has behind it                        */
+  PZ_SC_DEVICE_BYTES = 4, /* device memory the context holds right now (input + history + room)    */
+  PZ_SC_DEVICE_PEAK = 5,  /* ... and the most it has ever held                                      */
+  PZ_SC_HOST_BYTES = 6    /* pinned host memory the context holds (decoded bytes not handed out yet, feed staging) */
 };
 uint64_t pz_stream_counter(const pz_stream *s, int which);
 
@@ -231,6 +248,8 @@ size_t pz_strerror(const pz_result *r, char *buf, size_t cap);
 int pz_compute_code_values(const int32_t *sym, const int32_t *len, int n, int32_t *out_triples);
 /* Adler-32 of a host buffer on the device (Adler32.hs:17-57); init = 1 for a fresh sum.  */
 uint32_t pz_adler32(uint32_t init, const uint8_t *data, size_t len);
+/* CRC-32 (RFC 1952 section 8) of a host buffer on the device, the checksum of the gzip framing; init = 0 for a fresh sum. */
+uint32_t pz_crc32(uint32_t init, const uint8_t *data, size_t len);
 
 #ifdef __cplusplus
 }

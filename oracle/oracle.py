@@ -53,6 +53,8 @@ def lib():
                                      C.POINTER(PzoResult), C.POINTER(PzoEvent), C.c_size_t,
                                      C.POINTER(C.c_size_t), C.POINTER(C.c_uint64)]
         L.pzo_decompress.restype = C.c_int
+        L.pzo_decompress_framed.argtypes = L.pzo_decompress.argtypes + [C.c_int]
+        L.pzo_decompress_framed.restype = C.c_int
         L.pzo_compute_code_values.argtypes = [C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_int32)]
         L.pzo_compute_code_values.restype = C.c_int
         L.pzo_tree_check.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_int64)]
@@ -90,9 +92,12 @@ class Verdict:
         return (self.status, self.detail, self.message)
 
 
-def decompress(chunks, out_cap: int | None = None, want_events: bool = False) -> Verdict:
+ZLIB, GZIP, RAW = 0, 1, 2
+
+
+def decompress(chunks, out_cap: int | None = None, want_events: bool = False, framing: int = ZLIB) -> Verdict:
     """`Codec.Compression.Zlib.decompress` on a lazy ByteString made of `chunks`
-    (bytes or a list of bytes)."""
+    (bytes or a list of bytes).  framing = GZIP / RAW: the extension of pz_oracle.h (pzo_decompress_framed)."""
     if isinstance(chunks, (bytes, bytearray, memoryview)):
         chunks = [bytes(chunks)]
     chunks = [bytes(c) for c in chunks]
@@ -110,8 +115,8 @@ def decompress(chunks, out_cap: int | None = None, want_events: bool = False) ->
         n_ev = C.c_size_t(0)
         pub = C.c_uint64(0)
         inbuf = C.create_string_buffer(blob, max(len(blob), 1))
-        L.pzo_decompress(inbuf, lens, n, out, out_cap, C.byref(res), ev if want_events else None, ev_cap,
-                         C.byref(n_ev), C.byref(pub))
+        L.pzo_decompress_framed(inbuf, lens, n, out, out_cap, C.byref(res), ev if want_events else None, ev_cap,
+                                C.byref(n_ev), C.byref(pub), framing)
         if res.out_len <= out_cap:
             break
         out_cap = int(res.out_len)

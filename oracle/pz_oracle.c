@@ -21,8 +21,9 @@ enum { ST_OK = 0, ST_HUFF = 1, ST_FORMAT = 2, ST_DECOMP = 3, ST_HEADER = 4, ST_C
 enum { D_TWO_VALUES = 1, D_VALUE_HIT = 2, D_LEAF_IS_NODE = 3, D_ADV_EMPTY_TREE = 4, D_ADV_TO_EMPTY = 5 };
 enum { D_LEN_NLEN = 1, D_BAD_BTYPE = 2 };
 enum { D_RAN_OUT = 1, D_DATA_REMAINING = 2 };
-enum { D_HDR_CHECKSUM = 1, D_HDR_METHOD = 2, D_HDR_WINDOW = 3 };
-enum { D_ADLER_MISMATCH = 1 };
+enum { D_HDR_CHECKSUM = 1, D_HDR_METHOD = 2, D_HDR_WINDOW = 3, D_HDR_GZIP_MAGIC = 4, D_HDR_GZIP_FLAGS = 5 };
+enum { D_ADLER_MISMATCH = 1, D_LENGTH_MISMATCH = 2 };
+enum { FRAME_ZLIB = 0, FRAME_GZIP = 1, FRAME_RAW = 2 };
 enum { D_BOT_LENGTH_SYM = 1, D_BOT_DIST_SYM = 2, D_BOT_DIST_TOO_FAR = 3, D_BOT_WINDOW_OVERFLOW = 4 };
 
 #define WINDOW_SIZE (128 * 1024) /* OutputWindow.hs:29-30 */
@@ -156,6 +157,8 @@ typedef struct {
   int bitno;           /* dcsNextBitNo */
   uint8_t cur;         /* dcsCurByte   */
   uint32_t a, b;       /* dcsAdler32   */
+  int framing;         /* FRAME_*: gzip / raw-deflate are extensions beyond the reference (its README's TODO, lines 42-50) */
+  uint32_t crc;        /* running CRC-32 register (gzip), pre-conditioned with 0xffffffff */
   const uint8_t *inp;  /* dcsInput     */
   size_t inp_len;
   uint8_t *win;        /* dcsOutput: owWindow */
@@ -261,11 +264,22 @@ static int next_code(St *s, const Tree *t) {
 }
 
 /* ---------------------------------------------------------------- Adler32.hs */
+/* CRC-32 (RFC 1952 section 8: reflected polynomial 0xedb88320), bit-serial: slow on purpose, obviously right */
+static void crc_bytes(St *s, const uint8_t *p, size_t n) {
+  uint32_t c = s->crc;
+  for (size_t i = 0; i < n; i++) {
+    c ^= p[i];
+    for (int k = 0; k < 8; k++) c = (c >> 1) ^ (0xedb88320u & (0u - (c & 1u)));
+  }
+  s->crc = c;
+}
 static void adler_byte(St *s, uint8_t v) { /* advanceAdler :22-27 */
+  if (s->framing == FRAME_GZIP) crc_bytes(s, &v, 1);
   s->a = (s->a + v) % ADLER_MOD;
   s->b = (s->b + s->a) % ADLER_MOD;
 }
 static void adler_block(St *s, const uint8_t *p, size_t n) { /* advanceAdlerBlock :44-51 */
+  if (s->framing == FRAME_GZIP) crc_bytes(s, p, n);
   while (n >= 5552) {
     uint64_t a = s->a, b = s->b;
     for (size_t i = 0; i < 5551; i++) { a += p[i]; b += a; }
@@ -334,7 +348,9 @@ static void stored_block(St *s, unsigned len16) {
   long len = (long)len16;
   /* nextBitNo is always 8 here (nextByte leaves it at 8), so only getBlock is reachable */
   for (;;) {
-    if (len < (long)s->inp_len) {
+    /* raw deflate (extension): nothing follows the last block, so a stored block may end exactly at the end of the
+     * input; there the quirk above would turn every such stream into "Ran out of data" */
+    if (len < (long)s->inp_len || (s->framing == FRAME_RAW && len == (long)s->inp_len)) {
       size_t take = len < 0 ? 0 : (size_t)len; /* S.splitAt of a negative count takes nothing */
       memcpy(buf + nbuf, s->inp, take); nbuf += take;
       s->inp += take; s->inp_len -= take; s->bytes_taken += take;
@@ -442,16 +458,37 @@ static int inflate_block(St *s, const Tree *fixed_lit, const Tree *fixed_dist, T
 }
 
 /* inflateWithHeaders (Zlib.hs:53-69) then inflate (Deflate.hs:39-63) */
-static void inflate_with_headers(St *s, Tree *fixed_lit, Tree *fixed_dist, Tree *t_code, Tree *t_lit, Tree *t_dist) {
-  unsigned cmf = next_byte(s);
-  unsigned flg = next_byte(s);
-  unsigned both = (cmf << 8) | flg;
-  unsigned cm = cmf & 0x0f, cinfo = cmf >> 4;
-  int fdict = (flg >> 5) & 1;
-  if (both % 31 != 0) raise_(s, ST_HEADER, D_HDR_CHECKSUM, 0, 0);
+/* EXTENSION (not in the reference; its README lists gzip as the first TODO): the member header of RFC 1952 section 2.3,
+ * parsed in the reference's style -- byte reads that run into the truncation verdict, checks in stream order, optional
+ * fields skipped the way inflateWithHeaders skips FDICT.  FHCRC is skipped, not verified. */
+static void gzip_header(St *s) {
+  unsigned id1 = next_byte(s), id2 = next_byte(s);
+  if (id1 != 0x1f || id2 != 0x8b) raise_(s, ST_HEADER, D_HDR_GZIP_MAGIC, (int64_t)((id1 << 8) | id2), 0);
+  unsigned cm = next_byte(s);
   if (cm != 8) raise_(s, ST_HEADER, D_HDR_METHOD, cm, 0);
-  if (cinfo > 7) raise_(s, ST_HEADER, D_HDR_WINDOW, cinfo, 0);
-  if (fdict) for (int i = 0; i < 4; i++) (void)next_byte(s);
+  unsigned flg = next_byte(s);
+  if (flg & 0xe0) raise_(s, ST_HEADER, D_HDR_GZIP_FLAGS, flg, 0);
+  for (int i = 0; i < 6; i++) (void)next_byte(s); /* MTIME, XFL, OS */
+  if (flg & 4) { unsigned xlen = next_word16(s); for (unsigned i = 0; i < xlen; i++) (void)next_byte(s); }
+  if (flg & 8) while (next_byte(s) != 0) {}
+  if (flg & 16) while (next_byte(s) != 0) {}
+  if (flg & 2) { (void)next_byte(s); (void)next_byte(s); }
+}
+
+static void inflate_with_headers(St *s, Tree *fixed_lit, Tree *fixed_dist, Tree *t_code, Tree *t_lit, Tree *t_dist) {
+  if (s->framing == FRAME_GZIP) {
+    gzip_header(s);
+  } else if (s->framing == FRAME_ZLIB) {
+    unsigned cmf = next_byte(s);
+    unsigned flg = next_byte(s);
+    unsigned both = (cmf << 8) | flg;
+    unsigned cm = cmf & 0x0f, cinfo = cmf >> 4;
+    int fdict = (flg >> 5) & 1;
+    if (both % 31 != 0) raise_(s, ST_HEADER, D_HDR_CHECKSUM, 0, 0);
+    if (cm != 8) raise_(s, ST_HEADER, D_HDR_METHOD, cm, 0);
+    if (cinfo > 7) raise_(s, ST_HEADER, D_HDR_WINDOW, cinfo, 0);
+    if (fdict) for (int i = 0; i < 4; i++) (void)next_byte(s);
+  }
   /* buildFixedLitTree / buildFixedDistanceTree (Deflate.hs:241-251) */
   {
     int sym[288], len[288];
@@ -469,9 +506,21 @@ static void inflate_with_headers(St *s, Tree *fixed_lit, Tree *fixed_dist, Tree 
   s->bitno = 8;
   uint32_t ours = (s->b << 16) | s->a; /* finalizeAdler (Adler32.hs:53-57) */
   s->res->adler_computed = ours;
-  uint32_t theirs = next_word32(s);
-  s->res->adler_stored = theirs;
-  if (theirs != ours) raise_(s, ST_CHECKSUM, D_ADLER_MISMATCH, 0, 0);
+  if (s->framing == FRAME_GZIP) { /* RFC 1952 2.3.1: CRC32 then ISIZE, least significant byte first, checked in that order */
+    ours = ~s->crc;
+    s->res->adler_computed = ours;
+    uint32_t lo = next_word16(s), hi = next_word16(s);
+    uint32_t theirs = (hi << 16) | lo;
+    s->res->adler_stored = theirs;
+    if (theirs != ours) raise_(s, ST_CHECKSUM, D_ADLER_MISMATCH, 0, 0);
+    lo = next_word16(s); hi = next_word16(s);
+    uint32_t isize = (hi << 16) | lo, total = (uint32_t)(s->published + s->ow_next);
+    if (isize != total) raise_(s, ST_CHECKSUM, D_LENGTH_MISMATCH, isize, 0);
+  } else if (s->framing == FRAME_ZLIB) {
+    uint32_t theirs = next_word32(s);
+    s->res->adler_stored = theirs;
+    if (theirs != ours) raise_(s, ST_CHECKSUM, D_ADLER_MISMATCH, 0, 0);
+  } /* raw deflate: no trailer, nothing to compare (adler_computed is still reported) */
   /* finalize (Monad.hs:349-353) */
   publish(s, s->win, s->ow_next);
   s->ow_next = 0; /* the window is not reused; zero so out_len below is not double counted */
@@ -480,7 +529,14 @@ static void inflate_with_headers(St *s, Tree *fixed_lit, Tree *fixed_dist, Tree 
 int pzo_decompress(const uint8_t *in, const size_t *chunk_len, size_t nchunks, uint8_t *out,
                    size_t out_cap, pzo_result *res, pzo_event *ev, size_t ev_cap, size_t *n_ev,
                    uint64_t *published) {
+  return pzo_decompress_framed(in, chunk_len, nchunks, out, out_cap, res, ev, ev_cap, n_ev, published, FRAME_ZLIB);
+}
+
+int pzo_decompress_framed(const uint8_t *in, const size_t *chunk_len, size_t nchunks, uint8_t *out,
+                          size_t out_cap, pzo_result *res, pzo_event *ev, size_t ev_cap, size_t *n_ev,
+                          uint64_t *published, int framing) {
   St *s = calloc(1, sizeof(St));
+  s->framing = framing; s->crc = 0xffffffffu;
   Tree fl, fd, tc, tl, td;
   tree_init(&fl); tree_init(&fd); tree_init(&tc); tree_init(&tl); tree_init(&td);
   memset(res, 0, sizeof *res);
@@ -508,7 +564,7 @@ int pzo_decompress(const uint8_t *in, const size_t *chunk_len, size_t nchunks, u
   }
   res->out_len = s->published + s->ow_next;
   if (res->status != ST_OK && res->status != ST_CHECKSUM && !(res->status == ST_DECOMP && res->detail == D_DATA_REMAINING))
-    res->adler_computed = (s->b << 16) | s->a;
+    res->adler_computed = framing == FRAME_GZIP ? ~s->crc : (s->b << 16) | s->a;
   if (n_ev) *n_ev = s->n_ev;
   if (published) *published = s->published;
   tree_free(&fl); tree_free(&fd); tree_free(&tc); tree_free(&tl); tree_free(&td);
@@ -567,10 +623,13 @@ size_t pzo_strerror(const pzo_result *r, char *buf, size_t cap) {
   case ST_HEADER:
     if (r->detail == D_HDR_CHECKSUM) snprintf(tmp, sizeof tmp, "Header error: Header checksum failed");
     else if (r->detail == D_HDR_METHOD) snprintf(tmp, sizeof tmp, "Header error: Bad compression method: %lld", (long long)r->payload[0]);
+    else if (r->detail == D_HDR_GZIP_MAGIC) snprintf(tmp, sizeof tmp, "Header error: Not a gzip stream: %llx", (long long)r->payload[0]);
+    else if (r->detail == D_HDR_GZIP_FLAGS) snprintf(tmp, sizeof tmp, "Header error: Reserved gzip flags set: %lld", (long long)r->payload[0]);
     else snprintf(tmp, sizeof tmp, "Header error: Window size too big: %lld", (long long)r->payload[0]);
     break;
   case ST_CHECKSUM:
-    snprintf(tmp, sizeof tmp, "Checksum error: checksum mismatch: %x != %x", r->adler_stored, r->adler_computed);
+    if (r->detail == D_LENGTH_MISMATCH) snprintf(tmp, sizeof tmp, "Checksum error: length mismatch: %lld != %lld", (long long)r->payload[0], (long long)(uint32_t)r->out_len);
+    else snprintf(tmp, sizeof tmp, "Checksum error: checksum mismatch: %x != %x", r->adler_stored, r->adler_computed);
     break;
   case ST_BOTTOM:
     snprintf(tmp, sizeof tmp, "_|_ %s", r->detail == D_BOT_LENGTH_SYM ? "lengthArray index" : r->detail == D_BOT_DIST_SYM ? "distanceArray index" : r->detail == D_BOT_DIST_TOO_FAR ? "negative slice" : "window overflow");

@@ -50,6 +50,15 @@ int pzo_decompress(const uint8_t *in, const size_t *chunk_len, size_t nchunks, u
                    size_t out_cap, pzo_result *res, pzo_event *ev, size_t ev_cap, size_t *n_ev,
                    uint64_t *published);
 
+/* EXTENSION beyond the reference (gzip is the first TODO of its README, lines 42-50; docs/rfc1952.html ships with it):
+ * the same decoder behind another framing.  framing 0 = zlib (pzo_decompress), 1 = gzip member (RFC 1952: header with
+ * FEXTRA / FNAME / FCOMMENT / FHCRC skipped, CRC-32 + ISIZE trailer; res->adler_computed / adler_stored then hold the
+ * CRC-32s), 2 = raw deflate (no header, no trailer).  Pinned against system zlib (wbits 31 / -15) on valid streams by
+ * tests/test_oracle.py; error verdicts follow the reference's conventions and are this repository's definition. */
+int pzo_decompress_framed(const uint8_t *in, const size_t *chunk_len, size_t nchunks, uint8_t *out,
+                          size_t out_cap, pzo_result *res, pzo_event *ev, size_t ev_cap, size_t *n_ev,
+                          uint64_t *published, int framing);
+
 /* `computeCodeValues` (Deflate.hs:261-288). Returns the number of triples. */
 int pzo_compute_code_values(const int32_t *sym, const int32_t *len, int n, int32_t *out_triples);
 

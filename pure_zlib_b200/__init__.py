@@ -9,8 +9,10 @@ There is no CPU decode path: every call goes to the GPU or raises.
 """
 from .zlib import (ChecksumError, Chunk, DecompError, DecompressionError, DecompressionError_, Done, FormatError,  # noqa: F401
                    HeaderError, HuffmanTreeError, Left, NeedMore, ReferenceBottom, Right, compute_code_values,
-                   decompress, decompress_batch, decompress_incremental, decompress_many, IncrementalSet)
+                   decompress, decompress_batch, decompress_incremental, decompress_many, IncrementalSet,
+                   decompress_gzip, decompress_raw, ZLIB, GZIP, RAW)
 
 __all__ = ["decompress", "decompress_incremental", "decompress_batch", "DecompressionError", "HuffmanTreeError",
            "FormatError", "DecompressionError_", "HeaderError", "ChecksumError", "ReferenceBottom", "NeedMore", "Chunk",
-           "Done", "DecompError", "Left", "Right", "compute_code_values", "decompress_many", "IncrementalSet"]
+           "Done", "DecompError", "Left", "Right", "compute_code_values", "decompress_many", "IncrementalSet",
+           "decompress_gzip", "decompress_raw", "ZLIB", "GZIP", "RAW"]

@@ -11,8 +11,9 @@ SO_PATH = os.environ.get("PZ_LIBPZCUDA") or os.path.join(_HERE, "libpzcuda.so") 
 PZ_OK, PZ_ERR_HUFFMAN_TREE, PZ_ERR_FORMAT, PZ_ERR_DECOMPRESSION, PZ_ERR_HEADER, PZ_ERR_CHECKSUM, PZ_REF_BOTTOM, \
     PZ_OUTPUT_FULL, PZ_NEED_MORE = range(9)
 PZ_S_NEED_MORE, PZ_S_CHUNK, PZ_S_DONE, PZ_S_ERROR = range(4)
-PZ_SC_PUMPS, PZ_SC_RESUMED, PZ_SC_CKPT_BIT, PZ_SC_CKPT_BYTES = range(4)  # pz_stream_counter
+PZ_SC_PUMPS, PZ_SC_RESUMED, PZ_SC_CKPT_BIT, PZ_SC_CKPT_BYTES, PZ_SC_DEVICE_BYTES, PZ_SC_DEVICE_PEAK, PZ_SC_HOST_BYTES = range(7)  # pz_stream_counter
 PZ_F_NO_ADLER, PZ_F_COUNT_ONLY = 1, 2
+PZ_F_GZIP, PZ_F_RAW = 0x20, 0x40  # framing (extension): gzip member (RFC 1952) / raw deflate (RFC 1951); default zlib
 PZ_E_OK, PZ_E_CUDA, PZ_E_ARG, PZ_E_NOMEM, PZ_E_STATE = 0, -1, -2, -3, -4
 
 
@@ -35,7 +36,7 @@ PZ_OPT_HUGE_BYTES = 1
 PZ_F_NO_HUGE = 0x10
 
 SYMBOLS = [
-    ("pz_init", C.c_int, [C.c_void_p]),
+    ("pz_init", C.c_int, [C.POINTER(PzConfig)]),
     ("pz_shutdown", None, []),
     ("pz_abi_version", C.c_int, []),
     ("pz_set_option", C.c_int, [C.c_int, C.c_uint64]),
@@ -58,6 +59,7 @@ SYMBOLS = [
     ("pz_pinned_alloc", C.c_void_p, [C.c_size_t]),
     ("pz_pinned_free", None, [C.c_void_p]),
     ("pz_stream_new", C.c_void_p, []),
+    ("pz_stream_new_framed", C.c_void_p, [C.c_uint32]),
     ("pz_stream_feed", C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
     ("pz_stream_next", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(PzResult)]),
     ("pz_stream_free", None, [C.c_void_p]),
@@ -67,6 +69,7 @@ SYMBOLS = [
     ("pz_strerror", C.c_size_t, [C.POINTER(PzResult), C.c_char_p, C.c_size_t]),
     ("pz_compute_code_values", C.c_int, [C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_int32)]),
     ("pz_adler32", C.c_uint32, [C.c_uint32, C.c_char_p, C.c_size_t]),
+    ("pz_crc32", C.c_uint32, [C.c_uint32, C.c_char_p, C.c_size_t]),
 ]
 
 _lib = None

@@ -44,7 +44,6 @@ int fail_cuda(cudaError_t e, const char *what) {
 
 std::atomic<uint64_t> g_huge_bytes{4ull << 20}; /* compressed size from which a stream goes to K4 (PZ_HUGE_BYTES overrides) */
 std::atomic<uint64_t> g_huge_done{0}, g_huge_declined{0};
-std::atomic<int> g_stream_resume{1}; /* PZ_OPT_STREAM_RESUME */
 std::once_flag g_once;
 int g_init_rc = PZ_E_STATE;
 int g_device = -1;          /* the primary device: resident batches, incremental contexts, device-pointer calls */
@@ -150,6 +149,8 @@ int ensure_init() {
 }
 
 inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
+/* PZ_F_GZIP / PZ_F_RAW -> PZ_FRAME_* of pz_device.cuh (0 zlib, 1 gzip, 2 raw deflate) */
+inline uint32_t framing_of(uint32_t flags) { return (flags & PZ_F_GZIP) ? 1u : (flags & PZ_F_RAW) ? 2u : 0u; }
 
 bool is_device_ptr(const void *p) {
   cudaPointerAttributes at;
@@ -288,20 +289,37 @@ constexpr uint32_t kBlockCap = 32u << 20; /* most bytes one speculative block ma
 constexpr int kMaxGaps = 256; /* blocks the search cannot see (stored, fixed) that K4 will size one by one before giving up */
 
 int huge_stream(const uint8_t *d_in_blob, const uint64_t *d_in_off_i, uint64_t in_byte_off, uint64_t in_len, uint8_t *d_out_i,
-                uint64_t out_cap, pz_result *out, cudaStream_t st) {
+                uint64_t out_cap, pz_result *out, cudaStream_t st, uint32_t framing) {
   Workspace &ws = g_ws;
   if (in_len < 16 || in_len > PZ_MAX_STREAM_BYTES) return 0;
   static const bool trace = getenv("PZ_TRACE") != nullptr;
   const auto t_start = std::chrono::steady_clock::now();
   auto now_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
   const uint8_t *d_stream = d_in_blob + in_byte_off;
-  uint8_t head[8];
-  PZ_CUDA(cudaMemcpyAsync(head, d_stream, 8, cudaMemcpyDeviceToHost, st));
+  uint8_t head[1024];
+  const size_t head_len = (size_t)std::min<uint64_t>(sizeof head, in_len);
+  PZ_CUDA(cudaMemcpyAsync(head, d_stream, head_len, cudaMemcpyDeviceToHost, st));
   PZ_CUDA(cudaStreamSynchronize(st));
-  const uint32_t cmf = head[0], flg = head[1];
-  if (((cmf << 8) | flg) % 31u != 0u || (cmf & 15u) != 8u || (cmf >> 4) > 7u) return 0; /* Zlib.hs:53-69: the serial path words the verdict */
-  const uint64_t first_bit = (flg & 0x20u) ? 48u : 16u;
-  const uint64_t total_bits = in_len * 8u, last_bit = total_bits - 32u; /* four trailer bytes must follow the last block */
+  uint64_t first_bit = 0;
+  uint32_t trailer_bytes = 0;
+  if (framing == 0u) {
+    const uint32_t cmf = head[0], flg = head[1];
+    if (((cmf << 8) | flg) % 31u != 0u || (cmf & 15u) != 8u || (cmf >> 4) > 7u) return 0; /* Zlib.hs:53-69: the serial path words the verdict */
+    first_bit = (flg & 0x20u) ? 48u : 16u;
+    trailer_bytes = 4;
+  } else if (framing == 1u) { /* gzip member header (RFC 1952 2.3): anything but a plain, complete header inside the first KiB is the serial path's */
+    if (head[0] != 0x1f || head[1] != 0x8b || head[2] != 8 || (head[3] & 0xe0)) return 0;
+    size_t at = 10;
+    const uint32_t fl = head[3];
+    if (fl & 4u) { if (at + 2 > head_len) return 0; at += 2u + ((size_t)head[at] | ((size_t)head[at + 1] << 8)); }
+    for (uint32_t bit = 8u; bit <= 16u; bit <<= 1)
+      if (fl & bit) { while (at < head_len && head[at] != 0) at++; at++; }
+    if (fl & 2u) at += 2;
+    if (at >= head_len) return 0;
+    first_bit = at * 8u;
+    trailer_bytes = 8;
+  }
+  const uint64_t total_bits = in_len * 8u, last_bit = total_bits - 8u * trailer_bytes; /* the trailer must follow the last block */
   int rc;
   /* K4a: candidates */
   const uint32_t cap = (uint32_t)(total_bits / 128u + 4096u);
@@ -465,9 +483,9 @@ int huge_stream(const uint8_t *d_in_blob, const uint64_t *d_in_off_i, uint64_t i
   if (trace) fprintf(stderr, "[pz-k4] %8.3f ms: chain of %zu blocks, %llu bytes, %d found one by one\n", now_ms(), c_start.size(), (unsigned long long)total, gaps);
   }
   const uint64_t tb = (end_bit + 7u) / 8u;
-  if (tb + 4u > in_len) return 0;
-  uint8_t trailer[4];
-  PZ_CUDA(cudaMemcpyAsync(trailer, d_stream + tb, 4, cudaMemcpyDeviceToHost, st));
+  if (tb + trailer_bytes > in_len) return 0;
+  uint8_t trailer[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (trailer_bytes) PZ_CUDA(cudaMemcpyAsync(trailer, d_stream + tb, trailer_bytes, cudaMemcpyDeviceToHost, st));
   /* decode pass: 16-bit symbols of every chain block, at its final position */
   const size_t nb = c_start.size();
   if ((rc = ws.k4_start.reserve(nb * 4u)) != PZ_E_OK || (rc = ws.k4_len.reserve(nb * 4u)) != PZ_E_OK || (rc = ws.k4_off.reserve(nb * 8u)) != PZ_E_OK ||
@@ -510,7 +528,11 @@ int huge_stream(const uint8_t *d_in_blob, const uint64_t *d_in_off_i, uint64_t i
   out->status = PZ_OK;
   out->out_len = total;
   out->adler_stored = ((uint32_t)trailer[0] << 24) | ((uint32_t)trailer[1] << 16) | ((uint32_t)trailer[2] << 8) | trailer[3];
-  out->err_bitpos = tb * 8u + 32u;
+  if (framing == 1u) { /* CRC-32 and ISIZE, least significant byte first; K3 compares both */
+    out->adler_stored = ((uint32_t)trailer[3] << 24) | ((uint32_t)trailer[2] << 16) | ((uint32_t)trailer[1] << 8) | trailer[0];
+    out->payload[0] = (int64_t)(((uint32_t)trailer[7] << 24) | ((uint32_t)trailer[6] << 16) | ((uint32_t)trailer[5] << 8) | trailer[4]);
+  }
+  out->err_bitpos = tb * 8u + 8u * trailer_bytes;
   /* bytes the reference has published as 32 KiB chunks when it reaches the trailer: one chunk per
    * moveWindow call that finds 64 KiB in the window (Monad.hs:338-347).  Every block job has checked that no
    * more than 32 KiB lie between two calls (PzCtx::mark), so the window never holds 96 KiB after a call, every
@@ -530,10 +552,17 @@ int run_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uint8_t *d_out, c
     for (uint32_t i = first; i < first + count; i++)
       if (h_in_off[i + 1] - h_in_off[i] >= g_huge_bytes) huge.push_back(i);
   if (huge.empty()) {
-    PZ_CUDA(pz_launch_inflate(d_in, d_in_off, d_out, d_out_off, first, count, d_res, st, nullptr, nullptr, PZ_PHASE_ALL, d_parts, d_seg_off));
+    PZ_CUDA(pz_launch_inflate(d_in, d_in_off, d_out, d_out_off, first, count, d_res, st, nullptr, nullptr, PZ_PHASE_ALL, d_parts, d_seg_off, framing_of(flags)));
     return PZ_E_OK;
   }
-  PZ_CUDA(pz_launch_inflate(d_in, d_in_off, d_out, d_out_off, first, count, d_res, st, nullptr, nullptr, PZ_PHASE_K2, d_parts, d_seg_off));
+  const uint32_t framing = framing_of(flags);
+  if (framing != 0u) { /* K2 reads zlib framing only, and it is K2 that marks the streams PENDING for the K1 launch below */
+    std::vector<pz_result> pend(count);
+    for (pz_result &r : pend) { memset(&r, 0, sizeof r); r.status = PZ_ST_PENDING_HOST; }
+    PZ_CUDA(cudaMemcpyAsync(d_res + first, pend.data(), count * sizeof(pz_result), cudaMemcpyHostToDevice, st));
+    PZ_CUDA(cudaStreamSynchronize(st));
+  }
+  PZ_CUDA(pz_launch_inflate(d_in, d_in_off, d_out, d_out_off, first, count, d_res, st, nullptr, nullptr, PZ_PHASE_K2, d_parts, d_seg_off, framing));
   /* K2's verdicts for the span of the huge streams, in one copy: a stored-block stream is done */
   std::vector<pz_result> after_k2(huge.back() - huge.front() + 1u);
   PZ_CUDA(cudaMemcpyAsync(after_k2.data(), d_res + huge.front(), after_k2.size() * sizeof(pz_result), cudaMemcpyDeviceToHost, st));
@@ -541,7 +570,7 @@ int run_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uint8_t *d_out, c
   for (uint32_t i : huge) {
     if (after_k2[i - huge.front()].status != PZ_ST_PENDING_HOST) continue; /* K2 has copied it */
     pz_result r;
-    const int k = huge_stream(d_in, d_in_off + i, h_in_off[i], h_in_off[i + 1] - h_in_off[i], d_out + h_out_off[i], h_out_off[i + 1] - h_out_off[i], &r, st);
+    const int k = huge_stream(d_in, d_in_off + i, h_in_off[i], h_in_off[i + 1] - h_in_off[i], d_out + h_out_off[i], h_out_off[i + 1] - h_out_off[i], &r, st, framing);
     if (k < 0) return k;
     (k == 1 ? g_huge_done : g_huge_declined)++;
     if (k == 1) {
@@ -549,7 +578,7 @@ int run_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uint8_t *d_out, c
       PZ_CUDA(cudaStreamSynchronize(st)); /* r lives on this stack frame */
     }
   }
-  PZ_CUDA(pz_launch_inflate(d_in, d_in_off, d_out, d_out_off, first, count, d_res, st, nullptr, nullptr, PZ_PHASE_K1));
+  PZ_CUDA(pz_launch_inflate(d_in, d_in_off, d_out, d_out_off, first, count, d_res, st, nullptr, nullptr, PZ_PHASE_K1, nullptr, nullptr, framing | 0x100u));
   return PZ_E_OK;
 }
 
@@ -576,7 +605,7 @@ uint64_t pz_get_counter(int which) {
 
 int pz_set_option(int key, uint64_t value) {
   if (key == PZ_OPT_HUGE_BYTES && value > 0) { g_huge_bytes = value; return PZ_E_OK; }
-  if (key == PZ_OPT_STREAM_RESUME) { g_stream_resume = value != 0; return PZ_E_OK; }
+  if (key == PZ_OPT_STREAM_RESUME) return PZ_E_OK; /* accepted, ignored: contexts no longer keep what a restart from the first byte would need */
   return PZ_E_ARG;
 }
 
@@ -637,7 +666,7 @@ int pz_batch_run(pz_batch *b, const uint8_t *d_in, uint8_t *d_out, void *stream)
     if (rc != PZ_E_OK) return rc;
   }
   if (!count_only && !(b->flags & PZ_F_NO_ADLER))
-    PZ_CUDA(pz_launch_adler(d_out, b->d_out_off, b->d_seg_off, (uint32_t)b->n, 0, (uint32_t)b->n, 0, b->total_segs, b->d_res, b->d_parts, st));
+    PZ_CUDA(pz_launch_adler(d_out, b->d_out_off, b->d_seg_off, (uint32_t)b->n, 0, (uint32_t)b->n, 0, b->total_segs, b->d_res, b->d_parts, st, framing_of(b->flags)));
   return PZ_E_OK;
 }
 
@@ -708,7 +737,7 @@ int contig_one_device(const uint8_t *in_blob, const uint64_t *in_off, uint8_t *o
     if (adler) PZ_CUDA(cudaMemcpyAsync(d_seg_off, seg.data(), ob, cudaMemcpyHostToDevice, st));
     if ((rc = run_inflate(in_blob, d_in_off, count_only ? nullptr : out_blob, d_out_off, 0, (uint32_t)n, d_res, st, in_off, out_off, flags,
                           adler ? d_parts : nullptr, d_seg_off)) != PZ_E_OK) return rc;
-    if (adler) PZ_CUDA(pz_launch_adler(out_blob, d_out_off, d_seg_off, (uint32_t)n, 0, (uint32_t)n, 0, total_segs, d_res, d_parts, st));
+    if (adler) PZ_CUDA(pz_launch_adler(out_blob, d_out_off, d_seg_off, (uint32_t)n, 0, (uint32_t)n, 0, total_segs, d_res, d_parts, st, framing_of(flags)));
     PZ_CUDA(cudaMemcpyAsync(res, d_res, n * sizeof(pz_result), cudaMemcpyDeviceToHost, st));
     PZ_CUDA(cudaStreamSynchronize(st));
     return PZ_E_OK;
@@ -740,7 +769,7 @@ int contig_one_device(const uint8_t *in_blob, const uint64_t *in_off, uint8_t *o
    * the whole input instead. */
   const bool in_place = (flags & PZ_F_INPUT_IN_PLACE) != 0;
   bool progressive = columns && !in_place && n >= 8 * kGroups && n <= 2 * (size_t)pz_inflate_slots();
-  for (size_t i = 0; progressive && i < n; i++) {
+  for (size_t i = 0; progressive && framing_of(flags) == 0u && i < n; i++) {
     const uint64_t len = in_off[i + 1] - in_off[i];
     const uint8_t *p = in_blob + in_off[i];
     progressive = len >= 3 && len < g_huge_bytes && ((p[(p[1] & 0x20u) && len >= 7 ? 6 : 2] >> 1) & 3u) != 0u;
@@ -839,7 +868,7 @@ int contig_one_device(const uint8_t *in_blob, const uint64_t *in_off, uint8_t *o
         }
         if (adler)
           PZ_CUDA(pz_launch_adler(d_out, d_out_off, d_seg_off, (uint32_t)n, (uint32_t)first, (uint32_t)(last - first), seg[first],
-                                  seg[last] - seg[first], d_res, d_parts, s0));
+                                  seg[last] - seg[first], d_res, d_parts, s0, framing_of(flags)));
         PZ_CUDA(cudaEventRecord(ev_k, s0));
         if (!count_only) {
           const uint64_t o0 = out_off[first], o1 = out_off[last];
@@ -855,9 +884,9 @@ int contig_one_device(const uint8_t *in_blob, const uint64_t *in_off, uint8_t *o
       return PZ_E_OK;
     }
     PZ_CUDA(cudaEventRecord(k1_start, s0));
-    PZ_CUDA(pz_launch_inflate(d_in, d_in_off, d_out, d_out_off, 0, (uint32_t)n, d_res, s0, d_prog, d_ready));
+    PZ_CUDA(pz_launch_inflate(d_in, d_in_off, d_out, d_out_off, 0, (uint32_t)n, d_res, s0, d_prog, d_ready, PZ_PHASE_ALL, nullptr, nullptr, framing_of(flags)));
     PZ_CUDA(cudaEventRecord(k1_done, s0));
-    if (adler) PZ_CUDA(pz_launch_adler(d_out, d_out_off, d_seg_off, (uint32_t)n, 0, (uint32_t)n, 0, total_segs, d_res, d_parts, s0));
+    if (adler) PZ_CUDA(pz_launch_adler(d_out, d_out_off, d_seg_off, (uint32_t)n, 0, (uint32_t)n, 0, total_segs, d_res, d_parts, s0, framing_of(flags)));
     PZ_CUDA(cudaMemcpyAsync(h_res, d_res, n * sizeof(pz_result), cudaMemcpyDeviceToHost, s0));
     if (count_only) return PZ_E_OK;
     /* drain: columns [0, sent[g]) of the rows of piece g are on their way home */
@@ -1081,16 +1110,28 @@ void pool_init() {
 
 struct pz_stream {
   cudaStream_t st = nullptr;
-  /* device context */
-  uint8_t *d_in = nullptr, *d_out = nullptr;
-  size_t d_in_cap = 0, d_out_cap = 0;
-  size_t in_len = 0;               /* compressed bytes on the device */
-  uint32_t ck[4] = {0, 0, 0, 0};   /* where the next pump picks the stream up (PzJob::ckpt) */
   int pool_idx = 0;                /* st == g_pool[pool_idx] */
+  uint32_t framing = 0;            /* PZ_FRAME_*: zlib, gzip, raw deflate */
+  /* The device context is O(1) in the length of the stream (the reference's is its 128 KiB window, OutputWindow.hs:29-54):
+   * the compressed bytes from the header of the block the decoder is in, the last 32 KiB of decoded bytes (the LZ77
+   * history) plus room for what one pump adds, and a checkpoint.  Everything behind them is dropped as the stream goes. */
+  /* input: d_in[0] is byte in_base of the stream; bytes [in_base, in_total) are on the device */
+  uint8_t *d_in = nullptr;
+  size_t d_in_cap = 0;
+  uint64_t in_total = 0, in_base = 0;
+  uint64_t lead = 0;               /* stream byte the checkpoint's bit positions are counted from (in_base <= lead) */
+  uint32_t ck[4] = {0, 0, 0, 0};   /* where the next pump picks the stream up (PzJob::ckpt): {bit of the block header, bit of the
+                                      symbol, -, -} counted from `lead`; the byte counters of the checkpoint are kept below */
+  /* output: d_out[0] is decoded byte out_base; bytes [out_base, pos) are on the device, at least the last 32 KiB of them */
+  uint8_t *d_out = nullptr;
+  size_t d_out_cap = 0;
+  uint64_t out_base = 0, pos = 0;  /* absolute counts: they may pass 4 GiB, the kernel sees them relative to base_abs */
+  uint64_t base_abs = 0;           /* bytes the reference has published at the checkpoint (multiple of 32 KiB) */
+  uint32_t sum = 1;                /* running checksum of the decoded bytes: Adler-32 (zlib, raw) or CRC-32 (gzip) */
   /* the feed on its way: pinned staging, reused once its copy has finished */
   PinnedBuf stage;
   cudaEvent_t staged = nullptr;
-  /* decoded bytes on the host: [h_first, h_to) of the stream, h_first <= published */
+  /* decoded bytes on the host: [h_first, h_to) of the stream, h_first <= published; h_to == pos after every pump */
   PinnedBuf h_out;
   uint64_t h_first = 0, h_to = 0;
   uint64_t published = 0;    /* bytes already handed out as chunks */
@@ -1102,21 +1143,22 @@ struct pz_stream {
   pz_result verdict{};
   uint64_t pumps = 0, resumed = 0; /* launches that decoded this stream; those that started from a checkpoint */
   uint64_t feed_stamp = 0;         /* the pz_stream_feed_many call that last took a chunk for this stream */
+  size_t peak_device = 0;          /* most device memory the context has held (PZ_SC_DEVICE_PEAK) */
 };
 
 namespace {
 /* per-thread control tables of a pump: [in pairs | out pairs | resume] go up, [ckpt | res] come back */
 struct PumpSpace {
-  Buf h_ctl, d_ctl, d_parts, d_tab, d_gather, h_feed, d_feed;
+  Buf h_ctl, d_ctl, d_parts, d_tab, h_tab, d_gather, h_feed, d_feed;
   cudaEvent_t fed[kPoolStreams] = {};
-  PumpSpace() { h_ctl.pinned = true; h_feed.pinned = true; }
+  PumpSpace() { h_ctl.pinned = true; h_feed.pinned = true; h_tab.pinned = true; }
   int ensure_events() {
     for (int i = 0; i < kPoolStreams; i++)
       if (!fed[i]) PZ_CUDA(cudaEventCreateWithFlags(&fed[i], cudaEventDisableTiming));
     return PZ_E_OK;
   }
   ~PumpSpace() {
-    h_ctl.release(); d_ctl.release(); d_parts.release(); d_tab.release(); d_gather.release(); h_feed.release(); d_feed.release();
+    h_ctl.release(); d_ctl.release(); d_parts.release(); d_tab.release(); h_tab.release(); d_gather.release(); h_feed.release(); d_feed.release();
     for (int i = 0; i < kPoolStreams; i++) if (fed[i]) cudaEventDestroy(fed[i]);
   }
 };
@@ -1134,26 +1176,61 @@ int grow_device(uint8_t *&d, size_t &cap, size_t want, size_t keep, cudaStream_t
   return PZ_E_OK;
 }
 
-/* The state a verdict puts the stream in (what stream_next hands out afterwards). */
+/* Replaces the buffer by one of `want` bytes holding bytes [from, from + keep) of the old one (a context gives memory back
+ * when what it must keep has become much smaller than what it holds). */
+int shrink_device(uint8_t *&d, size_t &cap, size_t want, size_t from, size_t keep, cudaStream_t st) {
+  size_t n = align_up(want + 64, 1 << 16);
+  uint8_t *q = nullptr;
+  cudaError_t e = cudaMallocAsync((void **)&q, n, st);
+  if (e != cudaSuccess) { fail_cuda(e, "cudaMallocAsync"); return PZ_E_NOMEM; }
+  if (keep) PZ_CUDA(cudaMemcpyAsync(q, d + from, keep, cudaMemcpyDeviceToDevice, st));
+  if (d) PZ_CUDA(cudaFreeAsync(d, st));
+  d = q; cap = n;
+  return PZ_E_OK;
+}
+
+constexpr uint64_t kHistory = 32768;          /* the farthest a match reaches back (Deflate.hs:199-237) */
+constexpr uint64_t kRoomMin = 256 << 10;      /* decoded bytes a context has room for in one launch, at least ... */
+constexpr uint64_t kRoomMax = 64 << 20;       /* ... and at most: a stream that expands further takes another launch of the same pump */
+
+uint32_t adler_combine(uint32_t s1, uint32_t s2, uint64_t len2) { /* Adler-32 of A || B from those of A and B (a0 = 1, b0 = 0: Adler32.hs:19-20) */
+  const uint32_t M = 65521u;
+  const uint32_t a1 = s1 & 0xffffu, b1 = s1 >> 16, a2 = s2 & 0xffffu, b2 = s2 >> 16;
+  const uint32_t a = (a1 + a2 + M - 1u) % M;
+  const uint32_t b = (uint32_t)((b1 + b2 + (len2 % M) * ((a1 + M - 1u) % M)) % M);
+  return (b << 16) | a;
+}
+uint32_t crc_gf_mul(uint32_t a, uint32_t b) {
+  uint32_t p = 0;
+  for (uint32_t m = 0x80000000u; m != 0u && a != 0u; m >>= 1) {
+    if (a & m) { p ^= b; a &= ~m; }
+    b = (b >> 1) ^ (0xedb88320u & (0u - (b & 1u)));
+  }
+  return p;
+}
+uint32_t crc_combine(uint32_t c1, uint32_t c2, uint64_t len2) { /* CRC-32 of A || B: crc(A) * x^(8|B|) + crc(B) over GF(2) mod P */
+  uint32_t xp = 0x80000000u, sq = 0x40000000u;
+  for (int k = 0; k < 3; k++) sq = crc_gf_mul(sq, sq);
+  for (uint64_t n = len2; n != 0u; n >>= 1) {
+    if (n & 1u) xp = crc_gf_mul(sq, xp);
+    sq = crc_gf_mul(sq, sq);
+  }
+  return crc_gf_mul(xp, c1) ^ c2;
+}
+
+/* The state a verdict puts the stream in (what stream_next hands out afterwards).  r is in absolute byte counts. */
 void stream_settle(pz_stream *s, const pz_result &r) {
   s->verdict = r;
   const bool need_more = r.status == PZ_ERR_DECOMPRESSION && r.detail == PZ_D_RAN_OUT;
-  const uint64_t base = (r.status == PZ_REF_BOTTOM && r.detail == PZ_D_BOT_DIST_TOO_FAR) ? r.out_len - (uint64_t)r.payload[1]
-                                                                                          : (uint64_t)r.payload[1];
-  s->publish_to = base;
+  s->publish_to = s->base_abs;
   if (!need_more) {
     s->terminal = true;
     s->final_pending = (r.status == PZ_OK); /* finalize publishes what is left (Monad.hs:349-353) */
   }
 }
 
-int pump(pz_stream *const *all, size_t n_all) {
-  std::vector<pz_stream *> act;
-  for (size_t i = 0; i < n_all; i++) {
-    pz_stream *s = all[i];
-    if (!s) return PZ_E_ARG;
-    if (s->dirty && !s->terminal && std::find(act.begin(), act.end(), s) == act.end()) act.push_back(s);
-  }
+/* One framing at a time: the streams of `act` all read the same framing (PzJob::framing belongs to the launch). */
+int pump_framed(const std::vector<pz_stream *> &act, uint32_t framing) {
   if (act.empty()) return PZ_E_OK;
   cudaStream_t st = act[0]->st;
   PumpSpace &ps = g_pump;
@@ -1181,101 +1258,170 @@ int pump(pz_stream *const *all, size_t n_all) {
     for (size_t i = 0; i < n; i++) {
       pz_stream *s = run[i];
       /* room for what this input may add before the kernel has to stop for a larger buffer */
-      const size_t want = std::min<uint64_t>(0xfffdff00ull, (uint64_t)s->ck[2] + std::max<uint64_t>(1 << 16, 4 * (uint64_t)(s->in_len - s->ck[0] / 8)));
-      if ((rc = grow_device(s->d_out, s->d_out_cap, want, s->ck[2], st)) != PZ_E_OK) return rc; /* d_out is only ever touched by pumps, which end synchronised */
+      const uint64_t room = std::min<uint64_t>(kRoomMax, std::max<uint64_t>(kRoomMin, 4 * (s->in_total - s->lead)));
+      uint64_t hist = s->pos - s->out_base; /* decoded bytes on the device */
+      if (hist >= 2 * kHistory && hist + room + 64 > s->d_out_cap) { /* only the last 32 KiB can still be referenced: move them to the front */
+        PZ_CUDA(cudaMemcpyAsync(s->d_out, s->d_out + (hist - kHistory), kHistory, cudaMemcpyDeviceToDevice, st)); /* disjoint: hist >= 64 KiB */
+        s->out_base = s->pos - kHistory;
+        hist = kHistory;
+      }
+      if ((rc = grow_device(s->d_out, s->d_out_cap, hist + room + 64, hist, st)) != PZ_E_OK) return rc; /* d_out is only ever touched by pumps, which end synchronised */
       if (!s->d_in && (rc = grow_device(s->d_in, s->d_in_cap, 64, 0, s->st)) != PZ_E_OK) return rc; /* a stream nothing was fed to yet */
-      in_pairs[2 * i] = (uint64_t)(uintptr_t)s->d_in; in_pairs[2 * i + 1] = in_pairs[2 * i] + s->in_len;
-      out_pairs[2 * i] = (uint64_t)(uintptr_t)s->d_out; out_pairs[2 * i + 1] = out_pairs[2 * i] + std::min<uint64_t>(s->d_out_cap - 64, 0xfffdff00ull);
-      memcpy(resume + 4 * i, s->ck, 16);
-      if (!g_stream_resume) memset(resume + 4 * i, 0, 16); /* A/B: from the first byte again */
+      s->peak_device = std::max(s->peak_device, s->d_in_cap + s->d_out_cap);
+      /* the kernel counts decoded bytes from base_abs (a multiple of 32 KiB): its `base` is 0, its position the window's fill */
+      const uint64_t fill = s->pos - s->base_abs;
+      in_pairs[2 * i] = (uint64_t)(uintptr_t)(s->d_in + (s->lead - s->in_base));
+      in_pairs[2 * i + 1] = (uint64_t)(uintptr_t)(s->d_in + (s->in_total - s->in_base));
+      const uint64_t out0 = (uint64_t)(uintptr_t)s->d_out + (s->base_abs - s->out_base); /* address of decoded byte base_abs (may lie before the buffer: never touched) */
+      out_pairs[2 * i] = out0;
+      out_pairs[2 * i + 1] = out0 + std::min<uint64_t>((s->out_base - s->base_abs) + (s->d_out_cap - 64), 0xfffdff00ull);
+      resume[4 * i] = s->ck[0]; resume[4 * i + 1] = s->ck[1]; resume[4 * i + 2] = (uint32_t)fill; resume[4 * i + 3] = 0;
     }
     PZ_CUDA(cudaMemcpyAsync(d, h, up, cudaMemcpyHostToDevice, st));
     uint32_t *d_ck = (uint32_t *)(d + up);
     pz_result *d_res = (pz_result *)(d + up + 16 * n);
-    PZ_CUDA(pz_launch_resume((const uint64_t *)d, (const uint64_t *)(d + 16 * n), (uint32_t)n, d_res, (const uint32_t *)(d + 32 * n), d_ck, st));
+    PZ_CUDA(pz_launch_resume((const uint64_t *)d, (const uint64_t *)(d + 16 * n), (uint32_t)n, d_res, (const uint32_t *)(d + 32 * n), d_ck, st, framing));
     PZ_CUDA(cudaMemcpyAsync(h + up, d + up, down, cudaMemcpyDeviceToHost, st));
     PZ_CUDA(cudaStreamSynchronize(st));
     const uint32_t *ck = (const uint32_t *)(h + up);
     const pz_result *res = (const pz_result *)(h + up + 16 * n);
-    /* streams that are complete get their Adler-32 verdict: K3 over their whole decoded output, ONE launch pair for
-     * all of them (a table over the pump's n streams in which the unfinished ones own no segments) */
-    std::vector<uint64_t> tab(2 * n + 1); /* [0, n): where each stream's output begins; [n, 2n]: its first segment */
+    /* What this launch decoded, per stream: its checksum (K3 over the new bytes only, folded into the running sum with the
+     * combine identities) and its way home (ONE kernel stores the small pieces of all streams into their pinned buffers: a
+     * cudaMemcpyAsync each costs more host time than the copy takes; long pieces go by copy engine). */
+    std::vector<uint64_t> tab(2 * n + 1), gat; /* [0, n): where each new piece begins; [n, 2n]: its first checksum segment */
+    std::vector<uint64_t> newpos(n);
     uint64_t segs = 0;
+    bool any_new = false;
+    if ((rc = ps.h_tab.reserve(n * sizeof(pz_result))) != PZ_E_OK) return rc;
+    pz_result *piece = (pz_result *)ps.h_tab.p;
     for (size_t i = 0; i < n; i++) {
-      tab[i] = (uint64_t)(uintptr_t)run[i]->d_out;
+      pz_stream *s = run[i];
+      newpos[i] = s->base_abs + ck[4 * i + 2];
+      const uint64_t len = newpos[i] - s->pos;
+      tab[i] = (uint64_t)(uintptr_t)(s->d_out + (s->pos - s->out_base));
       tab[n + i] = segs;
-      if (res[i].status == PZ_OK) segs += (res[i].out_len + PZ_ADLER_SEG - 1) / PZ_ADLER_SEG;
+      memset(&piece[i], 0, sizeof(pz_result));
+      piece[i].status = len ? PZ_OK : PZ_ST_PENDING_HOST;
+      piece[i].out_len = len;
+      if (len) { segs += (len + PZ_ADLER_SEG - 1) / PZ_ADLER_SEG; any_new = true; }
     }
     tab[2 * n] = segs;
-    bool any_ok = false;
-    for (size_t i = 0; i < n; i++) any_ok = any_ok || res[i].status == PZ_OK;
-    if (any_ok) {
+    if (any_new) {
       if ((rc = ps.d_parts.reserve(std::max<uint64_t>(segs, 1) * sizeof(uint2))) != PZ_E_OK) return rc;
-      if ((rc = ps.d_tab.reserve(tab.size() * 8u)) != PZ_E_OK) return rc;
+      if ((rc = ps.d_tab.reserve(tab.size() * 8u + n * sizeof(pz_result))) != PZ_E_OK) return rc;
+      pz_result *d_piece = (pz_result *)((uint8_t *)ps.d_tab.p + tab.size() * 8u);
       PZ_CUDA(cudaMemcpyAsync(ps.d_tab.p, tab.data(), tab.size() * 8u, cudaMemcpyHostToDevice, st));
-      PZ_CUDA(pz_launch_adler(nullptr, (const uint64_t *)ps.d_tab.p, (const uint64_t *)ps.d_tab.p + n, (uint32_t)n, 0, (uint32_t)n, 0, segs, d_res,
-                              (uint2 *)ps.d_parts.p, st));
-      PZ_CUDA(cudaMemcpyAsync(h + up + 16 * n, d_res, n * sizeof(pz_result), cudaMemcpyDeviceToHost, st));
+      PZ_CUDA(cudaMemcpyAsync(d_piece, piece, n * sizeof(pz_result), cudaMemcpyHostToDevice, st));
+      PZ_CUDA(pz_launch_adler(nullptr, (const uint64_t *)ps.d_tab.p, (const uint64_t *)ps.d_tab.p + n, (uint32_t)n, 0, (uint32_t)n, 0, segs, d_piece,
+                              (uint2 *)ps.d_parts.p, st, framing | 0x200u /* checksums only: nothing to compare with yet */));
+      PZ_CUDA(cudaMemcpyAsync(piece, d_piece, n * sizeof(pz_result), cudaMemcpyDeviceToHost, st));
+      for (size_t i = 0; i < n; i++) {
+        pz_stream *s = run[i];
+        const uint64_t len = newpos[i] - s->pos;
+        if (!len) continue;
+        /* host side: handed-out bytes in front of the buffer are dropped once they outweigh what is still owed */
+        if (s->published == s->h_to) s->h_first = s->h_to;
+        else if (s->published - s->h_first >= std::max<uint64_t>(1 << 20, s->h_to - s->published)) {
+          memmove(s->h_out.p, s->h_out.p + (s->published - s->h_first), (size_t)(s->h_to - s->published));
+          s->h_first = s->published;
+        }
+        const uint64_t keep = s->h_to - s->h_first;
+        if ((rc = s->h_out.reserve_keep((size_t)(keep + len), (size_t)keep)) != PZ_E_OK) return rc;
+        if (len > kGatherMax) {
+          PZ_CUDA(cudaMemcpyAsync(s->h_out.p + keep, s->d_out + (s->pos - s->out_base), len, cudaMemcpyDeviceToHost, st));
+        } else {
+          gat.push_back(tab[i]); gat.push_back((uint64_t)(uintptr_t)(s->h_out.p + keep)); gat.push_back(len);
+        }
+        s->h_to = newpos[i];
+      }
+      if (!gat.empty()) {
+        if ((rc = ps.d_gather.reserve(gat.size() * 8u)) != PZ_E_OK) return rc;
+        PZ_CUDA(cudaMemcpyAsync(ps.d_gather.p, gat.data(), gat.size() * 8u, cudaMemcpyHostToDevice, st));
+        PZ_CUDA(pz_launch_gather((const uint64_t *)ps.d_gather.p, (uint32_t)(gat.size() / 3), st));
+      }
       PZ_CUDA(cudaStreamSynchronize(st));
     }
     std::vector<pz_stream *> again;
     for (size_t i = 0; i < n; i++) {
       pz_stream *s = run[i];
       s->pumps++;
-      if (s->ck[0] != 0 && g_stream_resume) s->resumed++;
-      memcpy(s->ck, ck + 4 * i, 16);
-      if (res[i].status == PZ_OUTPUT_FULL) { /* the buffer, not the stream: enlarge it and go on from the checkpoint */
-        if (s->d_out_cap - 64 >= 0xfffdff00ull) { stream_settle(s, res[i]); continue; }
-        if ((rc = grow_device(s->d_out, s->d_out_cap, std::min<uint64_t>(0xfffdff00ull + 64, (uint64_t)s->d_out_cap * 4), s->ck[2], st)) != PZ_E_OK) return rc;
+      if (s->ck[0] != 0 || s->lead != 0) s->resumed++;
+      /* the running checksum takes the new piece in */
+      const uint64_t len = newpos[i] - s->pos;
+      if (len) s->sum = framing == 1u ? crc_combine(s->sum, piece[i].adler_computed, len) : adler_combine(s->sum, piece[i].adler_computed, len);
+      s->pos = newpos[i];
+      s->base_abs += ck[4 * i + 3];
+      /* the checkpoint moves on, and the input behind its block header is dead: bit positions are re-based on a byte
+       * shortly before that header (never ON it: a checkpoint whose first word is 0 reads as "no checkpoint") */
+      const uint64_t old_lead = s->lead;
+      const uint64_t hdr_byte = s->lead + ck[4 * i] / 8u;
+      const uint64_t new_lead = hdr_byte >= 17u ? (hdr_byte - 1u) & ~(uint64_t)15u : 0u;
+      const uint32_t shift = new_lead > s->lead ? (uint32_t)((new_lead - s->lead) * 8u) : 0u;
+      s->ck[0] = ck[4 * i] - shift;
+      s->ck[1] = (ck[4 * i + 1] == 0u || ck[4 * i + 1] == PZ_CK_TRAILER_HOST) ? ck[4 * i + 1] : ck[4 * i + 1] - shift;
+      if (shift) s->lead = new_lead;
+      const uint64_t dead = s->lead - s->in_base, live = s->in_total - s->lead;
+      if (dead >= std::max<uint64_t>(1 << 16, live)) { /* give the dead input back (amortised: the copy is at most what was freed) */
+        if ((rc = shrink_device(s->d_in, s->d_in_cap, std::max<uint64_t>(2 * live, 1 << 16), (size_t)dead, (size_t)live, s->st)) != PZ_E_OK) return rc;
+        s->in_base = s->lead;
+      }
+      /* the verdict in absolute byte counts */
+      pz_result r = res[i];
+      r.out_len = s->pos;
+      r.err_bitpos += old_lead * 8u;
+      if (!(r.status == PZ_REF_BOTTOM && r.detail == PZ_D_BOT_DIST_TOO_FAR)) r.payload[1] = (int64_t)s->base_abs;
+      r.adler_computed = s->sum;
+      if (r.status == PZ_OUTPUT_FULL) { /* the buffer, not the stream: the next launch of this pump starts from the checkpoint with room again */
+        if (s->pos >= (1ull << 62)) { stream_settle(s, r); continue; }
         again.push_back(s);
         continue;
       }
-      stream_settle(s, res[i]);
+      if (r.status == PZ_OK && framing != 2u) { /* checkChecksum (Deflate.hs:52-63) against the running sum; gzip: then ISIZE */
+        if (r.adler_stored != s->sum) { r.status = PZ_ERR_CHECKSUM; r.detail = PZ_D_ADLER_MISMATCH; }
+        else if (framing == 1u && (uint32_t)r.payload[0] != (uint32_t)s->pos) { r.status = PZ_ERR_CHECKSUM; r.detail = PZ_D_LENGTH_MISMATCH; r.payload[0] = (int64_t)(uint32_t)r.payload[0]; }
+      }
+      stream_settle(s, r);
     }
     run.swap(again);
   }
-  /* bring home what the streams may now hand out: ONE kernel stores the small pieces of all streams into their pinned
-   * buffers (a cudaMemcpyAsync each costs more host time than the copy takes); long pieces go by copy engine */
-  std::vector<uint64_t> gat; /* (source, destination, length) triples */
-  for (pz_stream *s : act) {
-    s->dirty = false;
-    const uint64_t to = (s->terminal && s->verdict.status == PZ_OK) ? s->verdict.out_len : s->publish_to;
-    if (s->published == s->h_to) s->h_first = s->h_to; /* everything fetched so far has been handed out */
-    if (to <= s->h_to) continue;
-    const uint64_t keep = s->h_to - s->h_first;
-    if ((rc = s->h_out.reserve_keep((size_t)(to - s->h_first), (size_t)keep)) != PZ_E_OK) return rc;
-    const uint64_t len = to - s->h_to;
-    if (len > kGatherMax) {
-      PZ_CUDA(cudaMemcpyAsync(s->h_out.p + keep, s->d_out + s->h_to, len, cudaMemcpyDeviceToHost, st));
-    } else {
-      gat.push_back((uint64_t)(uintptr_t)(s->d_out + s->h_to)); gat.push_back((uint64_t)(uintptr_t)(s->h_out.p + keep)); gat.push_back(len);
-    }
-    s->h_to = to;
+  for (pz_stream *s : act) s->dirty = false;
+  return PZ_E_OK;
+}
+
+int pump(pz_stream *const *all, size_t n_all) {
+  std::vector<pz_stream *> act[3];
+  for (size_t i = 0; i < n_all; i++) {
+    pz_stream *s = all[i];
+    if (!s) return PZ_E_ARG;
+    std::vector<pz_stream *> &v = act[s->framing % 3u];
+    if (s->dirty && !s->terminal && std::find(v.begin(), v.end(), s) == v.end()) v.push_back(s);
   }
-  if (!gat.empty()) {
-    if ((rc = ps.d_gather.reserve(gat.size() * 8u)) != PZ_E_OK) return rc;
-    PZ_CUDA(cudaMemcpyAsync(ps.d_gather.p, gat.data(), gat.size() * 8u, cudaMemcpyHostToDevice, st));
-    PZ_CUDA(pz_launch_gather((const uint64_t *)ps.d_gather.p, (uint32_t)(gat.size() / 3), st));
+  for (uint32_t f = 0; f < 3u; f++) {
+    const int rc = pump_framed(act[f], f);
+    if (rc != PZ_E_OK) return rc;
   }
-  PZ_CUDA(cudaStreamSynchronize(st));
   return PZ_E_OK;
 }
 }  // namespace
 
 extern "C" {
 
-pz_stream *pz_stream_new(void) {
+pz_stream *pz_stream_new_framed(uint32_t flags) {
   if (ensure_init() != PZ_E_OK) return nullptr;
   std::call_once(g_pool_once, pool_init);
   if (g_pool_rc != cudaSuccess) { fail_cuda(g_pool_rc, "pz_stream_new (stream pool)"); return nullptr; }
   pz_stream *s = new (std::nothrow) pz_stream();
   if (!s) return nullptr;
+  s->framing = framing_of(flags);
+  s->sum = s->framing == 1u ? 0u : 1u; /* CRC-32 of nothing / initialAdlerState (Adler32.hs:19-20) */
   s->pool_idx = (int)(g_pool_next++ % kPoolStreams);
   s->st = g_pool[s->pool_idx];
   cudaError_t e = cudaEventCreateWithFlags(&s->staged, cudaEventDisableTiming);
   if (e != cudaSuccess) { fail_cuda(e, "pz_stream_new"); pz_stream_free(s); return nullptr; }
   return s;
 }
+
+pz_stream *pz_stream_new(void) { return pz_stream_new_framed(0); }
 
 void pz_stream_free(pz_stream *s) {
   if (!s) return;
@@ -1292,19 +1438,20 @@ void pz_stream_free(pz_stream *s) {
 int pz_stream_feed(pz_stream *s, const uint8_t *data, size_t len) {
   if (!s || (len && !data)) return PZ_E_ARG;
   if (s->terminal) return PZ_E_STATE; /* the decoder never asked for this chunk */
-  if (s->in_len + len > PZ_MAX_STREAM_BYTES) return PZ_E_ARG;
+  if ((s->in_total - s->lead) + len > PZ_MAX_STREAM_BYTES) return PZ_E_ARG; /* ONE deflate block (plus the chunk) beyond 512 MiB */
   s->dirty = true;
   if (len == 0) return PZ_E_OK; /* empty chunks are accepted and ignored (Monad.hs:193-195) */
-  int rc = grow_device(s->d_in, s->d_in_cap, s->in_len + len + 64, s->in_len, s->st);
+  const size_t have = (size_t)(s->in_total - s->in_base);
+  int rc = grow_device(s->d_in, s->d_in_cap, have + len + 64, have, s->st);
   if (rc != PZ_E_OK) return rc;
   for (size_t at = 0; at < len;) {
     const size_t piece = std::min(len - at, kStageBytes);
     PZ_CUDA(cudaEventSynchronize(s->staged));
     if ((rc = s->stage.reserve_keep(piece, 0)) != PZ_E_OK) return rc;
     memcpy(s->stage.p, data + at, piece);
-    PZ_CUDA(cudaMemcpyAsync(s->d_in + s->in_len, s->stage.p, piece, cudaMemcpyHostToDevice, s->st));
+    PZ_CUDA(cudaMemcpyAsync(s->d_in + (s->in_total - s->in_base), s->stage.p, piece, cudaMemcpyHostToDevice, s->st));
     PZ_CUDA(cudaEventRecord(s->staged, s->st));
-    s->in_len += piece;
+    s->in_total += piece;
     at += piece;
   }
   return PZ_E_OK;
@@ -1327,7 +1474,7 @@ int pz_stream_feed_many(pz_stream *const *streams, const uint8_t *const *data, c
     pz_stream *s = streams[i];
     if (!s || (len[i] && !data[i])) return PZ_E_ARG;
     if (s->terminal) return PZ_E_STATE;
-    if (s->in_len + len[i] > PZ_MAX_STREAM_BYTES) return PZ_E_ARG;
+    if ((s->in_total - s->lead) + len[i] > PZ_MAX_STREAM_BYTES) return PZ_E_ARG;
     if (s->feed_stamp == stamp) return PZ_E_ARG; /* one chunk per stream and call */
     s->feed_stamp = stamp;
     total += (len[i] + 15u) & ~(uint64_t)15u;
@@ -1341,19 +1488,22 @@ int pz_stream_feed_many(pz_stream *const *streams, const uint8_t *const *data, c
   uint64_t at = base;
   bool seen[kPoolStreams] = {};
   size_t m = 0;
+  std::vector<CopyJob> jobs;
   for (size_t i = 0; i < n; i++) {
     pz_stream *s = streams[i];
     s->dirty = true;
     if (len[i] == 0) continue; /* empty chunks are accepted and ignored (Monad.hs:193-195) */
-    if ((rc = grow_device(s->d_in, s->d_in_cap, s->in_len + len[i] + 64, s->in_len, s->st)) != PZ_E_OK) return rc;
+    const size_t have = (size_t)(s->in_total - s->in_base);
+    if ((rc = grow_device(s->d_in, s->d_in_cap, have + len[i] + 64, have, s->st)) != PZ_E_OK) return rc;
     seen[s->pool_idx] = true;
-    memcpy(hp + at, data[i], len[i]);
-    tri[3 * m] = (uint64_t)(uintptr_t)(dp + at); tri[3 * m + 1] = (uint64_t)(uintptr_t)(s->d_in + s->in_len); tri[3 * m + 2] = len[i];
-    s->in_len += len[i];
+    jobs.push_back(CopyJob{hp + at, data[i], len[i]});
+    tri[3 * m] = (uint64_t)(uintptr_t)(dp + at); tri[3 * m + 1] = (uint64_t)(uintptr_t)(s->d_in + have); tri[3 * m + 2] = len[i];
+    s->in_total += len[i];
     at += (len[i] + 15u) & ~(uint64_t)15u;
     m++;
   }
   if (m == 0) return PZ_E_OK;
+  parallel_copy(jobs);
   /* the streams' buffers may just have moved (and earlier single feeds may still be in flight) on their own CUDA streams */
   for (int k = 0; k < kPoolStreams; k++)
     if (seen[k] && g_pool[k] != st) {
@@ -1375,8 +1525,16 @@ int pz_stream_pump(pz_stream *const *streams, size_t n) {
 
 uint64_t pz_stream_counter(const pz_stream *s, int which) {
   if (!s) return 0;
-  return which == PZ_SC_PUMPS ? s->pumps : which == PZ_SC_RESUMED ? s->resumed : which == PZ_SC_CKPT_BIT ? (s->ck[1] != 0 && s->ck[1] != PZ_CK_TRAILER_HOST ? s->ck[1] : s->ck[0])
-       : which == PZ_SC_CKPT_BYTES ? s->ck[2] : 0;
+  switch (which) {
+    case PZ_SC_PUMPS: return s->pumps;
+    case PZ_SC_RESUMED: return s->resumed;
+    case PZ_SC_CKPT_BIT: return s->lead * 8u + ((s->ck[1] != 0 && s->ck[1] != PZ_CK_TRAILER_HOST) ? s->ck[1] : s->ck[0]);
+    case PZ_SC_CKPT_BYTES: return s->pos;
+    case PZ_SC_DEVICE_BYTES: return s->d_in_cap + s->d_out_cap;
+    case PZ_SC_DEVICE_PEAK: return s->peak_device;
+    case PZ_SC_HOST_BYTES: return s->h_out.cap + s->stage.cap;
+    default: return 0;
+  }
 }
 
 int pz_stream_next(pz_stream *s, const uint8_t **chunk, size_t *len, pz_result *res) {
@@ -1495,10 +1653,13 @@ size_t pz_strerror(const pz_result *r, char *buf, size_t cap) {
     case PZ_ERR_HEADER:
       if (r->detail == PZ_D_HDR_CHECKSUM) snprintf(tmp, sizeof tmp, "Header error: Header checksum failed");
       else if (r->detail == PZ_D_HDR_METHOD) snprintf(tmp, sizeof tmp, "Header error: Bad compression method: %lld", p0);
+      else if (r->detail == PZ_D_HDR_GZIP_MAGIC) snprintf(tmp, sizeof tmp, "Header error: Not a gzip stream: %llx", p0);
+      else if (r->detail == PZ_D_HDR_GZIP_FLAGS) snprintf(tmp, sizeof tmp, "Header error: Reserved gzip flags set: %lld", p0);
       else snprintf(tmp, sizeof tmp, "Header error: Window size too big: %lld", p0);
       break;
     case PZ_ERR_CHECKSUM:
-      snprintf(tmp, sizeof tmp, "Checksum error: checksum mismatch: %x != %x", r->adler_stored, r->adler_computed);
+      if (r->detail == PZ_D_LENGTH_MISMATCH) snprintf(tmp, sizeof tmp, "Checksum error: length mismatch: %lld != %lld", p0, (long long)(uint32_t)r->out_len);
+      else snprintf(tmp, sizeof tmp, "Checksum error: checksum mismatch: %x != %x", r->adler_stored, r->adler_computed);
       break;
     case PZ_REF_BOTTOM:
       snprintf(tmp, sizeof tmp, "_|_ %s",
@@ -1568,6 +1729,48 @@ uint32_t pz_adler32(uint32_t init, const uint8_t *data, size_t len) {
   uint32_t a = (a1 + a2 + M - 1u) % M;
   uint32_t b = (uint32_t)((b1 + b2 + (uint64_t)(len % M) * ((a1 + M - 1u) % M)) % M);
   return (b << 16) | a;
+}
+
+/* CRC-32 of a host buffer with the kernels of the gzip framing; `init` continues an earlier sum through the combine
+ * identity crc(A || B) = crc(A) * x^(8|B|) + crc(B) over GF(2) modulo the CRC polynomial (no bytes touched here). */
+uint32_t pz_crc32(uint32_t init, const uint8_t *data, size_t len) {
+  if (ensure_init() != PZ_E_OK) return 0;
+  Workspace &ws = g_ws;
+  uint64_t off[2] = {0, len};
+  std::vector<uint64_t> seg;
+  uint64_t total = build_seg_off(off, 1, seg);
+  if (ws.d_out.reserve(len + 64) != PZ_E_OK || ws.d_out_off.reserve(16) != PZ_E_OK || ws.d_seg_off.reserve(16) != PZ_E_OK ||
+      ws.d_res.reserve(sizeof(pz_result)) != PZ_E_OK || ws.d_parts.reserve(std::max<uint64_t>(total, 1) * sizeof(uint2)) != PZ_E_OK)
+    return 0;
+  pz_result r;
+  memset(&r, 0, sizeof r);
+  r.status = PZ_OK; r.out_len = len; r.payload[0] = (int64_t)(uint32_t)len; /* ISIZE agrees: only the CRC is of interest */
+  if (len && cudaMemcpy(ws.d_out.p, data, len, cudaMemcpyHostToDevice) != cudaSuccess) return 0;
+  if (cudaMemcpy(ws.d_out_off.p, off, 16, cudaMemcpyHostToDevice) != cudaSuccess) return 0;
+  if (cudaMemcpy(ws.d_seg_off.p, seg.data(), 16, cudaMemcpyHostToDevice) != cudaSuccess) return 0;
+  if (cudaMemcpy(ws.d_res.p, &r, sizeof r, cudaMemcpyHostToDevice) != cudaSuccess) return 0;
+  if (pz_launch_adler((const uint8_t *)ws.d_out.p, (const uint64_t *)ws.d_out_off.p, (const uint64_t *)ws.d_seg_off.p, 1, 0, 1, 0, total,
+                      (pz_result *)ws.d_res.p, (uint2 *)ws.d_parts.p, nullptr, 1u) != cudaSuccess)
+    return 0;
+  if (cudaMemcpy(&r, ws.d_res.p, sizeof r, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+  const uint32_t crc2 = r.adler_computed;
+  if (init == 0u) return crc2;
+  /* x^(8 len) mod P by square and multiply, then crc(init-part) * x^(8 len) + crc2 */
+  auto mul = [](uint32_t a, uint32_t b) {
+    uint32_t p = 0;
+    for (uint32_t m = 0x80000000u; m != 0u && a != 0u; m >>= 1) {
+      if (a & m) { p ^= b; a &= ~m; }
+      b = (b >> 1) ^ (0xedb88320u & (0u - (b & 1u)));
+    }
+    return p;
+  };
+  uint32_t xp = 0x80000000u, sq = 0x40000000u; /* x^0, x^1 */
+  for (int k = 0; k < 3; k++) sq = mul(sq, sq); /* x^8 */
+  for (uint64_t n = len; n != 0u; n >>= 1) {
+    if (n & 1u) xp = mul(sq, xp);
+    sq = mul(sq, sq);
+  }
+  return mul(xp, init) ^ crc2;
 }
 
 }  // extern "C"

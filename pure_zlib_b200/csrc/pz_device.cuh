@@ -282,7 +282,13 @@ struct PzJob {
    * instead of being dealt out by index: blocks differ in length, and with two or three units per slot the
    * longest deal sets the time of the launch. */
   uint32_t *next_unit = nullptr;
+  /* Framing of every stream of the job (PZ_FRAME_*).  zlib (RFC 1950) is the reference's; gzip members (RFC 1952)
+   * and raw deflate are the extension its README names as the first TODO (README.md:42-50). */
+  uint32_t framing = 0;
 };
+#define PZ_FRAME_ZLIB 0u
+#define PZ_FRAME_GZIP 1u /* header: magic, CM, FLG, MTIME/XFL/OS, FEXTRA / FNAME / FCOMMENT / FHCRC skipped; trailer: CRC-32, ISIZE (little-endian) */
+#define PZ_FRAME_RAW 2u  /* no header, no trailer */
 #define PZ_CK_TRAILER 0xffffffffu
 #define PZ_ADLER_FUSED 0xffffffffu /* no Adler-32 value: both halves of one are below 65521 */
 #define PZ_BLK_BIAS 65536u /* a block job counts its output from here: the window model then always
@@ -306,6 +312,7 @@ struct PzCtx {
   bool pending;         /* a quarter requested while the hot lane owns the stream has not been awaited */
   bool starved;         /* idle because the next stream's input has not reached the device yet */
   bool block_job;       /* the unit is one deflate block (PzJob::blk_start), not a zlib stream     */
+  uint32_t framing;     /* PzJob::framing */
   uint32_t pos;  /* bytes decoded                                                          */
   uint32_t base; /* bytes the reference would already have published (multiple of 32 KiB)  */
   uint32_t mark; /* block jobs: pos at the last moveWindow call (after a match, at a block's start).  The bytes
@@ -1336,8 +1343,9 @@ PZ_DEV bool pz_stored_block(PzCtx &c, PzStreamSmem *sm) {
   if (len != ((~nlen) & 0xffffu)) { pz_fail(c, PZ_ERR_FORMAT, PZ_D_LEN_NLEN); return false; }
   uint32_t boff = c.bp >> 3;
   uint32_t remaining = (c.end_bit >> 3) - boff;
-  /* getBlock takes the data only when strictly more than len bytes are left in the chunk */
-  if (len >= remaining) { pz_fail(c, PZ_ERR_DECOMPRESSION, PZ_D_RAN_OUT); return false; }
+  /* getBlock takes the data only when strictly more than len bytes are left in the chunk (with zlib and gzip framing a
+   * trailer always follows; a raw deflate stream may end with the last byte of a stored block) */
+  if (len >= remaining && !(c.framing == PZ_FRAME_RAW && len == remaining)) { pz_fail(c, PZ_ERR_DECOMPRESSION, PZ_D_RAN_OUT); return false; }
   uint32_t fill = c.pos - c.base;
   if (fill + len > PZ_WINDOW) { pz_fail(c, PZ_REF_BOTTOM, PZ_D_BOT_WINDOW_OVERFLOW); return false; }
   if (len > c.cap - c.pos) { pz_fail(c, PZ_OUTPUT_FULL, 0); return false; }
@@ -1381,7 +1389,15 @@ PZ_DEV void pz_trailer(PzCtx &c, PzStreamSmem *sm) {
   c.hdr_bp = c.bp; c.sym_bp = PZ_CK_TRAILER; /* a stream that stops here is picked up here */
   pz_align_byte(c, sm);
   uint32_t hi, lo;
-  if (pz_avail(c) < 32u) pz_fail(c, PZ_ERR_DECOMPRESSION, PZ_D_RAN_OUT);
+  if (c.framing == PZ_FRAME_RAW) {
+    /* nothing follows the last block */
+  } else if (c.framing == PZ_FRAME_GZIP) { /* RFC 1952 2.3.1: CRC32, ISIZE, least significant byte first; K3 compares both */
+    uint32_t s0, s1;
+    if (pz_take(c, sm, 16, lo) && pz_take(c, sm, 16, hi)) {
+      c.adler_stored = (hi << 16) | lo;
+      if (pz_take(c, sm, 16, s0) && pz_take(c, sm, 16, s1)) c.p0 = (int64_t)((s1 << 16) | s0);
+    }
+  } else if (pz_avail(c) < 32u) pz_fail(c, PZ_ERR_DECOMPRESSION, PZ_D_RAN_OUT);
   else if (pz_take(c, sm, 16, hi) && pz_take(c, sm, 16, lo))
     c.adler_stored = ((hi & 0xffu) << 24) | ((hi >> 8) << 16) | ((lo & 0xffu) << 8) | (lo >> 8);
   pz_finish(c);
@@ -1390,10 +1406,11 @@ PZ_DEV void pz_trailer(PzCtx &c, PzStreamSmem *sm) {
 /* `decompress` for one single-chunk stream starts here: inflateWithHeaders (Zlib.hs:53-69). */
 template <bool COUNT_ONLY>
 PZ_DEV void pz_begin(PzCtx &c, PzStreamSmem *sm, uint32_t s, const uint8_t *in, uint64_t in_len, uint64_t out_cap, pz_result *res,
-                     const uint32_t *rs = nullptr, uint32_t *ck = nullptr) {
+                     const uint32_t *rs = nullptr, uint32_t *ck = nullptr, uint32_t framing = PZ_FRAME_ZLIB) {
   uint32_t mis = (uint32_t)((uintptr_t)in & 15u);
   c.in_al = in - mis;
   c.res = res;
+  c.framing = framing;
   c.pos = 0; c.base = 0; c.mark = 0;
   c.cap = out_cap > 0xfffdff00ull ? 0xfffdff00u : (uint32_t)out_cap; /* base + 128 KiB stays in 32 bits */
   c.status = PZ_OK; c.detail = 0; c.p0 = 0; c.p1 = 0;
@@ -1424,6 +1441,28 @@ PZ_DEV void pz_begin(PzCtx &c, PzStreamSmem *sm, uint32_t s, const uint8_t *in, 
     return;
   }
   pz_seek(c, sm, c.start_bit);
+  if (framing == PZ_FRAME_RAW) { c.mode = PZ_M_HDR; return; }
+  if (framing == PZ_FRAME_GZIP) { /* the member header of RFC 1952 2.3, checks in stream order, optional fields skipped */
+    uint32_t id1, id2, cm, fl, v;
+    bool good = pz_take(c, sm, 8, id1) && pz_take(c, sm, 8, id2);
+    if (good && (id1 != 0x1fu || id2 != 0x8bu)) { pz_fail(c, PZ_ERR_HEADER, PZ_D_HDR_GZIP_MAGIC, (id1 << 8) | id2); good = false; }
+    good = good && pz_take(c, sm, 8, cm);
+    if (good && cm != 8u) { pz_fail(c, PZ_ERR_HEADER, PZ_D_HDR_METHOD, cm); good = false; }
+    good = good && pz_take(c, sm, 8, fl);
+    if (good && (fl & 0xe0u)) { pz_fail(c, PZ_ERR_HEADER, PZ_D_HDR_GZIP_FLAGS, fl); good = false; }
+    for (int k = 0; good && k < 6; k++) good = pz_take(c, sm, 8, v); /* MTIME, XFL, OS */
+    if (good && (fl & 4u)) { /* FEXTRA */
+      uint32_t xlen = 0;
+      good = pz_take(c, sm, 16, xlen);
+      for (uint32_t k = 0; good && k < xlen; k++) good = pz_take(c, sm, 8, v);
+    }
+    for (uint32_t bit = 8u; bit <= 16u; bit <<= 1) /* FNAME, FCOMMENT: zero-terminated */
+      if (good && (fl & bit)) do { good = pz_take(c, sm, 8, v); } while (good && v != 0u);
+    if (good && (fl & 2u)) good = pz_take(c, sm, 16, v); /* FHCRC: skipped, not verified */
+    if (!good) { pz_finish(c); return; }
+    c.mode = PZ_M_HDR;
+    return;
+  }
   uint32_t cmf, flg;
   bool ok = pz_take(c, sm, 8, cmf) && pz_take(c, sm, 8, flg);
   if (ok) {
@@ -1446,6 +1485,7 @@ PZ_DEV void pz_begin_block(PzCtx &c, PzStreamSmem *sm, uint32_t j, const uint8_t
   c.in_al = in - mis;
   c.res = res;
   c.pos = PZ_BLK_BIAS; c.base = 0; c.mark = PZ_BLK_BIAS;
+  c.framing = PZ_FRAME_ZLIB; /* a block job never reads framing; its stored blocks always have bytes behind them or are declined */
   c.cap = PZ_BLK_BIAS + cap;
   c.status = PZ_OK; c.detail = 0; c.p0 = 0; c.p1 = 0;
   c.adler_stored = 0; c.bfinal = 0; c.need_careful = false;
@@ -1511,11 +1551,11 @@ PZ_DEV void pz_slow_step(PzCtx &c, PzStreamSmem *sm, const PzJob &job, uint32_t 
     const uint32_t e = s << job.pair_off;
     const uint64_t i0 = job.in_off[e], i1 = job.in_off[e + 1];
     if (COUNT_ONLY) {
-      pz_begin<true>(c, sm, s, job.in_blob + i0, i1 - i0, ~0ull, job.res + s);
+      pz_begin<true>(c, sm, s, job.in_blob + i0, i1 - i0, ~0ull, job.res + s, nullptr, nullptr, job.framing);
     } else {
       const uint64_t o0 = job.out_off[e], o1 = job.out_off[e + 1];
       pz_begin<false>(c, sm, s, job.in_blob + i0, i1 - i0, o1 - o0, job.res + s, job.resume ? job.resume + 4u * s : nullptr,
-                      job.ckpt ? job.ckpt + 4u * s : nullptr);
+                      job.ckpt ? job.ckpt + 4u * s : nullptr, job.framing);
     }
   } else if (c.mode == PZ_M_HDR) { /* inflateBlock (Deflate.hs:65-104) */
     uint32_t btype;
@@ -1573,6 +1613,7 @@ PZ_DEV void pz_decoder_warp(const PzJob &job, uint32_t first_stream, uint32_t st
   c.mode = PZ_M_IDLE;
   c.next = first_stream;
   c.in_al = nullptr; c.in_al_bytes = 0; c.bp = 0; c.q = 0; c.next_q = 0; c.pending = false; c.starved = false; c.block_job = false; c.res = nullptr;
+  c.framing = PZ_FRAME_ZLIB;
   c.hdr_bp = 0; c.sym_bp = 0; c.resume_sym = 0; c.ck = nullptr; c.mark = 0;
   c.qhead = 0; c.qtailc = 0;
   c.fixed_ready = false;

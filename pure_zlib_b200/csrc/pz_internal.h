@@ -38,7 +38,7 @@ static_assert(PZ_HOT_SCHED_SERVICE + (PZ_WARPS_PER_CTA - 1u - PZ_HOT_SCHED_WARPS
 cudaError_t pz_launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uint8_t *d_out, const uint64_t *d_out_off,
                               uint32_t first, uint32_t count, pz_result *d_res, cudaStream_t st, uint32_t *d_prog = nullptr,
                               const uint32_t *d_in_ready = nullptr, int phase = 0, uint2 *d_parts = nullptr,
-                              const uint64_t *d_seg_off = nullptr);
+                              const uint64_t *d_seg_off = nullptr, uint32_t framing = 0 /* PZ_FRAME_*: 0 zlib, 1 gzip, 2 raw deflate */);
 #define PZ_PHASE_ALL 0
 #define PZ_PHASE_K2 1 /* only the stored-stream kernels (they also mark every other stream PENDING) */
 #define PZ_PHASE_K1 2 /* only K1: decodes the streams that are still PENDING */
@@ -46,7 +46,7 @@ cudaError_t pz_launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uin
 /* Resumable contexts: count streams in buffers of their own ((begin, end) device addresses), each continuing from
  * d_resume[4s..] and leaving its next checkpoint in d_ckpt[4s..] (PzJob::resume / ckpt in pz_device.cuh).  K1 only. */
 cudaError_t pz_launch_resume(const uint64_t *d_in_pairs, const uint64_t *d_out_pairs, uint32_t count, pz_result *d_res,
-                             const uint32_t *d_resume, uint32_t *d_ckpt, cudaStream_t st);
+                             const uint32_t *d_resume, uint32_t *d_ckpt, cudaStream_t st, uint32_t framing = 0);
 /* count pieces of decoded output go to pinned host memory: (device source, host destination, bytes) triples of uint64 */
 cudaError_t pz_launch_gather(const uint64_t *d_triples, uint32_t count, cudaStream_t st);
 #define PZ_CK_TRAILER_HOST 0xffffffffu /* == PZ_CK_TRAILER in pz_device.cuh */
@@ -70,7 +70,7 @@ cudaError_t pz_launch_blk_resolve(uint16_t *d_sym16, uint8_t *d_out, const uint6
  * trailer comparison that completes the verdict (Deflate.hs:52-63). */
 cudaError_t pz_launch_adler(const uint8_t *d_out, const uint64_t *d_out_off, const uint64_t *d_seg_off, uint32_t n_total,
                             uint32_t first, uint32_t count, uint64_t seg_first, uint64_t seg_count, pz_result *d_res,
-                            uint2 *d_parts, cudaStream_t st);
+                            uint2 *d_parts, cudaStream_t st, uint32_t framing = 0 /* gzip: CRC-32 + ISIZE instead of Adler-32; raw: no compare */);
 /* canonical codes of lens[0..n) (n <= 288) into codes[0..n) */
 cudaError_t pz_launch_code_values(const uint8_t *d_lens, int n, uint16_t *d_codes, cudaStream_t st);
 cudaError_t pz_kernels_configure(void);

@@ -142,7 +142,7 @@ pz_adler_partial_kernel(const uint8_t *__restrict__ out_blob, const uint64_t *__
  * (initialAdlerState a = 1, b = 0: Adler32.hs:19-20). */
 __global__ void __launch_bounds__(128)
 pz_adler_finish_kernel(const uint64_t *__restrict__ seg_off, uint32_t first, uint32_t count, pz_result *res,
-                       const uint2 *__restrict__ parts) {
+                       const uint2 *__restrict__ parts, uint32_t compare) {
   const uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t lane = threadIdx.x & 31u;
   if (k >= count) return;
@@ -183,12 +183,156 @@ pz_adler_finish_kernel(const uint64_t *__restrict__ seg_off, uint32_t first, uin
   const uint32_t a = (1u + s1) % PZ_ADLER_MOD, b = (uint32_t)((len % PZ_ADLER_MOD + s2) % PZ_ADLER_MOD);
   const uint32_t adler = (b << 16) | a; /* finalizeAdler (Adler32.hs:53-57) */
   res[i].adler_computed = adler;
-  if (adler != res[i].adler_stored) { /* checkChecksum (Deflate.hs:56-63) */
+  if (compare && adler != res[i].adler_stored) { /* checkChecksum (Deflate.hs:56-63); raw deflate has no trailer to compare with */
     res[i].status = PZ_ERR_CHECKSUM;
     res[i].detail = PZ_D_ADLER_MISMATCH;
   }
 }
 
+
+/* ---- CRC-32 (RFC 1952 section 8; gzip framing, an extension beyond the reference) as a segmented reduction ----------
+ * Arithmetic: polynomials over GF(2) modulo P = 0xedb88320 (reflected: bit 31 is x^0).  For the register R(M, init) after
+ * message M:  R(A || B, init) = R(A, init) * x^(8|B|) + R(B, 0)  (mod P), so a message is cut into pieces, each piece gives
+ * its zero-init register, and pieces are put together with multiplications by x^(8 * bytes behind the piece):
+ *   lane      512 consecutive bytes of a 16 KiB segment, four table look-ups per 32-bit word (tables in shared memory);
+ *   segment   the 32 lanes' registers, each times x^(8 * bytes behind its piece in the segment), XORed (one shuffle tree);
+ *   stream    the segments folded the same way by one warp (pz_crc_finish_kernel); CRC = ~(R + 0xffffffff * x^(8 len)). */
+#define PZ_CRC_POLY 0xedb88320u
+__device__ __forceinline__ uint32_t pz_gf_mul(uint32_t a, uint32_t b) { /* a * b mod P */
+  uint32_t p = 0;
+#pragma unroll 1
+  for (uint32_t m = 0x80000000u; m != 0u && a != 0u; m >>= 1) {
+    if (a & m) { p ^= b; a &= ~m; }
+    b = (b >> 1) ^ (PZ_CRC_POLY & (0u - (b & 1u)));
+  }
+  return p;
+}
+/* x^(8 n) mod P from the table sq[j] = x^(2^j) mod P */
+__device__ __forceinline__ uint32_t pz_gf_xpow8(uint64_t n, const uint32_t *sq) {
+  uint32_t p = 0x80000000u; /* x^0 */
+  uint32_t j = 3;
+#pragma unroll 1
+  for (; n != 0u; n >>= 1, j++) {
+    if (n & 1u) p = pz_gf_mul(sq[j & 63u], p);
+  }
+  return p;
+}
+struct PzCrcSmem {
+  uint32_t t[4][256]; /* t[0] = the byte table; t[k][i] = t[0][i] advanced by k more zero bytes */
+  uint32_t sq[64];    /* x^(2^j) mod P (j < 64: byte counts below 2^61) */
+  uint32_t behind[32];/* x^(8 * 512 * (31 - lane)): bytes behind lane's piece in a full segment */
+};
+__device__ void pz_crc_tables(PzCrcSmem &sm) {
+  for (uint32_t i = threadIdx.x; i < 256u; i += blockDim.x) {
+    uint32_t c = i;
+    for (int k = 0; k < 8; k++) c = (c >> 1) ^ (PZ_CRC_POLY & (0u - (c & 1u)));
+    sm.t[0][i] = c;
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < 256u; i += blockDim.x) {
+    uint32_t c = sm.t[0][i];
+    for (int k = 1; k < 4; k++) { c = sm.t[0][c & 0xffu] ^ (c >> 8); sm.t[k][i] = c; }
+  }
+  if (threadIdx.x == 0) {
+    uint32_t v = 0x40000000u; /* x^1 */
+    for (int j = 0; j < 64; j++) { sm.sq[j] = v; v = pz_gf_mul(v, v); }
+  }
+  __syncthreads();
+  if (threadIdx.x < 32u) sm.behind[threadIdx.x] = pz_gf_xpow8(512u * (31u - threadIdx.x), sm.sq);
+  __syncthreads();
+}
+
+/* parts[g] = (zero-init CRC register of segment g, its length): one warp per 16 KiB segment, as pz_adler_partial_kernel */
+__global__ void __launch_bounds__(256)
+pz_crc_partial_kernel(const uint8_t *__restrict__ out_blob, const uint64_t *__restrict__ out_off,
+                      const uint64_t *__restrict__ seg_off, uint32_t n_total, uint64_t seg_first, uint64_t seg_count,
+                      const pz_result *__restrict__ res, uint2 *__restrict__ parts) {
+  __shared__ PzCrcSmem sm;
+  pz_crc_tables(sm);
+  const uint64_t gw = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (gw >= seg_count) return;
+  const uint64_t g = seg_first + gw;
+  const uint32_t lane = threadIdx.x & 31u;
+  uint32_t lo = 0, hi = n_total;
+  while (hi - lo > 1) {
+    uint32_t mid = lo + (hi - lo) / 2;
+    if (seg_off[mid] <= g) lo = mid; else hi = mid;
+  }
+  const uint32_t i = lo;
+  if (res[i].status != PZ_OK) return;
+  const uint64_t len = res[i].out_len;
+  const uint64_t start = (g - seg_off[i]) * (uint64_t)PZ_ADLER_SEG;
+  if (start >= len) return;
+  const uint32_t L = (uint32_t)(len - start < PZ_ADLER_SEG ? len - start : PZ_ADLER_SEG);
+  const uint8_t *p0 = out_blob + out_off[i] + start;
+  /* lane's piece: bytes [512 lane, min(512 lane + 512, L)) */
+  const uint32_t b0 = 512u * lane, b1 = b0 + 512u < L ? b0 + 512u : L;
+  uint32_t c = 0;
+  if (b0 < L) {
+    const uint8_t *p = p0 + b0, *e = p0 + b1;
+    while (p < e && ((uintptr_t)p & 3u)) { c = sm.t[0][(c ^ *p++) & 0xffu] ^ (c >> 8); }
+    for (; p + 4 <= e; p += 4) {
+      c ^= *reinterpret_cast<const uint32_t *>(p);
+      c = sm.t[3][c & 0xffu] ^ sm.t[2][(c >> 8) & 0xffu] ^ sm.t[1][(c >> 16) & 0xffu] ^ sm.t[0][c >> 24];
+    }
+    while (p < e) { c = sm.t[0][(c ^ *p++) & 0xffu] ^ (c >> 8); }
+    /* bytes of the segment behind this piece */
+    c = pz_gf_mul(c, L == PZ_ADLER_SEG ? sm.behind[lane] : pz_gf_xpow8(L - b1, sm.sq));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c ^= __shfl_down_sync(0xffffffffu, c, o);
+  if (lane == 0) parts[g] = make_uint2(c, L);
+}
+
+/* One warp per stream: folds the segments' registers, finishes the CRC and compares it and ISIZE with the trailer
+ * (RFC 1952 2.3.1; the checks of checkChecksum, Deflate.hs:52-63, for this framing). */
+__global__ void __launch_bounds__(128)
+pz_crc_finish_kernel(const uint64_t *__restrict__ seg_off, uint32_t first, uint32_t count, pz_result *res,
+                     const uint2 *__restrict__ parts, uint32_t compare) {
+  __shared__ PzCrcSmem sm;
+  pz_crc_tables(sm);
+  const uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31u;
+  if (k >= count) return;
+  const uint32_t i = first + k;
+  if (res[i].status != PZ_OK) return;
+  const uint64_t len = res[i].out_len;
+  const uint64_t nseg = (len + PZ_ADLER_SEG - 1) / PZ_ADLER_SEG;
+  const uint2 *p = parts + seg_off[i];
+  const uint64_t per = (nseg + 31u) / 32u;
+  const uint64_t j0 = per * lane < nseg ? per * lane : nseg, j1 = j0 + per < nseg ? j0 + per : nseg;
+  const uint32_t x16k = pz_gf_xpow8(PZ_ADLER_SEG, sm.sq);
+  uint32_t c = 0;
+  uint64_t n = 0; /* bytes this lane has folded */
+  for (uint64_t j = j0; j < j1; j++) {
+    const uint2 s = p[j];
+    c = pz_gf_mul(c, s.y == PZ_ADLER_SEG ? x16k : pz_gf_xpow8(s.y, sm.sq)) ^ s.x;
+    n += s.y;
+  }
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { /* lane l absorbs the 'o' lanes to its right, pairwise */
+    const uint32_t tc = __shfl_down_sync(0xffffffffu, c, o);
+    const uint64_t tn = __shfl_down_sync(0xffffffffu, n, o);
+    if ((lane & (2u * (uint32_t)o - 1u)) == 0u) {
+      c = pz_gf_mul(c, pz_gf_xpow8(tn, sm.sq)) ^ tc;
+      n += tn;
+    }
+  }
+  if (lane != 0) return;
+  const uint32_t crc = ~(c ^ pz_gf_mul(0xffffffffu, pz_gf_xpow8(len, sm.sq)));
+  res[i].adler_computed = crc;
+  if (!compare) return; /* the incremental driver folds piece checksums itself */
+  if (crc != res[i].adler_stored) {
+    res[i].status = PZ_ERR_CHECKSUM;
+    res[i].detail = PZ_D_ADLER_MISMATCH;
+  } else if ((uint32_t)res[i].payload[0] != (uint32_t)len) { /* ISIZE: the decoded length modulo 2^32 */
+    res[i].status = PZ_ERR_CHECKSUM;
+    res[i].detail = PZ_D_LENGTH_MISMATCH;
+    res[i].payload[0] = (int64_t)(uint32_t)res[i].payload[0]; /* payload[1] stays the published-bytes count */
+  }
+}
+
+/* host-buffer CRC-32 for pz_crc32(): one stream, the two kernels above */
 __global__ void pz_code_values_kernel(const uint8_t *lens, int n, uint16_t *codes) {
   __shared__ PzStreamSmem sm; /* launched with one group (PZ_G threads) */
   for (int i = threadIdx.x; i < n; i += PZ_G) sm.lens[i] = lens[i];
@@ -260,7 +404,7 @@ int pz_inflate_slots(void) { return g_sm_count * g_inflate_ctas_per_sm[0] * (int
 /* One resident wave of persistent CTAs: one per SM (148 on B200), fewer for small batches. */
 cudaError_t pz_launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uint8_t *d_out, const uint64_t *d_out_off,
                               uint32_t first, uint32_t count, pz_result *d_res, cudaStream_t st, uint32_t *d_prog,
-                              const uint32_t *d_in_ready, int phase, uint2 *d_parts, const uint64_t *d_seg_off) {
+                              const uint32_t *d_in_ready, int phase, uint2 *d_parts, const uint64_t *d_seg_off, uint32_t framing) {
   if (count == 0) return cudaSuccess;
   const bool count_only = d_out == nullptr;
   const unsigned wave = (unsigned)(g_sm_count * g_inflate_ctas_per_sm[count_only ? 1 : 0]);
@@ -273,6 +417,15 @@ cudaError_t pz_launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uin
   job.in_ready = d_in_ready;
   job.blk_start = nullptr; job.blk_out = nullptr; job.blk_len = nullptr; job.out16 = nullptr; job.blk_stream = 0; job.blk_cap = 0;
   job.parts = d_seg_off ? d_parts : nullptr; job.seg_off = d_seg_off;
+  /* bit 8 of `framing`: the caller has marked the streams PENDING itself (K4 ran in between): K1 keeps skipping the others */
+  const bool premarked = (framing & 0x100u) != 0u;
+  framing &= 0xffu;
+  job.framing = framing;
+  if (framing != PZ_FRAME_ZLIB) { /* K2 reads zlib framing only (and it is K2 that marks streams PENDING) */
+    if (phase == PZ_PHASE_K2) return cudaSuccess;
+    if (!premarked) job.skip_done = 0;
+    phase = PZ_PHASE_K1;
+  }
   if (d_in_ready) job.skip_done = 0; /* K2 would read input that is not there yet: K1 decodes every stream */
   if (count_only) {
     pz_inflate_kernel<true><<<grid, PZ_THREADS_PER_CTA, smem, st>>>(job);
@@ -297,7 +450,7 @@ cudaError_t pz_launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uin
  * [d_out_pairs[2s], d_out_pairs[2s+1]) -- device ADDRESSES, every stream in buffers of its own -- starting from the
  * checkpoint d_resume[4s..] and leaving the next one in d_ckpt[4s..] (PzJob::resume, PzJob::ckpt).  K1 only. */
 cudaError_t pz_launch_resume(const uint64_t *d_in_pairs, const uint64_t *d_out_pairs, uint32_t count, pz_result *d_res,
-                             const uint32_t *d_resume, uint32_t *d_ckpt, cudaStream_t st) {
+                             const uint32_t *d_resume, uint32_t *d_ckpt, cudaStream_t st, uint32_t framing) {
   if (count == 0) return cudaSuccess;
   const unsigned wave = (unsigned)(g_sm_count * g_inflate_ctas_per_sm[0]);
   const unsigned grid = count < wave ? count : wave;
@@ -307,7 +460,7 @@ cudaError_t pz_launch_resume(const uint64_t *d_in_pairs, const uint64_t *d_out_p
   job.first = 0; job.count = count; job.skip_done = 0; job.prog = nullptr; job.in_ready = nullptr;
   job.blk_start = nullptr; job.blk_out = nullptr; job.blk_len = nullptr; job.out16 = nullptr; job.blk_stream = 0; job.blk_cap = 0;
   job.parts = nullptr; job.seg_off = nullptr;
-  job.resume = d_resume; job.ckpt = d_ckpt; job.pair_off = 1u;
+  job.resume = d_resume; job.ckpt = d_ckpt; job.pair_off = 1u; job.framing = framing;
   pz_inflate_kernel<false><<<grid, PZ_THREADS_PER_CTA, smem, st>>>(job);
   return cudaGetLastError();
 }
@@ -378,14 +531,19 @@ cudaError_t pz_launch_blk_resolve(uint16_t *d_sym16, uint8_t *d_out, const uint6
 
 cudaError_t pz_launch_adler(const uint8_t *d_out, const uint64_t *d_out_off, const uint64_t *d_seg_off, uint32_t n_total,
                             uint32_t first, uint32_t count, uint64_t seg_first, uint64_t seg_count, pz_result *d_res,
-                            uint2 *d_parts, cudaStream_t st) {
+                            uint2 *d_parts, cudaStream_t st, uint32_t framing) {
   if (count == 0) return cudaSuccess;
-  if (seg_count) {
-    const uint64_t warps_per_cta = 8;
-    const unsigned grid = (unsigned)((seg_count + warps_per_cta - 1) / warps_per_cta);
-    pz_adler_partial_kernel<<<grid, 256, 0, st>>>(d_out, d_out_off, d_seg_off, n_total, seg_first, seg_count, d_res, d_parts);
+  const uint32_t compare = (framing & 0x200u) ? 0u : 1u; /* bit 9: checksums only, no trailer comparison */
+  framing &= 0xffu;
+  const uint64_t warps_per_cta = 8;
+  const unsigned grid = (unsigned)((seg_count + warps_per_cta - 1) / warps_per_cta);
+  if (framing == PZ_FRAME_GZIP) { /* the checksum of this framing is CRC-32 */
+    if (seg_count) pz_crc_partial_kernel<<<grid, 256, 0, st>>>(d_out, d_out_off, d_seg_off, n_total, seg_first, seg_count, d_res, d_parts);
+    pz_crc_finish_kernel<<<(count + 3) / 4, 128, 0, st>>>(d_seg_off, first, count, d_res, d_parts, compare);
+    return cudaGetLastError();
   }
-  pz_adler_finish_kernel<<<(count + 3) / 4, 128, 0, st>>>(d_seg_off, first, count, d_res, d_parts); /* one warp per stream */
+  if (seg_count) pz_adler_partial_kernel<<<grid, 256, 0, st>>>(d_out, d_out_off, d_seg_off, n_total, seg_first, seg_count, d_res, d_parts);
+  pz_adler_finish_kernel<<<(count + 3) / 4, 128, 0, st>>>(d_seg_off, first, count, d_res, d_parts, framing == PZ_FRAME_ZLIB ? compare : 0u); /* one warp per stream */
   return cudaGetLastError();
 }
 

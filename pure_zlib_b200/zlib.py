@@ -23,6 +23,10 @@ from ._lib import PzResult
 
 LazyByteString = Union[bytes, bytearray, memoryview, Sequence[bytes]]
 
+# Framing (EXTENSION beyond the reference, whose README lists gzip as its first TODO): the same decoder behind a gzip member
+# header / CRC-32 + ISIZE trailer (RFC 1952) or no framing at all (raw deflate, RFC 1951).  Values are the PZ_F_* flags.
+ZLIB, GZIP, RAW = 0, _lib.PZ_F_GZIP, _lib.PZ_F_RAW
+
 
 # ---- DecompressionError (Monad.hs:87-104) ---------------------------------------------------
 class DecompressionError(Exception):
@@ -138,10 +142,10 @@ class DecompError:
 
 
 class _Decoder:
-    def __init__(self):
+    def __init__(self, framing: int = ZLIB):
         L = _lib.load()
         self._L = L
-        self._s = L.pz_stream_new()
+        self._s = L.pz_stream_new_framed(framing) if framing else L.pz_stream_new()
         if not self._s:
             msg = L.pz_last_error()
             raise _lib.PzCudaError("pz_stream_new failed: " + (msg.decode() if msg else ""))
@@ -172,9 +176,9 @@ class _Decoder:
         return self.state()
 
 
-def decompress_incremental():
+def decompress_incremental(framing: int = ZLIB):
     """`decompressIncremental` (Zlib.hs:29-30): the initial decoder state (always NeedMore)."""
-    return _Decoder().state()
+    return _Decoder(framing).state()
 
 
 class IncrementalSet:
@@ -183,8 +187,8 @@ class IncrementalSet:
     each from its device-resident checkpoint, not from its first byte -- and `events(i)` then yields
     stream i's states up to its next NeedMore / Done / DecompError without touching the device."""
 
-    def __init__(self, n: int):
-        self.decoders = [_Decoder() for _ in range(n)]
+    def __init__(self, n: int, framing: int = ZLIB):
+        self.decoders = [_Decoder(framing) for _ in range(n)]
         self._L = _lib.load()
 
     def feed(self, i: int, chunk: bytes):
@@ -264,13 +268,23 @@ def _chunks_of(lazy: LazyByteString) -> List[bytes]:
     return [bytes(c) for c in lazy if len(c)]
 
 
-def decompress(ifile: LazyByteString):
+def decompress_gzip(ifile: LazyByteString):
+    """`decompress` for one gzip member (extension)."""
+    return decompress(ifile, GZIP)
+
+
+def decompress_raw(ifile: LazyByteString):
+    """`decompress` for a raw deflate stream (extension)."""
+    return decompress(ifile, RAW)
+
+
+def decompress(ifile: LazyByteString, framing: int = ZLIB):
     """`decompress` (Zlib.hs:32-51)."""
     chunks = _chunks_of(ifile)
     if len(chunks) <= 1:
-        return decompress_batch([chunks[0] if chunks else b""])[0]
+        return decompress_batch([chunks[0] if chunks else b""], framing)[0]
     # the driver loop `run` (Zlib.hs:37-51) over the incremental decoder
-    state = decompress_incremental()
+    state = decompress_incremental(framing)
     acc = []
     rest = list(chunks)
     while True:
@@ -334,11 +348,11 @@ def decompress_batch_raw(streams: Sequence[bytes], flags: int = 0):
     return [res[i] for i in range(n)], outs
 
 
-def decompress_batch(streams: Iterable[bytes]):
+def decompress_batch(streams: Iterable[bytes], framing: int = ZLIB):
     """Extension (not in the reference): `map decompress` over independent single-chunk
     streams, one kernel launch for the whole list."""
     streams = [bytes(s) for s in streams]
-    res, outs = decompress_batch_raw(streams)
+    res, outs = decompress_batch_raw(streams, framing)
     out = []
     for r, data in zip(res, outs):
         if r.status == _lib.PZ_OK:

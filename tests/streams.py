@@ -272,3 +272,48 @@ def small_text(n: int, seed: int) -> bytes:
         i += 1
         out += b".\n" if i % 17 == 0 else b", " if i % 7 == 0 else b" "
     return bytes(out[:n])
+
+
+# ---- gzip / raw deflate (the framing extension): streams and their expected verdict kinds ---------------------------
+def gzip_cases():
+    """[(name, framing flag name, stream bytes)]: valid members from system zlib (wbits 31 / -15), headers with every
+    optional field, and the faults the extension defines verdicts for."""
+    import gzip
+    import io
+    rng = np.random.default_rng(41)
+    out = []
+    for i, (n, lvl) in enumerate([(0, 6), (1, 9), (5000, 1), (70_000, 6), (300_000, 9)]):
+        data = small_text(n, 60 + i)
+        co = zlib.compressobj(lvl, zlib.DEFLATED, 31)
+        out.append((f"gz-text{n}", "gzip", co.compress(data) + co.flush()))
+        co = zlib.compressobj(lvl, zlib.DEFLATED, -15)
+        out.append((f"raw-text{n}", "raw", co.compress(data) + co.flush()))
+    rnd = rng.integers(0, 256, 90_000, dtype=np.uint8).tobytes()
+    co = zlib.compressobj(6, zlib.DEFLATED, 31)
+    out.append(("gz-stored", "gzip", co.compress(rnd) + co.flush()))
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    out.append(("raw-stored", "raw", co.compress(rnd) + co.flush()))   # ends with the last byte of a stored block
+    buf = io.BytesIO()
+    with gzip.GzipFile(filename="hello.txt", mode="wb", fileobj=buf, mtime=0) as f:
+        f.write(b"hello hello hello")
+    g = buf.getvalue()
+    out.append(("gz-fname", "gzip", g))
+    body = g[10 + len("hello.txt") + 1:]
+    hdr = bytes([0x1f, 0x8b, 8, 4 | 8 | 16 | 2, 0, 0, 0, 0, 0, 3]) + (5).to_bytes(2, "little") + b"EXTRA" + b"name\0" + b"comment\0"
+    hdr += (zlib.crc32(hdr) & 0xffff).to_bytes(2, "little")             # FHCRC (the extension skips it, system zlib checks it)
+    out.append(("gz-all-fields", "gzip", hdr + body))
+    out.append(("gz-two-members", "gzip", g + g))                       # bytes behind the trailer are ignored
+    bad = bytearray(g); bad[-5] ^= 1
+    out.append(("gz-bad-crc", "gzip", bytes(bad)))
+    bad = bytearray(g); bad[-1] ^= 1
+    out.append(("gz-bad-isize", "gzip", bytes(bad)))
+    out.append(("gz-bad-magic", "gzip", b"\x1f\x8c" + g[2:]))
+    out.append(("gz-bad-method", "gzip", g[:2] + b"\x07" + g[3:]))
+    out.append(("gz-reserved-flags", "gzip", g[:3] + b"\x80" + g[4:]))
+    out.append(("gz-truncated-trailer", "gzip", g[:-3]))
+    out.append(("gz-truncated-header", "gzip", g[:12]))
+    out.append(("gz-empty", "gzip", b""))
+    out.append(("raw-empty", "raw", b""))
+    out.append(("raw-truncated", "raw", out[7][2][:-10]))
+    out.append(("zlib-as-gzip", "gzip", zlib.compress(b"abc")))
+    return out

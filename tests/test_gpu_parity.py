@@ -852,7 +852,7 @@ from pure_zlib_b200 import _lib
 from oracle import oracle
 L = _lib.load()
 cfg = _lib.PzConfig(); cfg.device = -1; cfg.n_devices = -1
-assert L.pz_init(cfg) == 0 and L.pz_device_count() >= 2, L.pz_device_count()
+assert L.pz_init(__import__("ctypes").byref(cfg)) == 0 and L.pz_device_count() >= 2, L.pz_device_count()
 rng = np.random.default_rng(3)
 cases = [zlib.compress(streams.small_text(int(rng.integers(100, 200_000)), i), int(rng.integers(1, 10))) for i in range(97)]
 cases[5] = cases[5][:-2]; cases[40] = bytes.fromhex("789c4b04620000000001"); cases[96] = b""
@@ -869,3 +869,150 @@ print("multi-gpu ok", L.pz_device_count())
 '''
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0 and "multi-gpu ok" in r.stdout, (r.stdout[-500:], r.stderr[-1500:])
+
+
+# ---- the framing extension: gzip members (RFC 1952) and raw deflate --------------------------------------------------
+def _framing_flags(pz, kind):
+    return pz.GZIP if kind == "gzip" else pz.RAW
+
+
+def test_gzip_and_raw_batch_matches_oracle(pz, oracle):
+    """Every case of streams.gzip_cases() through the batch entry points (one call per framing), verdicts, messages and
+    CRC-32 / Adler-32 words equal to the oracle's; valid members also against system zlib."""
+    from pure_zlib_b200 import _lib
+    cases = streams.gzip_cases()
+    for kind in ("gzip", "raw"):
+        sub = [(n, z) for n, k, z in cases if k == kind]
+        for fn in (pz.zlib.decompress_batch_raw, pz.zlib.inflate_batch_raw):
+            res, outs = fn([z for _, z in sub], _framing_flags(pz, kind))
+            for (name, z), r, out in zip(sub, res, outs):
+                o = oracle.decompress(z, framing=oracle.GZIP if kind == "gzip" else oracle.RAW)
+                assert (r.status, r.detail, r.out_len) == (o.status, o.detail, o.out_len), (name, r.status, r.detail, o.message)
+                assert out == o.data, name
+                if o.status in (0, 5):
+                    assert (r.adler_computed, r.adler_stored) == (o.adler_computed, o.adler_stored), name
+                if o.status != 0:
+                    assert _lib.strerror(r) == o.message, name
+                else:
+                    assert zlib.decompressobj(31 if kind == "gzip" else -15).decompress(z) == out
+    # the mirror's entry points
+    g = [z for n, k, z in cases if n == "gz-fname"][0]
+    assert pz.decompress_gzip(g) == pz.Right(b"hello hello hello")
+    assert pz.decompress_gzip(g[:-8] + b"\0" * 8).value == pz.ChecksumError("checksum mismatch: 0 != " + format(zlib.crc32(b"hello hello hello"), "x"))
+    co = zlib.compressobj(9, zlib.DEFLATED, -15)
+    assert pz.decompress_raw(co.compress(b"abc" * 1000) + co.flush()) == pz.Right(b"abc" * 1000)
+
+
+def test_gzip_and_raw_incremental(pz, oracle):
+    """decompressIncremental behind the other framings: the event sequence of the oracle over the same chunk lists."""
+    rng = np.random.default_rng(17)
+    n = 0
+    for name, kind, z in streams.gzip_cases():
+        if len(z) < 4:
+            continue
+        for cuts in ([int(x) for x in rng.integers(1, len(z), 3)], list(range(0, len(z), 997))[:40]):
+            pieces = _pieces(z, cuts)
+            o = oracle.decompress(pieces, want_events=True, framing=oracle.GZIP if kind == "gzip" else oracle.RAW)
+            st = pz.zlib.decompress_incremental(_framing_flags(pz, kind))
+            events, acc, rest, err = [], b"", list(pieces), None
+            while True:
+                if isinstance(st, pz.NeedMore):
+                    events.append((0, 0))
+                    if not rest:
+                        events.append((3, 0))
+                        break
+                    st = st.feed(rest.pop(0))
+                elif isinstance(st, pz.Chunk):
+                    events.append((1, len(st.data))); acc += st.data; st = st.next()
+                elif isinstance(st, pz.Done):
+                    events.append((2, 0)); break
+                else:
+                    events.append((3, 0)); err = st.error; break
+            assert events == o.events, (name, cuts[:4], events[:6], o.events[:6])
+            assert acc == o.data[: len(acc)] and (o.status != 0 or acc == o.data), name
+            if err is not None and not (o.status == 3 and o.detail == 1):
+                assert str(err) == o.message, name
+            n += 1
+    assert n > 30
+
+
+def test_gzip_huge_stream_block_parallel(pz, oracle, huge_threshold):
+    """K4 behind the gzip and raw framings (header length, 8-byte / no trailer, CRC-32 + ISIZE in K3)."""
+    from pure_zlib_b200 import _lib, corpus
+    L = _lib.load()
+    text = corpus.text(3 << 20, 91)
+    for kind, wbits in (("gzip", 31), ("raw", -15)):
+        co = zlib.compressobj(9, zlib.DEFLATED, wbits)
+        z = co.compress(text) + co.flush()
+        bad = bytearray(z); bad[len(z) // 2] ^= 0x10
+        done0 = L.pz_get_counter(1)
+        res, outs = pz.zlib.inflate_batch_raw([z, bytes(bad), z[: len(z) // 3]], _framing_flags(pz, kind))
+        assert L.pz_get_counter(1) - done0 >= 1, kind
+        for zz, r, out in zip([z, bytes(bad), z[: len(z) // 3]], res, outs):
+            o = oracle.decompress(zz, framing=oracle.GZIP if kind == "gzip" else oracle.RAW)
+            assert (r.status, r.detail, r.out_len) == (o.status, o.detail, o.out_len), (kind, r.status, r.detail, o.message)
+            assert out == o.data
+            if o.status in (0, 5):
+                assert (r.adler_computed, r.adler_stored) == (o.adler_computed, o.adler_stored), kind
+
+
+def test_crc32_entry_point(pz):
+    from pure_zlib_b200 import _lib
+    L = _lib.load()
+    rng = np.random.default_rng(5)
+    for n in (0, 1, 3, 511, 512, 513, 16383, 16384, 16385, 100_000, 1 << 20, (1 << 20) + 7):
+        d = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        assert L.pz_crc32(0, d, n) == zlib.crc32(d), n
+        assert L.pz_crc32(zlib.crc32(b"prefix"), d, n) == zlib.crc32(b"prefix" + d), n
+
+
+# ---- O(1)-memory incremental contexts --------------------------------------------------------------------------------
+def test_incremental_context_memory_is_bounded(pz):
+    """A context keeps the live input (from the header of the block it is in), the last 32 KiB of output plus room for
+    one launch, and a checkpoint -- not the stream (the reference's decoder is O(128 KiB), OutputWindow.hs:29-54):
+    96 MiB of text through one decoder in 64 KiB pieces must never hold more than a few MiB on the device, and a
+    zero run of more than 4 GiB (beyond the 32-bit counters of one launch) decodes with the right length and checksum."""
+    from pure_zlib_b200 import _lib, corpus
+    L = _lib.load()
+    text = b"".join(corpus.text(16 << 20, 500 + k) for k in range(6))
+    z = zlib.compress(text, 6)
+    d = pz.zlib._Decoder()
+    got = []
+    adler = 1
+    peak_now = 0
+    for at in range(0, len(z), 1 << 16):
+        piece = z[at: at + (1 << 16)]
+        _lib.check(L.pz_stream_feed(d._s, piece, len(piece)), "feed")
+        st = d.state()
+        while isinstance(st, pz.Chunk):
+            adler = zlib.adler32(st.data, adler)
+            got.append(len(st.data))
+            st = st.next()
+        peak_now = max(peak_now, L.pz_stream_counter(d._s, _lib.PZ_SC_DEVICE_BYTES))
+    assert isinstance(st, pz.Done), st
+    assert sum(got) == len(text) and adler == zlib.adler32(text)
+    assert all(g == 32768 for g in got[:-1])
+    peak = L.pz_stream_counter(d._s, _lib.PZ_SC_DEVICE_PEAK)
+    assert peak < 4 << 20, peak            # against 96 MiB of output + 30 MiB of input
+    assert L.pz_stream_counter(d._s, _lib.PZ_SC_HOST_BYTES) < 8 << 20
+    # more than 4 GiB from one stream: 4.25 GiB of zeros
+    total = (17 << 28)
+    co = zlib.compressobj(9)
+    zero = bytes(1 << 24)
+    parts = [co.compress(zero) for _ in range(total >> 24)] + [co.flush()]
+    zz = b"".join(parts)
+    d = pz.zlib._Decoder()
+    n_out, adler, ok_zero = 0, 1, True
+    zeros32k = bytes(32768)
+    a32k = None
+    for at in range(0, len(zz), 1 << 18):
+        piece = zz[at: at + (1 << 18)]
+        _lib.check(L.pz_stream_feed(d._s, piece, len(piece)), "feed")
+        st = d.state()
+        while isinstance(st, pz.Chunk):
+            n_out += len(st.data)
+            ok_zero = ok_zero and (st.data == zeros32k if len(st.data) == 32768 else st.data.count(0) == len(st.data))
+            st = st.next()
+    assert isinstance(st, pz.Done), getattr(st, "error", st)
+    assert n_out == total and ok_zero
+    assert L.pz_stream_counter(d._s, _lib.PZ_SC_DEVICE_PEAK) < 160 << 20

@@ -130,3 +130,36 @@ def test_adler():
         assert oracle.adler32(d) == zlib.adler32(d)
     d = b"\xff" * 200000
     assert oracle.adler32(d) == zlib.adler32(d)
+
+
+# ---- the framing extension (gzip members, raw deflate): pinned against system zlib on valid streams -----------------
+def test_gzip_and_raw_agree_with_system_zlib():
+    rng = np.random.default_rng(1)
+    for i in range(40):
+        n = int(rng.integers(0, 150_000))
+        lvl = int(rng.integers(1, 10))
+        data = streams.small_text(n, i) if i % 3 else rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        co = zlib.compressobj(lvl, zlib.DEFLATED, 31)
+        g = co.compress(data) + co.flush()
+        v = oracle.decompress(g, framing=oracle.GZIP)
+        assert v.status == 0 and v.data == data and v.adler_computed == zlib.crc32(data) == v.adler_stored, (i, v.message)
+        co = zlib.compressobj(lvl, zlib.DEFLATED, -15)
+        r = co.compress(data) + co.flush()
+        v = oracle.decompress(r, framing=oracle.RAW)
+        assert v.status == 0 and v.data == data and v.adler_computed == zlib.adler32(data), (i, v.message)
+
+
+def test_gzip_verdicts():
+    want = {"gz-bad-crc": (5, 1), "gz-bad-isize": (5, 2), "gz-bad-magic": (4, 4), "gz-bad-method": (4, 2), "gz-reserved-flags": (4, 5),
+            "gz-truncated-trailer": (3, 1), "gz-truncated-header": (3, 1), "gz-empty": (3, 1), "raw-empty": (3, 1),
+            "raw-truncated": (3, 1), "zlib-as-gzip": (4, 4)}
+    msgs = {"gz-bad-isize": "Checksum error: length mismatch: 16777233 != 17", "gz-bad-magic": "Header error: Not a gzip stream: 1f8c",
+            "gz-reserved-flags": "Header error: Reserved gzip flags set: 128", "gz-bad-method": "Header error: Bad compression method: 7"}
+    for name, kind, z in streams.gzip_cases():
+        v = oracle.decompress(z, framing=oracle.GZIP if kind == "gzip" else oracle.RAW)
+        assert (v.status, v.detail) == want.get(name, (0, 0)), (name, v.status, v.detail, v.message)
+        if name in msgs:
+            assert v.message == msgs[name]
+        if v.status == 0:  # system zlib reads the same bytes (one member / the whole raw stream)
+            d = zlib.decompressobj(31 if kind == "gzip" else -15)
+            assert d.decompress(z) == v.data

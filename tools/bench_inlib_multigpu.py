@@ -28,7 +28,7 @@ def child(config, n_dev, steps):
     cfg.device, cfg.n_devices = -1, n_dev
     for k in range(n_dev):
         cfg.devices[k] = k
-    _lib.check(L.pz_init(cfg), "pz_init")
+    _lib.check(L.pz_init(C.byref(cfg)), "pz_init")
     assert L.pz_device_count() == n_dev
     p64 = C.POINTER(C.c_uint64)
     hin = L.pz_pinned_alloc(c.in_blob.nbytes)

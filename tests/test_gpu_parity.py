@@ -995,8 +995,8 @@ def test_incremental_context_memory_is_bounded(pz):
     peak = L.pz_stream_counter(d._s, _lib.PZ_SC_DEVICE_PEAK)
     assert peak < 4 << 20, peak            # against 96 MiB of output + 30 MiB of input
     assert L.pz_stream_counter(d._s, _lib.PZ_SC_HOST_BYTES) < 8 << 20
-    # more than 4 GiB from one stream: 4.25 GiB of zeros
-    total = (17 << 28)
+    # more than 4 GiB from one stream: 4 GiB + 64 MiB of zeros
+    total = (65 << 26)
     co = zlib.compressobj(9)
     zero = bytes(1 << 24)
     parts = [co.compress(zero) for _ in range(total >> 24)] + [co.flush()]

@@ -165,6 +165,8 @@ int pz_inflate_batch_contig(const uint8_t *in_blob, const uint64_t *in_off, uint
 /* Sizing pass: the decoded length of each stream (res[i].out_len), nothing written.
  * Lets the shim implement `decompress` without caller-supplied capacities.               */
 int pz_inflate_sizes(const uint8_t *const *in, const size_t *in_len, size_t n, pz_result *res);
+/* The same behind another framing (flags: PZ_F_GZIP or PZ_F_RAW, see there). */
+int pz_inflate_sizes_framed(const uint8_t *const *in, const size_t *in_len, size_t n, pz_result *res, uint32_t flags);
 
 /* `map decompress` in ONE call (Zlib.hs:32-51 for each of n single-chunk streams): sizing pass, output allocation and
  * decode inside the library, so the compressed bytes are packed once and nothing is copied on the host on the way out:

@@ -47,6 +47,7 @@ SYMBOLS = [
     ("pz_inflate_batch_contig", C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p, C.POINTER(C.c_uint64),
                                           C.c_size_t, C.POINTER(PzResult), C.c_void_p, C.c_uint32]),
     ("pz_inflate_sizes", C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_size_t, C.POINTER(PzResult)]),
+    ("pz_inflate_sizes_framed", C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_size_t, C.POINTER(PzResult), C.c_uint32]),
     ("pz_decompress_batch", C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_size_t, C.POINTER(PzResult),
                                       C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_uint32]),
     ("pz_outputs_free", None, [C.c_void_p]),

@@ -768,8 +768,8 @@ int contig_one_device(const uint8_t *in_blob, const uint64_t *in_off, uint8_t *o
    * batches with stored-block streams -- recognisable from their first block header -- wait for
    * the whole input instead. */
   const bool in_place = (flags & PZ_F_INPUT_IN_PLACE) != 0;
-  bool progressive = columns && !in_place && n >= 8 * kGroups && n <= 2 * (size_t)pz_inflate_slots();
-  for (size_t i = 0; progressive && framing_of(flags) == 0u && i < n; i++) {
+  bool progressive = columns && !in_place && n >= 8 * kGroups && n <= 2 * (size_t)pz_inflate_slots() && framing_of(flags) == 0u; /* (the peek below reads a zlib header) */
+  for (size_t i = 0; progressive && i < n; i++) {
     const uint64_t len = in_off[i + 1] - in_off[i];
     const uint8_t *p = in_blob + in_off[i];
     progressive = len >= 3 && len < g_huge_bytes && ((p[(p[1] & 0x20u) && len >= 7 ? 6 : 2] >> 1) & 3u) != 0u;
@@ -1027,6 +1027,10 @@ int pz_inflate_batch(const uint8_t *const *in, const size_t *in_len, uint8_t *co
 
 int pz_inflate_sizes(const uint8_t *const *in, const size_t *in_len, size_t n, pz_result *res) {
   return inflate_ptrs(in, in_len, nullptr, nullptr, n, res, PZ_F_COUNT_ONLY);
+}
+
+int pz_inflate_sizes_framed(const uint8_t *const *in, const size_t *in_len, size_t n, pz_result *res, uint32_t flags) {
+  return inflate_ptrs(in, in_len, nullptr, nullptr, n, res, (flags & (PZ_F_GZIP | PZ_F_RAW)) | PZ_F_COUNT_ONLY);
 }
 
 /* ---- incremental decoder (decompressIncremental, Zlib.hs:29-30) -----------------------

@@ -1010,9 +1010,32 @@ struct PzFast { /* the registers of the hot loop */
 #endif
 };
 
+/* The two table look-ups of the symbol chain.  On the device the address is ONE multiply-add behind the mask (index * size +
+ * table base in the shared window) instead of the shift / mask / add ptxas derives from an array subscript: every
+ * instruction between the two dependent loads of a symbol is four to five cycles of the chain. */
+#if defined(PZ_HOSTSIM) || !defined(PZ_OPT_MAD)
+PZ_DEV uint32_t pz_lit_at(const PzStreamSmem *sm, uint32_t bits) { return sm->lit_lut[bits & ((1u << PZ_LIT_BITS) - 1u)]; }
+PZ_DEV uint32_t pz_dist_at(const PzStreamSmem *sm, uint32_t bits) { return sm->dist_lut[bits & ((1u << PZ_DIST_BITS) - 1u)]; }
+#else
+PZ_DEV uint32_t pz_lit_at(const PzStreamSmem *sm, uint32_t bits) {
+  const uint32_t base = (uint32_t)__cvta_generic_to_shared(sm->lit_lut);
+  uint32_t a, v;
+  asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(a) : "r"(bits & ((1u << PZ_LIT_BITS) - 1u)), "r"(base));
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+PZ_DEV uint32_t pz_dist_at(const PzStreamSmem *sm, uint32_t bits) {
+  const uint32_t base = (uint32_t)__cvta_generic_to_shared(sm->dist_lut);
+  uint32_t a, v;
+  asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(a) : "r"(bits & ((1u << PZ_DIST_BITS) - 1u)), "r"(base));
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+#endif
+
 PZ_DEV void pz_fast_fetch(PzFast &f, const PzStreamSmem *sm, uint32_t bp) {
   pz_peek96(sm->ring, bp, f.b0, f.b1, f.b2);
-  f.e = sm->lit_lut[f.b0 & ((1u << PZ_LIT_BITS) - 1u)];
+  f.e = pz_lit_at(sm, f.b0);
 }
 
 /* One trip = PZ_TRIP symbols.  The serial chain of a stream is
@@ -1074,10 +1097,10 @@ PZ_DEV bool pz_fast_trip(PzFast &f, PzStreamSmem *sm, const bool run) {
     /* the funnel shifts take their amount modulo 32: e itself serves as tb (tb <= 20) */
     const uint32_t wd = pz_funnel_r(b0, b1, e);  /* the 32 bits after the literal/length symbol */
     const uint32_t wd1 = pz_funnel_r(b1, b2, e); /* and the 32 after those (off the chain)     */
-    const uint32_t d = sm->dist_lut[wd & ((1u << PZ_DIST_BITS) - 1u)];
+    const uint32_t d = pz_dist_at(sm, wd);
     const uint32_t tb2 = d & (is_lit ? 0u : 31u); /* <= 28 */
     const uint32_t nb0 = pz_funnel_r(wd, wd1, tb2);
-    const uint32_t ne = sm->lit_lut[nb0 & ((1u << PZ_LIT_BITS) - 1u)];
+    const uint32_t ne = pz_lit_at(sm, nb0);
     const uint32_t nbp = bp + tb + tb2;
     uint32_t nb1, nb2;
     pz_peek_tail(sm->ring, nbp, nb1, nb2);

@@ -320,7 +320,7 @@ def inflate_batch_raw(streams: Sequence[bytes], flags: int = 0):
         return [], []
     keep, ptrs, lens = _ptr_arrays(streams)
     sizes = (PzResult * n)()
-    _lib.check(L.pz_inflate_sizes(ptrs, lens, n, sizes), "pz_inflate_sizes")
+    _lib.check(L.pz_inflate_sizes_framed(ptrs, lens, n, sizes, flags), "pz_inflate_sizes_framed")
     caps = (C.c_size_t * n)(*[int(sizes[i].out_len) for i in range(n)])
     outs = [C.create_string_buffer(max(int(caps[i]), 1)) for i in range(n)]
     optrs = (C.c_void_p * n)(*[C.addressof(o) for o in outs])

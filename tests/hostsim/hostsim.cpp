@@ -13,8 +13,8 @@
 #include <stdlib.h>
 
 /* resume / ckpt (four words each, may be null): PzJob::resume, PzJob::ckpt; `out` then holds the stream's history */
-extern "C" int hs_inflate_resume(const uint8_t *in, uint64_t in_len, uint8_t *out, uint64_t out_cap, pz_result *res, int count_only,
-                                 const uint32_t *resume, uint32_t *ckpt) {
+extern "C" int hs_inflate_framed(const uint8_t *in, uint64_t in_len, uint8_t *out, uint64_t out_cap, pz_result *res, int count_only,
+                                 const uint32_t *resume, uint32_t *ckpt, uint32_t framing) {
   /* the device reads whole 16-byte pieces around the stream: give it a padded, aligned copy
    * with a deliberately odd misalignment so the (mis != 0) paths run */
   size_t mis = 5;
@@ -34,7 +34,7 @@ extern "C" int hs_inflate_resume(const uint8_t *in, uint64_t in_len, uint8_t *ou
   }
   PzJob job;
   job.in_blob = pairs ? nullptr : buf + mis; job.in_off = in_off; job.out_blob = (count_only || pairs) ? nullptr : out; job.out_off = out_off;
-  job.pair_off = pairs ? 1u : 0u; job.resume = resume; job.ckpt = ckpt;
+  job.pair_off = pairs ? 1u : 0u; job.resume = resume; job.ckpt = ckpt; job.framing = framing;
   job.parts = nullptr; job.seg_off = nullptr;
   job.res = res; job.first = 0; job.count = 1; job.skip_done = 0; job.prog = nullptr; job.in_ready = nullptr; job.blk_start = nullptr; job.blk_out = nullptr; job.blk_len = nullptr; job.out16 = nullptr; job.blk_stream = 0; job.blk_cap = 0;
   PzWriter hw; /* tokens are applied as they are pushed */
@@ -44,6 +44,11 @@ extern "C" int hs_inflate_resume(const uint8_t *in, uint64_t in_len, uint8_t *ou
   free(sm);
   free(buf);
   return 0;
+}
+
+extern "C" int hs_inflate_resume(const uint8_t *in, uint64_t in_len, uint8_t *out, uint64_t out_cap, pz_result *res, int count_only,
+                                 const uint32_t *resume, uint32_t *ckpt) {
+  return hs_inflate_framed(in, in_len, out, out_cap, res, count_only, resume, ckpt, 0);
 }
 
 extern "C" int hs_inflate(const uint8_t *in, uint64_t in_len, uint8_t *out, uint64_t out_cap, pz_result *res, int count_only) {

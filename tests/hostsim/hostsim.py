@@ -22,15 +22,18 @@ def lib():
         subprocess.check_call(["make", "-C", _HERE, "-s", "libpzhostsim.so"])
         _lib = C.CDLL(_SO)
         _lib.hs_inflate.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(PzResult), C.c_int]
+        _lib.hs_inflate_framed.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(PzResult), C.c_int,
+                                           C.c_void_p, C.c_void_p, C.c_uint32]
         _lib.hs_inflate_resume.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(PzResult), C.c_int,
                                            C.c_void_p, C.c_void_p]
     return _lib
 
 
-def inflate(data: bytes, out_cap: int, count_only: bool = False):
+def inflate(data: bytes, out_cap: int, count_only: bool = False, framing: int = 0):
+    """framing: PZ_FRAME_* of pz_device.cuh (0 zlib, 1 gzip, 2 raw deflate)."""
     out = C.create_string_buffer(max(out_cap, 1))
     res = PzResult()
-    lib().hs_inflate(bytes(data), len(data), out, out_cap, C.byref(res), int(count_only))
+    lib().hs_inflate_framed(bytes(data), len(data), out, out_cap, C.byref(res), int(count_only), None, None, framing)
     return res, out.raw[: min(res.out_len, out_cap)]
 
 

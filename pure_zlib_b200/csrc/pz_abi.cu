@@ -1349,7 +1349,7 @@ int pump_framed(const std::vector<pz_stream *> &act, uint32_t framing) {
     for (size_t i = 0; i < n; i++) {
       pz_stream *s = run[i];
       s->pumps++;
-      if (s->ck[0] != 0 || s->lead != 0) s->resumed++;
+      if ((s->ck[0] | s->ck[1]) != 0 || s->lead != 0 || s->pos != 0) s->resumed++;
       /* the running checksum takes the new piece in */
       const uint64_t len = newpos[i] - s->pos;
       if (len) s->sum = framing == 1u ? crc_combine(s->sum, piece[i].adler_computed, len) : adler_combine(s->sum, piece[i].adler_computed, len);

@@ -47,9 +47,9 @@ pz_inflate_kernel(const PzJob job) {
   PzStreamSmem *slots = reinterpret_cast<PzStreamSmem *>(pz_smem_raw);
   /* empty token queues: every slot carries the phase the reader does NOT expect on lap 0 */
   for (uint32_t i = threadIdx.x; i < PZ_SLOTS * PZ_QLEN; i += PZ_THREADS_PER_CTA)
-    slots[i / PZ_QLEN].q[i % PZ_QLEN] = 0x80000000u;
+    slots[i / PZ_QLEN].q[i % PZ_QLEN] = make_uint2(0x80000000u, 0u);
   if (threadIdx.x < PZ_SLOTS) {
-    slots[threadIdx.x].qtail = 0;
+    slots[threadIdx.x].qtail = 0; slots[threadIdx.x].wpos = 0; slots[threadIdx.x].wmark = 0; slots[threadIdx.x].wbad = 0;
     slots[threadIdx.x].mail.state = PZ_MS_SERVICE;
     slots[threadIdx.x].mail.ring_hi = 0;
     slots[threadIdx.x].mail.hot_bp = 0;

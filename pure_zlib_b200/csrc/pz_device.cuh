@@ -794,6 +794,7 @@ PZ_DEV void pz_writer_apply(PzWriter &w, uint32_t raw) {
   } else {
     const uint32_t op = (raw >> 26) & 7u;
     if (op == PZ_C_EXIT) { pz_publish(w, PZ_PROG_DONE); w.exited = true; }
+    else if (op == PZ_C_FLUSH) { /* nothing: its consumption is the message (pz_lean_drain) */ }
     else { w.op = op; w.need = op == PZ_C_NEWSTREAM ? 1u : 2u; }
   }
 }
@@ -1425,6 +1426,7 @@ PZ_DEV void pz_service_poll(PzCtx &c, PzStreamSmem *sm) {
     while (c.next_q < c.q + 3u) pz_ring_issue(c, sm, c.next_q++);
     c.mode = PZ_M_SYMS;
     c.need_careful = true;
+    if (c.lean) { c.mode = PZ_M_DRAIN; c.flush_sent = false; } /* bytes, base and mark are the writer's to tell (the mailbox words are stale) */
     return;
   }
   const uint32_t hq = pz_vload(&sm->mail.hot_bp) >> PZ_QUARTER_SHIFT;
@@ -1434,6 +1436,40 @@ PZ_DEV void pz_service_poll(PzCtx &c, PzStreamSmem *sm) {
   }
 }
 #endif /* !PZ_HOSTSIM */
+
+#ifndef PZ_HOSTSIM
+/* Lean kernel: the service group asks the writer where the bytes stand.  A FLUSH token goes behind whatever is queued (it
+ * never joins a batch, so the writer does not wait for more tokens), and once the writer has consumed it the slot's status
+ * block holds the byte count, the end of the last match and the verdict of the writer's checks.
+ *   PZ_M_DRAIN      the stream came back from the hot lane: the careful path needs the counters
+ *   PZ_M_FINDRAIN   a verdict is ready: it is only published once every token has passed the writer's checks
+ * A failed check sends the stream to the exact kernel (status PENDING: the launch behind this one decodes it from scratch). */
+PZ_DEV void pz_finish(PzCtx &c);
+PZ_DEV bool pz_lean_drain(PzCtx &c, PzStreamSmem *sm) { /* true: still waiting for the writer */
+  if (!c.flush_sent) {
+    pz_push<false>(c, sm, PZ_TOKEN(PZ_Q_CTRL, PZ_C_FLUSH << 26));
+    c.flush_sent = true;
+  }
+  uint32_t tail, wpos, wmark, wbad;
+  asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(tail), "=r"(wpos), "=r"(wmark), "=r"(wbad)
+               : "r"((unsigned)__cvta_generic_to_shared(&sm->qtail)) : "memory");
+  if (tail != c.qhead) return true;
+  c.flush_sent = false;
+  if (wbad != 0u) {
+    pz_syncwarp();
+    if (pz_lane() == 0) c.res->status = PZ_ST_PENDING;
+    c.mode = PZ_M_IDLE;
+    return false;
+  }
+  if (c.mode == PZ_M_FINDRAIN) { pz_finish(c); return false; }
+  c.pos = wpos;
+  if (wmark > c.mark) c.mark = wmark;
+  c.base = c.mark >= 2u * PZ_EXCESS ? (c.mark / PZ_EXCESS - 1u) * PZ_EXCESS : 0u; /* closed form of the window's base while every gap is <= 32 KiB (PzCtx::mark) */
+  c.mode = PZ_M_SYMS;
+  c.need_careful = true;
+  return false;
+}
+#endif
 
 /* One symbol of the code-length code (getCodeLengths, Deflate.hs:124-156). */
 PZ_DEV int pz_pre_symbol(PzCtx &c, PzStreamSmem *sm, const uint32_t *pre_lut) {
@@ -1529,6 +1565,11 @@ PZ_DEV bool pz_stored_block(PzCtx &c, PzStreamSmem *sm) {
 /* ---- the state machine ------------------------------------------------------------------ */
 /* Publishes the verdict of the current stream and frees the group for its next one. */
 PZ_DEV void pz_finish(PzCtx &c) {
+#ifndef PZ_HOSTSIM
+  /* lean kernel: the writer checks tokens the decoder side could not (pz_hot_warp_lean); the verdict waits until it has
+   * confirmed the last one (pz_lean_drain, which calls this function again) */
+  if (c.lean && c.mode != PZ_M_FINDRAIN) { c.mode = PZ_M_FINDRAIN; c.flush_sent = false; return; }
+#endif
   pz_syncwarp();
   if (pz_lane() == 0) {
     pz_result *res = c.res;
@@ -1673,6 +1714,7 @@ PZ_DEV void pz_begin_block(PzCtx &c, PzStreamSmem *sm, uint32_t j, const uint8_t
  * (checkChecksum, Deflate.hs:52-63: align, four bytes, most significant first). */
 PZ_DEV void pz_block_end(PzCtx &c, PzStreamSmem *sm) {
   pz_move_window(c);
+  c.mark = c.pos; /* a moveWindow call ends a gap (PzCtx::mark) */
   if (c.block_job) { pz_finish(c); return; } /* err_bitpos = first bit after the block */
   if (!c.bfinal) { c.mode = PZ_M_HDR; return; }
   pz_trailer(c, sm);
@@ -1774,11 +1816,15 @@ PZ_DEV void pz_decoder_warp(const PzJob &job, uint32_t first_stream, uint32_t st
 #ifdef PZ_HOSTSIM
                             , PzWriter *hw
 #else
-                            , bool present
+                            , bool present, bool lean = false
 #endif
 ) {
   PzCtx c;
   c.mode = PZ_M_IDLE;
+  c.lean = false; c.flush_sent = false;
+#ifndef PZ_HOSTSIM
+  c.lean = lean;
+#endif
   c.next = first_stream;
   c.in_al = nullptr; c.in_al_bytes = 0; c.bp = 0; c.q = 0; c.next_q = 0; c.pending = false; c.starved = false; c.block_job = false; c.res = nullptr;
   c.framing = PZ_FRAME_ZLIB;
@@ -1795,13 +1841,18 @@ PZ_DEV void pz_decoder_warp(const PzJob &job, uint32_t first_stream, uint32_t st
 #else
   if (!present) c.mode = PZ_M_DEAD; /* a group without a slot */
   for (;;) {
+    bool draining = false;
     if (c.mode == PZ_M_WAIT) {
       pz_service_poll(c, sm);
+    } else if (c.mode == PZ_M_DRAIN || c.mode == PZ_M_FINDRAIN) {
+      draining = pz_lean_drain(c, sm);
     } else if (c.mode != PZ_M_DEAD) {
       pz_slow_step<COUNT_ONLY>(c, sm, job, stride);
       if (c.mode == PZ_M_FAST) pz_post_hot(c, sm);
       else if (c.mode == PZ_M_DEAD && pz_lane() == 0) pz_vstore(&sm->mail.state, PZ_MS_DEAD);
     }
+    /* groups that only wait for their writer do not keep the warp spinning at full speed */
+    if (pz_warp_any(draining) && !pz_warp_any(!draining && c.mode != PZ_M_WAIT && c.mode != PZ_M_DEAD && !(c.mode == PZ_M_IDLE && c.starved))) __nanosleep(100);
     if (!pz_warp_any(c.mode != PZ_M_WAIT && c.mode != PZ_M_DEAD && !(c.mode == PZ_M_IDLE && c.starved))) {
       if (!pz_warp_any(c.mode != PZ_M_DEAD)) break;
       /* every group waits for its hot lane: doze until one of them needs something (its stream

@@ -39,8 +39,10 @@ __device__ __forceinline__ void pz_role(uint32_t w, uint32_t &role, uint32_t &in
   index = PZ_HOT_SCHED_SERVICE + (k - PZ_WRITER_WARPS);
 }
 
-/* WIDE = block jobs (K4): 16-bit output symbols, and the gap rule of PzCtx::mark in the hot warp */
-template <bool COUNT_ONLY, bool WIDE = false>
+/* WIDE = block jobs (K4): 16-bit output symbols, and the gap rule of PzCtx::mark in the hot warp.
+ * LEAN = plain batches: the hot warp decodes tokens without counting bytes, the writers check them (pz_hot_warp_lean); a
+ * stream whose token fails a check is left PENDING for the exact kernel (LEAN = false), launched right behind. */
+template <bool COUNT_ONLY, bool WIDE = false, bool LEAN = false>
 __global__ void __launch_bounds__(PZ_THREADS_PER_CTA, 1)
 pz_inflate_kernel(const PzJob job) {
   extern __shared__ __align__(16) unsigned char pz_smem_raw[];
@@ -58,7 +60,8 @@ pz_inflate_kernel(const PzJob job) {
   uint32_t role, index;
   pz_role(threadIdx.x >> 5, role, index);
   if (role == 0u) {
-    pz_hot_warp<COUNT_ONLY, WIDE>(slots, PZ_SLOTS);
+    if (LEAN) pz_hot_warp_lean(slots, PZ_SLOTS);
+    else pz_hot_warp<COUNT_ONLY, WIDE>(slots, PZ_SLOTS);
     return;
   }
   if (role == 3u) return;
@@ -68,9 +71,9 @@ pz_inflate_kernel(const PzJob job) {
   const bool present = slot < PZ_SLOTS;
   PzStreamSmem *sm = slots + (present ? slot : 0u);
   if (role == 1u) {
-    pz_decoder_warp<COUNT_ONLY>(job, job.first + blockIdx.x + gridDim.x * slot, gridDim.x * PZ_SLOTS, sm, present);
+    pz_decoder_warp<COUNT_ONLY>(job, job.first + blockIdx.x + gridDim.x * slot, gridDim.x * PZ_SLOTS, sm, present, LEAN);
   } else if (!COUNT_ONLY) {
-    pz_writer_warp<WIDE>(job, sm, present);
+    pz_writer_warp<WIDE, LEAN>(job, sm, present);
   }
 }
 
@@ -389,6 +392,10 @@ cudaError_t pz_kernels_configure(void) {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(pz_inflate_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute((pz_inflate_kernel<false, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute((pz_inflate_kernel<false, false, true>), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(pz_blk_tails_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PZ_TAIL * sizeof(uint16_t)));
   if (e != cudaSuccess) return e;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_inflate_ctas_per_sm[0], pz_inflate_kernel<false>, PZ_THREADS_PER_CTA, smem);
@@ -441,7 +448,14 @@ cudaError_t pz_launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uin
       const unsigned tiles = (count + tile - 1u) / tile;
       pz_stored_copy_kernel<<<tiles < ctas ? tiles : ctas, PZ_ST_THREADS, 0, st>>>(job, tile);
     }
-    if (phase != PZ_PHASE_K2) pz_inflate_kernel<false><<<grid, PZ_THREADS_PER_CTA, smem, st>>>(job);
+    if (phase != PZ_PHASE_K2) {
+      static const bool no_lean = getenv("PZ_NO_LEAN") != nullptr; /* A/B: the exact kernel alone, as before the lean one existed */
+      if (!no_lean && d_prog == nullptr) {
+        pz_inflate_kernel<false, false, true><<<grid, PZ_THREADS_PER_CTA, smem, st>>>(job);
+        job.skip_done = 1; /* only what the lean kernel left PENDING: streams a writer's check refused */
+      }
+      pz_inflate_kernel<false><<<grid, PZ_THREADS_PER_CTA, smem, st>>>(job);
+    }
   }
   return cudaGetLastError();
 }

@@ -650,7 +650,7 @@ pz_batch *pz_batch_create(const uint64_t *in_off, const uint64_t *out_off, size_
     }
   }
   if (e != cudaSuccess) { fail_cuda(e, "pz_batch_create"); pz_batch_destroy(b); return nullptr; }
-  b->launches = (count_only ? 1 : 4) + ((count_only || (flags & PZ_F_NO_ADLER)) ? 0 : (b->total_segs ? 2 : 1)); /* K2 probe + K2 copy + K1 lean + K1 exact (what the lean kernel left), then K3a + K3b */
+  b->launches = (count_only ? 1 : 3) + ((count_only || (flags & PZ_F_NO_ADLER)) ? 0 : (b->total_segs ? 2 : 1)); /* K2 probe + K2 copy + K1, then K3a + K3b (PZ_LEAN=1 adds a launch) */
   return b;
 }
 

@@ -1231,30 +1231,15 @@ PZ_DEV void pz_hot_warp(PzStreamSmem *slots, uint32_t n_slots) {
   f.live = false;
   f.bp = 0; f.pos = 0; f.base = 0; f.lim = 0; f.safe_end = 0; f.qhead = 0; f.qtailc = 0; f.mark = 0; f.b0 = 0; f.b1 = 0; f.b2 = 0; f.e = 0;
   bool dead = lane >= n_slots;
-  /* A lone warp pays every branch in full (nothing else issues on its scheduler while one
-   * resolves), and most of the time some lane or other is between two postings (its stream is with
-   * the service group for a header, a long code, ...).  So the poll of the mailboxes is straight-line
-   * code: a predicated load in the lanes without a stream, two votes, and two warp-uniform
-   * branches that are only taken when a posting has actually arrived or nothing is left to do. */
+  /* A lone warp pays every branch in full (nothing else issues on its scheduler while one resolves: ncu attributes a third
+   * of a trip's cycles to the code AROUND the symbols -- the loop's back edge, two votes and two convergence regions for
+   * "a posting has arrived" and "a stream has stopped", profiles/r02g_*).  So a trip has ONE vote and ONE warp-uniform branch:
+   * the mailbox of a lane without a stream is read at the top (a predicated load whose latency the symbols hide), and
+   * whatever needs attention -- a stream that stopped, a posting that arrived, a service group that has no streams left --
+   * is looked at behind the trip, together.  While nothing is live the trips run empty; that is the idle loop. */
   for (;;) {
     uint32_t st = PZ_MS_SERVICE;
     pz_vload_if(!f.live && !dead, &sm->mail.state, st);
-    const bool pick = st == PZ_MS_HOT;
-    dead = dead || st == PZ_MS_DEAD;
-    const bool any_pick = __any_sync(0xffffffffu, pick), any_live = __any_sync(0xffffffffu, f.live);
-    if (any_pick) {
-      if (pick) {
-        pz_fence_cta();
-        f.bp = pz_vload(&sm->mail.bp); f.pos = pz_vload(&sm->mail.pos); f.base = pz_vload(&sm->mail.base);
-        f.lim = pz_vload(&sm->mail.lim); f.safe_end = pz_vload(&sm->mail.safe_end); f.qhead = pz_vload(&sm->mail.qhead);
-        if (BLK) f.mark = pz_vload(&sm->mail.mark);
-        pz_fast_fetch(f, sm, f.bp);
-        f.live = true;
-      }
-    } else if (!any_live) { /* nothing to do yet (or any more): the trip below then runs empty, which is harmless */
-      if (__all_sync(0xffffffffu, dead)) break;
-      __nanosleep(100);
-    }
     /* PZ_TRIP symbols per trip: the input the trip can touch (PZ_TRIP x 48 bits + the 128-bit
      * look-ahead) lies in quarters q and q+1, which must be resident; a lane whose input is late
      * idles this trip */
@@ -1263,7 +1248,8 @@ PZ_DEV void pz_hot_warp(PzStreamSmem *slots, uint32_t n_slots) {
     const bool run = f.live && (f.bp >> PZ_QUARTER_SHIFT) + 1u < ring_hi;
     const bool stop = pz_fast_trip<COUNT_ONLY, BLK>(f, sm, run);
     if (run) pz_vstore(&sm->mail.hot_bp, f.bp);
-    if (__any_sync(0xffffffffu, stop)) {
+    const bool pick = st == PZ_MS_HOT, died = st == PZ_MS_DEAD;
+    if (__any_sync(0xffffffffu, stop || pick || died)) {
       const bool full = !COUNT_ONLY && f.qhead - f.qtailc >= PZ_QLEN;
       if (stop && full) pz_fast_fetch(f, sm, f.bp); /* stays live: the queue drains, the window is re-read */
       if (stop && !full) { /* hand the stream back: the careful path decides the next symbol */
@@ -1274,6 +1260,16 @@ PZ_DEV void pz_hot_warp(PzStreamSmem *slots, uint32_t n_slots) {
         pz_vstore(&sm->mail.state, PZ_MS_SERVICE);
         f.live = false;
       }
+      if (pick) {
+        pz_fence_cta();
+        f.bp = pz_vload(&sm->mail.bp); f.pos = pz_vload(&sm->mail.pos); f.base = pz_vload(&sm->mail.base);
+        f.lim = pz_vload(&sm->mail.lim); f.safe_end = pz_vload(&sm->mail.safe_end); f.qhead = pz_vload(&sm->mail.qhead);
+        if (BLK) f.mark = pz_vload(&sm->mail.mark);
+        pz_fast_fetch(f, sm, f.bp);
+        f.live = true;
+      }
+      dead = dead || died;
+      if (__all_sync(0xffffffffu, dead)) break;
     }
   }
 }

@@ -449,8 +449,12 @@ cudaError_t pz_launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uin
       pz_stored_copy_kernel<<<tiles < ctas ? tiles : ctas, PZ_ST_THREADS, 0, st>>>(job, tile);
     }
     if (phase != PZ_PHASE_K2) {
-      static const bool no_lean = getenv("PZ_NO_LEAN") != nullptr; /* A/B: the exact kernel alone, as before the lean one existed */
-      if (!no_lean && d_prog == nullptr) {
+      /* The lean kernel is OFF unless PZ_LEAN is set: measured on B200 (profiles/r02f_*, r02g_*) it is slower than the exact
+       * kernel alone (8.4 against 7.8 ms on config 2): a symbol costs the lone hot warp the same ~145 issue slots whether
+       * its body has 46 instructions or 67 (the chain of dependent ALU operations and two table loads sets the pace, not
+       * the instruction count), and every hand-over now waits for the writer.  Kept as a measured design alternative. */
+      static const bool lean = getenv("PZ_LEAN") != nullptr;
+      if (lean && d_prog == nullptr) {
         pz_inflate_kernel<false, false, true><<<grid, PZ_THREADS_PER_CTA, smem, st>>>(job);
         job.skip_done = 1; /* only what the lean kernel left PENDING: streams a writer's check refused */
       }

@@ -1,10 +1,10 @@
 #!/usr/bin/env python
 """Throughput of the incremental API (pz_stream_feed / pz_stream_pump / pz_stream_next): N concurrent
 `decompressIncremental` consumers, each fed its stream in K pieces, one pump (one kernel launch) per round.
-Prints one JSON line: decompressed GB/s end to end (host chunks in, host chunks out), per-round times, and
-the same run with PZ_OPT_STREAM_RESUME = 0 (every round decodes every stream from its first byte again,
-which is what the API did before the device-resident contexts) and with one pz_stream_feed per stream
-instead of one pz_stream_feed_many per round.
+Prints one JSON line: decompressed GB/s end to end (host chunks in, host chunks out), per-round times, the device
+and pinned host memory the contexts hold at their peak (they are O(1) in the stream: live input, the last 32 KiB of
+output plus room for one launch, a checkpoint), and the same run with one pz_stream_feed per stream instead of one
+pz_stream_feed_many per round.
 
   python tools/bench_incremental.py --streams 1024 --pieces 8
 """
@@ -57,9 +57,12 @@ def run(L, c, pieces: int, many: bool):
     assert done == n, (done, n)
     assert out_bytes == int(c.out_len.sum()), (out_bytes, int(c.out_len.sum()))
     resumed = sum(L.pz_stream_counter(s, _lib.PZ_SC_RESUMED) for s in streams)
+    mem = {"device_peak_bytes_per_context": max(L.pz_stream_counter(s, _lib.PZ_SC_DEVICE_PEAK) for s in streams),
+           "device_peak_bytes_all_contexts": sum(L.pz_stream_counter(s, _lib.PZ_SC_DEVICE_PEAK) for s in streams),
+           "host_bytes_all_contexts": sum(L.pz_stream_counter(s, _lib.PZ_SC_HOST_BYTES) for s in streams)}
     for s in streams:
         L.pz_stream_free(s)
-    return total, rounds, out_bytes, resumed
+    return total, rounds, out_bytes, resumed, mem
 
 
 def main():
@@ -71,15 +74,13 @@ def main():
     c = corpus.text256k(a.streams, workers=min(16, os.cpu_count() or 1))
     line = {"metric": "decompressed GB/s through the incremental API", "unit": "GB/s", "streams": a.streams, "pieces": a.pieces,
             "workload": f"{a.streams} x 256 KiB synthetic text (level 6), each stream fed in {a.pieces} pieces, one pz_stream_pump per round"}
-    for label, resume, many in (("warmup", 1, True), ("resumed", 1, True), ("resumed_single_feeds", 1, False), ("from_first_byte", 0, True)):
-        _lib.check(L.pz_set_option(2, resume), "pz_set_option")
-        total, rounds, out_bytes, resumed = run(L, c, a.pieces, many)
+    for label, many in (("warmup", True), ("resumed", True), ("resumed_single_feeds", False)):
+        total, rounds, out_bytes, resumed, mem = run(L, c, a.pieces, many)
         if label == "warmup":
             continue
         line[label] = {"value": out_bytes / total / 1e9, "seconds": total, "pump_ms": [round(r["pump_ms"], 2) for r in rounds],
                        "feed_ms": round(sum(r["feed_ms"] for r in rounds), 1), "drain_ms": round(sum(r["drain_ms"] for r in rounds), 1),
-                       "pump_ms_total": round(sum(r["pump_ms"] for r in rounds), 1), "launches_from_checkpoint": int(resumed)}
-    _lib.check(L.pz_set_option(2, 1), "pz_set_option")
+                       "pump_ms_total": round(sum(r["pump_ms"] for r in rounds), 1), "launches_from_checkpoint": int(resumed), "memory": mem}
     print(json.dumps(line))
 
 

@@ -439,7 +439,14 @@ def measure(ctx: Ctx, config: str, c, steps: int, warmup: int, headline: bool, s
         st2 = np.frombuffer(res, dtype=RES_DTYPE)
         assert (st2["status"] == 0).all() and (st2["adler_c"] == c.adler).all(), f"{config}: e2e verdicts differ"
         verify_bytes(c, config, hview, min(a.verify, 8) or 1, getattr(c, "first", 0))
-        line["e2e"] = {"value": out_bytes_total * e2e_steps / sec / 1e9, "unit": "GB/s",
+        ceiling = None
+        try:  # what N GPUs of one box can copy home at all (tools/pcie_ceiling.py, measured on this pool)
+            ceiling = json.load(open(os.path.join(ROOT, "profiles", "pcie_ceiling.json")))["d2h_GBps_by_gpus"].get(str(ctx.world))
+        except Exception:
+            pass
+        line["e2e"] = {"value": out_bytes_total * e2e_steps / sec / 1e9, "unit": "GB/s", "ceiling": ceiling,
+                       "ceiling_note": "aggregate pinned D2H GB/s of N GPUs on one box with the H2D copies running (profiles/pcie_ceiling.json): "
+                                       "the host side of the box bounds e2e, not the kernels",
                        "h2d_bytes_per_step": int(c.in_off[-1]) + 3 * 8 * (c.n + 1),
                        "d2h_bytes_per_step": int(c.out_off[-1]) + 48 * c.n, "steps": e2e_steps,
                        "api": "pz_inflate_batch_contig(host pinned in/out): H2D, kernels and D2H inside the timed region"}

@@ -1,0 +1,184 @@
+/*
+ * pz_fixed.cuh -- K5: small streams made of fixed-Huffman blocks, one LANE per stream.
+ *
+ * K1 gives every stream a slot of shared memory (two look-up tables, an input ring, a token queue) and a lane of the one
+ * hot warp of its SM: 28 chains per SM, each paced by the latency of its own symbol chain.  That is the right shape for a
+ * few thousand long streams and the wrong one for a million 4 KiB records (BASELINE configs[2]): there the parallelism is
+ * across streams, not inside them.  A record compressed with the fixed code (BTYPE 1, Deflate.hs:79-82, 241-251) needs no
+ * table at all -- the code is arithmetic: 7 bits for 256..279, 8 for 0..143 and 280..287, 9 for 144..255, 5-bit distances --
+ * so here a stream is ONE thread: it reads its bits with two aligned word loads per symbol, decodes the symbol from the
+ * bit-reversed window, writes literals and copies matches itself (byte by byte: the replicate semantics of copyChunked,
+ * OutputWindow.hs:94-101, come for free), and 2 048 of them per SM hide each other's latencies.  A loop iteration is either
+ * "one symbol" or "up to eight bytes of the pending copy", so lanes of a warp that sit in a long match hold the others up
+ * for at most a few iterations.
+ *
+ * The kernel only ever reports SUCCESS.  Anything else -- a header that is not a plain zlib header, a block that is not a
+ * fixed one, a symbol the reference cannot index, a distance beyond the output, the end of the input or of the caller's
+ * buffer in sight, a gap of more than 32 KiB between two moveWindow calls (PzCtx::mark: the window's base is then no
+ * longer the closed form) -- leaves the stream PENDING, and K1, launched behind, decodes it from its first byte with the
+ * reference's exact order of checks.  So every verdict other than plain success still comes from the one place that
+ * reproduces the reference, as with K2 (pz_stored.cuh).  Adler-32 is K3's, as for any other stream.
+ *
+ * Runs between K2 and K1 on batches of at least PZ_FIXED_MIN_STREAMS streams, for streams of at most PZ_FIXED_MAX_IN
+ * compressed bytes (a lone thread is slower than K1's hot lane: it is the number of streams that makes this path fast).
+ */
+#pragma once
+#include <stdint.h>
+
+#include "pz_device.cuh"
+
+#define PZ_FIXED_MAX_IN 16384u
+#ifndef PZ_FIXED_MIN_STREAMS
+#define PZ_FIXED_MIN_STREAMS 8192u
+#endif
+#define PZ_FIXED_THREADS 256
+
+/* Deflate.hs:160-237, indexed by symbol - 257 / distance symbol: base | extra bits << 16 */
+#ifdef PZ_HOSTSIM
+#define PZ_FX_TABLE static const
+#else
+#define PZ_FX_TABLE static __constant__
+#endif
+PZ_FX_TABLE uint32_t PZ_FX_LEN[29] = {
+    3 | 0 << 16, 4 | 0 << 16, 5 | 0 << 16, 6 | 0 << 16, 7 | 0 << 16, 8 | 0 << 16, 9 | 0 << 16, 10 | 0 << 16, 11 | 1 << 16, 13 | 1 << 16,
+    15 | 1 << 16, 17 | 1 << 16, 19 | 2 << 16, 23 | 2 << 16, 27 | 2 << 16, 31 | 2 << 16, 35 | 3 << 16, 43 | 3 << 16, 51 | 3 << 16, 59 | 3 << 16,
+    67 | 4 << 16, 83 | 4 << 16, 99 | 4 << 16, 115 | 4 << 16, 131 | 5 << 16, 163 | 5 << 16, 195 | 5 << 16, 227 | 5 << 16, 258 | 0 << 16};
+PZ_FX_TABLE uint32_t PZ_FX_DIST[30] = {
+    1 | 0 << 16, 2 | 0 << 16, 3 | 0 << 16, 4 | 0 << 16, 5 | 1 << 16, 7 | 1 << 16, 9 | 2 << 16, 13 | 2 << 16, 17 | 3 << 16, 25 | 3 << 16,
+    33 | 4 << 16, 49 | 4 << 16, 65 | 5 << 16, 97 | 5 << 16, 129 | 6 << 16, 193 | 6 << 16, 257 | 7 << 16, 385 | 7 << 16, 513 | 8 << 16, 769 | 8 << 16,
+    1025 | 9 << 16, 1537 | 9 << 16, 2049 | 10 << 16, 3073 | 10 << 16, 4097 | 11 << 16, 6145 | 11 << 16, 8193 | 12 << 16, 12289 | 12 << 16,
+    16385 | 13 << 16, 24577 | 13 << 16};
+
+/* One stream, start to finish, by the calling thread.  Returns true with *res filled (status PZ_OK last) if the stream
+ * decoded completely; false -- nothing of *res touched -- if it is K1's (see the header of this file). */
+template <bool COUNT_ONLY>
+PZ_DEV bool pz_fixed_stream(const uint8_t *in, uint64_t n64, uint8_t *out, uint64_t cap64, pz_result *res) {
+  if (n64 < 8u || n64 > PZ_FIXED_MAX_IN) return false;
+  const uint32_t n = (uint32_t)n64;
+  /* inflateWithHeaders (Zlib.hs:53-69): only a header that passes every check; FDICT skips four bytes */
+  const uint32_t cmf = in[0], flg = in[1];
+  if (((cmf << 8) | flg) % 31u != 0u || (cmf & 15u) != 8u || (cmf >> 4) > 7u) return false;
+  const uint32_t p = (flg & 0x20u) ? 6u : 2u;
+  if (p >= n || ((in[p] >> 1) & 3u) != 1u) return false; /* the first block decides whether the stream is tried at all */
+  const uint32_t cap = (COUNT_ONLY || cap64 > 0xfffdff00ull) ? 0xfffdff00u : (uint32_t)cap64;
+  /* bit positions count from the aligned word at or before the stream's first byte (the blob has 15 readable bytes of slack
+   * at both ends, pzcuda.h) */
+  const uint32_t mis = (uint32_t)((uintptr_t)in & 3u);
+  const uint32_t *w = reinterpret_cast<const uint32_t *>(in - mis);
+  uint32_t bp = (mis + p) * 8u;
+  const uint32_t end_bit = (mis + n) * 8u;
+  uint32_t pos = 0, mark = 0; /* bytes produced; bytes produced at the last moveWindow call (Monad.hs:338-347: after every match and block) */
+  uint32_t rem = 0, dist = 0; /* the pending copy */
+  uint32_t bfinal = 0;
+  bool in_block = false;
+  for (;;) {
+    if (rem != 0u) { /* emitPastChunk (Monad.hs:324-333): up to eight bytes of the copy per iteration */
+      const uint32_t c = rem < 8u ? rem : 8u;
+      if (!COUNT_ONLY) {
+        uint8_t *d = out + pos;
+        const uint8_t *q = d - dist;
+#pragma unroll
+        for (uint32_t j = 0; j < 8u; j++)
+          if (j < c) d[j] = q[j]; /* in order: a byte may be one this loop has just written (dist < len) */
+      }
+      pos += c;
+      rem -= c;
+      if (rem == 0u) mark = pos;
+      continue;
+    }
+    /* the 32 stream bits at bp: a length / distance pair of the fixed code takes at most 8 + 5 + 5 + 13 = 31 of them */
+    const uint32_t t = bp >> 5;
+    const uint32_t lo = pz_funnel_r(w[t], w[t + 1u], bp);
+    if (!in_block) { /* inflateBlock (Deflate.hs:65-104): BFINAL, BTYPE */
+      if (bp + 3u > end_bit || ((lo >> 1) & 3u) != 1u) return false;
+      bfinal = lo & 1u;
+      bp += 3u;
+      in_block = true;
+      continue;
+    }
+    /* the fixed literal/length code, first bit of a code = its most significant one (HuffmanTree.hs:73-83) */
+    const uint32_t r = pz_brev(lo) >> 23; /* the next nine stream bits as a number, first bit on top */
+    uint32_t sym, nb;
+    if ((r >> 2) < 24u) { sym = 256u + (r >> 2); nb = 7u; }
+    else if ((r >> 1) < 192u) { sym = (r >> 1) - 48u; nb = 8u; }
+    else if ((r >> 1) < 200u) { sym = 280u + ((r >> 1) - 192u); nb = 8u; }
+    else { sym = 144u + (r - 400u); nb = 9u; }
+    if (sym < 256u) { /* emitByte (Monad.hs:309-315) */
+      if (bp + nb > end_bit || pos >= cap || pos + 1u - mark > PZ_EXCESS) return false;
+      if (!COUNT_ONLY) out[pos] = (uint8_t)sym;
+      pos++;
+      bp += nb;
+      continue;
+    }
+    if (sym == 256u) { /* end of block: moveWindow, then the next block or the trailer (Deflate.hs:45-50) */
+      if (bp + nb > end_bit) return false;
+      bp += nb;
+      mark = pos;
+      in_block = false;
+      if (!bfinal) continue;
+      break;
+    }
+    if (sym > 285u) return false; /* lengthArray ! 286 / 287 (Deflate.hs:161,167): the exact kernel words it */
+    const uint32_t le = PZ_FX_LEN[sym - 257u];
+    const uint32_t len = (le & 0xffffu) + ((lo >> nb) & ~(0xffffffffu << (le >> 16)));
+    nb += le >> 16; /* <= 13 */
+    const uint32_t dsym = pz_brev((lo >> nb) & 31u) >> 27;
+    nb += 5u; /* <= 18 */
+    if (dsym > 29u) return false; /* distanceArray ! 30 / 31 (Deflate.hs:200,206) */
+    const uint32_t de = PZ_FX_DIST[dsym];
+    const uint32_t x = de >> 16; /* <= 13 */
+    dist = (de & 0xffffu) + ((lo >> nb) & ~(0xffffffffu << x));
+    nb += x; /* <= 31 */
+    /* what pz_match() checks: the distance lies inside what exists (OutputWindow.hs:82-89: below 64 KiB of output that is all
+     * of it, above it at least 32 KiB are retained), the bytes fit, and the gap rule */
+    if (bp + nb > end_bit || dist > pos || len > cap - pos || pos + len - mark > PZ_EXCESS) return false;
+    bp += nb;
+    if (COUNT_ONLY) { pos += len; mark = pos; }
+    else rem = len;
+  }
+  /* checkChecksum (Deflate.hs:52-63): to the next byte boundary, four bytes, most significant first; K3 compares */
+  const uint32_t tb = ((bp + 7u) >> 3) - mis; /* byte offset of the trailer in the stream */
+  if (tb + 4u > n) return false;
+  res->detail = 0;
+  res->out_len = pos;
+  res->adler_computed = 0;
+  res->adler_stored = ((uint32_t)in[tb] << 24) | ((uint32_t)in[tb + 1u] << 16) | ((uint32_t)in[tb + 2u] << 8) | in[tb + 3u];
+  res->err_bitpos = (uint64_t)(tb + 4u) * 8u;
+  res->payload[0] = 0;
+  /* bytes the reference has published when it reaches the trailer: the window's base after the last moveWindow call, in
+   * closed form because no gap exceeded 32 KiB (PzCtx::mark) */
+  res->payload[1] = pos >= 2u * PZ_EXCESS ? (int64_t)((pos / PZ_EXCESS - 1u) * PZ_EXCESS) : 0;
+#ifndef PZ_HOSTSIM
+  __threadfence();
+#endif
+  res->status = PZ_OK;
+  return true;
+}
+
+#ifndef PZ_HOSTSIM
+/* the sizing pass has no K2 in front of it to mark the streams */
+__global__ void __launch_bounds__(256)
+pz_mark_pending_kernel(const PzJob job) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < job.count) job.res[job.first + k].status = PZ_ST_PENDING;
+}
+
+template <bool COUNT_ONLY>
+__global__ void __launch_bounds__(PZ_FIXED_THREADS)
+pz_fixed_kernel(const PzJob job) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= job.count) return;
+  const uint32_t s = job.first + k;
+  pz_result *res = job.res + s;
+  if (res->status != PZ_ST_PENDING) return; /* K2 has finished it */
+  const uint64_t i0 = job.in_off[s], n = job.in_off[s + 1] - i0;
+  uint8_t *out = nullptr;
+  uint64_t cap = 0;
+  if (!COUNT_ONLY) {
+    const uint64_t o0 = job.out_off[s];
+    cap = job.out_off[s + 1] - o0;
+    out = job.out_blob + o0;
+  }
+  (void)pz_fixed_stream<COUNT_ONLY>(job.in_blob + i0, n, out, cap, res);
+}
+#endif

@@ -29,6 +29,7 @@ static_assert(PZ_HOT_SCHED_SERVICE + (PZ_WARPS_PER_CTA - 1u - PZ_HOT_SCHED_WARPS
               "warp roles do not add up: adjust PZ_PAD_WARPS");
 #define PZ_MAX_STREAM_BYTES 0x1ffffff0ull /* == PZ_MAX_IN_BYTES in pz_device.cuh */
 #define PZ_ADLER_SEG 16384u /* bytes per checksum segment (one warp each) */
+#define PZ_FIXED_MIN_STREAMS 8192u /* batches from this size on run K5 (pz_fixed.cuh: a lane per small fixed-Huffman stream) between K2 and K1 */
 
 /* Stream s = first + k decodes in_blob[in_off[s], in_off[s+1]) into out_blob[out_off[s], out_off[s+1]).
  * d_out == nullptr selects the sizing pass.  d_prog (optional, host-mapped, one word per stream, zeroed by

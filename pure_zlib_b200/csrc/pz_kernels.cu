@@ -7,6 +7,8 @@
  *                            the tokens to the output (pz_device.cuh)
  *   pz_stored_probe_kernel,  K2: streams made of stored blocks only are copied with 16-byte
  *   pz_stored_copy_kernel    accesses by whole CTAs before K1 runs (pz_stored.cuh)
+ *   pz_fixed_kernel          K5: big batches of small streams: every fixed-Huffman stream is decoded by ONE thread
+ *                            (no tables: the fixed code is arithmetic) between K2 and K1 (pz_fixed.cuh)
  *   pz_adler_partial_kernel  K3a: one warp per 16 KiB segment of decoded output, dp4a sums
  *   pz_adler_finish_kernel   K3b: per stream, combines the segments (adler32-combine
  *                            identity) and compares with the stored trailer
@@ -18,6 +20,7 @@
 #include "pz_device.cuh"
 #include "pz_internal.h"
 #include "pz_stored.cuh"
+#include "pz_fixed.cuh"
 #include "pz_huge.cuh"
 
 /* Warp roles.  A CTA owns PZ_SLOTS stream slots: warp 0 is the hot warp (one lane per slot),
@@ -434,7 +437,14 @@ cudaError_t pz_launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uin
     phase = PZ_PHASE_K1;
   }
   if (d_in_ready) job.skip_done = 0; /* K2 would read input that is not there yet: K1 decodes every stream */
+  static const bool no_k5 = getenv("PZ_NO_K5") != nullptr; /* A/B */
+  const bool k5 = !no_k5 && count >= PZ_FIXED_MIN_STREAMS && framing == PZ_FRAME_ZLIB && d_in_ready == nullptr;
   if (count_only) {
+    if (k5) { /* K5 sizes the small fixed-Huffman streams, K1 what it left */
+      pz_mark_pending_kernel<<<(count + 255u) / 256u, 256, 0, st>>>(job);
+      pz_fixed_kernel<true><<<(count + PZ_FIXED_THREADS - 1u) / PZ_FIXED_THREADS, PZ_FIXED_THREADS, 0, st>>>(job);
+      job.skip_done = 1;
+    }
     pz_inflate_kernel<true><<<grid, PZ_THREADS_PER_CTA, smem, st>>>(job);
   } else if (d_in_ready) {
     pz_inflate_kernel<false><<<grid, PZ_THREADS_PER_CTA, smem, st>>>(job);
@@ -447,6 +457,7 @@ cudaError_t pz_launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uin
       tile = tile < 1u ? 1u : (tile > PZ_ST_THREADS ? PZ_ST_THREADS : tile);
       const unsigned tiles = (count + tile - 1u) / tile;
       pz_stored_copy_kernel<<<tiles < ctas ? tiles : ctas, PZ_ST_THREADS, 0, st>>>(job, tile);
+      if (k5) pz_fixed_kernel<false><<<(count + PZ_FIXED_THREADS - 1u) / PZ_FIXED_THREADS, PZ_FIXED_THREADS, 0, st>>>(job);
     }
     if (phase != PZ_PHASE_K2) {
       /* The lean kernel is OFF unless PZ_LEAN is set: measured on B200 (profiles/r02f_*, r02g_*) it is slower than the exact

@@ -9,6 +9,7 @@
  */
 #define PZ_HOSTSIM 1
 #include "../../pure_zlib_b200/csrc/pz_device.cuh"
+#include "../../pure_zlib_b200/csrc/pz_fixed.cuh"
 
 #include <stdlib.h>
 
@@ -56,3 +57,14 @@ extern "C" int hs_inflate(const uint8_t *in, uint64_t in_len, uint8_t *out, uint
 }
 
 extern "C" int hs_smem_bytes(void) { return (int)sizeof(PzStreamSmem); }
+
+/* K5's per-stream logic (pz_fixed.cuh) on the host: 1 if the stream decoded completely (res filled), 0 if it is left to K1 */
+extern "C" int hs_fixed(const uint8_t *in, uint64_t in_len, uint8_t *out, uint64_t out_cap, pz_result *res, int count_only) {
+  size_t mis = 3; /* an odd misalignment of the stream inside its (padded) buffer */
+  uint8_t *buf = (uint8_t *)aligned_alloc(16, ((in_len + mis + 15) & ~(size_t)15) + 64);
+  memset(buf, 0x5A, ((in_len + mis + 15) & ~(size_t)15) + 64);
+  memcpy(buf + mis, in, in_len);
+  const bool ok = count_only ? pz_fixed_stream<true>(buf + mis, in_len, nullptr, 0, res) : pz_fixed_stream<false>(buf + mis, in_len, out, out_cap, res);
+  free(buf);
+  return ok ? 1 : 0;
+}

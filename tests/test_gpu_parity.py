@@ -325,7 +325,7 @@ def _run_corpus(c):
     return rec, d_out
 
 
-@pytest.mark.parametrize("name,n", [("text256k", 512), ("records4k", 40_000), ("stored16m", 12)])
+@pytest.mark.parametrize("name,n", [("text256k", 512), ("records4k", 200_000), ("stored16m", 12)])
 def test_baseline_config_properties(pz, name, n):
     """Every stream OK, decoded length and Adler-32 equal to the generator's (the checksum of each
     output is the domain's size-independent check), spot streams byte-for-byte."""
@@ -340,6 +340,60 @@ def test_baseline_config_properties(pz, name, n):
     for i in np.linspace(0, c.n - 1, 8).astype(int):
         o = int(c.out_off[i])
         assert host[o:o + int(c.out_len[i])].tobytes() == corpus.decoded(c, int(i)), (name, i)
+    if name == "records4k":  # a sample against the oracle: fixed-Huffman records (K5) and dynamic ones (K1) alike
+        from oracle import oracle as orc
+        for i in np.linspace(0, c.n - 1, 300).astype(int):
+            z = bytes(c.in_blob[int(c.in_off[i]): int(c.in_off[i]) + int(c.in_len[i])])
+            v = orc.decompress(z, want_events=True)
+            o = int(c.out_off[i])
+            assert v.status == 0 and host[o:o + int(c.out_len[i])].tobytes() == v.data, i
+            assert (int(rec["out_len"][i]), int(rec["adler_c"][i]), int(rec["p1"][i])) == \
+                (v.out_len, v.adler_computed, sum(ln for kind, ln in v.events[:-2] if kind == 1)), i
+
+
+def test_small_stream_batch_mixed_verdicts(pz, oracle):
+    """A batch big enough for K5 (one thread per small fixed-Huffman stream, pz_fixed.cuh) whose streams are of every
+    kind: fixed, dynamic and stored, several blocks, and faults (truncated, flipped bits, bad checksum, symbols the
+    reference cannot index).  K5 only ever reports success; everything else must come out of K1 with the reference's
+    verdict -- through the decode, the one-call decode and the sizing pass."""
+    from pure_zlib_b200 import _lib
+    rng = np.random.default_rng(77)
+    base = []
+    for i in range(300):
+        n = int(rng.integers(0, 6000))
+        data = streams.small_text(n, 3000 + i) if i % 4 else bytes(rng.integers(0, 3, n, dtype=np.uint8))
+        strat = [zlib.Z_FIXED, zlib.Z_FIXED, zlib.Z_DEFAULT_STRATEGY, zlib.Z_HUFFMAN_ONLY][i % 4]
+        co = zlib.compressobj(int(rng.integers(1, 10)), zlib.DEFLATED, 15, 8, strat)
+        z = co.compress(data[: n // 2]) + (co.flush(zlib.Z_BLOCK) if i % 3 == 0 else b"") + co.compress(data[n // 2:]) + co.flush()
+        base.append(z)
+    faults = []
+    for i, z in enumerate(base[:120]):
+        b = bytearray(z)
+        if i % 4 == 0 and len(b) > 8:
+            b = b[: int(rng.integers(1, len(b)))]
+        elif i % 4 == 1 and len(b) > 8:
+            b[int(rng.integers(2, len(b)))] ^= 1 << int(rng.integers(0, 8))
+        elif i % 4 == 2:
+            b[-1] ^= 0x55
+        else:
+            b += b"trailing"
+        faults.append(bytes(b))
+    faults += [v[1] for v in streams.appendix_b_vectors()]
+    cases = (base + faults) * 24           # 10 000+ streams: above PZ_FIXED_MIN_STREAMS
+    assert len(cases) >= 8192
+    want = {}
+    for fn in (pz.zlib.decompress_batch_raw, pz.zlib.inflate_batch_raw):
+        res, outs = fn(cases)
+        for i in list(range(len(base) + len(faults))) + [len(cases) - 1 - k for k in range(50)]:
+            z = cases[i]
+            o = want.setdefault(z, oracle.decompress(z))
+            r = res[i]
+            assert (r.status, r.detail, r.out_len) == (o.status, o.detail, o.out_len), (i, r.status, r.detail, r.out_len, o.message)
+            assert outs[i] == o.data, i
+            if o.status in (0, 5):
+                assert (r.adler_computed, r.adler_stored) == (o.adler_computed, o.adler_stored), i
+            if o.status != 0:
+                assert _lib.strerror(r) == o.message, i
 
 
 def test_sizing_pass_matches_decode(pz):

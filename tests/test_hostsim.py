@@ -153,3 +153,104 @@ def test_gzip_and_raw_framing():
                 assert out == o.data, name
             if o.status == 0 and fr == 1:
                 assert r.adler_stored == o.adler_stored and r.payload[0] == o.out_len, name
+
+
+# ---- K5 (pz_fixed.cuh): one thread per small fixed-Huffman stream -----------------------------------------------------
+def _fixed_stream(data: bytes, level: int = 6, blocks: int = 1) -> bytes:
+    co = zlib.compressobj(level, zlib.DEFLATED, 15, 8, zlib.Z_FIXED)
+    step = max(1, (len(data) + blocks - 1) // blocks)
+    out = b""
+    for k in range(0, max(len(data), 1), step):
+        out += co.compress(data[k:k + step])
+        if k + step < len(data):
+            out += co.flush(zlib.Z_BLOCK)     # ends the block, no empty stored block: the next one is fixed again
+    return out + co.flush()
+
+
+def _check_fixed(z: bytes, expect_taken=None):
+    """What K5 completes must be the oracle's success, field by field; what the oracle does not call a success
+    K5 must leave to K1 (it never reports anything but success)."""
+    o = oracle.decompress(z, want_events=True)
+    for count_only in (False, True):
+        ok, r, out = hostsim.fixed(z, o.out_len + 64 if o.status == 0 else max(o.out_len, 1) + 64, count_only)
+        if o.status != 0:
+            assert not ok, (z.hex()[:120], o.message)
+            continue
+        if expect_taken is not None:
+            assert ok == expect_taken, (expect_taken, z.hex()[:80])
+        if not ok:
+            continue
+        published = sum(ln for kind, ln in o.events[:-2] if kind == 1)
+        assert (r.status, r.detail, r.out_len, r.adler_stored, r.payload[1]) == (0, 0, o.out_len, o.adler_stored, published), \
+            (r.out_len, o.out_len, r.payload[1], published)
+        if not count_only:
+            assert out == o.data
+        # err_bitpos is what K1 reports for the same stream
+        r1, _ = hostsim.inflate(z, o.out_len + 64)
+        assert r.err_bitpos == r1.err_bitpos
+    return o
+
+
+def test_fixed_kernel_logic_valid_streams():
+    import numpy as np
+    rng = np.random.default_rng(3)
+    taken = 0
+    for i in range(120):
+        n = int(rng.integers(0, 9000))
+        kind = i % 4
+        data = streams.small_text(n, i) if kind < 2 else rng.integers(0, 256, n, dtype=np.uint8).tobytes() if kind == 2 else bytes(n)
+        z = _fixed_stream(data, int(rng.integers(1, 10)), int(rng.integers(1, 4)))
+        if len(z) <= 16384:
+            # (random bytes leave zlib as STORED blocks even with Z_FIXED: K5 rightly leaves those alone)
+            _check_fixed(z, expect_taken=None if kind == 2 else True)
+            taken += kind != 2
+    assert taken > 80
+    # FDICT is skipped (Zlib.hs:68): the header's check bits have to fit the flag
+    z = bytearray(_fixed_stream(b"hello hello hello"))
+    body = bytes(z[2:])
+    hdr = bytes([0x78, 0xbb])
+    assert (hdr[0] * 256 + hdr[1]) % 31 == 0
+    o = _check_fixed(hdr + b"\xde\xad\xbe\xef" + body, expect_taken=True)
+    assert o.data == b"hello hello hello"
+    # streams K5 must not take although they are fine: a dynamic or stored first block, a dynamic block further on, too long
+    _check_fixed(zlib.compress(streams.small_text(3000, 1), 6), expect_taken=False)
+    _check_fixed(zlib.compress(rng.integers(0, 256, 3000, dtype=np.uint8).tobytes(), 6), expect_taken=False)
+    co = zlib.compressobj(6, zlib.DEFLATED, 15, 8, zlib.Z_FIXED)
+    z = co.compress(streams.small_text(2000, 2)) + co.flush(zlib.Z_FULL_FLUSH) + co.compress(b"tail") + co.flush()
+    _check_fixed(z, expect_taken=False)  # the flush leaves an empty stored block between the fixed ones
+    _check_fixed(_fixed_stream(streams.small_text(60000, 9)), expect_taken=False)
+    # more than 64 KiB of output (the window slides, payload[1] moves) does not fit 16 KiB of fixed-coded text; zeros do
+    _check_fixed(_fixed_stream(bytes(200_000)), expect_taken=True)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_fixed_kernel_logic_fuzz(seed):
+    """Mutated fixed-Huffman streams: whatever K5 completes is the oracle's success; every other verdict is K1's."""
+    import numpy as np
+    rng = np.random.default_rng(100 + seed)
+    done = left = 0
+    for i in range(300):
+        n = int(rng.integers(1, 3000))
+        data = streams.small_text(n, 1000 * seed + i) if i % 3 else bytes(rng.integers(0, 4, n, dtype=np.uint8))
+        z = bytearray(_fixed_stream(data, 6, int(rng.integers(1, 3))))
+        how = i % 5
+        if how == 0:
+            z = z[: int(rng.integers(0, len(z)))]                       # truncated
+        elif how == 1:
+            for _ in range(int(rng.integers(1, 4))):
+                z[int(rng.integers(0, len(z)))] ^= 1 << int(rng.integers(0, 8))   # bit flips
+        elif how == 2:
+            z[-1] ^= 0xff                                                # checksum (K3's verdict: K5 completes the stream)
+        elif how == 3:
+            z += bytes(rng.integers(0, 256, int(rng.integers(0, 9)), dtype=np.uint8))  # bytes behind the trailer
+        z = bytes(z)
+        o = oracle.decompress(z, want_events=True)
+        ok, r, out = hostsim.fixed(z, max(o.out_len, 1) + 64)
+        if o.status in (0, 5):  # success, or success up to the checksum comparison
+            if ok:
+                assert (r.out_len, r.adler_stored) == (o.out_len, o.adler_stored) and out == o.data
+                done += 1
+        else:
+            assert not ok, (z.hex()[:100], o.message, r.out_len)
+            left += 1
+    assert done > 60 and left > 40, (done, left)

@@ -289,9 +289,10 @@ struct PzJob {
   const uint32_t *resume = nullptr;
   uint32_t *ckpt = nullptr;
   uint32_t pair_off = 0;
-  /* Optional (block jobs): a zeroed device counter.  Units are then CLAIMED in order by whichever slot is free
-   * instead of being dealt out by index: blocks differ in length, and with two or three units per slot the
-   * longest deal sets the time of the launch. */
+  /* Optional: a zeroed device counter.  Units are then CLAIMED in order by whichever slot is free instead of being dealt
+   * out by index.  Block jobs: blocks differ in length, and with two or three units per slot the longest deal sets the
+   * time of the launch.  Batches behind K2 / K5: what those kernels left is no longer spread evenly over the slots (a
+   * corpus whose every fourth record is a dynamic one leaves ALL of K1's work to the CTAs whose index is 3 mod 4). */
   uint32_t *next_unit = nullptr;
   /* Framing of every stream of the job (PZ_FRAME_*).  zlib (RFC 1950) is the reference's; gzip members (RFC 1952)
    * and raw deflate are the extension its README names as the first TODO (README.md:42-50). */
@@ -1720,13 +1721,13 @@ PZ_DEV void pz_block_end(PzCtx &c, PzStreamSmem *sm) {
 template <bool COUNT_ONLY>
 PZ_DEV void pz_slow_step(PzCtx &c, PzStreamSmem *sm, const PzJob &job, uint32_t stride) {
   if (c.mode == PZ_M_IDLE) {
-    while (job.skip_done && c.next < job.first + job.count && job.res[c.next].status != PZ_ST_PENDING) {
+    while (job.next_unit == nullptr && job.skip_done && c.next < job.first + job.count && job.res[c.next].status != PZ_ST_PENDING) {
 #ifndef PZ_HOSTSIM
       if (job.prog != nullptr && pz_lane() == 0) *(volatile uint32_t *)(job.prog + c.next) = PZ_PROG_DONE; /* K2 wrote it before K1 started */
 #endif
       c.next += stride;
     }
-    if (job.next_unit != nullptr) { /* claim the next unit nobody has taken */
+    while (job.next_unit != nullptr) { /* claim the next unit nobody has taken (and that nobody has finished: K2, K5) */
       uint32_t v = 0;
 #ifdef PZ_HOSTSIM
       v = (*job.next_unit)++;
@@ -1735,6 +1736,7 @@ PZ_DEV void pz_slow_step(PzCtx &c, PzStreamSmem *sm, const PzJob &job, uint32_t 
       v = (uint32_t)pz_shfl((int)v, 0);
 #endif
       c.next = v < job.count ? job.first + v : job.first + job.count;
+      if (c.next >= job.first + job.count || !job.skip_done || job.res[c.next].status == PZ_ST_PENDING) break;
     }
     if (c.next >= job.first + job.count) {
       pz_push<COUNT_ONLY>(c, sm, PZ_TOKEN(PZ_Q_CTRL, PZ_C_EXIT << 26));

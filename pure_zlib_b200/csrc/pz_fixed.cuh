@@ -12,6 +12,14 @@
  * "one symbol" or "up to eight bytes of the pending copy", so lanes of a warp that sit in a long match hold the others up
  * for at most a few iterations.
  *
+ * Memory.  Thirty-two lanes of a warp write thirty-two different streams, so every access is a transaction of its own and
+ * the kernel is bound by their number, not by instructions (the sizing pass, which touches no output, runs eight times
+ * faster).  Output therefore leaves a lane as aligned 32-bit words: produced bytes are collected in a register (`acc`: the
+ * bytes of the word that contains position pos) and stored when the word is full, and a match whose source lies at least
+ * 11 bytes back -- every byte it reads is then in memory, not in the register -- is copied eight bytes at a time from
+ * three aligned word loads.  Closer matches (the replicate case, a few per cent of text) take the byte-wise path between a
+ * flush and a reload of the register.
+ *
  * The kernel only ever reports SUCCESS.  Anything else -- a header that is not a plain zlib header, a block that is not a
  * fixed one, a symbol the reference cannot index, a distance beyond the output, the end of the input or of the caller's
  * buffer in sight, a gap of more than 32 KiB between two moveWindow calls (PzCtx::mark: the window's base is then no
@@ -71,15 +79,48 @@ PZ_DEV bool pz_fixed_stream(const uint8_t *in, uint64_t n64, uint8_t *out, uint6
   uint32_t rem = 0, dist = 0; /* the pending copy */
   uint32_t bfinal = 0;
   bool in_block = false;
+  /* output as aligned words (see above): acc holds the bytes [pos & ~3, pos) of the output, which are NOT in memory yet */
+  const bool wide = !COUNT_ONLY && ((uintptr_t)out & 3u) == 0u;
+  uint32_t acc = 0;
   for (;;) {
     if (rem != 0u) { /* emitPastChunk (Monad.hs:324-333): up to eight bytes of the copy per iteration */
       const uint32_t c = rem < 8u ? rem : 8u;
       if (!COUNT_ONLY) {
-        uint8_t *d = out + pos;
-        const uint8_t *q = d - dist;
+        if (wide && dist >= 11u) { /* the source bytes [pos - dist, pos - dist + 8) lie below pos & ~3: all in memory */
+          const uint8_t *q = out + pos - dist;
+          const uint32_t *qa = reinterpret_cast<const uint32_t *>((uintptr_t)q & ~(uintptr_t)3);
+          const uint32_t qs = (uint32_t)((uintptr_t)q & 3u) * 8u;
+          const uint32_t s0 = qa[0], s1 = qa[1], s2 = qa[2];
+          uint64_t v = (uint64_t)pz_funnel_r(s0, s1, qs) | ((uint64_t)pz_funnel_r(s1, s2, qs) << 32);
+          if (c < 8u) v &= ~(~0ull << (8u * c));
+          /* append c bytes behind the a pending ones: up to 11 bytes = two full words and a rest */
+          const uint32_t a = pos & 3u;
+          const uint64_t comb = (uint64_t)acc | (v << (8u * a));
+          const uint32_t over = a ? (uint32_t)(v >> (64u - 8u * a)) : 0u;
+          const uint32_t total = a + c, full = total >> 2;
+          uint32_t *dw = reinterpret_cast<uint32_t *>(out + (pos & ~3u));
+          if (full >= 1u) dw[0] = (uint32_t)comb;
+          if (full >= 2u) dw[1] = (uint32_t)(comb >> 32);
+          const uint32_t restw = full == 0u ? (uint32_t)comb : full == 1u ? (uint32_t)(comb >> 32) : over;
+          const uint32_t rb = total & 3u;
+          acc = rb ? restw & ~(0xffffffffu << (8u * rb)) : 0u;
+        } else {
+          uint8_t *d = out + pos;
+          if (wide) { /* the pending bytes go to memory first: the copy may read them */
+            const uint32_t a = pos & 3u;
 #pragma unroll
-        for (uint32_t j = 0; j < 8u; j++)
-          if (j < c) d[j] = q[j]; /* in order: a byte may be one this loop has just written (dist < len) */
+            for (uint32_t j = 0; j < 3u; j++)
+              if (j < a) d[(int32_t)j - (int32_t)a] = (uint8_t)(acc >> (8u * j));
+          }
+          const uint8_t *q = d - dist;
+#pragma unroll
+          for (uint32_t j = 0; j < 8u; j++)
+            if (j < c) d[j] = q[j]; /* in order: a byte may be one this loop has just written (dist < len) */
+          if (wide) { /* and the register takes the bytes of the word the output now ends in */
+            const uint32_t np = pos + c, a2 = np & 3u;
+            acc = a2 ? *reinterpret_cast<const uint32_t *>(out + (np & ~3u)) & ~(0xffffffffu << (8u * a2)) : 0u;
+          }
+        }
       }
       pos += c;
       rem -= c;
@@ -105,7 +146,14 @@ PZ_DEV bool pz_fixed_stream(const uint8_t *in, uint64_t n64, uint8_t *out, uint6
     else { sym = 144u + (r - 400u); nb = 9u; }
     if (sym < 256u) { /* emitByte (Monad.hs:309-315) */
       if (bp + nb > end_bit || pos >= cap || pos + 1u - mark > PZ_EXCESS) return false;
-      if (!COUNT_ONLY) out[pos] = (uint8_t)sym;
+      if (!COUNT_ONLY) {
+        if (wide) {
+          acc |= sym << (8u * (pos & 3u));
+          if ((pos & 3u) == 3u) { *reinterpret_cast<uint32_t *>(out + (pos & ~3u)) = acc; acc = 0u; }
+        } else {
+          out[pos] = (uint8_t)sym;
+        }
+      }
       pos++;
       bp += nb;
       continue;
@@ -139,6 +187,10 @@ PZ_DEV bool pz_fixed_stream(const uint8_t *in, uint64_t n64, uint8_t *out, uint6
   /* checkChecksum (Deflate.hs:52-63): to the next byte boundary, four bytes, most significant first; K3 compares */
   const uint32_t tb = ((bp + 7u) >> 3) - mis; /* byte offset of the trailer in the stream */
   if (tb + 4u > n) return false;
+  if (wide) { /* the last, incomplete word */
+    const uint32_t a = pos & 3u;
+    for (uint32_t j = 0; j < a; j++) out[(pos & ~3u) + j] = (uint8_t)(acc >> (8u * j));
+  }
   res->detail = 0;
   res->out_len = pos;
   res->adler_computed = 0;

@@ -372,6 +372,23 @@ pz_gather_kernel(const uint64_t *__restrict__ g) {
 static int g_inflate_ctas_per_sm[2] = {0, 0};
 static int g_sm_count = 0;
 
+/* Unit counters for launches that claim their streams (PzJob::next_unit): a ring of words per device, one word per launch,
+ * zeroed on the launch's stream right before it (a word comes round again after 1024 launches). */
+#include <atomic>
+static uint32_t *g_claim_ring[PZ_MAX_DEVICES] = {};
+static std::atomic<unsigned> g_claim_next{0};
+static cudaError_t pz_claim_counter(cudaStream_t st, uint32_t **out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= PZ_MAX_DEVICES) { *out = nullptr; return cudaSuccess; }
+  if (g_claim_ring[dev] == nullptr) { *out = nullptr; return cudaSuccess; } /* not configured: deal by index */
+  uint32_t *p = g_claim_ring[dev] + (g_claim_next++ % 1024u);
+  e = cudaMemsetAsync(p, 0, sizeof(uint32_t), st);
+  *out = e == cudaSuccess ? p : nullptr;
+  return e;
+}
+
 /* Function attributes belong to the CURRENT device's context: call once per device the library uses. */
 cudaError_t pz_kernels_configure(void) {
   cudaError_t e;
@@ -379,6 +396,7 @@ cudaError_t pz_kernels_configure(void) {
   int dev = 0;
   if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
   if ((e = cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+  if (dev >= 0 && dev < PZ_MAX_DEVICES && g_claim_ring[dev] == nullptr && (e = cudaMalloc(&g_claim_ring[dev], 1024 * sizeof(uint32_t))) != cudaSuccess) return e;
   e = cudaFuncSetAttribute(pz_inflate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(pz_inflate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -444,6 +462,8 @@ cudaError_t pz_launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uin
       pz_mark_pending_kernel<<<(count + 255u) / 256u, 256, 0, st>>>(job);
       pz_fixed_kernel<true><<<(count + PZ_FIXED_THREADS - 1u) / PZ_FIXED_THREADS, PZ_FIXED_THREADS, 0, st>>>(job);
       job.skip_done = 1;
+      cudaError_t e = pz_claim_counter(st, &job.next_unit);
+      if (e != cudaSuccess) return e;
     }
     pz_inflate_kernel<true><<<grid, PZ_THREADS_PER_CTA, smem, st>>>(job);
   } else if (d_in_ready) {
@@ -459,6 +479,10 @@ cudaError_t pz_launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uin
       pz_stored_copy_kernel<<<tiles < ctas ? tiles : ctas, PZ_ST_THREADS, 0, st>>>(job, tile);
       if (k5) pz_fixed_kernel<false><<<(count + PZ_FIXED_THREADS - 1u) / PZ_FIXED_THREADS, PZ_FIXED_THREADS, 0, st>>>(job);
     }
+    if (phase != PZ_PHASE_K2 && job.skip_done && count > (unsigned)pz_inflate_slots()) { /* more streams than slots, some of them finished already: claim */
+      cudaError_t e = pz_claim_counter(st, &job.next_unit);
+      if (e != cudaSuccess) return e;
+    }
     if (phase != PZ_PHASE_K2) {
       /* The lean kernel is OFF unless PZ_LEAN is set: measured on B200 (profiles/r02f_*, r02g_*) it is slower than the exact
        * kernel alone (8.4 against 7.8 ms on config 2): a symbol costs the lone hot warp the same ~145 issue slots whether
@@ -468,6 +492,7 @@ cudaError_t pz_launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uin
       if (lean && d_prog == nullptr) {
         pz_inflate_kernel<false, false, true><<<grid, PZ_THREADS_PER_CTA, smem, st>>>(job);
         job.skip_done = 1; /* only what the lean kernel left PENDING: streams a writer's check refused */
+        if (job.next_unit != nullptr) { cudaError_t e = pz_claim_counter(st, &job.next_unit); if (e != cudaSuccess) return e; }
       }
       pz_inflate_kernel<false><<<grid, PZ_THREADS_PER_CTA, smem, st>>>(job);
     }

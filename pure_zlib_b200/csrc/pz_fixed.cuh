@@ -27,6 +27,14 @@
  * reference's exact order of checks.  So every verdict other than plain success still comes from the one place that
  * reproduces the reference, as with K2 (pz_stored.cuh).  Adler-32 is K3's, as for any other stream.
  *
+ * DYNAMIC blocks (DYN = true, the second kernel of this file: K6).  zlib writes a dynamic block for 4 KiB of text unless told
+ * otherwise, so the same one-thread-per-stream decoder also exists with tables: the thread parses the block header itself
+ * (Deflate.hs:83-101, 124-156), builds a 10-bit literal/length and a 9-bit distance look-up table in its LOCAL memory
+ * (3 KiB per thread, served by L1 / L2: a look-up costs a few hundred cycles, and a few hundred threads per SM wait
+ * for one at any time -- K1 has 28 chains per SM, here there are up to 1 024) and decodes with them.  It takes exactly what
+ * zlib's tree builder emits and nothing else: more than 286 / 30 codes, a repeat code that starts the list or runs past it,
+ * an over-subscribed code, no end-of-block code, a code longer than its table's index, an unused table entry -- all K1's.
+ *
  * Runs between K2 and K1 on batches of at least PZ_FIXED_MIN_STREAMS streams, for streams of at most PZ_FIXED_MAX_IN
  * compressed bytes (a lone thread is slower than K1's hot lane: it is the number of streams that makes this path fast).
  */
@@ -59,15 +67,30 @@ PZ_FX_TABLE uint32_t PZ_FX_DIST[30] = {
 
 /* One stream, start to finish, by the calling thread.  Returns true with *res filled (status PZ_OK last) if the stream
  * decoded completely; false -- nothing of *res touched -- if it is K1's (see the header of this file). */
-template <bool COUNT_ONLY>
+#ifndef PZ_SM_LIT_BITS
+#define PZ_SM_LIT_BITS 10 /* K6: index bits of a thread's literal/length table (entries: symbol | code length << 9) */
+#endif
+#ifndef PZ_SM_DIST_BITS
+#define PZ_SM_DIST_BITS 9 /* ... and of its distance table (entries: symbol | code length << 5) */
+#endif
+template <bool COUNT_ONLY, bool DYN = false>
 PZ_DEV bool pz_fixed_stream(const uint8_t *in, uint64_t n64, uint8_t *out, uint64_t cap64, pz_result *res) {
+  /* K6's tables: thread-private, i.e. local memory */
+  uint16_t lit_t[DYN ? (1 << PZ_SM_LIT_BITS) : 1];
+  uint16_t dist_t[DYN ? (1 << PZ_SM_DIST_BITS) : 1];
+  uint8_t lens[DYN ? 320 : 1];
+  uint8_t pre_t[DYN ? 128 : 1];
+  bool dyn_block = false;
   if (n64 < 8u || n64 > PZ_FIXED_MAX_IN) return false;
   const uint32_t n = (uint32_t)n64;
   /* inflateWithHeaders (Zlib.hs:53-69): only a header that passes every check; FDICT skips four bytes */
   const uint32_t cmf = in[0], flg = in[1];
   if (((cmf << 8) | flg) % 31u != 0u || (cmf & 15u) != 8u || (cmf >> 4) > 7u) return false;
   const uint32_t p = (flg & 0x20u) ? 6u : 2u;
-  if (p >= n || ((in[p] >> 1) & 3u) != 1u) return false; /* the first block decides whether the stream is tried at all */
+  {
+    const uint32_t bt = p < n ? (in[p] >> 1) & 3u : 3u; /* the first block decides whether the stream is tried at all */
+    if (!(bt == 1u || (DYN && bt == 2u))) return false;
+  }
   const uint32_t cap = (COUNT_ONLY || cap64 > 0xfffdff00ull) ? 0xfffdff00u : (uint32_t)cap64;
   /* bit positions count from the aligned word at or before the stream's first byte (the blob has 15 readable bytes of slack
    * at both ends, pzcuda.h) */
@@ -75,6 +98,12 @@ PZ_DEV bool pz_fixed_stream(const uint8_t *in, uint64_t n64, uint8_t *out, uint6
   const uint32_t *w = reinterpret_cast<const uint32_t *>(in - mis);
   uint32_t bp = (mis + p) * 8u;
   const uint32_t end_bit = (mis + n) * 8u;
+  /* The bits at bp live in a 64-bit register that takes one aligned word whenever fewer than 33 are left (a symbol needs at
+   * most 31): one load per 32 bits of input instead of two per symbol -- in this kernel every load of a lane is a
+   * transaction of its own, and their number is what bounds it. */
+  uint32_t wi = (bp >> 5) + 1u;                /* next word to take */
+  uint64_t bb = (uint64_t)w[bp >> 5] >> (bp & 31u);
+  uint32_t bc = 32u - (bp & 31u);              /* valid bits in bb */
   uint32_t pos = 0, mark = 0; /* bytes produced; bytes produced at the last moveWindow call (Monad.hs:338-347: after every match and block) */
   uint32_t rem = 0, dist = 0; /* the pending copy */
   uint32_t bfinal = 0;
@@ -128,22 +157,105 @@ PZ_DEV bool pz_fixed_stream(const uint8_t *in, uint64_t n64, uint8_t *out, uint6
       continue;
     }
     /* the 32 stream bits at bp: a length / distance pair of the fixed code takes at most 8 + 5 + 5 + 13 = 31 of them */
-    const uint32_t t = bp >> 5;
-    const uint32_t lo = pz_funnel_r(w[t], w[t + 1u], bp);
+    if (bc <= 32u) { bb |= (uint64_t)w[wi++] << bc; bc += 32u; }
+    const uint32_t lo = (uint32_t)bb;
     if (!in_block) { /* inflateBlock (Deflate.hs:65-104): BFINAL, BTYPE */
-      if (bp + 3u > end_bit || ((lo >> 1) & 3u) != 1u) return false;
+      const uint32_t bt = (lo >> 1) & 3u;
+      if (bp + 3u > end_bit || !(bt == 1u || (DYN && bt == 2u))) return false;
       bfinal = lo & 1u;
-      bp += 3u;
+      bp += 3u; bb >>= 3; bc -= 3u;
       in_block = true;
+      dyn_block = false;
+      if (DYN && bt == 2u) { /* the dynamic arm (Deflate.hs:83-101): code lengths, then the two tables of this block */
+        dyn_block = true;
+#define PZ_SM_TAKE(nbits, v) do { if (bc <= 32u) { bb |= (uint64_t)w[wi++] << bc; bc += 32u; } (v) = (uint32_t)bb & ((1u << (nbits)) - 1u); bb >>= (nbits); bc -= (nbits); bp += (nbits); } while (0)
+        uint32_t hlit, hdist, hclen, v;
+        PZ_SM_TAKE(5, hlit); PZ_SM_TAKE(5, hdist); PZ_SM_TAKE(4, hclen);
+        hlit += 257u; hdist += 1u; hclen += 4u;
+        if (hlit > 286u || hdist > 30u) return false; /* the reference takes up to 288 / 32: K1's */
+        /* code-length code: 3 bits per symbol in codeLengthOrder (Deflate.hs:290-292); complete or K1's */
+        uint32_t pl[19];
+#pragma unroll
+        for (int k = 0; k < 19; k++) pl[k] = 0;
+        uint32_t kraft = 0;
+        for (uint32_t k = 0; k < hclen; k++) {
+          PZ_SM_TAKE(3, v);
+          pl[PZ_CL_ORDER[k]] = v;
+          if (v) kraft += 128u >> v;
+        }
+        if (kraft != 128u || bp > end_bit) return false;
+        {
+          uint32_t code = 0;
+          for (uint32_t l = 1; l <= 7u; l++) { /* canonical codes (computeCodeValues, Deflate.hs:261-288), most significant bit first */
+            for (uint32_t sy = 0; sy < 19u; sy++) {
+              if (pl[sy] != l) continue;
+              for (uint32_t e = pz_brev(code) >> (32u - l); e < 128u; e += 1u << l) pre_t[e] = (uint8_t)(sy | (l << 5));
+              code++;
+            }
+            code <<= 1;
+          }
+        }
+        /* getCodeLengths (Deflate.hs:124-156) as zlib writes them: no repeat at the start, none past the end */
+        const uint32_t total = hlit + hdist;
+        uint32_t nl = 0, prev = 0;
+        while (nl < total) {
+          if (bc <= 32u) { bb |= (uint64_t)w[wi++] << bc; bc += 32u; }
+          const uint32_t e = pre_t[(uint32_t)bb & 127u];
+          const uint32_t sy = e & 31u, l = e >> 5;
+          bb >>= l; bc -= l; bp += l;
+          uint32_t rep = 1, val = sy;
+          if (sy == 16u) { if (nl == 0u) return false; PZ_SM_TAKE(2, rep); rep += 3u; val = prev; }
+          else if (sy == 17u) { PZ_SM_TAKE(3, rep); rep += 3u; val = 0; }
+          else if (sy == 18u) { PZ_SM_TAKE(7, rep); rep += 11u; val = 0; }
+          if (nl + rep > total || bp > end_bit) return false;
+          for (uint32_t k = 0; k < rep; k++) lens[nl + k] = (uint8_t)val;
+          nl += rep;
+          prev = val;
+        }
+        if (lens[256] == 0u) return false; /* no end-of-block code: the reference would run on */
+        /* the two tables: every entry starts as "not mine" (0), then each code of at most the table's index bits fills the
+         * entries that end in its reversed bits; an over-subscribed code is K1's to reject (HuffmanTree.hs:25-71) */
+        for (int pass = 0; pass < 2; pass++) {
+          const uint32_t nsym = pass == 0 ? hlit : hdist, off = pass == 0 ? 0u : hlit;
+          const uint32_t bits = pass == 0 ? PZ_SM_LIT_BITS : PZ_SM_DIST_BITS, shift = pass == 0 ? 9u : 5u;
+          uint16_t *tab = pass == 0 ? lit_t : dist_t;
+          uint32_t cnt[16];
+#pragma unroll
+          for (int k = 0; k < 16; k++) cnt[k] = 0;
+          for (uint32_t sy = 0; sy < nsym; sy++) cnt[lens[off + sy]]++;
+          cnt[0] = 0;
+          uint32_t next[16], code = 0, kr = 0;
+#pragma unroll
+          for (int l = 1; l < 16; l++) { code = (code + cnt[l - 1]) << 1; next[l] = code; kr += cnt[l] << (15 - l); }
+          if (kr > 32768u) return false;
+          for (uint32_t e = 0; e < (1u << bits); e++) tab[e] = 0;
+          for (uint32_t sy = 0; sy < nsym; sy++) {
+            const uint32_t l = lens[off + sy];
+            if (l == 0u) continue;
+            uint32_t cv = 0;
+#pragma unroll
+            for (int k = 1; k < 16; k++) if ((uint32_t)k == l) cv = next[k]++;
+            if (l > bits) continue; /* a longer code: its entries stay "not mine" */
+            for (uint32_t e = pz_brev(cv) >> (32u - l); e < (1u << bits); e += 1u << l) tab[e] = (uint16_t)(sy | (l << shift));
+          }
+        }
+#undef PZ_SM_TAKE
+      }
       continue;
     }
-    /* the fixed literal/length code, first bit of a code = its most significant one (HuffmanTree.hs:73-83) */
-    const uint32_t r = pz_brev(lo) >> 23; /* the next nine stream bits as a number, first bit on top */
     uint32_t sym, nb;
-    if ((r >> 2) < 24u) { sym = 256u + (r >> 2); nb = 7u; }
-    else if ((r >> 1) < 192u) { sym = (r >> 1) - 48u; nb = 8u; }
-    else if ((r >> 1) < 200u) { sym = 280u + ((r >> 1) - 192u); nb = 8u; }
-    else { sym = 144u + (r - 400u); nb = 9u; }
+    if (DYN && dyn_block) { /* this block's own code: one look-up (local memory) */
+      const uint32_t e = lit_t[lo & ((1u << PZ_SM_LIT_BITS) - 1u)];
+      if (e == 0u) return false; /* a code longer than the table's index, or a prefix nothing is assigned to */
+      sym = e & 511u; nb = e >> 9;
+    } else {
+      /* the fixed literal/length code, first bit of a code = its most significant one (HuffmanTree.hs:73-83) */
+      const uint32_t r = pz_brev(lo) >> 23; /* the next nine stream bits as a number, first bit on top */
+      if ((r >> 2) < 24u) { sym = 256u + (r >> 2); nb = 7u; }
+      else if ((r >> 1) < 192u) { sym = (r >> 1) - 48u; nb = 8u; }
+      else if ((r >> 1) < 200u) { sym = 280u + ((r >> 1) - 192u); nb = 8u; }
+      else { sym = 144u + (r - 400u); nb = 9u; }
+    }
     if (sym < 256u) { /* emitByte (Monad.hs:309-315) */
       if (bp + nb > end_bit || pos >= cap || pos + 1u - mark > PZ_EXCESS) return false;
       if (!COUNT_ONLY) {
@@ -155,12 +267,12 @@ PZ_DEV bool pz_fixed_stream(const uint8_t *in, uint64_t n64, uint8_t *out, uint6
         }
       }
       pos++;
-      bp += nb;
+      bp += nb; bb >>= nb; bc -= nb;
       continue;
     }
     if (sym == 256u) { /* end of block: moveWindow, then the next block or the trailer (Deflate.hs:45-50) */
       if (bp + nb > end_bit) return false;
-      bp += nb;
+      bp += nb; bb >>= nb; bc -= nb;
       mark = pos;
       in_block = false;
       if (!bfinal) continue;
@@ -169,18 +281,29 @@ PZ_DEV bool pz_fixed_stream(const uint8_t *in, uint64_t n64, uint8_t *out, uint6
     if (sym > 285u) return false; /* lengthArray ! 286 / 287 (Deflate.hs:161,167): the exact kernel words it */
     const uint32_t le = PZ_FX_LEN[sym - 257u];
     const uint32_t len = (le & 0xffffu) + ((lo >> nb) & ~(0xffffffffu << (le >> 16)));
-    nb += le >> 16; /* <= 13 */
-    const uint32_t dsym = pz_brev((lo >> nb) & 31u) >> 27;
-    nb += 5u; /* <= 18 */
+    nb += le >> 16; /* <= 13 (fixed code), <= 15 (a table's) */
+    uint32_t dsym, lo2 = lo;
+    if (DYN && dyn_block) { /* length and distance part may take 10 + 5 + 9 + 13 bits together: consume the first, look again */
+      if (bp + nb > end_bit) return false;
+      bp += nb; bb >>= nb; bc -= nb; nb = 0;
+      if (bc <= 32u) { bb |= (uint64_t)w[wi++] << bc; bc += 32u; }
+      lo2 = (uint32_t)bb;
+      const uint32_t e = dist_t[lo2 & ((1u << PZ_SM_DIST_BITS) - 1u)];
+      if (e == 0u) return false;
+      dsym = e & 31u; nb = e >> 5;
+    } else {
+      dsym = pz_brev((lo >> nb) & 31u) >> 27;
+      nb += 5u; /* <= 18 */
+    }
     if (dsym > 29u) return false; /* distanceArray ! 30 / 31 (Deflate.hs:200,206) */
     const uint32_t de = PZ_FX_DIST[dsym];
     const uint32_t x = de >> 16; /* <= 13 */
-    dist = (de & 0xffffu) + ((lo >> nb) & ~(0xffffffffu << x));
+    dist = (de & 0xffffu) + ((lo2 >> nb) & ~(0xffffffffu << x));
     nb += x; /* <= 31 */
     /* what pz_match() checks: the distance lies inside what exists (OutputWindow.hs:82-89: below 64 KiB of output that is all
      * of it, above it at least 32 KiB are retained), the bytes fit, and the gap rule */
     if (bp + nb > end_bit || dist > pos || len > cap - pos || pos + len - mark > PZ_EXCESS) return false;
-    bp += nb;
+    bp += nb; bb >>= nb; bc -= nb;
     if (COUNT_ONLY) { pos += len; mark = pos; }
     else rem = len;
   }
@@ -215,7 +338,9 @@ pz_mark_pending_kernel(const PzJob job) {
   if (k < job.count) job.res[job.first + k].status = PZ_ST_PENDING;
 }
 
-template <bool COUNT_ONLY>
+/* DYN = false: K5 (fixed-Huffman streams, no tables, full occupancy); DYN = true: K6 (dynamic blocks too, 3 KiB of tables per
+ * thread in local memory) */
+template <bool COUNT_ONLY, bool DYN = false>
 __global__ void __launch_bounds__(PZ_FIXED_THREADS)
 pz_fixed_kernel(const PzJob job) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -231,6 +356,6 @@ pz_fixed_kernel(const PzJob job) {
     cap = job.out_off[s + 1] - o0;
     out = job.out_blob + o0;
   }
-  (void)pz_fixed_stream<COUNT_ONLY>(job.in_blob + i0, n, out, cap, res);
+  (void)pz_fixed_stream<COUNT_ONLY, DYN>(job.in_blob + i0, n, out, cap, res);
 }
 #endif

@@ -7,8 +7,9 @@
  *                            the tokens to the output (pz_device.cuh)
  *   pz_stored_probe_kernel,  K2: streams made of stored blocks only are copied with 16-byte
  *   pz_stored_copy_kernel    accesses by whole CTAs before K1 runs (pz_stored.cuh)
- *   pz_fixed_kernel          K5: big batches of small streams: every fixed-Huffman stream is decoded by ONE thread
- *                            (no tables: the fixed code is arithmetic) between K2 and K1 (pz_fixed.cuh)
+ *   pz_fixed_kernel          K5 / K6: big batches of small streams: every fixed-Huffman stream is decoded by ONE thread
+ *                            (no tables: the fixed code is arithmetic), then every small stream with dynamic blocks by
+ *                            one thread with tables in its local memory, between K2 and K1 (pz_fixed.cuh)
  *   pz_adler_partial_kernel  K3a: one warp per 16 KiB segment of decoded output, dp4a sums
  *   pz_adler_finish_kernel   K3b: per stream, combines the segments (adler32-combine
  *                            identity) and compares with the stored trailer
@@ -417,6 +418,11 @@ cudaError_t pz_kernels_configure(void) {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute((pz_inflate_kernel<false, false, true>), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return e;
+  /* K6's occupancy is set by a shared-memory request it never touches (its tables live in local memory: see pz_launch_inflate) */
+  e = cudaFuncSetAttribute((pz_fixed_kernel<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute((pz_fixed_kernel<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(pz_blk_tails_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PZ_TAIL * sizeof(uint16_t)));
   if (e != cudaSuccess) return e;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_inflate_ctas_per_sm[0], pz_inflate_kernel<false>, PZ_THREADS_PER_CTA, smem);
@@ -455,12 +461,20 @@ cudaError_t pz_launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uin
     phase = PZ_PHASE_K1;
   }
   if (d_in_ready) job.skip_done = 0; /* K2 would read input that is not there yet: K1 decodes every stream */
-  static const bool no_k5 = getenv("PZ_NO_K5") != nullptr; /* A/B */
+  static const bool no_k5 = getenv("PZ_NO_K5") != nullptr, no_k6 = getenv("PZ_NO_K6") != nullptr; /* A/B */
   const bool k5 = !no_k5 && count >= PZ_FIXED_MIN_STREAMS && framing == PZ_FRAME_ZLIB && d_in_ready == nullptr;
+  const bool k6 = k5 && !no_k6;
+  /* K6 keeps 3.5 KiB of tables per thread in local memory: with every thread an SM can hold resident that is 7 MiB per SM,
+   * a gigabyte in all, and every look-up would go to DRAM.  A shared-memory request the kernel never touches limits it to
+   * PZ_K6_BLOCKS blocks of 256 threads per SM (default 2: 270 MB of tables in all, about twice the L2). */
+  static const int k6_blocks = getenv("PZ_K6_BLOCKS") ? atoi(getenv("PZ_K6_BLOCKS")) : 2;
+  const size_t k6_smem = k6_blocks >= 8 ? 0 : (size_t)(220 * 1024 / (k6_blocks < 1 ? 1 : k6_blocks)) - 2048;
+  const unsigned small_grid = (count + PZ_FIXED_THREADS - 1u) / PZ_FIXED_THREADS;
   if (count_only) {
     if (k5) { /* K5 sizes the small fixed-Huffman streams, K1 what it left */
       pz_mark_pending_kernel<<<(count + 255u) / 256u, 256, 0, st>>>(job);
-      pz_fixed_kernel<true><<<(count + PZ_FIXED_THREADS - 1u) / PZ_FIXED_THREADS, PZ_FIXED_THREADS, 0, st>>>(job);
+      pz_fixed_kernel<true><<<small_grid, PZ_FIXED_THREADS, 0, st>>>(job);
+      if (k6) pz_fixed_kernel<true, true><<<small_grid, PZ_FIXED_THREADS, k6_smem, st>>>(job);
       job.skip_done = 1;
       cudaError_t e = pz_claim_counter(st, &job.next_unit);
       if (e != cudaSuccess) return e;
@@ -477,7 +491,8 @@ cudaError_t pz_launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uin
       tile = tile < 1u ? 1u : (tile > PZ_ST_THREADS ? PZ_ST_THREADS : tile);
       const unsigned tiles = (count + tile - 1u) / tile;
       pz_stored_copy_kernel<<<tiles < ctas ? tiles : ctas, PZ_ST_THREADS, 0, st>>>(job, tile);
-      if (k5) pz_fixed_kernel<false><<<(count + PZ_FIXED_THREADS - 1u) / PZ_FIXED_THREADS, PZ_FIXED_THREADS, 0, st>>>(job);
+      if (k5) pz_fixed_kernel<false><<<small_grid, PZ_FIXED_THREADS, 0, st>>>(job);
+      if (k6) pz_fixed_kernel<false, true><<<small_grid, PZ_FIXED_THREADS, k6_smem, st>>>(job);
     }
     if (phase != PZ_PHASE_K2 && job.skip_done && count > (unsigned)pz_inflate_slots()) { /* more streams than slots, some of them finished already: claim */
       cudaError_t e = pz_claim_counter(st, &job.next_unit);

@@ -61,7 +61,7 @@ extern "C" int hs_smem_bytes(void) { return (int)sizeof(PzStreamSmem); }
 /* K5's per-stream logic (pz_fixed.cuh) on the host: 1 if the stream decoded completely (res filled), 0 if it is left to K1.
  * out_mis (0..3) is the misalignment of the output inside a buffer of its own: 0 takes the word-wide stores, the others the
  * byte-wide ones; the bytes around the output are checked to be untouched. */
-extern "C" int hs_fixed(const uint8_t *in, uint64_t in_len, uint8_t *out, uint64_t out_cap, pz_result *res, int count_only, int out_mis) {
+extern "C" int hs_fixed(const uint8_t *in, uint64_t in_len, uint8_t *out, uint64_t out_cap, pz_result *res, int count_only, int out_mis, int dyn) {
   size_t mis = 3; /* an odd misalignment of the stream inside its (padded) buffer */
   uint8_t *buf = (uint8_t *)aligned_alloc(16, ((in_len + mis + 15) & ~(size_t)15) + 64);
   memset(buf, 0x5A, ((in_len + mis + 15) & ~(size_t)15) + 64);
@@ -69,7 +69,8 @@ extern "C" int hs_fixed(const uint8_t *in, uint64_t in_len, uint8_t *out, uint64
   uint8_t *obuf = (uint8_t *)aligned_alloc(16, ((out_cap + 15) & ~(size_t)15) + 64);
   memset(obuf, 0xEE, ((out_cap + 15) & ~(size_t)15) + 64);
   uint8_t *o = obuf + 16 + out_mis;
-  const bool ok = count_only ? pz_fixed_stream<true>(buf + mis, in_len, nullptr, 0, res) : pz_fixed_stream<false>(buf + mis, in_len, o, out_cap, res);
+  const bool ok = dyn ? (count_only ? pz_fixed_stream<true, true>(buf + mis, in_len, nullptr, 0, res) : pz_fixed_stream<false, true>(buf + mis, in_len, o, out_cap, res))
+                      : (count_only ? pz_fixed_stream<true>(buf + mis, in_len, nullptr, 0, res) : pz_fixed_stream<false>(buf + mis, in_len, o, out_cap, res));
   int rc = ok ? 1 : 0;
   if (!count_only) {
     for (int k = 0; k < 16 + out_mis; k++) if (obuf[k] != 0xEE) rc = -1;          /* nothing before the output ... */

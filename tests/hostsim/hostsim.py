@@ -26,16 +26,16 @@ def lib():
                                            C.c_void_p, C.c_void_p, C.c_uint32]
         _lib.hs_inflate_resume.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(PzResult), C.c_int,
                                            C.c_void_p, C.c_void_p]
-        _lib.hs_fixed.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(PzResult), C.c_int, C.c_int]
+        _lib.hs_fixed.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(PzResult), C.c_int, C.c_int, C.c_int]
     return _lib
 
 
-def fixed(data: bytes, out_cap: int, count_only: bool = False, out_mis: int = 0):
-    """K5's per-stream logic (pz_fixed.cuh): (completed, PzResult, bytes).  out_mis = 0: word-wide stores, 1..3: byte-wide."""
+def fixed(data: bytes, out_cap: int, count_only: bool = False, out_mis: int = 0, dyn: bool = False):
+    """K5's (dyn: K6's) per-stream logic (pz_fixed.cuh): (completed, PzResult, bytes).  out_mis = 0: word-wide stores, 1..3: byte-wide."""
     out = C.create_string_buffer(max(out_cap, 1))
     res = PzResult()
     res.status = -1
-    ok = lib().hs_fixed(bytes(data), len(data), out, out_cap, C.byref(res), int(count_only), out_mis)
+    ok = lib().hs_fixed(bytes(data), len(data), out, out_cap, C.byref(res), int(count_only), out_mis, int(dyn))
     assert ok >= 0, "K5 wrote outside its output slice"
     return bool(ok), res, out.raw[: min(res.out_len, out_cap)] if ok else b""
 

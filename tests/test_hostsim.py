@@ -255,3 +255,80 @@ def test_fixed_kernel_logic_fuzz(seed):
             assert not ok, (z.hex()[:100], o.message, r.out_len)
             left += 1
     assert done > 60 and left > 40, (done, left)
+
+
+# ---- K6: the same one-thread-per-stream decoder with per-thread tables for dynamic blocks --------------------------------
+def _check_small(z: bytes):
+    """K6 (pz_fixed_stream<.., DYN = true>): what it completes is the oracle's success; anything else it leaves to K1."""
+    o = oracle.decompress(z, want_events=True)
+    took = False
+    for count_only, out_mis in ((False, 0), (False, 1 + len(z) % 3), (True, 0)):
+        ok, r, out = hostsim.fixed(z, o.out_len if o.status == 0 else max(o.out_len, 1) + 64, count_only, out_mis, dyn=True)
+        if o.status not in (0, 5):
+            assert not ok, (z.hex()[:120], o.message)
+            continue
+        if not ok:
+            continue
+        took = True
+        assert (r.out_len, r.adler_stored) == (o.out_len, o.adler_stored)
+        if o.status == 0:
+            assert r.payload[1] == sum(ln for kind, ln in o.events[:-2] if kind == 1)
+            r1, _ = hostsim.inflate(z, o.out_len + 64)
+            assert r.err_bitpos == r1.err_bitpos
+        if not count_only:
+            assert out == o.data
+    return o, took
+
+
+def test_small_stream_dynamic_logic():
+    import numpy as np
+    from pure_zlib_b200 import corpus
+    rng = np.random.default_rng(9)
+    taken = total = 0
+    for i in range(150):
+        n = int(rng.integers(1, 12000))
+        kind = i % 5
+        data = streams.small_text(n, 500 + i) if kind < 2 else corpus.text(n, 7_000_000 + i) if kind < 4 else bytes(rng.integers(0, 7, n, dtype=np.uint8))
+        co = zlib.compressobj(int(rng.integers(1, 10)), zlib.DEFLATED, 15, int(rng.integers(1, 10)),
+                              [zlib.Z_DEFAULT_STRATEGY, zlib.Z_FILTERED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE][i % 4])
+        z = co.compress(data[: n // 3]) + (co.flush(zlib.Z_BLOCK) if i % 2 else b"") + co.compress(data[n // 3:]) + co.flush()
+        if len(z) > 16384:
+            continue
+        o, took = _check_small(z)
+        assert o.status == 0
+        total += 1
+        taken += took
+    assert taken >= 0.8 * total, (taken, total)   # what it leaves: blocks with codes longer than its tables' index
+    # the benchmark's records: how many of the dynamic ones does K6 take?
+    got = 0
+    for i in range(3, 400, 4):
+        z = zlib.compress(corpus.text(4096, 2_000_000 + i), 6)
+        got += _check_small(z)[1]
+    assert got >= 90, got
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_small_stream_dynamic_fuzz(seed):
+    import numpy as np
+    rng = np.random.default_rng(300 + seed)
+    done = left = 0
+    cases = list(fuzzlib.fuzz_cases(40 + seed, 250))
+    for i in range(150):
+        n = int(rng.integers(1, 5000))
+        z = bytearray(zlib.compress(streams.small_text(n, 9000 + 200 * seed + i), int(rng.integers(1, 10))))
+        how = i % 4
+        if how == 0:
+            z = z[: int(rng.integers(0, len(z)))]
+        elif how == 1:
+            for _ in range(int(rng.integers(1, 4))):
+                z[int(rng.integers(0, len(z)))] ^= 1 << int(rng.integers(0, 8))
+        elif how == 2:
+            z[-2] ^= 0x10
+        cases.append(bytes(z))
+    for z in cases:
+        if len(z) > 16384:
+            continue
+        o, took = _check_small(z)
+        done += took
+        left += o.status not in (0, 5)
+    assert done > 40 and left > 40, (done, left)

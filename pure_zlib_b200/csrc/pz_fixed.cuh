@@ -111,61 +111,26 @@ PZ_DEV bool pz_fixed_stream(const uint8_t *in, uint64_t n64, uint8_t *out, uint6
   /* output as aligned words (see above): acc holds the bytes [pos & ~3, pos) of the output, which are NOT in memory yet */
   const bool wide = !COUNT_ONLY && ((uintptr_t)out & 3u) == 0u;
   uint32_t acc = 0;
+  /* One iteration = at most one symbol decoded (lanes whose copy is still running skip that part) and at most eight bytes
+   * produced -- the literal, or the next piece of the copy -- by ONE piece of code for both: the lanes of a warp are in
+   * different streams, and every path that only some of them take is time the others wait (ncu: with separate literal, match
+   * and copy paths 7.5 of 32 lanes were active on average). */
+  bool done = false;
   for (;;) {
-    if (rem != 0u) { /* emitPastChunk (Monad.hs:324-333): up to eight bytes of the copy per iteration */
-      const uint32_t c = rem < 8u ? rem : 8u;
-      if (!COUNT_ONLY) {
-        if (wide && dist >= 11u) { /* the source bytes [pos - dist, pos - dist + 8) lie below pos & ~3: all in memory */
-          const uint8_t *q = out + pos - dist;
-          const uint32_t *qa = reinterpret_cast<const uint32_t *>((uintptr_t)q & ~(uintptr_t)3);
-          const uint32_t qs = (uint32_t)((uintptr_t)q & 3u) * 8u;
-          const uint32_t s0 = qa[0], s1 = qa[1], s2 = qa[2];
-          uint64_t v = (uint64_t)pz_funnel_r(s0, s1, qs) | ((uint64_t)pz_funnel_r(s1, s2, qs) << 32);
-          if (c < 8u) v &= ~(~0ull << (8u * c));
-          /* append c bytes behind the a pending ones: up to 11 bytes = two full words and a rest */
-          const uint32_t a = pos & 3u;
-          const uint64_t comb = (uint64_t)acc | (v << (8u * a));
-          const uint32_t over = a ? (uint32_t)(v >> (64u - 8u * a)) : 0u;
-          const uint32_t total = a + c, full = total >> 2;
-          uint32_t *dw = reinterpret_cast<uint32_t *>(out + (pos & ~3u));
-          if (full >= 1u) dw[0] = (uint32_t)comb;
-          if (full >= 2u) dw[1] = (uint32_t)(comb >> 32);
-          const uint32_t restw = full == 0u ? (uint32_t)comb : full == 1u ? (uint32_t)(comb >> 32) : over;
-          const uint32_t rb = total & 3u;
-          acc = rb ? restw & ~(0xffffffffu << (8u * rb)) : 0u;
-        } else {
-          uint8_t *d = out + pos;
-          if (wide) { /* the pending bytes go to memory first: the copy may read them */
-            const uint32_t a = pos & 3u;
-#pragma unroll
-            for (uint32_t j = 0; j < 3u; j++)
-              if (j < a) d[(int32_t)j - (int32_t)a] = (uint8_t)(acc >> (8u * j));
-          }
-          const uint8_t *q = d - dist;
-#pragma unroll
-          for (uint32_t j = 0; j < 8u; j++)
-            if (j < c) d[j] = q[j]; /* in order: a byte may be one this loop has just written (dist < len) */
-          if (wide) { /* and the register takes the bytes of the word the output now ends in */
-            const uint32_t np = pos + c, a2 = np & 3u;
-            acc = a2 ? *reinterpret_cast<const uint32_t *>(out + (np & ~3u)) & ~(0xffffffffu << (8u * a2)) : 0u;
-          }
-        }
-      }
-      pos += c;
-      rem -= c;
-      if (rem == 0u) mark = pos;
-      continue;
-    }
-    /* the 32 stream bits at bp: a length / distance pair of the fixed code takes at most 8 + 5 + 5 + 13 = 31 of them */
-    if (bc <= 32u) { bb |= (uint64_t)w[wi++] << bc; bc += 32u; }
-    const uint32_t lo = (uint32_t)bb;
-    if (!in_block) { /* inflateBlock (Deflate.hs:65-104): BFINAL, BTYPE */
-      const uint32_t bt = (lo >> 1) & 3u;
-      if (bp + 3u > end_bit || !(bt == 1u || (DYN && bt == 2u))) return false;
-      bfinal = lo & 1u;
-      bp += 3u; bb >>= 3; bc -= 3u;
-      in_block = true;
-      dyn_block = false;
+    uint64_t v = 0;   /* the bytes this iteration produces, first byte lowest */
+    uint32_t c = 0;   /* how many: 0..8 */
+    bool is_literal = false;
+    if (rem == 0u) {
+      /* the 32 stream bits at bp: a length / distance pair of the fixed code takes at most 8 + 5 + 5 + 13 = 31 of them */
+      if (bc <= 32u) { bb |= (uint64_t)w[wi++] << bc; bc += 32u; }
+      const uint32_t lo = (uint32_t)bb;
+      if (!in_block) { /* inflateBlock (Deflate.hs:65-104): BFINAL, BTYPE */
+        const uint32_t bt = (lo >> 1) & 3u;
+        if (bp + 3u > end_bit || !(bt == 1u || (DYN && bt == 2u))) return false;
+        bfinal = lo & 1u;
+        bp += 3u; bb >>= 3; bc -= 3u;
+        in_block = true;
+        dyn_block = false;
       if (DYN && bt == 2u) { /* the dynamic arm (Deflate.hs:83-101): code lengths, then the two tables of this block */
         dyn_block = true;
 #define PZ_SM_TAKE(nbits, v) do { if (bc <= 32u) { bb |= (uint64_t)w[wi++] << bc; bc += 32u; } (v) = (uint32_t)bb & ((1u << (nbits)) - 1u); bb >>= (nbits); bc -= (nbits); bp += (nbits); } while (0)
@@ -241,71 +206,115 @@ PZ_DEV bool pz_fixed_stream(const uint8_t *in, uint64_t n64, uint8_t *out, uint6
         }
 #undef PZ_SM_TAKE
       }
-      continue;
-    }
-    uint32_t sym, nb;
-    if (DYN && dyn_block) { /* this block's own code: one look-up (local memory) */
-      const uint32_t e = lit_t[lo & ((1u << PZ_SM_LIT_BITS) - 1u)];
-      if (e == 0u) return false; /* a code longer than the table's index, or a prefix nothing is assigned to */
-      sym = e & 511u; nb = e >> 9;
-    } else {
-      /* the fixed literal/length code, first bit of a code = its most significant one (HuffmanTree.hs:73-83) */
-      const uint32_t r = pz_brev(lo) >> 23; /* the next nine stream bits as a number, first bit on top */
-      if ((r >> 2) < 24u) { sym = 256u + (r >> 2); nb = 7u; }
-      else if ((r >> 1) < 192u) { sym = (r >> 1) - 48u; nb = 8u; }
-      else if ((r >> 1) < 200u) { sym = 280u + ((r >> 1) - 192u); nb = 8u; }
-      else { sym = 144u + (r - 400u); nb = 9u; }
-    }
-    if (sym < 256u) { /* emitByte (Monad.hs:309-315) */
-      if (bp + nb > end_bit || pos >= cap || pos + 1u - mark > PZ_EXCESS) return false;
-      if (!COUNT_ONLY) {
-        if (wide) {
-          acc |= sym << (8u * (pos & 3u));
-          if ((pos & 3u) == 3u) { *reinterpret_cast<uint32_t *>(out + (pos & ~3u)) = acc; acc = 0u; }
-        } else {
-          out[pos] = (uint8_t)sym;
-        }
+        continue;
       }
-      pos++;
-      bp += nb; bb >>= nb; bc -= nb;
-      continue;
+      uint32_t sym, nb;
+      if (DYN && dyn_block) { /* this block's own code: one look-up (local memory) */
+        const uint32_t e = lit_t[lo & ((1u << PZ_SM_LIT_BITS) - 1u)];
+        if (e == 0u) return false; /* a code longer than the table's index, or a prefix nothing is assigned to */
+        sym = e & 511u; nb = e >> 9;
+      } else {
+        /* the fixed literal/length code, first bit of a code = its most significant one (HuffmanTree.hs:73-83) */
+        const uint32_t r = pz_brev(lo) >> 23; /* the next nine stream bits as a number, first bit on top */
+        if ((r >> 2) < 24u) { sym = 256u + (r >> 2); nb = 7u; }
+        else if ((r >> 1) < 192u) { sym = (r >> 1) - 48u; nb = 8u; }
+        else if ((r >> 1) < 200u) { sym = 280u + ((r >> 1) - 192u); nb = 8u; }
+        else { sym = 144u + (r - 400u); nb = 9u; }
+      }
+      if (sym < 256u) { /* emitByte (Monad.hs:309-315) */
+        if (bp + nb > end_bit || pos >= cap || pos + 1u - mark > PZ_EXCESS) return false;
+        bp += nb; bb >>= nb; bc -= nb;
+        v = sym; c = 1u; is_literal = true;
+      } else if (sym == 256u) { /* end of block: moveWindow, then the next block or the trailer (Deflate.hs:45-50) */
+        if (bp + nb > end_bit) return false;
+        bp += nb; bb >>= nb; bc -= nb;
+        mark = pos;
+        in_block = false;
+        if (bfinal) done = true;
+      } else {
+        if (sym > 285u) return false; /* lengthArray ! 286 / 287 (Deflate.hs:161,167): the exact kernel words it */
+        const uint32_t le = PZ_FX_LEN[sym - 257u];
+        const uint32_t len = (le & 0xffffu) + ((lo >> nb) & ~(0xffffffffu << (le >> 16)));
+        nb += le >> 16; /* <= 13 (fixed code), <= 15 (a table's) */
+        uint32_t dsym, lo2 = lo;
+        if (DYN && dyn_block) { /* length and distance part may take 10 + 5 + 9 + 13 bits together: consume the first, look again */
+          if (bp + nb > end_bit) return false;
+          bp += nb; bb >>= nb; bc -= nb; nb = 0;
+          if (bc <= 32u) { bb |= (uint64_t)w[wi++] << bc; bc += 32u; }
+          lo2 = (uint32_t)bb;
+          const uint32_t e = dist_t[lo2 & ((1u << PZ_SM_DIST_BITS) - 1u)];
+          if (e == 0u) return false;
+          dsym = e & 31u; nb = e >> 5;
+        } else {
+          dsym = pz_brev((lo >> nb) & 31u) >> 27;
+          nb += 5u; /* <= 18 */
+        }
+        if (dsym > 29u) return false; /* distanceArray ! 30 / 31 (Deflate.hs:200,206) */
+        const uint32_t de = PZ_FX_DIST[dsym];
+        const uint32_t x = de >> 16; /* <= 13 */
+        dist = (de & 0xffffu) + ((lo2 >> nb) & ~(0xffffffffu << x));
+        nb += x; /* <= 31 */
+        /* what pz_match() checks: the distance lies inside what exists (OutputWindow.hs:82-89: below 64 KiB of output that is
+         * all of it, above it at least 32 KiB are retained), the bytes fit, and the gap rule */
+        if (bp + nb > end_bit || dist > pos || len > cap - pos || pos + len - mark > PZ_EXCESS) return false;
+        bp += nb; bb >>= nb; bc -= nb;
+        if (COUNT_ONLY) { pos += len; mark = pos; }
+        else rem = len;
+      }
     }
-    if (sym == 256u) { /* end of block: moveWindow, then the next block or the trailer (Deflate.hs:45-50) */
-      if (bp + nb > end_bit) return false;
-      bp += nb; bb >>= nb; bc -= nb;
-      mark = pos;
-      in_block = false;
-      if (!bfinal) continue;
-      break;
+    if (done) break;
+    if (COUNT_ONLY) { pos += c; continue; } /* (c = 1 for a literal; matches were counted above) */
+    /* ---- produce: the literal, or up to eight bytes of the copy (emitPastChunk, Monad.hs:324-333) ---- */
+    if (rem != 0u) {
+      c = rem < 8u ? rem : 8u;
+      if (wide && dist >= 11u) { /* the source bytes [pos - dist, pos - dist + 8) lie below pos & ~3: all in memory */
+        const uint8_t *q = out + pos - dist;
+        const uint32_t *qa = reinterpret_cast<const uint32_t *>((uintptr_t)q & ~(uintptr_t)3);
+        const uint32_t qs = (uint32_t)((uintptr_t)q & 3u) * 8u;
+        const uint32_t s0 = qa[0], s1 = qa[1], s2 = qa[2];
+        v = (uint64_t)pz_funnel_r(s0, s1, qs) | ((uint64_t)pz_funnel_r(s1, s2, qs) << 32);
+        if (c < 8u) v &= ~(~0ull << (8u * c));
+      } else { /* a close match (or an output slice that is not word-aligned): byte by byte, in order -- a byte may be one
+                  this loop has just written (dist < len) */
+        uint8_t *d = out + pos;
+        if (wide) { /* the pending bytes go to memory first: the copy may read them */
+          const uint32_t a = pos & 3u;
+#pragma unroll
+          for (uint32_t j = 0; j < 3u; j++)
+            if (j < a) d[(int32_t)j - (int32_t)a] = (uint8_t)(acc >> (8u * j));
+        }
+        const uint8_t *q = d - dist;
+#pragma unroll
+        for (uint32_t j = 0; j < 8u; j++)
+          if (j < c) d[j] = q[j];
+        pos += c;
+        rem -= c;
+        if (rem == 0u) mark = pos;
+        if (wide) { /* and the register takes the bytes of the word the output now ends in */
+          const uint32_t a2 = pos & 3u;
+          acc = a2 ? *reinterpret_cast<const uint32_t *>(out + (pos & ~3u)) & ~(0xffffffffu << (8u * a2)) : 0u;
+        }
+        continue;
+      }
+      rem -= c;
     }
-    if (sym > 285u) return false; /* lengthArray ! 286 / 287 (Deflate.hs:161,167): the exact kernel words it */
-    const uint32_t le = PZ_FX_LEN[sym - 257u];
-    const uint32_t len = (le & 0xffffu) + ((lo >> nb) & ~(0xffffffffu << (le >> 16)));
-    nb += le >> 16; /* <= 13 (fixed code), <= 15 (a table's) */
-    uint32_t dsym, lo2 = lo;
-    if (DYN && dyn_block) { /* length and distance part may take 10 + 5 + 9 + 13 bits together: consume the first, look again */
-      if (bp + nb > end_bit) return false;
-      bp += nb; bb >>= nb; bc -= nb; nb = 0;
-      if (bc <= 32u) { bb |= (uint64_t)w[wi++] << bc; bc += 32u; }
-      lo2 = (uint32_t)bb;
-      const uint32_t e = dist_t[lo2 & ((1u << PZ_SM_DIST_BITS) - 1u)];
-      if (e == 0u) return false;
-      dsym = e & 31u; nb = e >> 5;
+    if (c == 0u) continue; /* a block header or an end of block: nothing to produce */
+    if (wide) { /* append c bytes behind the a pending ones: up to 11 bytes = two full words and a rest */
+      const uint32_t a = pos & 3u;
+      const uint64_t comb = (uint64_t)acc | (v << (8u * a));
+      const uint32_t over = a ? (uint32_t)(v >> (64u - 8u * a)) : 0u;
+      const uint32_t total = a + c, full = total >> 2;
+      uint32_t *dw = reinterpret_cast<uint32_t *>(out + (pos & ~3u));
+      if (full >= 1u) dw[0] = (uint32_t)comb;
+      if (full >= 2u) dw[1] = (uint32_t)(comb >> 32);
+      const uint32_t restw = full == 0u ? (uint32_t)comb : full == 1u ? (uint32_t)(comb >> 32) : over;
+      const uint32_t rb = total & 3u;
+      acc = rb ? restw & ~(0xffffffffu << (8u * rb)) : 0u;
     } else {
-      dsym = pz_brev((lo >> nb) & 31u) >> 27;
-      nb += 5u; /* <= 18 */
+      out[pos] = (uint8_t)v; /* only literals come here: copies of an unaligned slice took the byte path above */
     }
-    if (dsym > 29u) return false; /* distanceArray ! 30 / 31 (Deflate.hs:200,206) */
-    const uint32_t de = PZ_FX_DIST[dsym];
-    const uint32_t x = de >> 16; /* <= 13 */
-    dist = (de & 0xffffu) + ((lo2 >> nb) & ~(0xffffffffu << x));
-    nb += x; /* <= 31 */
-    /* what pz_match() checks: the distance lies inside what exists (OutputWindow.hs:82-89: below 64 KiB of output that is all
-     * of it, above it at least 32 KiB are retained), the bytes fit, and the gap rule */
-    if (bp + nb > end_bit || dist > pos || len > cap - pos || pos + len - mark > PZ_EXCESS) return false;
-    bp += nb; bb >>= nb; bc -= nb;
-    if (COUNT_ONLY) { pos += len; mark = pos; }
-    else rem = len;
+    pos += c;
+    if (!is_literal && rem == 0u) mark = pos;
   }
   /* checkChecksum (Deflate.hs:52-63): to the next byte boundary, four bytes, most significant first; K3 compares */
   const uint32_t tb = ((bp + 7u) >> 3) - mis; /* byte offset of the trailer in the stream */
@@ -338,16 +347,44 @@ pz_mark_pending_kernel(const PzJob job) {
   if (k < job.count) job.res[job.first + k].status = PZ_ST_PENDING;
 }
 
-/* DYN = false: K5 (fixed-Huffman streams, no tables, full occupancy); DYN = true: K6 (dynamic blocks too, 3 KiB of tables per
- * thread in local memory) */
+/* The streams a kernel of this file will try, packed: list[0] = how many, list[2 + i] = stream index.  Thread k of the decode
+ * kernel takes list[2 + k], so its warps are full whatever the mix of the batch is (in BASELINE configs[2] every fourth record
+ * is a dynamic one: with "thread k takes stream k", K6's warps would run with eight lanes).  want_dynamic = 0: streams whose
+ * first block is a fixed one (K5); 1: whatever is still pending and small enough (K6). */
+__global__ void __launch_bounds__(256)
+pz_small_list_kernel(const PzJob job, uint32_t *list, uint32_t want_dynamic) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  bool take = false;
+  uint32_t s = 0;
+  if (k < job.count) {
+    s = job.first + k;
+    const uint64_t i0 = job.in_off[s], n = job.in_off[s + 1] - i0;
+    if (job.res[s].status == PZ_ST_PENDING && n >= 8u && n <= PZ_FIXED_MAX_IN) {
+      const uint8_t *in = job.in_blob + i0;
+      const uint32_t p = (in[1] & 0x20u) ? 6u : 2u;
+      const uint32_t bt = (in[p] >> 1) & 3u;
+      take = bt == 1u || (want_dynamic != 0u && bt == 2u);
+    }
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, take);
+  if (m == 0u) return;
+  const uint32_t lane = threadIdx.x & 31u;
+  uint32_t base = 0;
+  if (lane == (uint32_t)__ffs((int)m) - 1u) base = atomicAdd(list, (uint32_t)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, __ffs((int)m) - 1);
+  if (take) list[2u + base + (uint32_t)__popc(m & ((1u << lane) - 1u))] = s;
+}
+
+/* DYN = false: K5 (fixed-Huffman streams, no tables, full occupancy); DYN = true: K6 (dynamic blocks too, 3.5 KiB of tables per
+ * thread in local memory).  list: see pz_small_list_kernel. */
 template <bool COUNT_ONLY, bool DYN = false>
 __global__ void __launch_bounds__(PZ_FIXED_THREADS)
-pz_fixed_kernel(const PzJob job) {
+pz_fixed_kernel(const PzJob job, const uint32_t *__restrict__ list) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= job.count) return;
-  const uint32_t s = job.first + k;
+  if (k >= list[0]) return;
+  const uint32_t s = list[2u + k];
   pz_result *res = job.res + s;
-  if (res->status != PZ_ST_PENDING) return; /* K2 has finished it */
+  if (res->status != PZ_ST_PENDING) return;
   const uint64_t i0 = job.in_off[s], n = job.in_off[s + 1] - i0;
   uint8_t *out = nullptr;
   uint64_t cap = 0;

@@ -398,6 +398,12 @@ cudaError_t pz_kernels_configure(void) {
   if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
   if ((e = cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
   if (dev >= 0 && dev < PZ_MAX_DEVICES && g_claim_ring[dev] == nullptr && (e = cudaMalloc(&g_claim_ring[dev], 1024 * sizeof(uint32_t))) != cudaSuccess) return e;
+  { /* stream-ordered scratch (the lists of K5 / K6, the incremental contexts) is handed back to the pool, not to the driver */
+    cudaMemPool_t pool;
+    uint64_t keep = ~0ull;
+    if ((e = cudaDeviceGetDefaultMemPool(&pool, dev)) != cudaSuccess) return e;
+    if ((e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep)) != cudaSuccess) return e;
+  }
   e = cudaFuncSetAttribute(pz_inflate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(pz_inflate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -419,6 +425,8 @@ cudaError_t pz_kernels_configure(void) {
   e = cudaFuncSetAttribute((pz_inflate_kernel<false, false, true>), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return e;
   /* K6's occupancy is set by a shared-memory request it never touches (its tables live in local memory: see pz_launch_inflate) */
+  e = cudaFuncSetAttribute((pz_fixed_kernel<false, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute((pz_fixed_kernel<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute((pz_fixed_kernel<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -467,14 +475,35 @@ cudaError_t pz_launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uin
   /* K6 keeps 3.5 KiB of tables per thread in local memory: with every thread an SM can hold resident that is 7 MiB per SM,
    * a gigabyte in all, and every look-up would go to DRAM.  A shared-memory request the kernel never touches limits it to
    * PZ_K6_BLOCKS blocks of 256 threads per SM (default 2: 270 MB of tables in all, about twice the L2). */
-  static const int k6_blocks = getenv("PZ_K6_BLOCKS") ? atoi(getenv("PZ_K6_BLOCKS")) : 2;
-  const size_t k6_smem = k6_blocks >= 8 ? 0 : (size_t)(220 * 1024 / (k6_blocks < 1 ? 1 : k6_blocks)) - 2048;
-  const unsigned small_grid = (count + PZ_FIXED_THREADS - 1u) / PZ_FIXED_THREADS;
+  static const int k6_blocks = getenv("PZ_K6_BLOCKS") ? atoi(getenv("PZ_K6_BLOCKS")) : 4;
+  static const unsigned k6_threads = getenv("PZ_K6_THREADS") ? (unsigned)atoi(getenv("PZ_K6_THREADS")) : 256u;
+  static const int k5_blocks = getenv("PZ_K5_BLOCKS") ? atoi(getenv("PZ_K5_BLOCKS")) : 8; /* (A/B: fewer streams in flight = a smaller working set in L2) */
+  const size_t k5_smem = k5_blocks >= 8 ? 0 : k5_blocks <= 1 ? 120 * 1024 : (size_t)(220 * 1024 / k5_blocks) - 2048;
+  const size_t k6_smem = k6_blocks >= 8 ? 0 : k6_blocks <= 1 ? 120 * 1024 : (size_t)(220 * 1024 / k6_blocks) - 2048;
+  const unsigned small_grid = (count + PZ_FIXED_THREADS - 1u) / PZ_FIXED_THREADS, k6_grid = (count + k6_threads - 1u) / k6_threads;
+  /* K5 then K6 over packed lists of the streams each will try (pz_small_list_kernel); the list lives in stream-ordered memory */
+  auto small_streams = [&](bool co) -> cudaError_t {
+    uint32_t *list = nullptr;
+    cudaError_t e = cudaMallocAsync((void **)&list, ((size_t)count + 2u) * sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+    for (int dyn = 0; dyn < (k6 ? 2 : 1); dyn++) {
+      if ((e = cudaMemsetAsync(list, 0, 8, st)) != cudaSuccess) return e;
+      pz_small_list_kernel<<<(count + 255u) / 256u, 256, 0, st>>>(job, list, (uint32_t)dyn);
+      if (!dyn) {
+        if (co) pz_fixed_kernel<true, false><<<small_grid, PZ_FIXED_THREADS, 0, st>>>(job, list);
+        else pz_fixed_kernel<false, false><<<small_grid, PZ_FIXED_THREADS, k5_smem, st>>>(job, list);
+      } else {
+        if (co) pz_fixed_kernel<true, true><<<k6_grid, k6_threads, k6_smem, st>>>(job, list);
+        else pz_fixed_kernel<false, true><<<k6_grid, k6_threads, k6_smem, st>>>(job, list);
+      }
+    }
+    return cudaFreeAsync(list, st);
+  };
   if (count_only) {
     if (k5) { /* K5 sizes the small fixed-Huffman streams, K1 what it left */
       pz_mark_pending_kernel<<<(count + 255u) / 256u, 256, 0, st>>>(job);
-      pz_fixed_kernel<true><<<small_grid, PZ_FIXED_THREADS, 0, st>>>(job);
-      if (k6) pz_fixed_kernel<true, true><<<small_grid, PZ_FIXED_THREADS, k6_smem, st>>>(job);
+      cudaError_t e5 = small_streams(true);
+      if (e5 != cudaSuccess) return e5;
       job.skip_done = 1;
       cudaError_t e = pz_claim_counter(st, &job.next_unit);
       if (e != cudaSuccess) return e;
@@ -491,8 +520,7 @@ cudaError_t pz_launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uin
       tile = tile < 1u ? 1u : (tile > PZ_ST_THREADS ? PZ_ST_THREADS : tile);
       const unsigned tiles = (count + tile - 1u) / tile;
       pz_stored_copy_kernel<<<tiles < ctas ? tiles : ctas, PZ_ST_THREADS, 0, st>>>(job, tile);
-      if (k5) pz_fixed_kernel<false><<<small_grid, PZ_FIXED_THREADS, 0, st>>>(job);
-      if (k6) pz_fixed_kernel<false, true><<<small_grid, PZ_FIXED_THREADS, k6_smem, st>>>(job);
+      if (k5) { cudaError_t e5 = small_streams(false); if (e5 != cudaSuccess) return e5; }
     }
     if (phase != PZ_PHASE_K2 && job.skip_done && count > (unsigned)pz_inflate_slots()) { /* more streams than slots, some of them finished already: claim */
       cudaError_t e = pz_claim_counter(st, &job.next_unit);

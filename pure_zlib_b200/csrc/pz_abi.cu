@@ -650,7 +650,7 @@ pz_batch *pz_batch_create(const uint64_t *in_off, const uint64_t *out_off, size_
     }
   }
   if (e != cudaSuccess) { fail_cuda(e, "pz_batch_create"); pz_batch_destroy(b); return nullptr; }
-  const int k5 = (n >= PZ_FIXED_MIN_STREAMS && framing_of(flags) == 0u) ? 4 : 0; /* K5 and K6 (pz_fixed.cuh), each behind its list kernel, run on big batches; the sizing pass marks the streams first */
+  const int k5 = pz_small_launches((uint32_t)n, framing_of(flags)); /* K5 (and K6 when asked for; pz_fixed.cuh), each behind its list kernel, run on big batches; the sizing pass marks the streams first */
   b->launches = (count_only ? 1 + (k5 ? k5 + 1 : 0) : 3 + k5) + ((count_only || (flags & PZ_F_NO_ADLER)) ? 0 : (b->total_segs ? 2 : 1)); /* K2 probe + K2 copy (+ K5) + K1, then K3a + K3b */
   return b;
 }

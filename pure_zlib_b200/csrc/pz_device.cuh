@@ -1805,6 +1805,9 @@ PZ_DEV void pz_slow_step(PzCtx &c, PzStreamSmem *sm, const PzJob &job, uint32_t 
   }
 }
 
+#if defined(PZ_PHASES) && !defined(PZ_HOSTSIM)
+__device__ unsigned long long pz_phase_ticks[16]; /* [mode at the start of a step] = clocks, [8] = all, [9] = groups */
+#endif
 /* The service warp (device) / the whole decoder (host build): every group takes streams
  * first_stream, first_stream + stride, ... of the job (first_stream differs per group) through
  * the state machine.  On the device a stream that reaches the symbol loop is posted to its lane
@@ -1838,8 +1841,16 @@ PZ_DEV void pz_decoder_warp(const PzJob &job, uint32_t first_stream, uint32_t st
   }
 #else
   if (!present) c.mode = PZ_M_DEAD; /* a group without a slot */
+#ifdef PZ_PHASES /* debug build: where a service group's time goes, in SM clocks, summed over the groups (pz_phase_ticks) */
+  long long ph_t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long ph_last = clock64();
+  const long long ph_begin = ph_last;
+#endif
   for (;;) {
     bool draining = false;
+#ifdef PZ_PHASES
+    const uint32_t ph_mode = c.mode;
+#endif
     if (c.mode == PZ_M_WAIT) {
       pz_service_poll(c, sm);
     } else if (c.mode == PZ_M_DRAIN || c.mode == PZ_M_FINDRAIN) {
@@ -1849,6 +1860,9 @@ PZ_DEV void pz_decoder_warp(const PzJob &job, uint32_t first_stream, uint32_t st
       if (c.mode == PZ_M_FAST) pz_post_hot(c, sm);
       else if (c.mode == PZ_M_DEAD && pz_lane() == 0) pz_vstore(&sm->mail.state, PZ_MS_DEAD);
     }
+#ifdef PZ_PHASES
+    { const long long now = clock64(); ph_t[ph_mode & 7u] += now - ph_last; ph_last = now; }
+#endif
     /* groups that only wait for their writer do not keep the warp spinning at full speed */
     if (pz_warp_any(draining) && !pz_warp_any(!draining && c.mode != PZ_M_WAIT && c.mode != PZ_M_DEAD && !(c.mode == PZ_M_IDLE && c.starved))) __nanosleep(100);
     if (!pz_warp_any(c.mode != PZ_M_WAIT && c.mode != PZ_M_DEAD && !(c.mode == PZ_M_IDLE && c.starved))) {
@@ -1866,6 +1880,13 @@ PZ_DEV void pz_decoder_warp(const PzJob &job, uint32_t first_stream, uint32_t st
         __nanosleep(PZ_DOZE_NS);
       }
     }
+  }
+#endif
+#if defined(PZ_PHASES) && !defined(PZ_HOSTSIM)
+  if (present && pz_lane() == 0) {
+    for (int k = 0; k < 8; k++) atomicAdd(&pz_phase_ticks[k], (unsigned long long)ph_t[k]);
+    atomicAdd(&pz_phase_ticks[8], (unsigned long long)(clock64() - ph_begin));
+    atomicAdd(&pz_phase_ticks[9], 1ull);
   }
 #endif
   pz_async_wait_all();

@@ -14,7 +14,8 @@
 #ifndef PZ_WGROUP
 #define PZ_WGROUP 16 /* lanes per stream in the writer warps (pz_device.cuh) */
 #endif
-#define PZ_SERVICE_WARPS ((PZ_SLOTS + 3u) / 4u) /* four slots (8 lanes each) per service warp */
+#define PZ_SLOTS_PER_SERVICE (32u / PZ_GROUP) /* four slots (8 lanes each) per service warp */
+#define PZ_SERVICE_WARPS ((PZ_SLOTS + PZ_SLOTS_PER_SERVICE - 1u) / PZ_SLOTS_PER_SERVICE)
 #define PZ_SLOTS_PER_WRITER (32u / PZ_WGROUP)
 #define PZ_WRITER_WARPS ((PZ_SLOTS + PZ_SLOTS_PER_WRITER - 1u) / PZ_SLOTS_PER_WRITER)
 #ifndef PZ_PAD_WARPS
@@ -77,3 +78,4 @@ cudaError_t pz_launch_code_values(const uint8_t *d_lens, int n, uint16_t *d_code
 cudaError_t pz_kernels_configure(void);
 /* streams K1 decodes at the same time on this device (SMs x slots per CTA) */
 int pz_inflate_slots(void);
+int pz_small_launches(uint32_t count, uint32_t framing); /* launches K5 (/ K6) add to a batch: 0, 2 or 4 */

@@ -71,7 +71,7 @@ pz_inflate_kernel(const PzJob job) {
   if (role == 3u) return;
   /* slot s of CTA b takes streams b + grid * (s + PZ_SLOTS * k): a batch spreads over the SMs
    * before it fills the slots of any of them */
-  const uint32_t slot = role == 1u ? index * 4u + (threadIdx.x & 31u) / PZ_G : index * PZ_SLOTS_PER_WRITER + (threadIdx.x & 31u) / PZ_WG;
+  const uint32_t slot = role == 1u ? index * PZ_SLOTS_PER_SERVICE + (threadIdx.x & 31u) / PZ_G : index * PZ_SLOTS_PER_WRITER + (threadIdx.x & 31u) / PZ_WG;
   const bool present = slot < PZ_SLOTS;
   PzStreamSmem *sm = slots + (present ? slot : 0u);
   if (role == 1u) {
@@ -444,6 +444,13 @@ cudaError_t pz_kernels_configure(void) {
 int pz_inflate_slots(void) { return g_sm_count * g_inflate_ctas_per_sm[0] * (int)PZ_SLOTS; }
 
 /* One resident wave of persistent CTAs: one per SM (148 on B200), fewer for small batches. */
+/* Launches the small-stream kernels add to a batch of `count` streams: 0 (not run), 2 (list + K5) or 4 (+ list + K6). */
+int pz_small_launches(uint32_t count, uint32_t framing) {
+  static const bool no_k5 = getenv("PZ_NO_K5") != nullptr, want_k6 = getenv("PZ_K6") != nullptr && getenv("PZ_NO_K6") == nullptr; /* A/B */
+  if (no_k5 || count < PZ_FIXED_MIN_STREAMS || (framing & 0xffu) != PZ_FRAME_ZLIB) return 0;
+  return want_k6 ? 4 : 2;
+}
+
 cudaError_t pz_launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uint8_t *d_out, const uint64_t *d_out_off,
                               uint32_t first, uint32_t count, pz_result *d_res, cudaStream_t st, uint32_t *d_prog,
                               const uint32_t *d_in_ready, int phase, uint2 *d_parts, const uint64_t *d_seg_off, uint32_t framing) {
@@ -469,9 +476,13 @@ cudaError_t pz_launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uin
     phase = PZ_PHASE_K1;
   }
   if (d_in_ready) job.skip_done = 0; /* K2 would read input that is not there yet: K1 decodes every stream */
-  static const bool no_k5 = getenv("PZ_NO_K5") != nullptr, no_k6 = getenv("PZ_NO_K6") != nullptr; /* A/B */
-  const bool k5 = !no_k5 && count >= PZ_FIXED_MIN_STREAMS && framing == PZ_FRAME_ZLIB && d_in_ready == nullptr;
-  const bool k6 = k5 && !no_k6;
+  /* K6 (the same kernel with private dynamic-code tables in local memory) is OFF unless PZ_K6 is set: measured on B200
+   * (profiles/r02n_*, r02k_*) it decodes the dynamic quarter of config 3 in 28 ms where K1 needs 25 ms, and sizes it in 17 ms
+   * against 16 ms: with a thread per stream the 3.5 KiB of tables per thread are a gigabyte in flight, every look-up is a DRAM
+   * sector (74 GB read for 1.07 GB decoded), and with few enough threads for the L2 to hold them nothing hides the latency
+   * (profiles/r02l_*: 64 / 128 / 256 threads per SM = 238 / 137 / 99 ms).  Kept as a measured design alternative. */
+  const int small = d_in_ready == nullptr ? pz_small_launches(count, framing) : 0;
+  const bool k5 = small != 0, k6 = small == 4;
   /* K6 keeps 3.5 KiB of tables per thread in local memory: with every thread an SM can hold resident that is 7 MiB per SM,
    * a gigabyte in all, and every look-up would go to DRAM.  A shared-memory request the kernel never touches limits it to
    * PZ_K6_BLOCKS blocks of 256 threads per SM (default 2: 270 MB of tables in all, about twice the L2). */
@@ -480,7 +491,8 @@ cudaError_t pz_launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uin
   static const int k5_blocks = getenv("PZ_K5_BLOCKS") ? atoi(getenv("PZ_K5_BLOCKS")) : 8; /* (A/B: fewer streams in flight = a smaller working set in L2) */
   const size_t k5_smem = k5_blocks >= 8 ? 0 : k5_blocks <= 1 ? 120 * 1024 : (size_t)(220 * 1024 / k5_blocks) - 2048;
   const size_t k6_smem = k6_blocks >= 8 ? 0 : k6_blocks <= 1 ? 120 * 1024 : (size_t)(220 * 1024 / k6_blocks) - 2048;
-  const unsigned small_grid = (count + PZ_FIXED_THREADS - 1u) / PZ_FIXED_THREADS, k6_grid = (count + k6_threads - 1u) / k6_threads;
+  static const unsigned k5_threads = getenv("PZ_K5_THREADS") ? (unsigned)atoi(getenv("PZ_K5_THREADS")) : PZ_FIXED_THREADS;
+  const unsigned small_grid = (count + k5_threads - 1u) / k5_threads, k6_grid = (count + k6_threads - 1u) / k6_threads;
   /* K5 then K6 over packed lists of the streams each will try (pz_small_list_kernel); the list lives in stream-ordered memory */
   auto small_streams = [&](bool co) -> cudaError_t {
     uint32_t *list = nullptr;
@@ -490,8 +502,8 @@ cudaError_t pz_launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uin
       if ((e = cudaMemsetAsync(list, 0, 8, st)) != cudaSuccess) return e;
       pz_small_list_kernel<<<(count + 255u) / 256u, 256, 0, st>>>(job, list, (uint32_t)dyn);
       if (!dyn) {
-        if (co) pz_fixed_kernel<true, false><<<small_grid, PZ_FIXED_THREADS, 0, st>>>(job, list);
-        else pz_fixed_kernel<false, false><<<small_grid, PZ_FIXED_THREADS, k5_smem, st>>>(job, list);
+        if (co) pz_fixed_kernel<true, false><<<small_grid, k5_threads, 0, st>>>(job, list);
+        else pz_fixed_kernel<false, false><<<small_grid, k5_threads, k5_smem, st>>>(job, list);
       } else {
         if (co) pz_fixed_kernel<true, true><<<k6_grid, k6_threads, k6_smem, st>>>(job, list);
         else pz_fixed_kernel<false, true><<<k6_grid, k6_threads, k6_smem, st>>>(job, list);
@@ -648,3 +660,12 @@ cudaError_t pz_launch_code_values(const uint8_t *d_lens, int n, uint16_t *d_code
   pz_code_values_kernel<<<1, PZ_G, 0, st>>>(d_lens, n, d_codes);
   return cudaGetLastError();
 }
+
+#ifdef PZ_PHASES
+extern "C" void pz_debug_phases(unsigned long long *out) { /* debug build only: read and clear pz_phase_ticks */
+  unsigned long long z[16] = {0};
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, pz_phase_ticks, sizeof(z));
+  cudaMemcpyToSymbol(pz_phase_ticks, z, sizeof(z));
+}
+#endif

@@ -3,6 +3,8 @@ and verdicts).  Mirrors test/Test.hs (2 KATs + 9 goldens) and widens to the beha
 reference's own tests do not reach."""
 import ctypes as C
 import os
+import subprocess
+import sys
 import zlib
 
 import numpy as np
@@ -394,6 +396,19 @@ def test_small_stream_batch_mixed_verdicts(pz, oracle):
                 assert (r.adler_computed, r.adler_stored) == (o.adler_computed, o.adler_stored), i
             if o.status != 0:
                 assert _lib.strerror(r) == o.message, i
+
+
+def test_small_stream_batch_with_k6_opt_in():
+    """K6 (the thread-per-stream kernel with private dynamic-code tables) is opt-in (PZ_K6=1, read once per process): the same
+    mixed batch in a child process that has it on."""
+    if os.environ.get("PZ_K6"):
+        pytest.skip("already the child")
+    env = dict(os.environ, PZ_K6="1")
+    env.pop("PZ_NO_K6", None)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k", "small_stream_batch_mixed_verdicts",
+                        "-p", "no:cacheprovider"], env=env, capture_output=True, text=True, timeout=900,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0 and "1 passed" in r.stdout, r.stdout[-2000:] + r.stderr[-1000:]
 
 
 def test_sizing_pass_matches_decode(pz):

@@ -25,7 +25,7 @@ def func_of(path, line):
     return starts[i][1] if i >= 0 else "?"
 # walk the disassembly of the <false> kernel
 lines = dis.splitlines()
-kern = "ILb1" if len(sys.argv) > 2 and sys.argv[2] == "count" else "ILb0"
+kern = "ILb1ELb0ELb0E" if len(sys.argv) > 2 and sys.argv[2] == "count" else "ILb0ELb0ELb0E"
 i0 = next(i for i, l in enumerate(lines) if l.startswith(".text._Z17pz_inflate_kernel" + kern))
 ONLY_KERNEL = False
 chain = []; last = [("?", 0)]; per_instr = []
@@ -40,7 +40,9 @@ for l in lines[i0 + 1:]:
         per_instr.append(last)
         chain = []
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
-rows = list(csv.reader(io.StringIO(out))); hdr = rows[1]; data = rows[2:]
+rows = list(csv.reader(io.StringIO(out))); hdr = rows[1]
+nxt = next((i for i, r in enumerate(rows[2:], 2) if r and r[0] == "Kernel Name"), len(rows))  # a report with several launches: the first one
+data = [r for r in rows[2:nxt] if len(r) == len(hdr)]
 ie = hdr.index("Instructions Executed"); sm = hdr.index("# Samples")
 print(f"sass instrs: ncu {len(data)}, nvdisasm {len(per_instr)}")
 TOP = {"pz_decoder_warp", "pz_writer_warp", "pz_slow_step", "pz_fast_loop"}

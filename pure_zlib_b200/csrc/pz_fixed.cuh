@@ -34,6 +34,8 @@
  * for one at any time -- K1 has 28 chains per SM, here there are up to 1 024) and decodes with them.  It takes exactly what
  * zlib's tree builder emits and nothing else: more than 286 / 30 codes, a repeat code that starts the list or runs past it,
  * an over-subscribed code, no end-of-block code, a code longer than its table's index, an unused table entry -- all K1's.
+ * MEASURED (B200, config 3): K6 is slower than K1 on the same streams (28 ms against 25 ms for the dynamic quarter): a gigabyte
+ * of tables is in flight, every look-up is a DRAM sector.  It is therefore opt-in (PZ_K6=1); see DESIGN.md, K5 / K6.
  *
  * Runs between K2 and K1 on batches of at least PZ_FIXED_MIN_STREAMS streams, for streams of at most PZ_FIXED_MAX_IN
  * compressed bytes (a lone thread is slower than K1's hot lane: it is the number of streams that makes this path fast).

@@ -1142,6 +1142,7 @@ struct pz_stream {
   uint64_t published = 0;    /* bytes already handed out as chunks */
   uint64_t publish_to = 0;   /* bytes the reference has published at the current state */
   bool dirty = false;        /* input arrived since the last decode */
+  bool queued = false;       /* inside pz_stream_pump: already on the list of the pump */
   bool terminal = false;     /* verdict reached */
   bool final_pending = false;/* the final (possibly empty) chunk has not been delivered */
   bool done_delivered = false;
@@ -1196,6 +1197,8 @@ int shrink_device(uint8_t *&d, size_t &cap, size_t want, size_t from, size_t kee
 
 constexpr uint64_t kHistory = 32768;          /* the farthest a match reaches back (Deflate.hs:199-237) */
 constexpr uint64_t kRoomMin = 256 << 10;      /* decoded bytes a context has room for in one launch, at least ... */
+constexpr uint64_t kDeadMin = 256 << 10;      /* consumed input a context may keep before it gives the memory back (an allocation, a copy and a free per
+                                                 stream: with thousands of consumers in step that is tens of milliseconds of a round) */
 constexpr uint64_t kRoomMax = 64 << 20;       /* ... and at most: a stream that expands further takes another launch of the same pump */
 
 uint32_t adler_combine(uint32_t s1, uint32_t s2, uint64_t len2) { /* Adler-32 of A || B from those of A and B (a0 = 1, b0 = 0: Adler32.hs:19-20) */
@@ -1260,13 +1263,19 @@ int pump_framed(const std::vector<pz_stream *> &act, uint32_t framing) {
     uint8_t *h = (uint8_t *)ps.h_ctl.p, *d = (uint8_t *)ps.d_ctl.p;
     uint64_t *in_pairs = (uint64_t *)h, *out_pairs = (uint64_t *)(h + 16 * n);
     uint32_t *resume = (uint32_t *)(h + 32 * n);
+    std::vector<uint64_t> moves; /* histories moved to the front of their buffers: ONE kernel for all of them (a cudaMemcpyAsync per
+                                    stream costs more host time than the copies take: 4096 consumers in step = 20 ms per round) */
     for (size_t i = 0; i < n; i++) {
       pz_stream *s = run[i];
       /* room for what this input may add before the kernel has to stop for a larger buffer */
       const uint64_t room = std::min<uint64_t>(kRoomMax, std::max<uint64_t>(kRoomMin, 4 * (s->in_total - s->lead)));
       uint64_t hist = s->pos - s->out_base; /* decoded bytes on the device */
       if (hist >= 2 * kHistory && hist + room + 64 > s->d_out_cap) { /* only the last 32 KiB can still be referenced: move them to the front */
-        PZ_CUDA(cudaMemcpyAsync(s->d_out, s->d_out + (hist - kHistory), kHistory, cudaMemcpyDeviceToDevice, st)); /* disjoint: hist >= 64 KiB */
+        if (kHistory + room + 64 <= s->d_out_cap) { /* stays in this buffer: queued for the one move kernel below (disjoint: hist >= 64 KiB) */
+          moves.push_back((uint64_t)(uintptr_t)(s->d_out + (hist - kHistory))); moves.push_back((uint64_t)(uintptr_t)s->d_out); moves.push_back(kHistory);
+        } else { /* the buffer is about to be replaced: move now, stream-ordered before the copy into the new one */
+          PZ_CUDA(cudaMemcpyAsync(s->d_out, s->d_out + (hist - kHistory), kHistory, cudaMemcpyDeviceToDevice, st));
+        }
         s->out_base = s->pos - kHistory;
         hist = kHistory;
       }
@@ -1281,6 +1290,11 @@ int pump_framed(const std::vector<pz_stream *> &act, uint32_t framing) {
       out_pairs[2 * i] = out0;
       out_pairs[2 * i + 1] = out0 + std::min<uint64_t>((s->out_base - s->base_abs) + (s->d_out_cap - 64), 0xfffdff00ull);
       resume[4 * i] = s->ck[0]; resume[4 * i + 1] = s->ck[1]; resume[4 * i + 2] = (uint32_t)fill; resume[4 * i + 3] = 0;
+    }
+    if (!moves.empty()) {
+      if ((rc = ps.d_gather.reserve(moves.size() * 8u)) != PZ_E_OK) return rc;
+      PZ_CUDA(cudaMemcpyAsync(ps.d_gather.p, moves.data(), moves.size() * 8u, cudaMemcpyHostToDevice, st));
+      PZ_CUDA(pz_launch_gather((const uint64_t *)ps.d_gather.p, (uint32_t)(moves.size() / 3), st));
     }
     PZ_CUDA(cudaMemcpyAsync(d, h, up, cudaMemcpyHostToDevice, st));
     uint32_t *d_ck = (uint32_t *)(d + up);
@@ -1326,12 +1340,12 @@ int pump_framed(const std::vector<pz_stream *> &act, uint32_t framing) {
         if (!len) continue;
         /* host side: handed-out bytes in front of the buffer are dropped once they outweigh what is still owed */
         if (s->published == s->h_to) s->h_first = s->h_to;
-        else if (s->published - s->h_first >= std::max<uint64_t>(1 << 20, s->h_to - s->published)) {
+        else if (s->published - s->h_first >= std::max<uint64_t>(128 << 10, s->h_to - s->published)) { /* (amortised: the move is at most what it frees) */
           memmove(s->h_out.p, s->h_out.p + (s->published - s->h_first), (size_t)(s->h_to - s->published));
           s->h_first = s->published;
         }
         const uint64_t keep = s->h_to - s->h_first;
-        if ((rc = s->h_out.reserve_keep((size_t)(keep + len), (size_t)keep)) != PZ_E_OK) return rc;
+        if ((rc = s->h_out.reserve_keep(std::max<size_t>((size_t)(keep + len), 64 << 10), (size_t)keep)) != PZ_E_OK) return rc; /* 64 KiB are buffered before the first chunk is due (Monad.hs:338-358) */
         if (len > kGatherMax) {
           PZ_CUDA(cudaMemcpyAsync(s->h_out.p + keep, s->d_out + (s->pos - s->out_base), len, cudaMemcpyDeviceToHost, st));
         } else {
@@ -1366,7 +1380,7 @@ int pump_framed(const std::vector<pz_stream *> &act, uint32_t framing) {
       s->ck[1] = (ck[4 * i + 1] == 0u || ck[4 * i + 1] == PZ_CK_TRAILER_HOST) ? ck[4 * i + 1] : ck[4 * i + 1] - shift;
       if (shift) s->lead = new_lead;
       const uint64_t dead = s->lead - s->in_base, live = s->in_total - s->lead;
-      if (dead >= std::max<uint64_t>(1 << 16, live)) { /* give the dead input back (amortised: the copy is at most what was freed) */
+      if (dead >= std::max<uint64_t>(kDeadMin, live)) { /* give the dead input back (amortised: the copy is at most what was freed) */
         if ((rc = shrink_device(s->d_in, s->d_in_cap, std::max<uint64_t>(2 * live, 1 << 16), (size_t)dead, (size_t)live, s->st)) != PZ_E_OK) return rc;
         s->in_base = s->lead;
       }
@@ -1398,9 +1412,9 @@ int pump(pz_stream *const *all, size_t n_all) {
   for (size_t i = 0; i < n_all; i++) {
     pz_stream *s = all[i];
     if (!s) return PZ_E_ARG;
-    std::vector<pz_stream *> &v = act[s->framing % 3u];
-    if (s->dirty && !s->terminal && std::find(v.begin(), v.end(), s) == v.end()) v.push_back(s);
+    if (s->dirty && !s->terminal && !s->queued) { s->queued = true; act[s->framing % 3u].push_back(s); } /* (a stream listed twice is pumped once) */
   }
+  for (auto &v : act) for (pz_stream *s : v) s->queued = false;
   for (uint32_t f = 0; f < 3u; f++) {
     const int rc = pump_framed(act[f], f);
     if (rc != PZ_E_OK) return rc;

@@ -62,7 +62,9 @@ ROOFLINE_KERNEL = {
     "text256k": ("pz_inflate_kernel", _ISSUE),
     "text256k_l1": ("pz_inflate_kernel", _ISSUE),
     "text256k_l9": ("pz_inflate_kernel", _ISSUE),
-    "records4k": ("pz_inflate_kernel", _ISSUE),
+    "records4k": ("pz_fixed_kernel (K5: a thread per small fixed-Huffman stream, 75 % of the records) + pz_inflate_kernel (K1: the dynamic quarter)",
+                  "K5 is bound by 32-byte DRAM sectors of LZ77 history (1.2 GB of 4 KiB histories in flight, ten times the L2: "
+                  "traffic is ~13x the algorithmic bytes); K1 is the issue-bound hot-warp kernel (DESIGN.md 3)"),
     "stored16m": ("pz_stored_copy_kernel (+ pz_stored_probe_kernel; pz_inflate_kernel skips what K2 finished)",
                   "HBM-bound copy with the Adler-32 partial sums fused in; K3 only folds them"),
     "huge": ("K4: pz_blk_search/verify, block jobs on pz_inflate_kernel (16-bit decode), pz_blk_compact/tails/windows/resolve",

@@ -273,7 +273,11 @@ PZ_DEV bool pz_fixed_stream(const uint8_t *in, uint64_t n64, uint8_t *out, uint6
         const uint8_t *q = out + pos - dist;
         const uint32_t *qa = reinterpret_cast<const uint32_t *>((uintptr_t)q & ~(uintptr_t)3);
         const uint32_t qs = (uint32_t)((uintptr_t)q & 3u) * 8u;
+#ifdef PZ_EXP_K5_NOLOAD /* timing experiment (wrong output): what the history reads cost */
+        const uint32_t s0 = (uint32_t)(uintptr_t)qa, s1 = s0 + 1u, s2 = s0 + 2u;
+#else
         const uint32_t s0 = qa[0], s1 = qa[1], s2 = qa[2];
+#endif
         v = (uint64_t)pz_funnel_r(s0, s1, qs) | ((uint64_t)pz_funnel_r(s1, s2, qs) << 32);
         if (c < 8u) v &= ~(~0ull << (8u * c));
       } else { /* a close match (or an output slice that is not word-aligned): byte by byte, in order -- a byte may be one
@@ -288,7 +292,13 @@ PZ_DEV bool pz_fixed_stream(const uint8_t *in, uint64_t n64, uint8_t *out, uint6
         const uint8_t *q = d - dist;
 #pragma unroll
         for (uint32_t j = 0; j < 8u; j++)
+#ifdef PZ_EXP_K5_NOLOAD
+          if (j < c) d[j] = (uint8_t)(uintptr_t)q;
+#elif defined(PZ_EXP_K5_NOSTORE)
+          if (j < c && q[j] == 0x7fu && dist == 0xffffffu) d[j] = q[j];
+#else
           if (j < c) d[j] = q[j];
+#endif
         pos += c;
         rem -= c;
         if (rem == 0u) mark = pos;
@@ -307,8 +317,13 @@ PZ_DEV bool pz_fixed_stream(const uint8_t *in, uint64_t n64, uint8_t *out, uint6
       const uint32_t over = a ? (uint32_t)(v >> (64u - 8u * a)) : 0u;
       const uint32_t total = a + c, full = total >> 2;
       uint32_t *dw = reinterpret_cast<uint32_t *>(out + (pos & ~3u));
+#ifdef PZ_EXP_K5_NOSTORE /* timing experiment (wrong output): what the stores cost (the condition is never true, the values stay live) */
+      if (full >= 1u && comb == 0x0123456789abcdefull) dw[0] = (uint32_t)comb;
+      if (full >= 2u && comb == 0x0123456789abcdefull) dw[1] = (uint32_t)(comb >> 32);
+#else
       if (full >= 1u) dw[0] = (uint32_t)comb;
       if (full >= 2u) dw[1] = (uint32_t)(comb >> 32);
+#endif
       const uint32_t restw = full == 0u ? (uint32_t)comb : full == 1u ? (uint32_t)(comb >> 32) : over;
       const uint32_t rb = total & 3u;
       acc = rb ? restw & ~(0xffffffffu << (8u * rb)) : 0u;

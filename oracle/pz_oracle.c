@@ -506,15 +506,18 @@ static void inflate_with_headers(St *s, Tree *fixed_lit, Tree *fixed_dist, Tree 
   s->bitno = 8;
   uint32_t ours = (s->b << 16) | s->a; /* finalizeAdler (Adler32.hs:53-57) */
   s->res->adler_computed = ours;
-  if (s->framing == FRAME_GZIP) { /* RFC 1952 2.3.1: CRC32 then ISIZE, least significant byte first, checked in that order */
+  if (s->framing == FRAME_GZIP) { /* RFC 1952 2.3.1: CRC32 then ISIZE, least significant byte first.  The WHOLE trailer is read
+                                     before anything is compared (a member cut inside its trailer is "ran out of data", whatever
+                                     its CRC: an incremental decoder must ask for more, not judge half a trailer); then the CRC,
+                                     then the length */
     ours = ~s->crc;
     s->res->adler_computed = ours;
     uint32_t lo = next_word16(s), hi = next_word16(s);
     uint32_t theirs = (hi << 16) | lo;
     s->res->adler_stored = theirs;
-    if (theirs != ours) raise_(s, ST_CHECKSUM, D_ADLER_MISMATCH, 0, 0);
     lo = next_word16(s); hi = next_word16(s);
     uint32_t isize = (hi << 16) | lo, total = (uint32_t)(s->published + s->ow_next);
+    if (theirs != ours) raise_(s, ST_CHECKSUM, D_ADLER_MISMATCH, 0, 0);
     if (isize != total) raise_(s, ST_CHECKSUM, D_LENGTH_MISMATCH, isize, 0);
   } else if (s->framing == FRAME_ZLIB) {
     uint32_t theirs = next_word32(s);

@@ -153,6 +153,35 @@ def fuzz_cases(seed: int, n: int):
             yield random_dynamic_stream(rng)
 
 
+def reframe(z: bytes, framing: int, k: int) -> bytes:
+    """The deflate body of a (possibly broken) zlib stream under gzip (1) or raw (2) framing.  gzip members get the trailer of
+    what system zlib decodes from the body (a made-up one if it cannot); every third keeps a wrong CRC, every seventh a wrong
+    ISIZE, every fifth has an FNAME field."""
+    body = z[2:-4] if len(z) >= 6 else z[2:]
+    if framing == 2:
+        return body
+    try:
+        data = zlib.decompressobj(-15).decompress(body)
+        crc, isz = zlib.crc32(data), len(data) & 0xffffffff
+    except Exception:
+        crc, isz = 0x12345678, 7
+    if k % 3 == 1:
+        crc ^= 1 << (k % 32)
+    if k % 7 == 3:
+        isz ^= 1
+    hdr = bytes([0x1f, 0x8b, 8, 0, 0, 0, 0, 0, 0, 255])
+    if k % 5 == 2:
+        hdr = bytes([0x1f, 0x8b, 8, 8, 0, 0, 0, 0, 0, 3]) + b"n\0"
+    return hdr + body + crc.to_bytes(4, "little") + isz.to_bytes(4, "little")
+
+
+def framed_fuzz_cases(seed: int, n: int):
+    """(framing, stream): three of five cases zlib, one gzip, one raw deflate (the same generators, re-framed)."""
+    for k, z in enumerate(fuzz_cases(seed, n)):
+        framing = (0, 0, 0, 1, 2)[k % 5]
+        yield framing, (reframe(z, framing, k) if framing else z)
+
+
 def device_expectation(o):
     """What the inflate kernel alone (before the checksum pass) must report for an oracle
     verdict `o`: the checksum comparison belongs to the Adler kernels."""

@@ -155,6 +155,26 @@ def test_gzip_and_raw_framing():
                 assert r.adler_stored == o.adler_stored and r.payload[0] == o.out_len, name
 
 
+@pytest.mark.parametrize("seed", [21, 22])
+def test_gzip_and_raw_framing_fuzz(seed):
+    """Mutated and generated deflate bodies under gzip and raw framing (fuzzlib.reframe: right and wrong CRC / ISIZE, FNAME
+    fields, truncated trailers): the device logic against the oracle's extension -- found by tools/fuzz_gpu.py: a member cut
+    inside its trailer is "ran out of data" whatever its CRC says."""
+    n = 0
+    for fr, z in fuzzlib.framed_fuzz_cases(seed, 1500):
+        if fr == 0:
+            continue
+        o = oracle.decompress(z, framing=fr)
+        r, out = hostsim.inflate(z, o.out_len + 300, False, framing=fr)
+        n += 1
+        if o.status == 5:  # comparing checksums is K3's business on the device
+            assert (r.status, r.out_len, r.adler_stored) == (0, o.out_len, o.adler_stored), (seed, n, z.hex()[:80])
+            continue
+        assert (r.status, r.detail, r.out_len) == (o.status, o.detail, o.out_len), (seed, n, r.status, r.detail, r.out_len, o.message, z.hex()[:80])
+        assert out == o.data
+    assert n >= 500
+
+
 # ---- K5 (pz_fixed.cuh): one thread per small fixed-Huffman stream -----------------------------------------------------
 def _fixed_stream(data: bytes, level: int = 6, blocks: int = 1) -> bytes:
     co = zlib.compressobj(level, zlib.DEFLATED, 15, 8, zlib.Z_FIXED)

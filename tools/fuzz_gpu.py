@@ -1,0 +1,114 @@
+#!/usr/bin/env python
+"""Deep differential fuzz of the CUDA path against the oracle (tests/fuzzlib.py generators, many seeds): every case goes
+through pz_decompress_batch AND pz_inflate_sizes_framed + pz_inflate_batch, in batches large enough for K2 / K5 to take part,
+with zlib, gzip and raw-deflate framing (the gzip / raw cases re-frame the same deflate bodies).  Compared per case: status,
+detail, decoded length, bytes, checksums where the verdict defines them, and the error string.  A sample of the zlib cases
+also goes through the incremental API in random pieces (event sequence against the oracle over the same chunk list).
+
+  python tools/fuzz_gpu.py --seeds 40 --per-seed 2500        # prints one JSON line; exit code 1 on any mismatch
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import sys
+import time
+import zlib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+
+def gen(args):
+    seed, n = args
+    import fuzzlib
+    import oracle
+    out = []
+    for framing, z in fuzzlib.framed_fuzz_cases(seed, n):
+        o = oracle.decompress(z, framing=framing)
+        out.append((framing, z, o.status, o.detail, o.out_len, o.data, o.adler_computed, o.adler_stored, o.message))
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seeds", type=int, default=40)
+    ap.add_argument("--per-seed", type=int, default=2500)
+    ap.add_argument("--first-seed", type=int, default=1000)
+    ap.add_argument("--incremental", type=int, default=3000, help="zlib cases also fed through the incremental API in random pieces")
+    a = ap.parse_args()
+    t0 = time.time()
+    import oracle
+    oracle.build()
+    with mp.get_context("fork").Pool(min(32, os.cpu_count() or 1)) as pool:
+        parts = pool.map(gen, [(a.first_seed + s, a.per_seed) for s in range(a.seeds)])
+    cases = [c for p in parts for c in p]
+    t1 = time.time()
+    import pure_zlib_b200 as pz
+    from pure_zlib_b200 import _lib
+    flags_of = {0: 0, 1: _lib.PZ_F_GZIP, 2: _lib.PZ_F_RAW}
+    bad = []
+    counts = {}
+    for framing in (0, 1, 2):
+        sub = [c for c in cases if c[0] == framing]
+        zs = [c[1] for c in sub]
+        for name, fn in (("decompress_batch", pz.zlib.decompress_batch_raw), ("sizes+inflate_batch", pz.zlib.inflate_batch_raw)):
+            res, outs = fn(zs, flags_of[framing])
+            for i, (c, r, out) in enumerate(zip(sub, res, outs)):
+                _, z, st, de, ln, data, ac, as_, msg = c
+                ok = (r.status, r.detail, r.out_len) == (st, de, ln) and out == data
+                if ok and st in (0, 5) and framing != 2:
+                    ok = (r.adler_computed, r.adler_stored) == (ac, as_)
+                if ok and st != 0:
+                    ok = _lib.strerror(r) == msg
+                if not ok and len(bad) < 20:
+                    bad.append({"framing": framing, "api": name, "case": i, "hex": z[:64].hex(), "len": len(z), "got": [r.status, r.detail, int(r.out_len)],
+                                "want": [st, de, ln], "msg": msg})
+                counts[(framing, st)] = counts.get((framing, st), 0) + 1
+    # the incremental API on a sample of the zlib cases: random pieces, the reference's event sequence (oracle over the same chunk list)
+    import numpy as np
+    import oracle as orc
+    rng = np.random.default_rng(a.first_seed)
+    inc_n = inc_bad = 0
+    zl = [c[1] for c in cases if c[0] == 0 and len(c[1]) >= 4]
+    for z in zl[:: max(1, len(zl) // a.incremental)][: a.incremental]:
+        cuts = sorted(set(int(x) for x in rng.integers(1, len(z), 3)))
+        pieces = [z[i:j] for i, j in zip([0] + cuts, cuts + [len(z)])]
+        o = orc.decompress(pieces, want_events=True)
+        events, err, st, rest = [], None, pz.decompress_incremental(), list(pieces)
+        try:
+            while True:
+                if isinstance(st, pz.NeedMore):
+                    events.append((0, 0))
+                    if not rest:
+                        events.append((3, 0))
+                        break
+                    st = st.feed(rest.pop(0))
+                elif isinstance(st, pz.Chunk):
+                    events.append((1, len(st.data)))
+                    st = st.next()
+                elif isinstance(st, pz.Done):
+                    events.append((2, 0))
+                    break
+                else:
+                    events.append((3, 0))
+                    err = st.error
+                    break
+            ok = o.status != 6 and events == o.events and (err is None or o.status in (0,) or str(err) == o.message or (o.status == 3 and o.detail != 2))
+        except pz.ReferenceBottom:
+            ok = o.status == 6
+        inc_n += 1
+        if not ok:
+            inc_bad += 1
+            if len(bad) < 20:
+                bad.append({"api": "incremental", "hex": z[:64].hex(), "len": len(z), "cuts": cuts, "got": events[:8], "want": o.events[:8], "msg": o.message})
+    line = {"incremental_cases": inc_n, "incremental_mismatches": inc_bad, "cases": len(cases), "compared": 2 * len(cases), "mismatches": len(bad), "generate_s": round(t1 - t0, 1), "gpu_s": round(time.time() - t1, 1),
+            "by_framing_and_oracle_status": {f"{f}:{s}": v // 2 for (f, s), v in sorted(counts.items())}, "first_mismatches": bad}
+    print(json.dumps(line))
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -287,7 +287,11 @@ static void adler_block(St *s, const uint8_t *p, size_t n) { /* advanceAdlerBloc
     p += 5551; n -= 5551;
   }
   if (n == 0) return;
-  if (n == 1) { adler_byte(s, p[0]); return; }
+  if (n == 1) { /* advanceAdler on the one byte (the CRC has already taken it above: found by tools/fuzz_gpu.py on a 1-byte stored block) */
+    s->a = (s->a + p[0]) % ADLER_MOD;
+    s->b = (s->b + s->a) % ADLER_MOD;
+    return;
+  }
   uint64_t a = s->a, b = s->b; /* advanceAdlerLimited :37-42 */
   for (size_t i = 0; i < n; i++) { a += p[i]; b += a; }
   s->a = (uint32_t)(a % ADLER_MOD); s->b = (uint32_t)(b % ADLER_MOD);

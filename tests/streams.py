@@ -316,4 +316,16 @@ def gzip_cases():
     out.append(("raw-empty", "raw", b""))
     out.append(("raw-truncated", "raw", out[7][2][:-10]))
     out.append(("zlib-as-gzip", "gzip", zlib.compress(b"abc")))
+    # one-byte stored blocks, an empty one in between (tools/fuzz_gpu.py found the oracle counting such a byte twice in its CRC);
+    # and the same member cut inside its trailer with a wrong CRC in front of the cut: "ran out of data", not a checksum verdict
+    import struct
+    data = bytes(range(9))
+    body = b""
+    for i in range(len(data)):
+        body += bytes([1 if i == len(data) - 1 else 0]) + struct.pack("<HH", 1, 0xfffe) + data[i:i + 1]
+        if i == 3:
+            body += b"\x00\x00\x00\xff\xff"
+    one = bytes([0x1f, 0x8b, 8, 0, 0, 0, 0, 0, 0, 255]) + body + struct.pack("<II", zlib.crc32(data), len(data))
+    out.append(("gz-one-byte-stored-blocks", "gzip", one))
+    out.append(("gz-bad-crc-cut-in-isize", "gzip", one[:-8] + bytes([one[-8] ^ 1]) + one[-7:-2]))
     return out

@@ -152,7 +152,7 @@ def test_gzip_and_raw_agree_with_system_zlib():
 def test_gzip_verdicts():
     want = {"gz-bad-crc": (5, 1), "gz-bad-isize": (5, 2), "gz-bad-magic": (4, 4), "gz-bad-method": (4, 2), "gz-reserved-flags": (4, 5),
             "gz-truncated-trailer": (3, 1), "gz-truncated-header": (3, 1), "gz-empty": (3, 1), "raw-empty": (3, 1),
-            "raw-truncated": (3, 1), "zlib-as-gzip": (4, 4)}
+            "raw-truncated": (3, 1), "zlib-as-gzip": (4, 4), "gz-bad-crc-cut-in-isize": (3, 1)}
     msgs = {"gz-bad-isize": "Checksum error: length mismatch: 16777233 != 17", "gz-bad-magic": "Header error: Not a gzip stream: 1f8c",
             "gz-reserved-flags": "Header error: Reserved gzip flags set: 128", "gz-bad-method": "Header error: Bad compression method: 7"}
     for name, kind, z in streams.gzip_cases():

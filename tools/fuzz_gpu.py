@@ -71,12 +71,18 @@ def main():
     import numpy as np
     import oracle as orc
     rng = np.random.default_rng(a.first_seed)
-    inc_n = inc_bad = 0
+    inc_n = inc_bad = inc_quirk = 0
     zl = [c[1] for c in cases if c[0] == 0 and len(c[1]) >= 4]
     for z in zl[:: max(1, len(zl) // a.incremental)][: a.incremental]:
         cuts = sorted(set(int(x) for x in rng.integers(1, len(z), 3)))
         pieces = [z[i:j] for i, j in zip([0] + cuts, cuts + [len(z)])]
         o = orc.decompress(pieces, want_events=True)
+        o1 = orc.decompress(z)
+        if (o.status, o.detail) != (o1.status, o1.detail) and (3, 2) not in ((o.status, o.detail), (o1.status, o1.detail)):
+            # the reference's getBlock quirk (a stored block that ends exactly at a chunk boundary swallows one more byte):
+            # the chunked verdict differs from the single-chunk one; not reproduced by design
+            inc_quirk += 1
+            continue
         events, err, st, rest = [], None, pz.decompress_incremental(), list(pieces)
         try:
             while True:
@@ -104,7 +110,7 @@ def main():
             inc_bad += 1
             if len(bad) < 20:
                 bad.append({"api": "incremental", "hex": z[:64].hex(), "len": len(z), "cuts": cuts, "got": events[:8], "want": o.events[:8], "msg": o.message})
-    line = {"incremental_cases": inc_n, "incremental_mismatches": inc_bad, "cases": len(cases), "compared": 2 * len(cases), "mismatches": len(bad), "generate_s": round(t1 - t0, 1), "gpu_s": round(time.time() - t1, 1),
+    line = {"incremental_cases": inc_n, "incremental_mismatches": inc_bad, "incremental_skipped_chunk_boundary_quirk": inc_quirk, "cases": len(cases), "compared": 2 * len(cases), "mismatches": len(bad), "generate_s": round(t1 - t0, 1), "gpu_s": round(time.time() - t1, 1),
             "by_framing_and_oracle_status": {f"{f}:{s}": v // 2 for (f, s), v in sorted(counts.items())}, "first_mismatches": bad}
     print(json.dumps(line))
     return 1 if bad else 0

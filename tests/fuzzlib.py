@@ -153,6 +153,47 @@ def fuzz_cases(seed: int, n: int):
             yield random_dynamic_stream(rng)
 
 
+def big_corpus(seed: int = 1, count: int = 12):
+    """Valid streams of 10 KB .. 400 KB: several blocks, long and overlapping matches, the window sliding (the reference
+    publishes from 64 KiB on), stored runs between compressed ones."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for it in range(count):
+        n = int(rng.integers(10_000, 400_000))
+        kind = it % 5
+        if kind == 0:
+            data = streams.small_text(n, 2000 + it + seed)
+        elif kind == 1:
+            data = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        elif kind == 2:
+            data = (rng.integers(0, 4, n, dtype=np.uint8) * 17 + 48).tobytes()
+        elif kind == 3:
+            unit = rng.integers(0, 256, int(rng.integers(1, 40)), dtype=np.uint8).tobytes()
+            data = (unit * (n // len(unit) + 1))[:n]
+        else:
+            data = streams.small_text(n // 2, 3000 + it) + rng.integers(0, 256, n - n // 2, dtype=np.uint8).tobytes()
+        co = zlib.compressobj(int(rng.integers(1, 10)), zlib.DEFLATED, 15, int(rng.integers(1, 10)),
+                              [zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FILTERED][it % 5])
+        z = b""
+        cuts = sorted(int(x) for x in rng.integers(0, n, int(rng.integers(0, 4))))
+        prev = 0
+        for c in cuts:
+            z += co.compress(data[prev:c]) + co.flush([zlib.Z_SYNC_FLUSH, zlib.Z_FULL_FLUSH, zlib.Z_BLOCK][c % 3])
+            prev = c
+        z += co.compress(data[prev:]) + co.flush()
+        out.append(z)
+    return out
+
+
+def big_fuzz_cases(seed: int, n: int):
+    """Mutations of big_corpus streams (every fourth case is the valid stream itself)."""
+    rng = np.random.default_rng(seed)
+    corpus = big_corpus(seed)
+    for i in range(n):
+        z = corpus[int(rng.integers(0, len(corpus)))]
+        yield z if i % 4 == 0 else mutate(z, rng)
+
+
 def reframe(z: bytes, framing: int, k: int) -> bytes:
     """The deflate body of a (possibly broken) zlib stream under gzip (1) or raw (2) framing.  gzip members get the trailer of
     what system zlib decodes from the body (a made-up one if it cannot); every third keeps a wrong CRC, every seventh a wrong

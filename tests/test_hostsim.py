@@ -52,6 +52,13 @@ def test_fuzz(seed):
         check(data)
 
 
+@pytest.mark.parametrize("seed", [1, 2])
+def test_fuzz_big_streams(seed):
+    """Mutations of 10 KB .. 400 KB streams (several blocks, long and overlapping matches, the window sliding)."""
+    for data in fuzzlib.big_fuzz_cases(seed, 24):
+        check(data)
+
+
 def test_output_full():
     data = streams.small_text(5000, 1)
     z = zlib.compress(data)

@@ -26,7 +26,10 @@ def gen(args):
     import fuzzlib
     import oracle
     out = []
-    for framing, z in fuzzlib.framed_fuzz_cases(seed, n):
+    src = fuzzlib.framed_fuzz_cases(seed, n)
+    if seed < 0:  # --big: mutations of 10 KB .. 400 KB streams, same re-framing
+        src = ((fr, (fuzzlib.reframe(z, fr, k) if fr else z)) for k, z in enumerate(fuzzlib.big_fuzz_cases(-seed, n)) for fr in [(0, 0, 0, 1, 2)[k % 5]])
+    for framing, z in src:
         o = oracle.decompress(z, framing=framing)
         out.append((framing, z, o.status, o.detail, o.out_len, o.data, o.adler_computed, o.adler_stored, o.message))
     return out
@@ -37,13 +40,14 @@ def main():
     ap.add_argument("--seeds", type=int, default=40)
     ap.add_argument("--per-seed", type=int, default=2500)
     ap.add_argument("--first-seed", type=int, default=1000)
+    ap.add_argument("--big", action="store_true", help="mutations of 10 KB .. 400 KB streams (fuzzlib.big_fuzz_cases) instead of the small ones")
     ap.add_argument("--incremental", type=int, default=3000, help="zlib cases also fed through the incremental API in random pieces")
     a = ap.parse_args()
     t0 = time.time()
     import oracle
     oracle.build()
     with mp.get_context("fork").Pool(min(32, os.cpu_count() or 1)) as pool:
-        parts = pool.map(gen, [(a.first_seed + s, a.per_seed) for s in range(a.seeds)])
+        parts = pool.map(gen, [((-1 if a.big else 1) * (a.first_seed + s), a.per_seed) for s in range(a.seeds)])
     cases = [c for p in parts for c in p]
     t1 = time.time()
     import pure_zlib_b200 as pz

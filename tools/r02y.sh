@@ -12,3 +12,6 @@ print("cases", sum(x["cases"] for x in t), "compared", sum(x["compared"] for x i
 for x in t:
     for m in x["first_mismatches"][:3]: print(json.dumps(m)[:600])
 PY
+# big streams: 40 seeds x 500 mutations of 10 KB .. 400 KB streams (20 000 cases, ~2 GB decoded per entry point)
+timeout 1200 python tools/fuzz_gpu.py --big --seeds 40 --per-seed 500 --first-seed 300 --incremental 1500 > $o/${tag}_fuzz_big.json 2>> $o/${tag}_fuzz.err; echo "big rc=$?"
+cut -c1-700 $o/${tag}_fuzz_big.json

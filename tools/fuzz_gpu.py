@@ -41,6 +41,7 @@ def main():
     ap.add_argument("--per-seed", type=int, default=2500)
     ap.add_argument("--first-seed", type=int, default=1000)
     ap.add_argument("--big", action="store_true", help="mutations of 10 KB .. 400 KB streams (fuzzlib.big_fuzz_cases) instead of the small ones")
+    ap.add_argument("--huge-bytes", type=int, default=0, help="lower PZ_OPT_HUGE_BYTES so that streams of this compressed size take K4")
     ap.add_argument("--incremental", type=int, default=3000, help="zlib cases also fed through the incremental API in random pieces")
     a = ap.parse_args()
     t0 = time.time()
@@ -52,6 +53,8 @@ def main():
     t1 = time.time()
     import pure_zlib_b200 as pz
     from pure_zlib_b200 import _lib
+    if a.huge_bytes:  # streams from this compressed size on take the block-parallel path K4 (which declines whatever it cannot bound)
+        _lib.check(_lib.load().pz_set_option(_lib.PZ_OPT_HUGE_BYTES, a.huge_bytes), "pz_set_option")
     flags_of = {0: 0, 1: _lib.PZ_F_GZIP, 2: _lib.PZ_F_RAW}
     bad = []
     counts = {}
@@ -77,7 +80,7 @@ def main():
     rng = np.random.default_rng(a.first_seed)
     inc_n = inc_bad = inc_quirk = 0
     zl = [c[1] for c in cases if c[0] == 0 and len(c[1]) >= 4]
-    for z in zl[:: max(1, len(zl) // a.incremental)][: a.incremental]:
+    for z in (zl[:: max(1, len(zl) // a.incremental)][: a.incremental] if a.incremental > 0 else []):
         cuts = sorted(set(int(x) for x in rng.integers(1, len(z), 3)))
         pieces = [z[i:j] for i, j in zip([0] + cuts, cuts + [len(z)])]
         o = orc.decompress(pieces, want_events=True)
@@ -114,7 +117,8 @@ def main():
             inc_bad += 1
             if len(bad) < 20:
                 bad.append({"api": "incremental", "hex": z[:64].hex(), "len": len(z), "cuts": cuts, "got": events[:8], "want": o.events[:8], "msg": o.message})
-    line = {"incremental_cases": inc_n, "incremental_mismatches": inc_bad, "incremental_skipped_chunk_boundary_quirk": inc_quirk, "cases": len(cases), "compared": 2 * len(cases), "mismatches": len(bad), "generate_s": round(t1 - t0, 1), "gpu_s": round(time.time() - t1, 1),
+    k4 = {"k4_done": int(_lib.load().pz_get_counter(1)), "k4_declined": int(_lib.load().pz_get_counter(2))}
+    line = {**k4, "incremental_cases": inc_n, "incremental_mismatches": inc_bad, "incremental_skipped_chunk_boundary_quirk": inc_quirk, "cases": len(cases), "compared": 2 * len(cases), "mismatches": len(bad), "generate_s": round(t1 - t0, 1), "gpu_s": round(time.time() - t1, 1),
             "by_framing_and_oracle_status": {f"{f}:{s}": v // 2 for (f, s), v in sorted(counts.items())}, "first_mismatches": bad}
     print(json.dumps(line))
     return 1 if bad else 0

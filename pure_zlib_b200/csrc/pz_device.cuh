@@ -1127,7 +1127,7 @@ PZ_DEV void pz_fast_fetch(PzFast &f, const PzStreamSmem *sm, uint32_t bp) {
  * token queue -- the chain keeps running on garbage for the rest of the trip (all table and ring
  * indices are masked, so that is harmless) and nothing more is committed.  Returns true if the
  * stream stopped inside this trip; f.b0/b1/b2/e are then stale. */
-/* Symbols per trip.  Measured (profiles/r03a_*, r03b_*): 2 / 3 / 4 / 5 / 6 symbols give 146 / 154 / 140 / 134 / 132 GB/s on config 2.
+/* Symbols per trip.  Measured (profiles/r02aa_*, r02ab_*): 2 / 3 / 4 / 5 / 6 symbols give 146 / 154 / 140 / 134 / 132 GB/s on config 2.
  * The trip is straight-line code (80 instructions per symbol) issued by ONE warp, and ncu shows `no_inst` at every eighth
  * instruction of the four-symbol trip (325 instructions = 5.2 KB): it does not fit the instruction cache next to the
  * scheduler, three symbols (3.9 KB) do.  (Four was the optimum while the loop around the trip still cost two votes and two

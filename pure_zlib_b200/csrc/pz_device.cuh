@@ -1123,8 +1123,7 @@ PZ_DEV void pz_fast_fetch(PzFast &f, const PzStreamSmem *sm, uint32_t bp) {
  *
  * The chain runs SPECULATIVELY: it never waits for the verdict on the symbol it has just consumed.
  * The verdict (`alive`, sticky within the trip) only gates what is committed: the token, and the
- * position registers in `f`.  Once a symbol fails -- something the loop must not decide, a full
- * token queue -- the chain keeps running on garbage for the rest of the trip (all table and ring
+ * position registers in `f`.  Once a symbol fails -- something the loop must not decide -- the chain keeps running on garbage for the rest of the trip (all table and ring
  * indices are masked, so that is harmless) and nothing more is committed.  Returns true if the
  * stream stopped inside this trip; f.b0/b1/b2/e are then stale. */
 /* Symbols per trip.  Measured (profiles/r02aa_*, r02ab_*): 2 / 3 / 4 / 5 / 6 symbols give 146 / 154 / 140 / 134 / 132 GB/s on config 2.
@@ -1159,17 +1158,15 @@ PZ_DEV bool pz_fast_trip(PzFast &f, PzStreamSmem *sm, const bool run) {
     const uint32_t dx = (d >> 9) & 15u; /* extra bits of the distance */
     const uint32_t dist = 1u + ((d >> 13) << dx) + ((wd >> ((d >> 5) & 15u)) & ~(0xffffffffu << dx));
     const uint32_t room = f.lim - pos;
-#ifdef PZ_HOSTSIM
-    const bool full = false;
-#else
-    const bool full = !COUNT_ONLY && qhead - f.qtailc >= PZ_QLEN;
-#endif
-    const bool pre_ok = bp <= f.safe_end && room != 0u && !full;
+    /* (room in the token queue for the whole trip is the caller's to check: one test per trip instead of one per symbol) */
+    const uint32_t adv = is_lit ? 1u : len;
+    /* the bytes of the symbol fit (one for a literal).  Two spellings of the same test: ptxas makes the faster trip out of
+     * the first in the decode kernel (6.67 against 6.69 ms) and out of the second in the sizing pass (5.38 against 5.75 ms) */
+    const bool pre_ok = bp <= f.safe_end && (COUNT_ONLY ? room != 0u : adv <= room);
     /* dist <= pos - base (OutputWindow.hs:82-89) is dist <= pos here: base only ever moves when 64 KiB
      * have accumulated, so base > 0 implies pos - base >= 32 KiB >= any distance */
-    const bool m_ok = tb != 0u && (d & 31u) != 0u && dist <= pos && len <= room;
+    const bool m_ok = tb != 0u && (d & 31u) != 0u && dist <= pos && (COUNT_ONLY ? len <= room : true);
     alive = alive && pre_ok && (is_lit || m_ok);
-    const uint32_t adv = is_lit ? 1u : len;
     if (BLK) { /* PzCtx::mark: a gap of more than 32 KiB between two moveWindow calls is the careful path's to refuse */
       alive = alive && pos + adv - mark <= PZ_EXCESS;
       mark = is_lit ? mark : pos + adv;
@@ -1251,14 +1248,13 @@ PZ_DEV void pz_hot_warp(PzStreamSmem *slots, uint32_t n_slots) {
      * idles this trip */
     const uint32_t ring_hi = pz_vload(&sm->mail.ring_hi);
     if (!COUNT_ONLY) f.qtailc = pz_vload(&sm->qtail);
-    const bool run = f.live && (f.bp >> PZ_QUARTER_SHIFT) + 1u < ring_hi;
+    /* ... and so does a lane whose token queue might not take a whole trip's tokens (the writer is behind) */
+    const bool run = f.live && (f.bp >> PZ_QUARTER_SHIFT) + 1u < ring_hi && (COUNT_ONLY || f.qhead - f.qtailc <= PZ_QLEN - PZ_TRIP);
     const bool stop = pz_fast_trip<COUNT_ONLY, BLK>(f, sm, run);
     if (run) pz_vstore(&sm->mail.hot_bp, f.bp);
     const bool pick = st == PZ_MS_HOT, died = st == PZ_MS_DEAD;
     if (__any_sync(0xffffffffu, stop || pick || died)) {
-      const bool full = !COUNT_ONLY && f.qhead - f.qtailc >= PZ_QLEN;
-      if (stop && full) pz_fast_fetch(f, sm, f.bp); /* stays live: the queue drains, the window is re-read */
-      if (stop && !full) { /* hand the stream back: the careful path decides the next symbol */
+      if (stop) { /* hand the stream back: the careful path decides the next symbol */
         pz_vstore(&sm->mail.bp, f.bp); pz_vstore(&sm->mail.pos, f.pos); pz_vstore(&sm->mail.base, f.base);
         pz_vstore(&sm->mail.qhead, f.qhead);
         if (BLK) pz_vstore(&sm->mail.mark, f.mark);

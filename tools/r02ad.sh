@@ -1,0 +1,15 @@
+#!/bin/bash
+# GPU call: token-queue room tested once per trip instead of once per symbol (quick parity subset + config 2 / 3 / huge)
+o=gpurun_out; tag=r02ad
+timeout 900 python -m pytest tests -m gpu -x -q -k "golden or appendix or mixed_verdicts or baseline_config or huge_stream_block or stream_pump or large_expansion" 2>&1 | tail -3 > $o/${tag}_pytest.log; tail -1 $o/${tag}_pytest.log
+for cfg in text256k records4k huge; do
+  timeout 600 python bench.py --steps 10 --warmup 3 --config $cfg --others none --no-e2e --no-cpu-baseline --verify 16 > $o/${tag}_bench_$cfg.json 2> $o/${tag}_$cfg.err
+done
+python - <<'PY'
+import json,glob
+for f in sorted(glob.glob("gpurun_out/r02ad_bench_*.json")):
+    try:
+        b=json.loads(open(f).read().strip().splitlines()[-1])
+        print(f[23:], "value", round(b["value"],1), "ms", round(b["ms_per_step"],3), "k1", round(b["roofline"]["kernel_ms"],3), "dec", b["roofline"]["decoder_only_ms"])
+    except Exception as e: print(f, "ERR", e)
+PY

@@ -447,7 +447,8 @@ def measure(ctx: Ctx, config: str, c, steps: int, warmup: int, headline: bool, s
         except Exception:
             pass
         line["e2e"] = {"value": out_bytes_total * e2e_steps / sec / 1e9, "unit": "GB/s", "ceiling": ceiling,
-                       "ceiling_note": "aggregate pinned D2H GB/s of N GPUs on one box with the H2D copies running (profiles/pcie_ceiling.json): "
+                       "ceiling_note": "aggregate pinned D2H GB/s of N GPUs on one box with the H2D copies running (profiles/pcie_ceiling.json, measured "
+                                       "with tools/pcie_ceiling.py on ONE box of the pool; boxes differ by 10-20 %, so e2e can pass it): "
                                        "the host side of the box bounds e2e, not the kernels",
                        "h2d_bytes_per_step": int(c.in_off[-1]) + 3 * 8 * (c.n + 1),
                        "d2h_bytes_per_step": int(c.out_off[-1]) + 48 * c.n, "steps": e2e_steps,

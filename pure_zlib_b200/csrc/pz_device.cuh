@@ -98,6 +98,7 @@ PZ_DEV void pz_smem_inc(uint32_t *p) { ++*p; }
 PZ_DEV int pz_popc(unsigned x) { return __builtin_popcount(x); }
 PZ_DEV int pz_ffs(unsigned x) { return __builtin_ffs((int)x); }
 PZ_DEV uint32_t pz_funnel_r(uint32_t lo, uint32_t hi, uint32_t s) { return (uint32_t)(((((uint64_t)hi) << 32) | lo) >> (s & 31u)); }
+PZ_DEV uint32_t pz_funnel_l(uint32_t lo, uint32_t hi, uint32_t s) { return (uint32_t)((((((uint64_t)hi) << 32) | lo) << (s & 31u)) >> 32); }
 PZ_DEV void pz_copy16_async(void *smem_dst, const void *gsrc) { memcpy(smem_dst, gsrc, 16); }
 PZ_DEV void pz_async_wait_all() {}
 #else
@@ -124,6 +125,7 @@ PZ_DEV void pz_smem_inc(uint32_t *p) { atomicAdd(p, 1u); }
 PZ_DEV int pz_popc(unsigned x) { return __popc(x); }
 PZ_DEV int pz_ffs(unsigned x) { return __ffs((int)x); }
 PZ_DEV uint32_t pz_funnel_r(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_r(lo, hi, s); }
+PZ_DEV uint32_t pz_funnel_l(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_l(lo, hi, s); }
 PZ_DEV void pz_copy16_async(void *smem_dst, const void *gsrc) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
@@ -165,19 +167,23 @@ PZ_DEV void pz_async_wait_all() {
                           distance LUT entry; the queue entry's second word holds the 32 stream bits behind the length code */
 #define PZ_TOKEN(type, payload) (((uint32_t)(type) << 29) | (uint32_t)(payload))
 
-/* LUT entry: total bits [0,5) | code bits [8,12) | type [12,14) | value [16,31) | literal flag 31.
+/* LUT entry: total bits [0,5) | code bits [8,12) | 0 | type [13,15) | value [16,31) | literal flag 31.
  * total == 0 marks an entry the hot loop must not act on (long code, dead prefix, end of
- * block, or a symbol the reference cannot index): the careful path decides. */
+ * block, or a symbol the reference cannot index): the careful path decides.
+ * Fields that are shift AMOUNTS sit where `entry >> k` has them in its low five bits with a zero above (the funnel shifts
+ * take their amount modulo 32): no mask instruction between the table and the shift -- every instruction of the hot trip
+ * is 0.4 % of K1. */
 #define PZ_T_LIT 0u
 #define PZ_T_BASE 1u /* length / distance base + extra bits */
 #define PZ_T_SLOW 3u
-#define PZ_ENTRY(total, nbits, type, value) ((uint32_t)(total) | ((uint32_t)(nbits) << 8) | ((uint32_t)(type) << 12) | ((uint32_t)(value) << 16))
+#define PZ_ENTRY(total, nbits, type, value) ((uint32_t)(total) | ((uint32_t)(nbits) << 8) | ((uint32_t)(type) << 13) | ((uint32_t)(value) << 16))
 #define PZ_SLOW_ENTRY PZ_ENTRY(0, 0, PZ_T_SLOW, 0)
 #define PZ_LIT_FLAG 0x80000000u
-/* Distance LUT entry (16 bits): total bits [0,5) | code bits [5,9) | extra bits [9,13) | m [13,15);
+/* Distance LUT entry (16 bits): total bits [0,5) | extra bits [5,9) | 0 | m [10,12);
  * distance = 1 + (m << extra) + extra-bit value (Deflate.hs:199-237: symbols 0,1 have m = 0,1 and
- * every later pair of symbols m = 2,3).  0 = not for the hot loop. */
-#define PZ_DENTRY(nbits, extra, m) ((uint32_t)((nbits) + (extra)) | ((uint32_t)(nbits) << 5) | ((uint32_t)(extra) << 9) | ((uint32_t)(m) << 13))
+ * every later pair of symbols m = 2,3); the code's own length is total - extra.  0 = not for the hot loop. */
+#define PZ_DENTRY(nbits, extra, m) ((uint32_t)((nbits) + (extra)) | ((uint32_t)(extra) << 5) | ((uint32_t)(m) << 10))
+#define PZ_DENTRY_DEFINED 1
 
 /* Canonical description of one prefix code: enough for the bit-serial walker to reproduce
  * the reference trie's accept / "Advanced to empty tree!" behaviour (HuffmanTree.hs:73-83). */
@@ -607,6 +613,15 @@ PZ_COLD int pz_build(const uint8_t *lens, int n, PzTree *t, uint16_t *perm, LutT
   return 0;
 }
 
+/* The distance a PZ_DENTRY d and the 32 stream bits wd at its code stand for: 1 + (m << extra) + the extra bits' value.
+ * sx = d >> 5 has the number of extra bits in its low five bits, d - sx the code's length (total - extra, modulo 32): both
+ * go into funnel shifts as they are. */
+PZ_DEV uint32_t pz_dist_value(uint32_t d, uint32_t wd) {
+  const uint32_t sx = d >> 5;
+  const uint32_t ex = pz_funnel_r(wd, 0u, d - sx) & ~pz_funnel_l(0u, 0xffffffffu, sx);
+  return 1u + pz_funnel_l(0u, d >> 10, sx) + ex;
+}
+
 /* ---- output side: the writer ---------------------------------------------------------------- */
 #ifdef PZ_HOSTSIM
 PZ_DEV void pz_st8_if(bool p, uint8_t *a, uint32_t v) { if (p) *a = (uint8_t)v; }
@@ -867,8 +882,7 @@ PZ_DEV void pz_writer_warp(const PzJob &job, PzStreamSmem *sm, bool present) {
       asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(raw), "=r"(y) : "r"((unsigned)__cvta_generic_to_shared(&sm->q[idx & (PZ_QLEN - 1u)])));
       const uint32_t t = (raw >> 29) & 3u;
       len = (raw >> 16) & 0x1ffu;
-      const uint32_t dx = (raw >> 9) & 15u; /* PZ_DENTRY: extra bits [9,13), m [13,15), code bits [5,9) */
-      const uint32_t dd = 1u + (((raw >> 13) & 3u) << dx) + ((y >> ((raw >> 5) & 15u)) & ~(0xffffffffu << dx));
+      const uint32_t dd = pz_dist_value(raw & 0xffffu, y);
       dist = t == PZ_Q_MATCHD ? dd : (raw & 0x7fffu) + 1u;
       if (t == PZ_Q_MATCHD) raw = (raw & 0x80000000u) | PZ_TOKEN(PZ_Q_MATCH, (len << 16) | (dist - 1u)); /* from here on an ordinary match token */
       is_lit = t == PZ_Q_LIT; is_match = t == PZ_Q_MATCH || t == PZ_Q_MATCHD;
@@ -1139,6 +1153,9 @@ PZ_DEV bool pz_fast_trip(PzFast &f, PzStreamSmem *sm, const bool run) {
   uint32_t bp = f.bp, pos = f.pos, base = f.base, qhead = f.qhead, mark = f.mark;
   uint32_t b0 = f.b0, b1 = f.b1, b2 = f.b2, e = f.e;
   bool alive = run;
+#ifndef PZ_HOSTSIM
+  const uint32_t qbase = (uint32_t)__cvta_generic_to_shared(sm->q);
+#endif
 #pragma unroll
   for (int k = 0; k < PZ_TRIP; k++) {
     const uint32_t tb = e & 31u;
@@ -1154,9 +1171,8 @@ PZ_DEV bool pz_fast_trip(PzFast &f, PzStreamSmem *sm, const bool run) {
     uint32_t nb1, nb2;
     pz_peek_tail(sm->ring, nbp, nb1, nb2);
     /* off the chain: the symbol's values and its verdict */
-    const uint32_t len = (e >> 16) + ((b0 & ~(0xffffffffu << tb)) >> ((e >> 8) & 15u));
-    const uint32_t dx = (d >> 9) & 15u; /* extra bits of the distance */
-    const uint32_t dist = 1u + ((d >> 13) << dx) + ((wd >> ((d >> 5) & 15u)) & ~(0xffffffffu << dx));
+    const uint32_t len = (e >> 16) + pz_funnel_r(b0 & ~(0xffffffffu << tb), 0u, e >> 8); /* (e >> 8) mod 32 = the code's bits */
+    const uint32_t dm1 = pz_dist_value(d, wd) - 1u; /* the token carries distance - 1; the + 1 and - 1 fold away */
     const uint32_t room = f.lim - pos;
     /* (room in the token queue for the whole trip is the caller's to check: one test per trip instead of one per symbol) */
     const uint32_t adv = is_lit ? 1u : len;
@@ -1165,18 +1181,23 @@ PZ_DEV bool pz_fast_trip(PzFast &f, PzStreamSmem *sm, const bool run) {
     const bool pre_ok = bp <= f.safe_end && (COUNT_ONLY ? room != 0u : adv <= room);
     /* dist <= pos - base (OutputWindow.hs:82-89) is dist <= pos here: base only ever moves when 64 KiB
      * have accumulated, so base > 0 implies pos - base >= 32 KiB >= any distance */
-    const bool m_ok = tb != 0u && (d & 31u) != 0u && dist <= pos && (COUNT_ONLY ? len <= room : true);
+    const bool m_ok = tb != 0u && (d & 31u) != 0u && dm1 < pos && (COUNT_ONLY ? len <= room : true);
     alive = alive && pre_ok && (is_lit || m_ok);
     if (BLK) { /* PzCtx::mark: a gap of more than 32 KiB between two moveWindow calls is the careful path's to refuse */
       alive = alive && pos + adv - mark <= PZ_EXCESS;
       mark = is_lit ? mark : pos + adv;
     }
     if (!COUNT_ONLY) {
-      const uint32_t tok = is_lit ? PZ_TOKEN(PZ_Q_LIT, (e >> 16) & 0xffu) : PZ_TOKEN(PZ_Q_MATCH, (len << 16) | (dist - 1u));
+      const uint32_t tok = is_lit ? PZ_TOKEN(PZ_Q_LIT, (e >> 16) & 0xffu) : PZ_TOKEN(PZ_Q_MATCH, (len << 16) | dm1);
 #ifdef PZ_HOSTSIM
       if (alive) pz_writer_apply<false>(*f.hw, tok);
 #else
-      if (alive) pz_vstore(&sm->q[qhead & (PZ_QLEN - 1u)].x, tok | (((qhead >> PZ_QSHIFT) & 1u) << 31));
+      { /* the queue slot's address is one multiply-add behind the mask, the store is predicated (no branch in the trip) */
+        uint32_t a;
+        asm("mad.lo.u32 %0, %1, 8, %2;" : "=r"(a) : "r"(qhead & (PZ_QLEN - 1u)), "r"(qbase));
+        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %0, 0;\n\t@q st.volatile.shared.u32 [%1], %2;\n\t}" ::"r"((int)alive), "r"(a),
+                     "r"(tok | ((qhead << (31 - PZ_QSHIFT)) & 0x80000000u)) : "memory");
+      }
       qhead += alive ? 1u : 0u;
 #endif
     }
@@ -1321,7 +1342,7 @@ PZ_DEV bool pz_lean_trip(PzLean &f, PzStreamSmem *sm, const bool run) {
     uint32_t nb1, nb2;
     pz_peek_tail(sm->ring, nbp, nb1, nb2);
     /* off the chain: the token */
-    const uint32_t len = (e >> 16) + ((b0 & ~(0xffffffffu << tb)) >> ((e >> 8) & 15u));
+    const uint32_t len = (e >> 16) + pz_funnel_r(b0 & ~(0xffffffffu << tb), 0u, e >> 8);
     alive = alive && tb != 0u && (is_lit || (d & 31u) != 0u) && bp <= f.safe_end;
     const uint32_t tok = (is_lit ? PZ_TOKEN(PZ_Q_LIT, (e >> 16) & 0xffu) : (PZ_TOKEN(PZ_Q_MATCHD, len << 16) | d)) | ((qhead << (31 - PZ_QSHIFT)) & 0x80000000u);
     {

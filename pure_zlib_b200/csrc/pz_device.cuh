@@ -975,8 +975,8 @@ PZ_DEV void pz_writer_warp(const PzJob &job, PzStreamSmem *sm, bool present) {
         }
       }
     }
-#ifdef PZ_EXP_NO_COPY
-    if (false)
+#if defined(PZ_EXP_NO_COPY) || defined(PZ_EXP_NO_STORE) /* (NO_STORE: the loads stay, kept alive by a store that never happens) */
+    if (max_b == 0x7fffffffu)
 #endif
 #pragma unroll
     for (int r = 0; r < PZ_ROUNDS; r++) {

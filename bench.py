@@ -16,7 +16,7 @@ the data path); with --shard the ranks split ONE batch by contiguous ranges bala
 (pure_zlib_b200/shard.py; strong scaling) and --gather adds the optional NCCL gather of output slabs
 and verdicts after the timed region.  `value` times the kernels with the compressed batch resident in
 HBM; `e2e` goes through pz_inflate_batch_contig with pinned HOST buffers (H2D + kernels + D2H inside
-the timed region); `e2e_shim` through pz_inflate_sizes + pz_inflate_batch with pageable pointer arrays
+the timed region); `e2e_shim` through pz_decompress_batch with pageable pointer arrays
 (exactly what the Haskell shim binds).
 
 The oracle (oracle/) is executed here only by the cpu_baseline leg and by --impl reference: it is the

@@ -769,7 +769,9 @@ int contig_one_device(const uint8_t *in_blob, const uint64_t *in_off, uint8_t *o
    * batches with stored-block streams -- recognisable from their first block header -- wait for
    * the whole input instead. */
   const bool in_place = (flags & PZ_F_INPUT_IN_PLACE) != 0;
-  bool progressive = columns && !in_place && n >= 8 * kGroups && n <= 2 * (size_t)pz_inflate_slots() && framing_of(flags) == 0u; /* (the peek below reads a zlib header) */
+  /* (a sizing pass has no output to drain but is the same serial chains: it takes the one-launch path too -- cut into slices
+   * it took 38 ms for config 2, eight kernels of one chain length each, where one launch fed in pieces takes 7) */
+  bool progressive = (columns || count_only) && !in_place && n >= 8 * kGroups && n <= 2 * (size_t)pz_inflate_slots() && framing_of(flags) == 0u; /* (the peek below reads a zlib header) */
   for (size_t i = 0; progressive && i < n; i++) {
     const uint64_t len = in_off[i + 1] - in_off[i];
     const uint8_t *p = in_blob + in_off[i];
@@ -800,11 +802,13 @@ int contig_one_device(const uint8_t *in_blob, const uint64_t *in_off, uint8_t *o
   pz_result *h_res = (pz_result *)ws.h_res.p;
   volatile uint32_t *h_prog = nullptr;
   uint32_t *d_prog = nullptr, *d_ready = nullptr, *h_ready = nullptr;
-  if (columns) {
+  if (columns || progressive) {
     if ((rc = ws.h_prog.reserve((n + kGroups) * sizeof(uint32_t))) != PZ_E_OK) return rc;
+    h_ready = (uint32_t *)ws.h_prog.p + n; /* the values the ready word takes, one per piece */
+  }
+  if (columns) {
     memset(ws.h_prog.p, 0, n * sizeof(uint32_t));
     h_prog = (volatile uint32_t *)ws.h_prog.p;
-    h_ready = (uint32_t *)ws.h_prog.p + n; /* the values the ready word takes, one per piece */
     PZ_CUDA(cudaHostGetDevicePointer((void **)&d_prog, ws.h_prog.p, 0));
   }
   if (progressive) {

@@ -7,7 +7,7 @@
  *
  *   hot warp       pz_hot_warp(): one LANE per slot runs the symbol loop (runInflate, Deflate.hs:106-120) of
  *                  that slot's stream -- window -> literal/length LUT -> shift -> distance LUT -> shift, the
- *                  96 stream bits at the bit position held in registers -- four symbols per trip
+ *                  96 stream bits at the bit position held in registers -- PZ_TRIP = three symbols per trip
  *                  (pz_fast_trip), speculatively: a symbol the loop must not decide (long code, end of block,
  *                  end of input or output in sight, a verdict) commits nothing and returns the stream to its
  *                  service group through the slot's mailbox (PzMail).  It never touches the output: every

@@ -277,6 +277,8 @@ class Ctx:
         torch, dist = self.torch, self.dist
         if self.distributed:
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+                os.environ["NCCL_DEBUG"] = "NONE"  # stdout carries ONE line: no NCCL version banner (VERSION and WARN both print it)
             torch.cuda.set_device(self.local_rank)
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
         if not torch.cuda.is_available():
